@@ -1,0 +1,398 @@
+#!/usr/bin/env python
+"""bench.py -- snapshot-stream GiB/s of the peer-bootstrap hot path on B200.
+
+One "step" = one full pass of the stage over the workload's synthetic ZFS-send
+stream.  Default workload = BASELINE.json configs[1]:
+16 GiB uncompressed stream, Fletcher-4 verification (mode VERIFY), per GPU.
+
+  value     whole-job GiB/s with the stream already resident in HBM
+            (mtz_dev_submit / mtz_dev_finish, CUDA events, max over ranks)
+  e2e       same metric through the host-facing C-ABI call mtz_process_host()
+            with the stream in pinned HOST memory: H2D copies inside the region
+  roofline  K1 (Fletcher-4 sums kernel) achieved HBM GB/s vs MEASURED_PEAKS.json
+  cpu_baseline / --impl reference
+            the oracle's scalar restatement of what runs today inside
+            `zfs send`/`zfs recv` (lib/backupSender.js:177, lib/zfsClient.js:793),
+            record-parallel over all host cores.  Reported, not the target.
+
+N > 1 (torchrun, one rank per GPU): ONE logical stream of N x 16 GiB partitioned
+by record index; each rank verifies its shard, the only exchange is an
+all-gather of the 40-byte shard aggregate (n,A,B,C,D) over NCCL.  Weak scaling.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+GIB = float(1 << 30)
+RECSIZE = 131072
+REC_BYTES = 312 + RECSIZE
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="verify", choices=["verify"])
+    ap.add_argument("--gib", type=float, default=16.0, help="stream GiB per GPU")
+    ap.add_argument("--ref-gib", type=float, default=16.0, help="CPU sample GiB")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    return ap.parse_args()
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) < 9:
+                continue
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2])); pw.append(float(r[3]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def make_shard(O, rank, world, nwrites, pinned_array):
+    """Rank's slice of ONE logical stream (record-index partition).  Payloads are
+    generated in parallel on every rank; the checksum chain hops rank to rank."""
+    import torch.distributed as dist
+    import torch
+    flags = (1 if rank == 0 else 0) | (2 if rank == world - 1 else 0)
+    buf, ppay = O.synth_shard_fill(nwrites, RECSIZE, O.PAYLOAD_PCG, rank * nwrites, flags,
+                                   out=pinned_array, nthreads=max(1, host_threads() // world))
+    state = (0, 0, 0, 0)
+    carry_in = state
+    for r in range(world):
+        if r == rank:
+            carry_in = state
+            state = O.synth_shard_stamp(buf, nwrites, RECSIZE, flags, ppay, state)
+        if world > 1:
+            # int64 view of the u64 state; gloo/nccl both move int64
+            t = torch.tensor([s - (1 << 64) if s >= (1 << 63) else s for s in state],
+                             dtype=torch.int64, device="cuda")
+            dist.broadcast(t, src=r)
+            state = tuple(int(x) & ((1 << 64) - 1) for x in t.cpu().tolist())
+    return buf, carry_in
+
+
+def to_i64(v):
+    return [x - (1 << 64) if x >= (1 << 63) else x for x in v]
+
+
+def from_i64(v):
+    return tuple(int(x) & ((1 << 64) - 1) for x in v)
+
+
+def run_reference(args):
+    """CPU arm: the oracle port of the path's arithmetic on all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import oracle as O
+    O.build()
+    nthreads = host_threads()
+    nwrites = max(1, int(args.ref_gib * GIB) // REC_BYTES)
+    s = O.synth_stream(nwrites, RECSIZE, O.PAYLOAD_PCG, nthreads=nthreads)
+    for _ in range(max(1, min(args.warmup, 2))):
+        rc, secs, st = O.mt_verify(s, nthreads)
+        assert rc == 0
+    t = []
+    for _ in range(args.steps):
+        rc, secs, st = O.mt_verify(s, nthreads)
+        assert rc == 0
+        t.append(secs)
+    # whole job on the CPU = the same arithmetic over N shards on the same cores
+    ms = 1e3 * sum(t) / len(t)
+    val = s.size / GIB / (ms / 1e3)
+    line = {
+        "impl": "reference", "metric": "snapshot_stream_gibs", "value": round(val, 3),
+        "unit": "GiB/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(ms, 3), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u32->u64 (mod 2^64)", "data": "synthetic",
+        "config": {"workload": "verify: %.2f GiB uncompressed ZFS-send stream, Fletcher-4 "
+                               "(BASELINE configs[1])" % (s.size / GIB),
+                   "records": int(st.records), "recordsize": RECSIZE},
+        "cpu_baseline": {"value": round(val, 3), "unit": "GiB/s", "cores": nthreads,
+                         "kind": "port",
+                         "sample": "whole %.2f GiB stream per step, record-parallel scalar "
+                                   "fletcher_4 + sequential combine (oracle/mt.c)" % (s.size / GIB)},
+        "e2e": {"value": round(val, 3), "unit": "GiB/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "reference = Node identity pipe + in-kernel ZFS arithmetic; node/zfs are not "
+                "installable here, so the oracle port of that arithmetic is timed (kind=port)",
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import oracle as O                      # generator + cpu_baseline leg only
+    from manatee_b200 import GpuSnapshotStage, PinnedBuffer, index_host
+    from manatee_b200 import _native as N
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus %d needs torchrun with one rank per GPU" % args.gpus)
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    O.build()
+
+    nwrites = max(1, int(args.gib * GIB) // REC_BYTES)
+    flags = (1 if rank == 0 else 0) | (2 if rank == world - 1 else 0)
+    nbytes = O.lib().orc_synth_shard_size(nwrites, RECSIZE, flags)
+    pin = PinnedBuffer(nbytes)
+    shard, carry_in = make_shard(O, rank, world, nwrites, pin.array)
+    recs, used = index_host(shard)
+    assert used == shard.size
+    d_stream = torch.empty(shard.size + 512, dtype=torch.uint8, device="cuda")
+    d_stream[:shard.size].copy_(torch.from_numpy(shard))
+    d_recs = torch.from_numpy(recs.view(np.uint8).copy()).cuda()
+    torch.cuda.synchronize()
+
+    st = torch.cuda.Stream()
+    agg_t = torch.zeros(5, dtype=torch.int64, device="cuda")
+
+    def carry_from_aggs(all_aggs):
+        c = (0, 0, 0, 0)
+        for r in range(rank):
+            a = all_aggs[r]
+            if a[0] >> 63:
+                c = (0, 0, 0, 0)
+            c = O.fletcher4_apply(c, (a[0] & ((1 << 63) - 1),) + tuple(a[1:]))
+        return c
+
+    def exchange(g):
+        """all-gather of the 40-byte shard aggregate; returns this rank's carry-in."""
+        agg = g.dev_aggregate()
+        agg_t.copy_(torch.tensor(to_i64(agg), dtype=torch.int64))
+        outs = [torch.zeros_like(agg_t) for _ in range(world)]
+        dist.all_gather(outs, agg_t)
+        return carry_from_aggs([from_i64(o.cpu().tolist()) for o in outs])
+
+    # ---------------- resident (HBM) timing: `value` ----------------
+    g = GpuSnapshotStage("verify", device=local)
+
+    def step_resident():
+        g.dev_submit(d_stream.data_ptr(), shard.size, d_recs.data_ptr(), len(recs),
+                     cuda_stream=st.cuda_stream)
+        c = exchange(g) if world > 1 else (0, 0, 0, 0)
+        _, carry, _ = g.dev_finish(carry_in=c)
+        return carry
+
+    for _ in range(args.warmup):
+        carry = step_resident()
+    if world > 1:
+        # the stamped stream is the oracle's: the carry-in we derived on the GPU must
+        # equal the generator's running checksum at the shard boundary
+        assert exchange(g) == carry_in, "GPU shard carry differs from the oracle's"
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    s0 = g.stats()
+    clocks = ClockSampler(local)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    clocks.start()
+    e0.record(st)
+    for _ in range(args.steps):
+        carry = step_resident()
+    e1.record(st)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms_total = e0.elapsed_time(e1)
+    clk = clocks.stop()
+    s1 = g.stats()
+    t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    total_bytes = torch.tensor([float(shard.size)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(total_bytes, op=dist.ReduceOp.SUM)
+    total_bytes = float(total_bytes.item())
+    value = total_bytes / GIB / (ms_step / 1e3)
+    k1_ms = (s1["k1_ms"] - s0["k1_ms"]) / max(1, s1["k1_launches"] - s0["k1_launches"])
+    launches = (s1["kernel_launches"] - s0["kernel_launches"]) // args.steps
+    end_ck = g.end_checksum()
+    g.close()
+
+    # ---------------- host-facing C-ABI timing: `e2e` ----------------
+    e2e = None
+    if not args.no_e2e:
+        flags_cfg = N.FLAG_DEFER_VERIFY if world > 1 else 0
+        ge = GpuSnapshotStage("verify", device=local, batch_bytes=64 << 20, n_slots=4,
+                              flags=flags_cfg)
+
+        def step_e2e():
+            ge.process_host(shard)
+            if world > 1:
+                c = exchange(ge)
+                ge.dev_finish(carry_in=c)
+                ge.dev_reset()
+
+        for _ in range(min(args.warmup, 2)):
+            step_e2e()
+        b0 = ge.stats()["batches"]
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step_e2e()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item()) / args.steps
+        nb = max(1, (shard.size + (64 << 20) - 1) // (64 << 20))
+        e2e = {"value": round(total_bytes / GIB / dt, 3), "unit": "GiB/s",
+               "h2d_bytes_per_step": int(shard.size + len(recs) * 32),
+               "d2h_bytes_per_step": int(nb * 120),
+               "call": "mtz_process_host (pinned host stream -> cudaMemcpyAsync H2D -> K1+scan "
+                       "-> verdict D2H), host wall clock around the synchronous call, max over ranks",
+               "note": "VERIFY output bytes are the input bytes (identity), so only the "
+                       "verdict crosses back"}
+        ge.close()
+
+    # ---------------- CPU baseline (rank 0, N=1) ----------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        nthreads = host_threads()
+        rc, secs, cst = O.mt_verify(shard, nthreads)
+        assert rc == 0
+        assert cst.end_cksum.tuple() == end_ck, "GPU END checksum differs from the oracle's"
+        rc, secs, cst = O.mt_verify(shard, nthreads)
+        cpu = {"value": round(shard.size / GIB / secs, 3), "unit": "GiB/s", "cores": nthreads,
+               "kind": "port",
+               "sample": "the whole %.2f GiB stream once: record-parallel scalar fletcher_4 "
+                         "(oracle/mt.c), %d threads" % (shard.size / GIB, nthreads)}
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        alg_bytes = float(shard.size)          # 312+P bytes read per record: 1.000 B / stream B
+        ach = alg_bytes / (k1_ms / 1e3) / 1e9 if k1_ms > 0 else None
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "k1_traffic.json"))).get(
+                "dram_bytes_per_stream_byte")
+            if traffic is not None:
+                traffic = traffic * alg_bytes
+        except Exception:
+            pass
+        line = {
+            "metric": "snapshot_stream_gibs", "value": round(value, 3), "unit": "GiB/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u32->u64 (mod 2^64)", "data": "synthetic",
+            "config": {
+                "workload": "verify: %.2f GiB/GPU uncompressed ZFS-send stream, Fletcher-4 "
+                            "(BASELINE configs[1])" % (shard.size / GIB),
+                "records_per_gpu": int(len(recs)), "recordsize": RECSIZE,
+                "partition": "record-index, contiguous shard per rank; all-gather of 40 B "
+                             "aggregates" if world > 1 else "single GPU",
+                "l2": "inputs_exceed_l2 (%.1f GiB >> 126 MB)" % (shard.size / GIB),
+                "payload": "PCG32 seed 0x4D414E41 (incompressible)"},
+            "e2e": e2e,
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "k1_record_sums",
+                         "achieved": round(ach, 1) if ach else None, "peak": peak,
+                         "unit": "GB/s", "frac": round(ach / peak, 4) if ach else None,
+                         "traffic": traffic,
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else
+                                        "fallback 6650 (B200_PROFILING.md)",
+                         "algorithmic_bytes_per_launch": alg_bytes,
+                         "k1_ms": round(k1_ms, 4)},
+            "cpu_baseline": cpu,
+            "clocks": clk,
+            "end_checksum": ["%016x" % x for x in (end_ck or ())],
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    pin.free()
+    return 0
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,173 @@
+/*
+ * manatee_gpu.h -- C ABI of libmanatee_gpu.so, the B200 snapshot-stream stage.
+ *
+ * This is the drop-in boundary for the one bulk-data path of
+ * TritonDataCenter/manatee: the ZFS-send byte stream that the sender pumps
+ * with   zfsSend.stdout.pipe(socket)        (lib/backupSender.js:179)
+ * and the receiver with   socket.pipe(zfsRecv.stdin)   (lib/zfsClient.js:826).
+ * The reference has no FFI for this path (it is two Node .pipe() calls); the
+ * entry points below are what an N-API addon for a `stream.Transform` spliced
+ * into those two pipes binds (INTEGRATION.md shows the binding and the two
+ * one-line patches).  Plain pointers and sizes only, no torch/CUDA types.
+ *
+ * Threading: one producer thread (ring_acquire/commit/write/flush) and one
+ * consumer thread (out_peek/out_consume/read) per handle; handles are
+ * independent.  Every call returns 0 (MTZ_OK) or a negative MTZ_E* code; the
+ * message for the last failure on a handle is mtz_last_error(h).  A failure
+ * is sticky: once a handle has failed every later call returns the same code,
+ * which the JS stage turns into destroy(err) => job.done='failed' exactly like
+ * a non-zero `zfs send` exit (lib/backupSender.js:214-221) or a `zfs recv`
+ * failure (lib/zfsClient.js:808-815, 867-876).
+ */
+#ifndef MANATEE_GPU_H
+#define MANATEE_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MTZ_ABI_VERSION 1
+
+/* ---- return codes ---- */
+#define MTZ_OK        0
+#define MTZ_EINVAL   -1   /* bad argument / bad state */
+#define MTZ_EAGAIN   -2   /* would block: ring full (producer) or empty (consumer) */
+#define MTZ_ECUDA    -3   /* CUDA runtime failure, see mtz_last_error */
+#define MTZ_EFORMAT  -4   /* malformed send stream (bad magic / type / length) */
+#define MTZ_ECKSUM   -5   /* embedded or END Fletcher-4 mismatch (like zfs recv ECKSUM) */
+#define MTZ_ECODEC   -6   /* LZ4 frame does not decode to drr_logical_size */
+#define MTZ_ENOSPC   -7   /* output capacity exceeded */
+#define MTZ_ENOMEM   -8
+#define MTZ_EOF      -9   /* consumer: stream finished and fully drained */
+#define MTZ_ENOGPU  -10   /* no usable sm_100 device: there is NO CPU fallback */
+
+/* ---- stage modes ---- */
+#define MTZ_MODE_VERIFY      0  /* identity bytes; every stream checksum verified */
+#define MTZ_MODE_COMPRESS    1  /* sender: raw DRR_WRITE payload -> ZFS-LZ4, re-stamp */
+#define MTZ_MODE_DECOMPRESS  2  /* receiver: exact inverse of COMPRESS */
+#define MTZ_MODE_RECOMPRESS  3  /* decode LZ4 records, verify, re-encode, re-stamp */
+#define MTZ_MODE_PASSTHROUGH 4  /* rings + H2D/D2H only, no parsing (plumbing tests) */
+
+/* config flags */
+#define MTZ_FLAG_DEFER_VERIFY 1u /* shard mode: mtz_process_host only accumulates per-record
+                                  * sums; verdict comes from mtz_dev_aggregate/mtz_dev_finish
+                                  * once the preceding shards' checksum is known */
+
+typedef struct mtz_handle mtz_handle;
+
+typedef struct mtz_config {
+	uint32_t struct_size;   /* sizeof(mtz_config), for ABI growth */
+	int32_t  device;        /* CUDA ordinal */
+	uint32_t mode;          /* MTZ_MODE_* */
+	uint32_t flags;         /* MTZ_FLAG_* */
+	uint64_t ring_bytes;    /* pinned input ring (0 = 256 MiB) */
+	uint64_t out_ring_bytes;/* pinned output ring, codec modes (0 = ring_bytes) */
+	uint64_t batch_bytes;   /* target bytes per GPU batch (0 = 32 MiB) */
+	uint32_t record_bytes;  /* expected recordsize hint (0 = 131072) */
+	uint32_t n_slots;       /* batches in flight (0 = 4) */
+} mtz_config;
+
+typedef struct mtz_stats {
+	uint64_t bytes_in;      /* stream bytes accepted */
+	uint64_t bytes_out;     /* stream bytes made available to the consumer */
+	uint64_t records;       /* DRR records processed */
+	uint64_t write_records; /* DRR_WRITE records */
+	uint64_t lz4_decoded;   /* records LZ4-decoded */
+	uint64_t lz4_encoded;   /* records stored LZ4-compressed on output */
+	uint64_t batches;       /* GPU batches completed */
+	uint64_t bad_record;    /* index of the first failing record, ~0 if none */
+	uint64_t kernel_launches;
+	double   gpu_ms;        /* sum of per-batch device time (CUDA events) */
+	uint64_t end_seen;      /* DRR_END processed */
+	double   k1_ms;         /* device time of the Fletcher-4 sums kernel (CUDA events) */
+	double   codec_ms;      /* device time of the LZ4 kernels */
+	uint64_t k1_launches;
+	uint64_t reserved[2];
+} mtz_stats;
+
+/* One DRR record as seen by the kernels (32 B, little endian). */
+typedef struct mtz_rec {
+	uint64_t off;      /* byte offset of the 312-byte header in the batch */
+	uint32_t payload;  /* payload bytes that follow the header */
+	uint32_t type;     /* drr_type */
+	uint32_t lsize;    /* DRR_WRITE: drr_logical_size, else 0 */
+	uint32_t comp;     /* DRR_WRITE: drr_compressiontype, else 0 */
+	uint64_t resv;
+} mtz_rec;
+
+/* ---- lifecycle ---- */
+int32_t     mtz_abi_version(void);
+int32_t     mtz_device_count(void);                 /* sm_100 devices visible, <0 on error */
+int32_t     mtz_open(const mtz_config *cfg, mtz_handle **out);
+int32_t     mtz_close(mtz_handle *h);
+const char *mtz_last_error(mtz_handle *h);          /* h may be NULL: last open() error */
+const char *mtz_strerror(int32_t code);
+
+/* ---- streaming API over pinned rings (what the N-API Transform binds) ---- */
+/* producer side == Transform._write(chunk): replaces the data path of
+ * zfsSend.stdout.pipe(...) (lib/backupSender.js:179) / socket.pipe(...)
+ * (lib/zfsClient.js:826).  acquire returns a slice of the PINNED input ring
+ * (read(2)/memcpy straight into it), commit publishes n bytes of it. */
+int32_t mtz_ring_acquire(mtz_handle *h, size_t want, void **ptr, size_t *got);
+int32_t mtz_ring_commit(mtz_handle *h, size_t n);
+int32_t mtz_write(mtz_handle *h, const void *buf, size_t n, int32_t block);
+/* end of input == Transform._flush(): like stdout 'end' on the zfs send child */
+int32_t mtz_flush(mtz_handle *h);
+/* consumer side == Transform.push(): processed stream bytes, in stream order */
+int32_t mtz_out_peek(mtz_handle *h, const void **ptr, size_t *n);
+int32_t mtz_out_consume(mtz_handle *h, size_t n);
+int32_t mtz_read(mtz_handle *h, void *buf, size_t cap, size_t *got, int32_t block);
+/* fd that becomes readable when output or an error is pending (eventfd): the
+ * addon's uv_poll_t / napi_threadsafe_function wake-up source */
+int32_t mtz_event_fd(mtz_handle *h);
+
+int32_t mtz_get_stats(mtz_handle *h, mtz_stats *st);
+/* running Fletcher-4 of the OUTPUT stream before DRR_END (== drr_end.drr_checksum) */
+int32_t mtz_end_checksum(mtz_handle *h, uint64_t out[4]);
+
+/* ---- bulk host API: a whole stream (or a whole-record slice of one) already in
+ * host memory; internally pipelined H2D -> kernels -> D2H over n_slots streams.
+ * in/out should come from mtz_host_alloc (pinned) for full PCIe rate. ---- */
+int32_t mtz_host_alloc(size_t bytes, void **ptr);
+int32_t mtz_host_free(void *ptr);
+int32_t mtz_process_host(mtz_handle *h, const void *in, size_t n, void *out,
+    size_t out_cap, size_t *out_n);
+
+/* ---- device-resident API (HBM in, HBM out): multi-GPU shards and kernel timing.
+ * Pointers are CUDA device pointers passed as integers-in-void*. ---- */
+/* host-side DRR parse: fills recs[] for whole records in [buf, buf+n) */
+int32_t mtz_index_host(const void *buf, size_t n, mtz_rec *recs, size_t cap,
+    size_t *nrec, size_t *consumed);
+/* GPU-side DRR parse of a resident stream (speculative strided header walk) */
+int32_t mtz_dev_index(mtz_handle *h, const void *d_in, size_t n, mtz_rec *d_recs,
+    size_t cap, size_t *nrec, void *cuda_stream);
+/* enqueue one batch on cuda_stream (NULL = handle's stream).  Phase A computes
+ * per-record Fletcher partials (+ codec work) and the batch aggregate. */
+int32_t mtz_dev_submit(mtz_handle *h, const void *d_in, size_t in_bytes,
+    const mtz_rec *d_recs, size_t nrec, void *d_out, size_t out_cap,
+    void *cuda_stream);
+/* aggregate (n,A,B,C,D) of the submitted batch's INPUT bytes: what a shard
+ * exchanges (all-gather of 40 B) before mtz_dev_finish */
+int32_t mtz_dev_aggregate(mtz_handle *h, uint64_t agg[5]);
+/* phase B: verify / stamp with the running checksum that precedes the batch */
+int32_t mtz_dev_finish(mtz_handle *h, const uint64_t carry_in[4],
+    const uint64_t carry_out_in[4], size_t *out_bytes, uint64_t carry[4],
+    uint64_t carry_out[4]);
+int32_t mtz_dev_reset(mtz_handle *h);
+/* set the running checksums a slice continues from (NULL = leave) */
+int32_t mtz_set_carry(mtz_handle *h, const uint64_t carry_in[4],
+    const uint64_t carry_out[4]);
+
+/* ---- synthetic-workload helpers for bench/tests (device-side generation of the
+ * BASELINE.md section 3 streams by tiling a seeded host corpus) ---- */
+int32_t mtz_synth_tile(mtz_handle *h, const void *d_corpus, size_t corpus_bytes,
+    size_t corpus_records, void *d_stream, size_t cap, uint64_t nwrites,
+    uint32_t recsize, mtz_rec *d_recs, size_t *out_bytes, size_t *nrec);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MANATEE_GPU_H */

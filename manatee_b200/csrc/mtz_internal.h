@@ -1,0 +1,87 @@
+// mtz_internal.h -- private state of a libmanatee_gpu handle.
+#pragma once
+#include <atomic>
+#include <condition_variable>
+#include <deque>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+#include <cuda_runtime.h>
+#include "../../include/manatee_gpu.h"
+#include "kernels_fletcher.cuh"
+
+namespace mtz {
+
+struct Slot {
+	uint8_t *d_in = nullptr;      // batch bytes (input stream slice)
+	uint8_t *d_out = nullptr;     // codec modes: output slice
+	size_t cap = 0, out_cap = 0;
+	mtz_rec *d_recs = nullptr;
+	mtz_rec *h_recs = nullptr;    // pinned staging
+	size_t rec_cap = 0;
+	RecSums *d_sums = nullptr;
+	ScanResult *d_res = nullptr;
+	ScanResult *h_res = nullptr;  // pinned
+	cudaStream_t st = nullptr;
+	cudaEvent_t ev_start = nullptr, ev_done = nullptr;
+	cudaEvent_t ev_k1a = nullptr, ev_k1b = nullptr;
+	bool busy = false;
+	size_t nrec = 0, bytes = 0, out_bytes = 0;
+	uint64_t first_rec = 0;       // stream-wide index of the batch's first record
+	uint64_t in_off = 0;          // absolute stream offset of the batch
+	uint64_t writes = 0;
+	void *codec = nullptr;        // per-slot codec scratch
+};
+
+struct Engine;                    // streaming state (rings + worker thread)
+
+} // namespace mtz
+
+struct mtz_handle {
+	mtz_config cfg{};
+	int device = 0;
+	int sm_count = 0;
+	std::string err;
+	std::mutex err_mu;
+	std::atomic<int32_t> failed{0};
+	mtz_stats stats{};
+	std::mutex stats_mu;
+
+	// running checksums (device resident, updated in stream order)
+	mtz::Ck4 *d_carry_in = nullptr;    // of the INPUT stream
+	mtz::Ck4 *d_carry_out = nullptr;   // of the OUTPUT stream (codec modes)
+	mtz::Ck4 *h_carry = nullptr;       // pinned scratch (4 entries)
+	uint64_t end_ck[4] = {0, 0, 0, 0};
+
+	std::vector<mtz::Slot> slots;
+	cudaStream_t st = nullptr;         // device-API stream
+	cudaEvent_t ev_prev_scan = nullptr;
+	bool have_prev_scan = false;
+	uint64_t records_done = 0;
+	uint64_t batch_seq = 0;
+
+	// device-API / deferred-verify state: one growing table of per-record sums
+	mtz::RecSums *dv_sums = nullptr;
+	size_t dv_sums_cap = 0;
+	size_t dv_nrec = 0, dv_in_bytes = 0;
+	mtz::ScanResult *dv_res = nullptr, *dv_hres = nullptr;
+	cudaStream_t dv_st = nullptr;
+	cudaEvent_t dv_k1a = nullptr, dv_k1b = nullptr;
+	bool dv_timed = false;
+
+	mtz::Engine *eng = nullptr;        // created on first streaming call
+	std::mutex eng_mu;
+};
+
+namespace mtz {
+int32_t fail(mtz_handle *h, int32_t code, const char *fmt, ...);
+int32_t fail_cuda(mtz_handle *h, cudaError_t e, const char *what);
+void engine_wake_all(mtz_handle *h);
+}
+
+#define MTZ_CU(h, call)                                                        \
+	do {                                                                       \
+		cudaError_t e__ = (call);                                              \
+		if (e__ != cudaSuccess) return mtz::fail_cuda((h), e__, #call);        \
+	} while (0)

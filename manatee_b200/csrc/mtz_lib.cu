@@ -1,0 +1,1033 @@
+// mtz_lib.cu -- C-ABI entry points of libmanatee_gpu.so (include/manatee_gpu.h).
+//
+// Replaces the data path of the reference's two pipes,
+//   zfsSend.stdout.pipe(socket)      lib/backupSender.js:179
+//   socket.pipe(zfsRecv.stdin)       lib/zfsClient.js:826
+// with: pinned host ring -> cudaMemcpyAsync -> HBM -> sm_100a kernels
+// (Fletcher-4 verify / LZ4 decode / LZ4 encode / re-stamp) -> pinned ring.
+// There is NO CPU fallback: without a usable device mtz_open fails MTZ_ENOGPU.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <algorithm>
+#include "mtz_internal.h"
+
+using namespace mtz;
+
+static thread_local std::string g_open_err;
+
+namespace mtz {
+
+int32_t fail(mtz_handle *h, int32_t code, const char *fmt, ...)
+{
+	char buf[512];
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(buf, sizeof buf, fmt, ap);
+	va_end(ap);
+	if (h) {
+		int32_t expect = 0;
+		{
+			std::lock_guard<std::mutex> g(h->err_mu);
+			if (h->failed.load() == 0) h->err = buf;
+		}
+		h->failed.compare_exchange_strong(expect, code);
+		engine_wake_all(h);
+	} else {
+		g_open_err = buf;
+	}
+	return code;
+}
+
+int32_t fail_cuda(mtz_handle *h, cudaError_t e, const char *what)
+{
+	return fail(h, MTZ_ECUDA, "CUDA error %d (%s) at %s", (int)e,
+	    cudaGetErrorString(e), what);
+}
+
+} // namespace mtz
+
+#define CHECK_H(h)                                                             \
+	do {                                                                       \
+		if ((h) == nullptr) return MTZ_EINVAL;                                 \
+		int32_t f__ = (h)->failed.load();                                      \
+		if (f__ != 0) return f__;                                              \
+	} while (0)
+
+extern "C" {
+
+int32_t mtz_abi_version(void) { return MTZ_ABI_VERSION; }
+
+const char *mtz_strerror(int32_t code)
+{
+	switch (code) {
+	case MTZ_OK: return "ok";
+	case MTZ_EINVAL: return "invalid argument or state";
+	case MTZ_EAGAIN: return "would block";
+	case MTZ_ECUDA: return "CUDA failure";
+	case MTZ_EFORMAT: return "malformed ZFS send stream";
+	case MTZ_ECKSUM: return "stream checksum mismatch";
+	case MTZ_ECODEC: return "LZ4 frame does not decode";
+	case MTZ_ENOSPC: return "output capacity exceeded";
+	case MTZ_ENOMEM: return "out of memory";
+	case MTZ_EOF: return "end of stream";
+	case MTZ_ENOGPU: return "no sm_100 GPU (no CPU fallback exists)";
+	default: return "unknown error";
+	}
+}
+
+const char *mtz_last_error(mtz_handle *h)
+{
+	if (h == nullptr) return g_open_err.c_str();
+	std::lock_guard<std::mutex> g(h->err_mu);
+	return h->err.c_str();
+}
+
+int32_t mtz_device_count(void)
+{
+	int n = 0;
+	cudaError_t e = cudaGetDeviceCount(&n);
+	if (e != cudaSuccess) { (void)cudaGetLastError(); return 0; }
+	int ok = 0;
+	for (int i = 0; i < n; i++) {
+		cudaDeviceProp p;
+		if (cudaGetDeviceProperties(&p, i) == cudaSuccess && p.major == 10) ok++;
+	}
+	return ok;
+}
+
+// ------------------------------------------------------------------ parse --
+static inline uint32_t rd32(const uint8_t *p) { uint32_t v; memcpy(&v, p, 4); return v; }
+static inline uint64_t rd64(const uint8_t *p) { uint64_t v; memcpy(&v, p, 8); return v; }
+
+// Payload sizing per record type (DRR header classify, K4's host half):
+// restated from sys/zfs_ioctl.h DRR_*_PAYLOAD_SIZE ([EXTERNAL]).
+static int64_t drr_payload(const uint8_t *h, uint32_t *lsize, uint32_t *comp)
+{
+	const uint32_t type = rd32(h);
+	*lsize = 0; *comp = 0;
+	switch (type) {
+	case 0: /* BEGIN */
+		if (rd64(h + 8) != 0x2F5bacbacULL) return -1;
+		return (int64_t)rd32(h + 4);
+	case 1: /* OBJECT */
+		return (int64_t)(((uint64_t)rd32(h + 28) + 7) & ~7ull);
+	case 3: { /* WRITE */
+		const uint64_t ls = rd64(h + 32);
+		const uint64_t l = h[50] ? rd64(h + 96) : ls;
+		if (l > (1ull << 30) || (l & 3) || ls > (1ull << 30)) return -1;
+		*lsize = (uint32_t)ls; *comp = h[50];
+		return (int64_t)l;
+	}
+	case 7: { /* SPILL */
+		const uint64_t l = rd64(h + 16);
+		if (l > (1ull << 30) || (l & 3)) return -1;
+		return (int64_t)l;
+	}
+	case 8: /* WRITE_EMBEDDED */
+		return (int64_t)(((uint64_t)rd32(h + 52) + 7) & ~7ull);
+	case 2: case 4: case 5: case 6:
+		return 0;
+	default:
+		return -1;
+	}
+}
+
+int32_t mtz_index_host(const void *buf, size_t n, mtz_rec *recs, size_t cap,
+    size_t *nrec, size_t *consumed)
+{
+	const uint8_t *s = (const uint8_t *)buf;
+	size_t off = 0, cnt = 0;
+	int32_t rc = MTZ_OK;
+	if (buf == nullptr && n != 0) return MTZ_EINVAL;
+	while (n - off >= DRR_HDR) {
+		uint32_t ls, comp;
+		const int64_t pl = drr_payload(s + off, &ls, &comp);
+		if (pl < 0) { rc = MTZ_EFORMAT; break; }
+		if ((uint64_t)pl > n - off - DRR_HDR) break;     // incomplete record
+		if (recs != nullptr) {
+			if (cnt >= cap) { rc = MTZ_ENOSPC; break; }
+			mtz_rec r;
+			r.off = off; r.payload = (uint32_t)pl; r.type = rd32(s + off);
+			r.lsize = ls; r.comp = comp; r.resv = 0;
+			recs[cnt] = r;
+		}
+		cnt++;
+		off += DRR_HDR + (size_t)pl;
+	}
+	if (nrec) *nrec = cnt;
+	if (consumed) *consumed = off;
+	return rc;
+}
+
+// ------------------------------------------------------------- lifecycle --
+static int32_t alloc_slot(mtz_handle *h, Slot &s, size_t cap, size_t rec_cap)
+{
+	s.cap = cap; s.rec_cap = rec_cap;
+	MTZ_CU(h, cudaMalloc(&s.d_in, cap + 512));
+	MTZ_CU(h, cudaMalloc(&s.d_recs, rec_cap * sizeof(mtz_rec)));
+	MTZ_CU(h, cudaHostAlloc(&s.h_recs, rec_cap * sizeof(mtz_rec), cudaHostAllocDefault));
+	MTZ_CU(h, cudaMalloc(&s.d_sums, rec_cap * sizeof(RecSums)));
+	MTZ_CU(h, cudaMalloc(&s.d_res, sizeof(ScanResult)));
+	MTZ_CU(h, cudaHostAlloc(&s.h_res, sizeof(ScanResult), cudaHostAllocDefault));
+	MTZ_CU(h, cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking));
+	MTZ_CU(h, cudaEventCreate(&s.ev_start));
+	MTZ_CU(h, cudaEventCreate(&s.ev_done));
+	MTZ_CU(h, cudaEventCreate(&s.ev_k1a));
+	MTZ_CU(h, cudaEventCreate(&s.ev_k1b));
+	return MTZ_OK;
+}
+
+static void free_slot(Slot &s)
+{
+	if (s.d_in) cudaFree(s.d_in);
+	if (s.d_out) cudaFree(s.d_out);
+	if (s.d_recs) cudaFree(s.d_recs);
+	if (s.h_recs) cudaFreeHost(s.h_recs);
+	if (s.d_sums) cudaFree(s.d_sums);
+	if (s.d_res) cudaFree(s.d_res);
+	if (s.h_res) cudaFreeHost(s.h_res);
+	if (s.st) cudaStreamDestroy(s.st);
+	if (s.ev_start) cudaEventDestroy(s.ev_start);
+	if (s.ev_done) cudaEventDestroy(s.ev_done);
+	if (s.ev_k1a) cudaEventDestroy(s.ev_k1a);
+	if (s.ev_k1b) cudaEventDestroy(s.ev_k1b);
+	s = Slot();
+}
+
+#define MAX_RECORD_BYTES ((size_t)(16u << 20) + 4096)
+
+int32_t mtz_open(const mtz_config *cfg, mtz_handle **out)
+{
+	if (cfg == nullptr || out == nullptr) return fail(nullptr, MTZ_EINVAL, "null argument");
+	*out = nullptr;
+	if (cfg->struct_size < sizeof(uint32_t) * 4)
+		return fail(nullptr, MTZ_EINVAL, "mtz_config.struct_size too small");
+	if (cfg->mode > MTZ_MODE_PASSTHROUGH)
+		return fail(nullptr, MTZ_EINVAL, "unknown mode %u", cfg->mode);
+	int ndev = 0;
+	cudaError_t e = cudaGetDeviceCount(&ndev);
+	if (e != cudaSuccess || ndev == 0) {
+		(void)cudaGetLastError();
+		return fail(nullptr, MTZ_ENOGPU, "no CUDA device: %s (there is no CPU fallback)",
+		    cudaGetErrorString(e));
+	}
+	if (cfg->device < 0 || cfg->device >= ndev)
+		return fail(nullptr, MTZ_EINVAL, "device %d out of range (%d visible)", cfg->device, ndev);
+	cudaDeviceProp prop;
+	if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess || prop.major != 10)
+		return fail(nullptr, MTZ_ENOGPU, "device %d is sm_%d%d; this library is built for sm_100a only",
+		    cfg->device, prop.major, prop.minor);
+
+	mtz_handle *h = new (std::nothrow) mtz_handle();
+	if (h == nullptr) return fail(nullptr, MTZ_ENOMEM, "handle allocation");
+	memset(&h->cfg, 0, sizeof h->cfg);
+	memcpy(&h->cfg, cfg, std::min((size_t)cfg->struct_size, sizeof h->cfg));
+	if (h->cfg.ring_bytes == 0) h->cfg.ring_bytes = 256ull << 20;
+	if (h->cfg.out_ring_bytes == 0) h->cfg.out_ring_bytes = h->cfg.ring_bytes;
+	if (h->cfg.batch_bytes == 0) h->cfg.batch_bytes = 32ull << 20;
+	if (h->cfg.record_bytes == 0) h->cfg.record_bytes = 131072;
+	if (h->cfg.n_slots == 0) h->cfg.n_slots = 4;
+	if (h->cfg.n_slots > 16) h->cfg.n_slots = 16;
+	h->device = cfg->device;
+	h->sm_count = prop.multiProcessorCount;
+	h->stats.bad_record = ~0ull;
+
+	int32_t rc = MTZ_OK;
+	auto init = [&]() -> int32_t {
+		MTZ_CU(h, cudaSetDevice(h->device));
+		MTZ_CU(h, cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
+		MTZ_CU(h, cudaEventCreateWithFlags(&h->ev_prev_scan, cudaEventDisableTiming));
+		MTZ_CU(h, cudaMalloc(&h->d_carry_in, sizeof(Ck4)));
+		MTZ_CU(h, cudaMalloc(&h->d_carry_out, sizeof(Ck4)));
+		MTZ_CU(h, cudaHostAlloc(&h->h_carry, 4 * sizeof(Ck4), cudaHostAllocDefault));
+		MTZ_CU(h, cudaMemset(h->d_carry_in, 0, sizeof(Ck4)));
+		MTZ_CU(h, cudaMemset(h->d_carry_out, 0, sizeof(Ck4)));
+		MTZ_CU(h, cudaMalloc(&h->dv_res, sizeof(ScanResult)));
+		MTZ_CU(h, cudaHostAlloc(&h->dv_hres, sizeof(ScanResult), cudaHostAllocDefault));
+		MTZ_CU(h, cudaEventCreate(&h->dv_k1a));
+		MTZ_CU(h, cudaEventCreate(&h->dv_k1b));
+		return MTZ_OK;
+	};
+	rc = init();
+	if (rc != MTZ_OK) {
+		g_open_err = h->err;
+		mtz_close(h);
+		return rc;
+	}
+	*out = h;
+	return MTZ_OK;
+}
+
+static void engine_destroy(mtz_handle *h);
+
+int32_t mtz_close(mtz_handle *h)
+{
+	if (h == nullptr) return MTZ_EINVAL;
+	cudaSetDevice(h->device);
+	engine_destroy(h);
+	cudaDeviceSynchronize();
+	if (h->dv_k1a) cudaEventDestroy(h->dv_k1a);
+	if (h->dv_k1b) cudaEventDestroy(h->dv_k1b);
+	for (auto &s : h->slots) free_slot(s);
+	if (h->dv_sums) cudaFree(h->dv_sums);
+	if (h->dv_res) cudaFree(h->dv_res);
+	if (h->dv_hres) cudaFreeHost(h->dv_hres);
+	if (h->d_carry_in) cudaFree(h->d_carry_in);
+	if (h->d_carry_out) cudaFree(h->d_carry_out);
+	if (h->h_carry) cudaFreeHost(h->h_carry);
+	if (h->ev_prev_scan) cudaEventDestroy(h->ev_prev_scan);
+	if (h->st) cudaStreamDestroy(h->st);
+	delete h;
+	return MTZ_OK;
+}
+
+int32_t mtz_get_stats(mtz_handle *h, mtz_stats *st)
+{
+	if (h == nullptr || st == nullptr) return MTZ_EINVAL;
+	std::lock_guard<std::mutex> g(h->stats_mu);
+	*st = h->stats;
+	return MTZ_OK;
+}
+
+int32_t mtz_end_checksum(mtz_handle *h, uint64_t out[4])
+{
+	if (h == nullptr || out == nullptr) return MTZ_EINVAL;
+	std::lock_guard<std::mutex> g(h->stats_mu);
+	if (!h->stats.end_seen) return MTZ_EAGAIN;
+	memcpy(out, h->end_ck, 32);
+	return MTZ_OK;
+}
+
+int32_t mtz_host_alloc(size_t bytes, void **ptr)
+{
+	if (ptr == nullptr) return MTZ_EINVAL;
+	cudaError_t e = cudaHostAlloc(ptr, bytes, cudaHostAllocPortable);
+	if (e != cudaSuccess) { (void)cudaGetLastError(); *ptr = nullptr; return MTZ_ENOMEM; }
+	return MTZ_OK;
+}
+
+int32_t mtz_host_free(void *ptr)
+{
+	if (ptr == nullptr) return MTZ_OK;
+	return cudaFreeHost(ptr) == cudaSuccess ? MTZ_OK : MTZ_ECUDA;
+}
+
+// ------------------------------------------------------- kernel launches --
+static inline void count_launch(mtz_handle *h, uint64_t n)
+{
+	std::lock_guard<std::mutex> g(h->stats_mu);
+	h->stats.kernel_launches += n;
+}
+
+// K1 over a batch: per-record Fletcher-4 sums into d_sums[0..nrec)
+static int32_t launch_k1(mtz_handle *h, cudaStream_t st, const uint8_t *d_in,
+    const mtz_rec *d_recs, size_t nrec, RecSums *d_sums, cudaEvent_t ea, cudaEvent_t eb)
+{
+	if (nrec == 0) return MTZ_OK;
+	const unsigned grid = (unsigned)std::min<size_t>(nrec, (size_t)h->sm_count * 64);
+	if (ea) MTZ_CU(h, cudaEventRecord(ea, st));
+	k1_record_sums<<<grid, K1_THREADS, 0, st>>>(d_in, d_recs, (uint32_t)nrec, d_sums, 280u);
+	MTZ_CU(h, cudaGetLastError());
+	if (eb) MTZ_CU(h, cudaEventRecord(eb, st));
+	count_launch(h, 1);
+	return MTZ_OK;
+}
+
+static int32_t launch_scan(mtz_handle *h, cudaStream_t st, const RecSums *d_sums, size_t nrec,
+    ScanResult *d_res, int phase)
+{
+	MTZ_CU(h, cudaMemsetAsync(d_res, 0, sizeof(ScanResult), st));
+	k_scan_verify<<<1, SCAN_THREADS, 0, st>>>(d_sums, (uint32_t)nrec, h->d_carry_in, d_res, phase);
+	MTZ_CU(h, cudaGetLastError());
+	count_launch(h, 1);
+	return MTZ_OK;
+}
+
+static int32_t ensure_dv_sums(mtz_handle *h, size_t need, cudaStream_t st)
+{
+	if (need <= h->dv_sums_cap) return MTZ_OK;
+	size_t ncap = std::max<size_t>(need + need / 2 + 1024, 4096);
+	RecSums *n = nullptr;
+	MTZ_CU(h, cudaMalloc(&n, ncap * sizeof(RecSums)));
+	if (h->dv_sums != nullptr) {
+		if (h->dv_nrec > 0) {
+			MTZ_CU(h, cudaDeviceSynchronize());
+			MTZ_CU(h, cudaMemcpy(n, h->dv_sums, h->dv_nrec * sizeof(RecSums), cudaMemcpyDeviceToDevice));
+		}
+		MTZ_CU(h, cudaFree(h->dv_sums));
+	}
+	(void)st;
+	h->dv_sums = n; h->dv_sums_cap = ncap;
+	return MTZ_OK;
+}
+
+// ------------------------------------------------------------ device API --
+int32_t mtz_dev_reset(mtz_handle *h)
+{
+	CHECK_H(h);
+	MTZ_CU(h, cudaSetDevice(h->device));
+	MTZ_CU(h, cudaMemsetAsync(h->d_carry_in, 0, sizeof(Ck4), h->st));
+	MTZ_CU(h, cudaMemsetAsync(h->d_carry_out, 0, sizeof(Ck4), h->st));
+	MTZ_CU(h, cudaStreamSynchronize(h->st));
+	h->records_done = 0;
+	h->dv_nrec = 0; h->dv_in_bytes = 0;
+	std::lock_guard<std::mutex> g(h->stats_mu);
+	h->stats = mtz_stats();
+	h->stats.bad_record = ~0ull;
+	return MTZ_OK;
+}
+
+int32_t mtz_set_carry(mtz_handle *h, const uint64_t carry_in[4], const uint64_t carry_out[4])
+{
+	CHECK_H(h);
+	MTZ_CU(h, cudaSetDevice(h->device));
+	if (carry_in) MTZ_CU(h, cudaMemcpy(h->d_carry_in, carry_in, 32, cudaMemcpyHostToDevice));
+	if (carry_out) MTZ_CU(h, cudaMemcpy(h->d_carry_out, carry_out, 32, cudaMemcpyHostToDevice));
+	return MTZ_OK;
+}
+
+int32_t mtz_dev_submit(mtz_handle *h, const void *d_in, size_t in_bytes,
+    const mtz_rec *d_recs, size_t nrec, void *d_out, size_t out_cap, void *cuda_stream)
+{
+	CHECK_H(h);
+	(void)d_out; (void)out_cap;
+	if (nrec > 0xfffffff0ull) return fail(h, MTZ_EINVAL, "too many records in one batch");
+	if (((uintptr_t)d_in & 3) != 0) return fail(h, MTZ_EINVAL, "d_in must be 4-byte aligned");
+	if (h->cfg.mode != MTZ_MODE_VERIFY)
+		return fail(h, MTZ_EINVAL, "mtz_dev_submit: mode %u not supported yet", h->cfg.mode);
+	MTZ_CU(h, cudaSetDevice(h->device));
+	cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : h->st;
+	int32_t rc = ensure_dv_sums(h, nrec, st);
+	if (rc != MTZ_OK) return rc;
+	h->dv_nrec = nrec; h->dv_in_bytes = in_bytes; h->dv_st = st;
+	rc = launch_k1(h, st, (const uint8_t *)d_in, d_recs, nrec, h->dv_sums, h->dv_k1a, h->dv_k1b);
+	h->dv_timed = (rc == MTZ_OK && nrec > 0);
+	return rc;
+}
+
+int32_t mtz_dev_aggregate(mtz_handle *h, uint64_t agg[5])
+{
+	CHECK_H(h);
+	if (agg == nullptr) return MTZ_EINVAL;
+	MTZ_CU(h, cudaSetDevice(h->device));
+	cudaStream_t st = h->dv_st ? h->dv_st : h->st;
+	int32_t rc = launch_scan(h, st, h->dv_sums, h->dv_nrec, h->dv_res, 0);
+	if (rc != MTZ_OK) return rc;
+	MTZ_CU(h, cudaMemcpyAsync(h->dv_hres, h->dv_res, sizeof(ScanResult), cudaMemcpyDeviceToHost, st));
+	MTZ_CU(h, cudaStreamSynchronize(st));
+	agg[0] = h->dv_hres->agg.n; agg[1] = h->dv_hres->agg.a; agg[2] = h->dv_hres->agg.b;
+	agg[3] = h->dv_hres->agg.c; agg[4] = h->dv_hres->agg.d;
+	return MTZ_OK;
+}
+
+static int32_t account_result(mtz_handle *h, const ScanResult &r, uint64_t first_rec, size_t nrec,
+    size_t bytes_in, size_t bytes_out)
+{
+	{
+		std::lock_guard<std::mutex> g(h->stats_mu);
+		h->stats.batches += 1;
+		h->stats.records += nrec;
+		h->stats.bytes_in += bytes_in;
+		h->stats.bytes_out += bytes_out;
+		if (r.end_seen) {
+			h->stats.end_seen = 1;
+			memcpy(h->end_ck, &r.end_ck, 32);
+		}
+	}
+	if (r.status != 0) {
+		const uint64_t bad = first_rec + r.bad;
+		{
+			std::lock_guard<std::mutex> g(h->stats_mu);
+			if (bad < h->stats.bad_record) h->stats.bad_record = bad;
+		}
+		return fail(h, -(int32_t)r.status, "stream checksum mismatch at record %llu",
+		    (unsigned long long)bad);
+	}
+	return MTZ_OK;
+}
+
+int32_t mtz_dev_finish(mtz_handle *h, const uint64_t carry_in[4], const uint64_t carry_out_in[4],
+    size_t *out_bytes, uint64_t carry[4], uint64_t carry_out[4])
+{
+	CHECK_H(h);
+	MTZ_CU(h, cudaSetDevice(h->device));
+	cudaStream_t st = h->dv_st ? h->dv_st : h->st;
+	if (carry_in != nullptr) {
+		memcpy(&h->h_carry[0], carry_in, 32);
+		MTZ_CU(h, cudaMemcpyAsync(h->d_carry_in, &h->h_carry[0], 32, cudaMemcpyHostToDevice, st));
+	}
+	if (carry_out_in != nullptr) {
+		memcpy(&h->h_carry[1], carry_out_in, 32);
+		MTZ_CU(h, cudaMemcpyAsync(h->d_carry_out, &h->h_carry[1], 32, cudaMemcpyHostToDevice, st));
+	}
+	int32_t rc = launch_scan(h, st, h->dv_sums, h->dv_nrec, h->dv_res, 1);
+	if (rc != MTZ_OK) return rc;
+	MTZ_CU(h, cudaMemcpyAsync(h->dv_hres, h->dv_res, sizeof(ScanResult), cudaMemcpyDeviceToHost, st));
+	MTZ_CU(h, cudaMemcpyAsync(h->d_carry_in, &h->dv_res->carry, 32, cudaMemcpyDeviceToDevice, st));
+	MTZ_CU(h, cudaStreamSynchronize(st));
+	if (h->dv_timed) {
+		float ms = 0;
+		if (cudaEventElapsedTime(&ms, h->dv_k1a, h->dv_k1b) == cudaSuccess) {
+			std::lock_guard<std::mutex> g(h->stats_mu);
+			h->stats.k1_ms += ms; h->stats.k1_launches += 1;
+		}
+		h->dv_timed = false;
+	}
+	const ScanResult &r = *h->dv_hres;
+	if (out_bytes) *out_bytes = h->dv_in_bytes;
+	if (carry) memcpy(carry, &r.carry, 32);
+	if (carry_out) memcpy(carry_out, &r.carry, 32);
+	rc = account_result(h, r, h->records_done, h->dv_nrec, h->dv_in_bytes, h->dv_in_bytes);
+	if (rc == MTZ_OK) h->records_done += h->dv_nrec;
+	return rc;
+}
+
+// ----------------------------------------------------- batch submission ---
+static int32_t ensure_slots(mtz_handle *h)
+{
+	if (!h->slots.empty()) return MTZ_OK;
+	const size_t cap = (size_t)h->cfg.batch_bytes + MAX_RECORD_BYTES;
+	const size_t rec_cap = std::max<size_t>(4096, cap / 1024);
+	h->slots.resize(h->cfg.n_slots);
+	for (auto &s : h->slots) {
+		int32_t rc = alloc_slot(h, s, cap, rec_cap);
+		if (rc != MTZ_OK) return rc;
+	}
+	return MTZ_OK;
+}
+
+// Wait for a slot's batch, fold its verdict into the handle.  on_done (optional)
+// is told how many output bytes the batch produced.
+static int32_t harvest(mtz_handle *h, Slot &s)
+{
+	if (!s.busy) return MTZ_OK;
+	MTZ_CU(h, cudaEventSynchronize(s.ev_done));
+	s.busy = false;
+	float ms = 0, k1 = 0;
+	cudaEventElapsedTime(&ms, s.ev_start, s.ev_done);
+	const bool k1ok = s.nrec > 0 && cudaEventElapsedTime(&k1, s.ev_k1a, s.ev_k1b) == cudaSuccess;
+	{
+		std::lock_guard<std::mutex> g(h->stats_mu);
+		h->stats.gpu_ms += ms;
+		h->stats.write_records += s.writes;
+		if (k1ok) { h->stats.k1_ms += k1; h->stats.k1_launches += 1; }
+	}
+	if (h->cfg.mode == MTZ_MODE_PASSTHROUGH || (h->cfg.flags & MTZ_FLAG_DEFER_VERIFY)) {
+		std::lock_guard<std::mutex> g(h->stats_mu);
+		h->stats.batches += 1; h->stats.bytes_in += s.bytes; h->stats.bytes_out += s.out_bytes;
+		h->stats.records += s.nrec;
+		return MTZ_OK;
+	}
+	return account_result(h, *s.h_res, s.first_rec, s.nrec, s.bytes, s.out_bytes);
+}
+
+// Enqueue one batch: the bytes come from up to two host pieces (ring wrap),
+// s.h_recs[0..nrec) is already filled with batch-relative offsets.
+static int32_t submit_batch(mtz_handle *h, Slot &s, const uint8_t *p0, size_t n0,
+    const uint8_t *p1, size_t n1, size_t nrec, uint64_t abs_off, uint8_t *host_out)
+{
+	const size_t bytes = n0 + n1;
+	s.nrec = nrec; s.bytes = bytes; s.out_bytes = bytes; s.in_off = abs_off;
+	s.first_rec = h->records_done;
+	h->records_done += nrec;
+	MTZ_CU(h, cudaEventRecord(s.ev_start, s.st));
+	if (nrec > 0)
+		MTZ_CU(h, cudaMemcpyAsync(s.d_recs, s.h_recs, nrec * sizeof(mtz_rec), cudaMemcpyHostToDevice, s.st));
+	if (n0) MTZ_CU(h, cudaMemcpyAsync(s.d_in, p0, n0, cudaMemcpyHostToDevice, s.st));
+	if (n1) MTZ_CU(h, cudaMemcpyAsync(s.d_in + n0, p1, n1, cudaMemcpyHostToDevice, s.st));
+	int32_t rc = MTZ_OK;
+	if (h->cfg.mode == MTZ_MODE_VERIFY) {
+		if (h->cfg.flags & MTZ_FLAG_DEFER_VERIFY) {
+			// shard mode: sums accumulate in the handle-wide table; verdict later
+			rc = ensure_dv_sums(h, h->dv_nrec + nrec, s.st);
+			if (rc != MTZ_OK) return rc;
+			rc = launch_k1(h, s.st, s.d_in, s.d_recs, nrec, h->dv_sums + h->dv_nrec, s.ev_k1a, s.ev_k1b);
+			if (rc != MTZ_OK) return rc;
+			h->dv_nrec += nrec; h->dv_in_bytes += bytes; h->dv_st = h->st;
+		} else {
+			rc = launch_k1(h, s.st, s.d_in, s.d_recs, nrec, s.d_sums, s.ev_k1a, s.ev_k1b);
+			if (rc != MTZ_OK) return rc;
+			if (h->have_prev_scan) MTZ_CU(h, cudaStreamWaitEvent(s.st, h->ev_prev_scan, 0));
+			rc = launch_scan(h, s.st, s.d_sums, nrec, s.d_res, 1);
+			if (rc != MTZ_OK) return rc;
+			MTZ_CU(h, cudaMemcpyAsync(h->d_carry_in, &s.d_res->carry, 32, cudaMemcpyDeviceToDevice, s.st));
+			MTZ_CU(h, cudaEventRecord(h->ev_prev_scan, s.st));
+			h->have_prev_scan = true;
+			MTZ_CU(h, cudaMemcpyAsync(s.h_res, s.d_res, sizeof(ScanResult), cudaMemcpyDeviceToHost, s.st));
+		}
+	}
+	if (host_out != nullptr)
+		MTZ_CU(h, cudaMemcpyAsync(host_out, s.d_in, bytes, cudaMemcpyDeviceToHost, s.st));
+	MTZ_CU(h, cudaEventRecord(s.ev_done, s.st));
+	s.busy = true;
+	h->batch_seq++;
+	return MTZ_OK;
+}
+
+// -------------------------------------------------------- bulk host API ---
+int32_t mtz_process_host(mtz_handle *h, const void *in, size_t n, void *out, size_t out_cap,
+    size_t *out_n)
+{
+	CHECK_H(h);
+	if (in == nullptr && n != 0) return MTZ_EINVAL;
+	if (h->cfg.mode != MTZ_MODE_VERIFY && h->cfg.mode != MTZ_MODE_PASSTHROUGH)
+		return fail(h, MTZ_EINVAL, "mtz_process_host: mode %u not supported yet", h->cfg.mode);
+	if (out != nullptr && out != in && out_cap < n)
+		return fail(h, MTZ_ENOSPC, "output buffer smaller than the stream");
+	MTZ_CU(h, cudaSetDevice(h->device));
+	int32_t rc = ensure_slots(h);
+	if (rc != MTZ_OK) return rc;
+
+	const uint8_t *src = (const uint8_t *)in;
+	const bool parse = h->cfg.mode != MTZ_MODE_PASSTHROUGH;
+	size_t off = 0;
+	uint64_t b = 0;
+	while (off < n && rc == MTZ_OK) {
+		Slot &s = h->slots[b % h->slots.size()];
+		rc = harvest(h, s);
+		if (rc != MTZ_OK) break;
+		size_t cnt = 0, used = 0;
+		s.writes = 0;
+		const size_t want = std::min(n - off, (size_t)h->cfg.batch_bytes);
+		if (!parse) {
+			used = want;
+		} else {
+			size_t pos = 0;
+			while (off + pos < n) {
+				const uint8_t *hp = src + off + pos;
+				uint32_t ls, comp;
+				if (n - off - pos < DRR_HDR) { rc = fail(h, MTZ_EFORMAT, "truncated record header at offset %zu", off + pos); break; }
+				const int64_t pl = drr_payload(hp, &ls, &comp);
+				if (pl < 0) { rc = fail(h, MTZ_EFORMAT, "malformed record header at offset %zu", off + pos); break; }
+				if ((uint64_t)pl > n - off - pos - DRR_HDR) { rc = fail(h, MTZ_EFORMAT, "truncated payload at offset %zu", off + pos); break; }
+				const size_t rl = DRR_HDR + (size_t)pl;
+				if (rl > s.cap) { rc = fail(h, MTZ_ENOSPC, "record larger than a batch slot"); break; }
+				if (cnt > 0 && (pos + rl > s.cap || cnt >= s.rec_cap)) break;
+				mtz_rec r;
+				r.off = pos; r.payload = (uint32_t)pl; r.type = rd32(hp);
+				r.lsize = ls; r.comp = comp; r.resv = 0;
+				s.h_recs[cnt++] = r;
+				pos += rl;
+				if (r.type == 3) s.writes++;
+				if (pos >= want) break;
+			}
+			used = pos;
+		}
+		if (rc != MTZ_OK) break;
+		uint8_t *ho = (out != nullptr && out != in) ? (uint8_t *)out + off : nullptr;
+		rc = submit_batch(h, s, src + off, used, nullptr, 0, cnt, off, ho);
+		off += used;
+		b++;
+	}
+	for (auto &s : h->slots) {
+		int32_t r2 = harvest(h, s);
+		if (rc == MTZ_OK) rc = r2;
+	}
+	if (out_n) *out_n = (rc == MTZ_OK) ? n : 0;
+	return rc;
+}
+
+} // extern "C"
+
+// ======================================================= streaming engine ==
+// Producer thread -> pinned input ring -> engine thread (parse DRR headers,
+// cut whole-record batches, H2D + kernels on n_slots CUDA streams, harvest in
+// order) -> consumer thread.  In VERIFY mode the output IS the input ring
+// (zero-copy: bytes become consumable once their batch verified); codec and
+// passthrough modes publish into a second pinned ring.
+#include <sys/eventfd.h>
+#include <unistd.h>
+#include <chrono>
+
+namespace mtz {
+
+struct InFlight { int slot; uint64_t in_begin, in_end; };
+
+struct Engine {
+	mtz_handle *h = nullptr;
+	uint8_t *in_buf = nullptr; size_t in_cap = 0;
+	uint8_t *out_buf = nullptr; size_t out_cap = 0;
+	bool own_out = false;          // false: VERIFY (output aliases the input ring)
+	// absolute stream positions, all monotonic
+	uint64_t in_acq = 0;           // end of the producer's outstanding acquire
+	uint64_t in_head = 0;          // committed
+	uint64_t in_tail = 0;          // released for reuse
+	uint64_t parse_pos = 0;        // engine: end of the last whole record parsed
+	uint64_t batch_begin = 0;      // engine: start of the batch being assembled
+	uint64_t out_head = 0;         // published to the consumer
+	uint64_t out_pos = 0;          // consumed
+	bool flushed = false, eof = false, stop = false;
+	std::mutex mu;
+	std::condition_variable cv_eng, cv_prod, cv_cons;
+	std::thread thr;
+	int efd = -1;
+	std::vector<mtz_rec> cur;      // records of the batch being assembled
+	uint64_t cur_writes = 0;
+	std::deque<InFlight> inflight;
+	uint64_t next_slot = 0;
+	std::chrono::steady_clock::time_point last_input;
+};
+
+static void signal_efd(Engine *e)
+{
+	if (e->efd >= 0) {
+		uint64_t one = 1;
+		ssize_t r = write(e->efd, &one, sizeof one);
+		(void)r;
+	}
+}
+
+void engine_wake_all(mtz_handle *h)
+{
+	Engine *e = h->eng;
+	if (e == nullptr) return;
+	e->cv_eng.notify_all(); e->cv_prod.notify_all(); e->cv_cons.notify_all();
+	signal_efd(e);
+}
+
+static void CUDART_CB engine_host_cb(void *p)
+{
+	Engine *e = (Engine *)p;
+	e->cv_eng.notify_one();
+}
+
+// copy n bytes at absolute position pos out of the ring (wrap aware)
+static void ring_read(const Engine *e, uint64_t pos, void *dst, size_t n)
+{
+	const size_t o = (size_t)(pos % e->in_cap);
+	const size_t a = std::min(n, e->in_cap - o);
+	memcpy(dst, e->in_buf + o, a);
+	if (n > a) memcpy((uint8_t *)dst + a, e->in_buf, n - a);
+}
+
+// engine thread body; e->mu held on entry to each helper
+static int32_t engine_parse(Engine *e, bool *cut)
+{
+	mtz_handle *h = e->h;
+	*cut = false;
+	const size_t slot_cap = h->slots[0].cap, rec_cap = h->slots[0].rec_cap;
+	if (h->cfg.mode == MTZ_MODE_PASSTHROUGH) {
+		const uint64_t lim = e->batch_begin + std::min<uint64_t>(h->cfg.batch_bytes, slot_cap);
+		e->parse_pos = std::min(e->in_head, lim);
+		*cut = (e->parse_pos == lim);
+		return MTZ_OK;
+	}
+	while (e->in_head - e->parse_pos >= DRR_HDR) {
+		uint8_t hdr[DRR_HDR];
+		ring_read(e, e->parse_pos, hdr, DRR_HDR);
+		uint32_t ls, comp;
+		const int64_t pl = drr_payload(hdr, &ls, &comp);
+		if (pl < 0)
+			return fail(h, MTZ_EFORMAT, "malformed record header at stream offset %llu",
+			    (unsigned long long)e->parse_pos);
+		const uint64_t rl = DRR_HDR + (uint64_t)pl;
+		if (rl > slot_cap || rl > e->in_cap)
+			return fail(h, MTZ_ENOSPC, "record of %llu bytes exceeds the batch/ring size",
+			    (unsigned long long)rl);
+		if (e->in_head - e->parse_pos < rl) break;                 // incomplete
+		const uint64_t bb = e->parse_pos - e->batch_begin;
+		if (!e->cur.empty() && (bb + rl > slot_cap || e->cur.size() >= rec_cap)) { *cut = true; break; }
+		mtz_rec r;
+		r.off = bb; r.payload = (uint32_t)pl; r.type = rd32(hdr);
+		r.lsize = ls; r.comp = comp; r.resv = 0;
+		e->cur.push_back(r);
+		if (r.type == 3) e->cur_writes++;
+		e->parse_pos += rl;
+		if (r.type == 5) { *cut = true; break; }                  // END: ship now
+		if (e->parse_pos - e->batch_begin >= h->cfg.batch_bytes) { *cut = true; break; }
+	}
+	return MTZ_OK;
+}
+
+static int32_t engine_submit(Engine *e)
+{
+	mtz_handle *h = e->h;
+	Slot &s = h->slots[e->next_slot % h->slots.size()];
+	const uint64_t b0 = e->batch_begin, b1 = e->parse_pos;
+	const size_t n = (size_t)(b1 - b0);
+	const size_t o = (size_t)(b0 % e->in_cap);
+	const size_t n0 = std::min(n, e->in_cap - o);
+	if (!e->cur.empty()) memcpy(s.h_recs, e->cur.data(), e->cur.size() * sizeof(mtz_rec));
+	s.writes = e->cur_writes;
+	int32_t rc = submit_batch(h, s, e->in_buf + o, n0, e->in_buf, n - n0, e->cur.size(), b0, nullptr);
+	if (rc != MTZ_OK) return rc;
+	MTZ_CU(h, cudaLaunchHostFunc(s.st, engine_host_cb, e));
+	InFlight f; f.slot = (int)(e->next_slot % h->slots.size()); f.in_begin = b0; f.in_end = b1;
+	e->inflight.push_back(f);
+	e->next_slot++;
+	e->batch_begin = b1;
+	e->cur.clear(); e->cur_writes = 0;
+	return MTZ_OK;
+}
+
+// harvest the oldest in-flight batch if it is done (or block when must_wait)
+static int32_t engine_harvest(Engine *e, std::unique_lock<std::mutex> &lk, bool *progress)
+{
+	mtz_handle *h = e->h;
+	while (!e->inflight.empty()) {
+		InFlight f = e->inflight.front();
+		Slot &s = h->slots[f.slot];
+		cudaError_t q = cudaEventQuery(s.ev_done);
+		if (q == cudaErrorNotReady) return MTZ_OK;
+		if (q != cudaSuccess) return fail_cuda(h, q, "cudaEventQuery(batch)");
+		int32_t rc = harvest(h, s);
+		if (rc != MTZ_OK) return rc;
+		const size_t n = (size_t)(f.in_end - f.in_begin);
+		if (e->own_out) {
+			// copy the batch result into the output ring (wait for room)
+			size_t done = 0;
+			while (done < n) {
+				while (e->out_cap - (size_t)(e->out_head - e->out_pos) == 0) {
+					if (e->stop || h->failed.load() != 0) return h->failed.load() ? h->failed.load() : MTZ_EINVAL;
+					e->cv_eng.wait_for(lk, std::chrono::milliseconds(2));
+				}
+				const size_t room = e->out_cap - (size_t)(e->out_head - e->out_pos);
+				const size_t oo = (size_t)(e->out_head % e->out_cap);
+				const size_t c = std::min(std::min(room, n - done), e->out_cap - oo);
+				lk.unlock();
+				cudaError_t ce = cudaMemcpyAsync(e->out_buf + oo, s.d_in + done, c, cudaMemcpyDeviceToHost, s.st);
+				if (ce == cudaSuccess) ce = cudaStreamSynchronize(s.st);
+				lk.lock();
+				if (ce != cudaSuccess) return fail_cuda(h, ce, "D2H to output ring");
+				done += c;
+				e->out_head += c;
+				e->cv_cons.notify_all();
+				signal_efd(e);
+			}
+			e->in_tail = f.in_end;               // input bytes no longer needed
+			e->cv_prod.notify_all();
+		} else {
+			e->out_head = f.in_end;              // verified: consumable in place
+			e->cv_cons.notify_all();
+			signal_efd(e);
+		}
+		e->inflight.pop_front();
+		*progress = true;
+	}
+	return MTZ_OK;
+}
+
+static void engine_main(Engine *e)
+{
+	mtz_handle *h = e->h;
+	cudaSetDevice(h->device);
+	std::unique_lock<std::mutex> lk(e->mu);
+	while (!e->stop) {
+		if (h->failed.load() != 0) { e->cv_eng.wait_for(lk, std::chrono::milliseconds(20)); continue; }
+		bool progress = false, cut = false;
+		int32_t rc = engine_harvest(e, lk, &progress);
+		if (rc == MTZ_OK && e->inflight.size() < h->slots.size()) {
+			const uint64_t before = e->parse_pos;
+			rc = engine_parse(e, &cut);
+			if (rc == MTZ_OK) {
+				if (e->parse_pos != before) progress = true;
+				const bool pending = e->parse_pos > e->batch_begin;
+				const auto idle = std::chrono::steady_clock::now() - e->last_input;
+				const bool all_parsed = (e->parse_pos == e->in_head);
+				const bool ring_full = (e->in_acq - e->in_tail) >= e->in_cap - DRR_HDR;
+				if (pending && (cut || (e->flushed && all_parsed) || ring_full ||
+				    (e->inflight.empty() && idle > std::chrono::milliseconds(5)))) {
+					rc = engine_submit(e);
+					progress = true;
+				}
+			}
+		}
+		if (rc == MTZ_OK && e->flushed && !e->eof && e->inflight.empty() &&
+		    e->parse_pos == e->batch_begin) {
+			if (e->parse_pos != e->in_head) {
+				rc = fail(h, MTZ_EFORMAT, "stream ends inside a record (%llu trailing bytes)",
+				    (unsigned long long)(e->in_head - e->parse_pos));
+			} else {
+				e->eof = true;
+				e->cv_cons.notify_all();
+				signal_efd(e);
+				progress = true;
+			}
+		}
+		if (rc != MTZ_OK) continue;               // fail() already woke everybody
+		if (!progress) e->cv_eng.wait_for(lk, std::chrono::milliseconds(2));
+	}
+}
+
+} // namespace mtz
+
+extern "C" {
+
+static int32_t engine_get(mtz_handle *h, Engine **out)
+{
+	std::lock_guard<std::mutex> g(h->eng_mu);
+	if (h->eng != nullptr) { *out = h->eng; return MTZ_OK; }
+	if (h->cfg.mode != MTZ_MODE_VERIFY && h->cfg.mode != MTZ_MODE_PASSTHROUGH)
+		return fail(h, MTZ_EINVAL, "streaming API: mode %u not supported yet", h->cfg.mode);
+	if (h->cfg.flags & MTZ_FLAG_DEFER_VERIFY)
+		return fail(h, MTZ_EINVAL, "streaming API cannot defer verification");
+	MTZ_CU(h, cudaSetDevice(h->device));
+	int32_t rc = ensure_slots(h);
+	if (rc != MTZ_OK) return rc;
+	Engine *e = new (std::nothrow) Engine();
+	if (e == nullptr) return fail(h, MTZ_ENOMEM, "engine allocation");
+	e->h = h;
+	e->in_cap = (size_t)h->cfg.ring_bytes;
+	if (e->in_cap < 2 * (size_t)h->cfg.batch_bytes) e->in_cap = 2 * (size_t)h->cfg.batch_bytes;
+	cudaError_t ce = cudaHostAlloc(&e->in_buf, e->in_cap, cudaHostAllocDefault);
+	if (ce != cudaSuccess) { delete e; return fail_cuda(h, ce, "cudaHostAlloc(input ring)"); }
+	e->own_out = (h->cfg.mode != MTZ_MODE_VERIFY);
+	if (e->own_out) {
+		e->out_cap = (size_t)h->cfg.out_ring_bytes;
+		ce = cudaHostAlloc(&e->out_buf, e->out_cap, cudaHostAllocDefault);
+		if (ce != cudaSuccess) { cudaFreeHost(e->in_buf); delete e; return fail_cuda(h, ce, "cudaHostAlloc(output ring)"); }
+	}
+	e->efd = eventfd(0, EFD_NONBLOCK | EFD_CLOEXEC);
+	e->last_input = std::chrono::steady_clock::now();
+	h->eng = e;
+	e->thr = std::thread(engine_main, e);
+	*out = e;
+	return MTZ_OK;
+}
+
+static void engine_destroy(mtz_handle *h)
+{
+	Engine *e = h->eng;
+	if (e == nullptr) return;
+	{
+		std::lock_guard<std::mutex> g(e->mu);
+		e->stop = true;
+	}
+	e->cv_eng.notify_all(); e->cv_prod.notify_all(); e->cv_cons.notify_all();
+	if (e->thr.joinable()) e->thr.join();
+	cudaDeviceSynchronize();
+	if (e->in_buf) cudaFreeHost(e->in_buf);
+	if (e->out_buf) cudaFreeHost(e->out_buf);
+	if (e->efd >= 0) close(e->efd);
+	h->eng = nullptr;
+	delete e;
+}
+
+#define GET_ENGINE(h, e)                                                       \
+	CHECK_H(h);                                                                \
+	Engine *e = nullptr;                                                       \
+	{ int32_t rc__ = engine_get((h), &e); if (rc__ != MTZ_OK) return rc__; }
+
+int32_t mtz_ring_acquire(mtz_handle *h, size_t want, void **ptr, size_t *got)
+{
+	GET_ENGINE(h, e);
+	if (ptr == nullptr || got == nullptr) return MTZ_EINVAL;
+	std::lock_guard<std::mutex> g(e->mu);
+	if (e->flushed) return fail(h, MTZ_EINVAL, "write after flush");
+	if (e->in_acq != e->in_head) return fail(h, MTZ_EINVAL, "acquire with an uncommitted slice outstanding");
+	const size_t used = (size_t)(e->in_head - e->in_tail);
+	const size_t o = (size_t)(e->in_head % e->in_cap);
+	size_t n = std::min(e->in_cap - used, e->in_cap - o);
+	if (want != 0) n = std::min(n, want);
+	*ptr = e->in_buf + o; *got = n;
+	if (n == 0) return MTZ_EAGAIN;
+	e->in_acq = e->in_head + n;
+	return MTZ_OK;
+}
+
+int32_t mtz_ring_commit(mtz_handle *h, size_t n)
+{
+	GET_ENGINE(h, e);
+	std::lock_guard<std::mutex> g(e->mu);
+	if (n > (size_t)(e->in_acq - e->in_head)) return fail(h, MTZ_EINVAL, "commit beyond the acquired slice");
+	e->in_head += n;
+	e->in_acq = e->in_head;
+	e->last_input = std::chrono::steady_clock::now();
+	e->cv_eng.notify_one();
+	return MTZ_OK;
+}
+
+int32_t mtz_write(mtz_handle *h, const void *buf, size_t n, int32_t block)
+{
+	GET_ENGINE(h, e);
+	const uint8_t *src = (const uint8_t *)buf;
+	size_t done = 0;
+	while (done < n) {
+		void *p = nullptr; size_t got = 0;
+		int32_t rc = mtz_ring_acquire(h, n - done, &p, &got);
+		if (rc == MTZ_EAGAIN) {
+			if (!block) return done ? (int32_t)MTZ_OK : (int32_t)MTZ_EAGAIN;
+			std::unique_lock<std::mutex> lk(e->mu);
+			if ((size_t)(e->in_head - e->in_tail) >= e->in_cap && h->failed.load() == 0)
+				e->cv_prod.wait_for(lk, std::chrono::milliseconds(50));
+			if (h->failed.load() != 0) return h->failed.load();
+			continue;
+		}
+		if (rc != MTZ_OK) return rc;
+		memcpy(p, src + done, got);
+		rc = mtz_ring_commit(h, got);
+		if (rc != MTZ_OK) return rc;
+		done += got;
+	}
+	return MTZ_OK;
+}
+
+int32_t mtz_flush(mtz_handle *h)
+{
+	GET_ENGINE(h, e);
+	std::lock_guard<std::mutex> g(e->mu);
+	e->flushed = true;
+	e->cv_eng.notify_one();
+	return MTZ_OK;
+}
+
+int32_t mtz_out_peek(mtz_handle *h, const void **ptr, size_t *n)
+{
+	GET_ENGINE(h, e);
+	if (ptr == nullptr || n == nullptr) return MTZ_EINVAL;
+	std::lock_guard<std::mutex> g(e->mu);
+	const uint8_t *buf = e->own_out ? e->out_buf : e->in_buf;
+	const size_t cap = e->own_out ? e->out_cap : e->in_cap;
+	const size_t avail = (size_t)(e->out_head - e->out_pos);
+	const size_t o = (size_t)(e->out_pos % cap);
+	*ptr = buf + o;
+	*n = std::min(avail, cap - o);
+	if (*n == 0) return e->eof ? MTZ_EOF : MTZ_EAGAIN;
+	return MTZ_OK;
+}
+
+int32_t mtz_out_consume(mtz_handle *h, size_t n)
+{
+	GET_ENGINE(h, e);
+	std::lock_guard<std::mutex> g(e->mu);
+	if (n > (size_t)(e->out_head - e->out_pos)) return fail(h, MTZ_EINVAL, "consume beyond published output");
+	e->out_pos += n;
+	if (!e->own_out) { e->in_tail = e->out_pos; e->cv_prod.notify_all(); }
+	e->cv_eng.notify_one();
+	return MTZ_OK;
+}
+
+int32_t mtz_read(mtz_handle *h, void *buf, size_t cap, size_t *got, int32_t block)
+{
+	GET_ENGINE(h, e);
+	if (got == nullptr) return MTZ_EINVAL;
+	*got = 0;
+	for (;;) {
+		const void *p = nullptr; size_t n = 0;
+		int32_t rc = mtz_out_peek(h, &p, &n);
+		if (rc == MTZ_OK) {
+			n = std::min(n, cap);
+			memcpy(buf, p, n);
+			*got = n;
+			return mtz_out_consume(h, n);
+		}
+		if (rc != MTZ_EAGAIN || !block) return rc;
+		std::unique_lock<std::mutex> lk(e->mu);
+		if (e->out_head == e->out_pos && !e->eof && h->failed.load() == 0)
+			e->cv_cons.wait_for(lk, std::chrono::milliseconds(50));
+		if (h->failed.load() != 0) return h->failed.load();
+	}
+}
+
+int32_t mtz_event_fd(mtz_handle *h)
+{
+	GET_ENGINE(h, e);
+	return e->efd;
+}
+
+// ------------------------------------------------- not yet implemented ----
+int32_t mtz_dev_index(mtz_handle *h, const void *, size_t, mtz_rec *, size_t, size_t *, void *) { CHECK_H(h); return MTZ_EINVAL; }
+int32_t mtz_synth_tile(mtz_handle *h, const void *, size_t, size_t, void *, size_t, uint64_t, uint32_t, mtz_rec *, size_t *, size_t *) { CHECK_H(h); return MTZ_EINVAL; }
+
+} // extern "C"

@@ -80,6 +80,9 @@ def lib():
         L.orc_gen_payload.argtypes = [i32, u64, vp, sz]; L.orc_gen_payload.restype = None
         L.orc_synth_stream_size.argtypes = [u64, u32]; L.orc_synth_stream_size.restype = sz
         L.orc_synth_stream.argtypes = [vp, sz, C.POINTER(sz), u64, u32, i32, u64, i32]
+        L.orc_synth_shard_size.argtypes = [u64, u32, i32]; L.orc_synth_shard_size.restype = sz
+        L.orc_synth_shard_fill.argtypes = [vp, sz, u64, u32, i32, u64, i32, vp, i32]
+        L.orc_synth_shard_stamp.argtypes = [vp, u64, u32, i32, vp, C.POINTER(Cksum)]
         L.orc_mt_verify.argtypes = [vp, sz, i32, C.POINTER(C.c_double), C.POINTER(StreamStats)]
         L.orc_mt_recompress.argtypes = [vp, sz, vp, sz, C.POINTER(sz), i32,
                                         C.POINTER(C.c_double), C.POINTER(StreamStats)]
@@ -142,6 +145,31 @@ def synth_stream(nwrites, recsize=131072, kind=PAYLOAD_PCG, first_rec=0, nthread
     if rc != OK:
         raise RuntimeError("orc_synth_stream rc=%d" % rc)
     return out[:n.value]
+
+
+def synth_shard_fill(nwrites, recsize, kind, first_rec, flags, out=None, nthreads=0):
+    """Step 1 of a record-index shard (see synth.c): returns (bytes, ppay)."""
+    L = lib()
+    need = L.orc_synth_shard_size(nwrites, recsize, flags)
+    if out is None:
+        out = np.empty(need, dtype=np.uint8)
+    ppay = np.zeros((nwrites + 1, 5), dtype=np.uint64)
+    rc = L.orc_synth_shard_fill(_ptr(out), out.size, nwrites, recsize, kind, first_rec, flags,
+                                _ptr(ppay), nthreads or (os.cpu_count() or 1))
+    if rc != OK:
+        raise RuntimeError("orc_synth_shard_fill rc=%d" % rc)
+    return out[:need], ppay
+
+
+def synth_shard_stamp(buf, nwrites, recsize, flags, ppay, state):
+    """Step 2: stamp checksums from running `state`; returns the state after the shard."""
+    ck = Cksum()
+    for i in range(4):
+        ck.w[i] = state[i]
+    rc = lib().orc_synth_shard_stamp(_ptr(buf), nwrites, recsize, flags, _ptr(ppay), C.byref(ck))
+    if rc != OK:
+        raise RuntimeError("orc_synth_shard_stamp rc=%d" % rc)
+    return ck.tuple()
 
 
 def stream_index(stream):

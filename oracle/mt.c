@@ -159,6 +159,7 @@ orc_mt_verify(const uint8_t *in, size_t n, int nthreads, double *secs,
 	for (i = 0; i < nrec; i++) {
 		const uint8_t *h = in + offs[i];
 		uint32_t type = g32(h);
+		if (type == ORC_DRR_BEGIN) memset(&s, 0, sizeof (s));
 		if (type == ORC_DRR_END && memcmp(h + 8, s.w, 32) != 0) {
 			rc = ORC_ECKSUM; st->bad_record = i; break;
 		}
@@ -244,6 +245,7 @@ orc_mt_recompress(const uint8_t *in, size_t n, uint8_t *out, size_t cap,
 		if (cap - oo < ORC_DRR_HDR + opl[i]) { rc = ORC_ENOSPC; goto done; }
 		if (type == ORC_DRR_BEGIN) {
 			uint64_t vi = g64(h + 16);
+			memset(&so, 0, sizeof (so));
 			vi |= (ORC_FEAT_COMPRESSED | ORC_FEAT_LZ4) << 2;
 			p64(h + 16, vi);
 		}

@@ -127,6 +127,13 @@ size_t orc_synth_stream_size(uint64_t nwrites, uint32_t recsize);
 int orc_synth_stream(uint8_t *out, size_t cap, size_t *outn, uint64_t nwrites,
     uint32_t recsize, int kind, uint64_t first_rec, int nthreads);
 
+size_t orc_synth_shard_size(uint64_t nwrites, uint32_t recsize, int flags);
+int orc_synth_shard_fill(uint8_t *out, size_t cap, uint64_t nwrites,
+    uint32_t recsize, int kind, uint64_t first_rec, int flags,
+    orc_partial_t *ppay, int nthreads);
+int orc_synth_shard_stamp(uint8_t *out, uint64_t nwrites, uint32_t recsize,
+    int flags, const orc_partial_t *ppay, orc_cksum_t *state);
+
 /* ---- multi-threaded CPU baseline drivers (bench.py --impl reference) ---- */
 /* record-parallel Fletcher-4 verify: per-record partials on nthreads, then
  * the O(records) combine; returns ORC_OK/ORC_ECKSUM, seconds in *secs */

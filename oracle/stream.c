@@ -152,6 +152,13 @@ walk(const uint8_t *in, size_t n, uint8_t *out, size_t cap, size_t *outn,
 			rc = ORC_EFORMAT; goto bad;
 		}
 
+		/* the stream checksum restarts at every BEGIN (sub-streams of a
+		 * compound `send -R` stream each carry their own) */
+		if (type == ORC_DRR_BEGIN) {
+			memset(&si, 0, sizeof (si));
+			memset(&so, 0, sizeof (so));
+		}
+
 		/* ---- verify input ---- */
 		if (type == ORC_DRR_END &&
 		    memcmp(h + OFF_END_CK, si.w, 32) != 0) {
@@ -308,6 +315,7 @@ orc_stream_restamp(uint8_t *s, size_t n, orc_cksum_t *end)
 		if (pl < 0 || (uint64_t)pl > n - off - ORC_DRR_HDR)
 			return (ORC_EFORMAT);
 		type = g32(h);
+		if (type == ORC_DRR_BEGIN) memset(&so, 0, sizeof (so));
 		if (type == ORC_DRR_END) {
 			memcpy(h + OFF_END_CK, so.w, 32);
 			if (end != NULL) *end = so;

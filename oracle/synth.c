@@ -236,44 +236,74 @@ gen_worker(void *v)
 	return (NULL);
 }
 
-int
-orc_synth_stream(uint8_t *out, size_t cap, size_t *outn, uint64_t nwrites,
-    uint32_t recsize, int kind, uint64_t first_rec, int nthreads)
+/*
+ * Shard-capable generator: a logical stream of BEGIN, OBJECT, W x WRITE, END is
+ * cut by record index; this call produces the slice holding writes
+ * [first_rec, first_rec + nwrites).  flags bit0: slice starts the stream (emit
+ * BEGIN+OBJECT), bit1: slice ends it (emit END).  Two steps so that the heavy
+ * part runs in parallel on every rank and only the O(records) checksum chain
+ * is sequential across slices:
+ *   fill  : headers (checksum fields zero) + payloads, payload sums -> ppay
+ *   stamp : dump_record() chain from *state (running checksum before the
+ *           slice), stamps every header, returns the state after the slice.
+ */
+size_t
+orc_synth_shard_size(uint64_t nwrites, uint32_t recsize, int flags)
 {
-	size_t need = orc_synth_stream_size(nwrites, recsize);
-	size_t off = 0, stride = (size_t)ORC_DRR_HDR + recsize;
-	orc_cksum_t so = { { 0, 0, 0, 0 } };
-	orc_partial_t *ppay;
-	pthread_t th[64];
-	gen_arg_t args[64];
-	uint64_t i;
+	size_t n = (size_t)nwrites * ((size_t)ORC_DRR_HDR + recsize);
+	if (flags & 1) n += (size_t)ORC_DRR_HDR * 2 + BONUSLEN;
+	if (flags & 2) n += ORC_DRR_HDR;
+	return (n);
+}
+
+int
+orc_synth_shard_fill(uint8_t *out, size_t cap, uint64_t nwrites, uint32_t recsize,
+    int kind, uint64_t first_rec, int flags, orc_partial_t *ppay, int nthreads)
+{
+	size_t need = orc_synth_shard_size(nwrites, recsize, flags), off = 0;
+	pthread_t th[256];
+	gen_arg_t args[256];
 	int t;
 
 	if (recsize < 512 || (recsize & 511) || cap < need) return (ORC_EINVAL);
 	if (nthreads < 1) nthreads = 1;
-	if (nthreads > 64) nthreads = 64;
-	ppay = (orc_partial_t *)malloc(sizeof (*ppay) * (size_t)(nwrites + 1));
-	if (ppay == NULL) return (ORC_ENOSPC);
-
-	hdr_begin(out);
-	orc_fletcher4_incremental(out, ORC_DRR_HDR, &so);
-	off = ORC_DRR_HDR;
-
-	hdr_object(out + off, recsize);
-	orc_gen_payload(ORC_PAYLOAD_PCG, ~(uint64_t)0, out + off + ORC_DRR_HDR,
-	    BONUSLEN);
-	orc_fletcher4_incremental(out + off, ORC_DRR_CKOFF, &so);
-	memcpy(out + off + ORC_DRR_CKOFF, so.w, 32);
-	orc_fletcher4_incremental(out + off + ORC_DRR_CKOFF, 32 + BONUSLEN, &so);
-	off += ORC_DRR_HDR + BONUSLEN;
-
+	if (nthreads > 256) nthreads = 256;
+	if (flags & 1) {
+		hdr_begin(out);
+		off = ORC_DRR_HDR;
+		hdr_object(out + off, recsize);
+		orc_gen_payload(ORC_PAYLOAD_PCG, ~(uint64_t)0, out + off + ORC_DRR_HDR,
+		    BONUSLEN);
+		off += ORC_DRR_HDR + BONUSLEN;
+	}
 	for (t = 0; t < nthreads; t++) {
 		args[t] = (gen_arg_t){ out + off, nwrites, first_rec, recsize, kind,
 		    t, nthreads, ppay };
 		pthread_create(&th[t], NULL, gen_worker, &args[t]);
 	}
 	for (t = 0; t < nthreads; t++) pthread_join(th[t], NULL);
+	off += (size_t)nwrites * ((size_t)ORC_DRR_HDR + recsize);
+	if (flags & 2) hdr_end(out + off);
+	return (ORC_OK);
+}
 
+int
+orc_synth_shard_stamp(uint8_t *out, uint64_t nwrites, uint32_t recsize, int flags,
+    const orc_partial_t *ppay, orc_cksum_t *state)
+{
+	size_t off = 0, stride = (size_t)ORC_DRR_HDR + recsize;
+	orc_cksum_t so = *state;
+	uint64_t i;
+
+	if (flags & 1) {
+		memset(&so, 0, sizeof (so));
+		orc_fletcher4_incremental(out, ORC_DRR_HDR, &so);
+		off = ORC_DRR_HDR;
+		orc_fletcher4_incremental(out + off, ORC_DRR_CKOFF, &so);
+		memcpy(out + off + ORC_DRR_CKOFF, so.w, 32);
+		orc_fletcher4_incremental(out + off + ORC_DRR_CKOFF, 32 + BONUSLEN, &so);
+		off += ORC_DRR_HDR + BONUSLEN;
+	}
 	for (i = 0; i < nwrites; i++) {
 		uint8_t *h = out + off;
 		orc_fletcher4_incremental(h, ORC_DRR_CKOFF, &so);
@@ -282,13 +312,33 @@ orc_synth_stream(uint8_t *out, size_t cap, size_t *outn, uint64_t nwrites,
 		orc_fletcher4_apply(&so, &ppay[i]);
 		off += stride;
 	}
-	free(ppay);
-
-	hdr_end(out + off);
-	memcpy(out + off + 8, so.w, 32);
-	orc_fletcher4_incremental(out + off, ORC_DRR_CKOFF, &so);
-	memcpy(out + off + ORC_DRR_CKOFF, so.w, 32);
-	off += ORC_DRR_HDR;
-	if (outn != NULL) *outn = off;
+	if (flags & 2) {
+		uint8_t *h = out + off;
+		memcpy(h + 8, so.w, 32);
+		orc_fletcher4_incremental(h, ORC_DRR_CKOFF, &so);
+		memcpy(h + ORC_DRR_CKOFF, so.w, 32);
+		orc_fletcher4_incremental(h + ORC_DRR_CKOFF, 32, &so);
+	}
+	*state = so;
 	return (ORC_OK);
+}
+
+int
+orc_synth_stream(uint8_t *out, size_t cap, size_t *outn, uint64_t nwrites,
+    uint32_t recsize, int kind, uint64_t first_rec, int nthreads)
+{
+	orc_cksum_t st = { { 0, 0, 0, 0 } };
+	orc_partial_t *ppay;
+	int rc;
+
+	ppay = (orc_partial_t *)malloc(sizeof (*ppay) * (size_t)(nwrites + 1));
+	if (ppay == NULL) return (ORC_ENOSPC);
+	rc = orc_synth_shard_fill(out, cap, nwrites, recsize, kind, first_rec, 3,
+	    ppay, nthreads);
+	if (rc == ORC_OK)
+		rc = orc_synth_shard_stamp(out, nwrites, recsize, 3, ppay, &st);
+	free(ppay);
+	if (rc == ORC_OK && outn != NULL)
+		*outn = orc_synth_shard_size(nwrites, recsize, 3);
+	return (rc);
 }

@@ -1,0 +1,72 @@
+"""CPU: libmanatee_gpu.so loads and exports every symbol include/manatee_gpu.h
+declares (no compute calls: there is no GPU here)."""
+import os
+import re
+import subprocess
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    src = open(os.path.join(ROOT, "include", "manatee_gpu.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(mtz_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol(native):
+    from manatee_b200 import _native
+    hdr = _header_symbols()
+    assert len(hdr) >= 20
+    assert sorted(_native.SYMBOLS) == hdr, "binding table and header disagree"
+    out = subprocess.check_output(["nm", "-D", "--defined-only", _native.SO_PATH]).decode()
+    exported = set(re.findall(r" T (mtz_[a-z0-9_]+)", out))
+    missing = [s for s in hdr if s not in exported]
+    assert not missing, missing
+    assert native.mtz_abi_version() == 1
+
+
+def test_error_strings_and_null_handles(native):
+    assert native.mtz_strerror(0) == b"ok"
+    assert b"checksum" in native.mtz_strerror(-5)
+    assert b"no CPU fallback" in native.mtz_strerror(-10)
+    assert native.mtz_close(None) == -1
+    assert native.mtz_get_stats(None, None) == -1
+
+
+def test_open_without_gpu_fails_loudly(native):
+    """No silent CPU fallback: on a box without a B200 mtz_open returns MTZ_ENOGPU."""
+    import ctypes as C
+    import torch
+    from manatee_b200 import _native as N
+    if torch.cuda.is_available():
+        return
+    cfg = N.Config()
+    cfg.struct_size = C.sizeof(N.Config)
+    h = C.c_void_p()
+    rc = native.mtz_open(C.byref(cfg), C.byref(h))
+    assert rc == N.ENOGPU
+    assert b"no CPU fallback" in native.mtz_last_error(None)
+
+
+def test_host_index_matches_oracle(native, oracle):
+    """mtz_index_host is host-side product logic (DRR parse): same record table as the oracle."""
+    import numpy as np
+    from manatee_b200 import index_host
+    s = oracle.synth_stream(17, recsize=4096, kind=oracle.PAYLOAD_PCG)
+    recs, used = index_host(s)
+    cnt, offs = oracle.stream_index(s)
+    assert used == s.size and len(recs) == cnt
+    assert np.array_equal(recs["off"], offs)
+    assert list(recs["type"][:3]) == [0, 1, 3] and recs["type"][-1] == 5
+    assert set(recs["payload"][2:-1]) == {4096}
+    # a compressed stream exposes lsize/comp
+    sp = oracle.synth_stream(6, recsize=131072, kind=oracle.PAYLOAD_PGPAGE)
+    rc, c, st = oracle.stream_compress(sp)
+    recs, used = index_host(c)
+    assert used == c.size
+    w = recs[recs["type"] == 3]
+    assert set(w["comp"]) == {15} and set(w["lsize"]) == {131072}
+    assert all(w["payload"] % 512 == 0) and all(w["payload"] < 131072)
+    # truncated tail: only whole records are reported
+    recs2, used2 = index_host(s[:-100])
+    assert len(recs2) == cnt - 1 and used2 == int(offs[-1])
