@@ -38,8 +38,19 @@ __host__ __device__ __forceinline__ uint64_t tri2(uint64_t n)
 	return x * y;
 }
 
+// n < 2^32 fast paths: 32-bit remainder instead of a 64-bit division
+__host__ __device__ __forceinline__ uint64_t tri3_u32(uint32_t n)
+{
+	uint64_t f0 = n, f1 = (uint64_t)n + 1, f2 = (uint64_t)n + 2;
+	if (!(n & 1u)) f0 >>= 1; else f1 >>= 1;
+	const uint32_t r = n % 3u;                     // n%3==0 -> f0, 2 -> f1, 1 -> f2
+	if (r == 0u) f0 /= 3u; else if (r == 2u) f1 /= 3u; else f2 /= 3u;
+	return f0 * f1 * f2;
+}
+
 __host__ __device__ __forceinline__ uint64_t tri3(uint64_t n)
 {
+	if (n < 0xfffffff0ull) return tri3_u32((uint32_t)n);
 	uint64_t f0 = n, f1 = n + 1, f2 = n + 2;
 	if (!(f0 & 1)) f0 >>= 1; else f1 >>= 1;          // one of n, n+1 is even
 	if (f0 % 3 == 0) f0 /= 3; else if (f1 % 3 == 0) f1 /= 3; else f2 /= 3;
@@ -170,6 +181,15 @@ __device__ __forceinline__ Ck4 warp_fletcher(const uint8_t *p0, uint32_t nwords,
 		// ---- full middle rows j = 1 .. NR-2, four loads in flight ----
 		uint32_t j = 1u;
 		const uint32_t jend = NR - 1u;
+		for (; j + 8u <= jend; j += 8u) {
+			uint4 v[8];
+#pragma unroll
+			for (int u = 0; u < 8; u++) v[u] = ldg_stream(rowp + 32u * (j + (uint32_t)u));
+#pragma unroll
+			for (int u = 0; u < 8; u++) {
+				t3 -= t2; t2 -= m; m -= 1u; acc.add(v[u], m, t2, t3);
+			}
+		}
 		for (; j + 4u <= jend; j += 4u) {
 			uint4 v0 = ldg_stream(rowp + 32u * (j + 0u));
 			uint4 v1 = ldg_stream(rowp + 32u * (j + 1u));
@@ -198,29 +218,30 @@ __device__ __forceinline__ Ck4 warp_fletcher(const uint8_t *p0, uint32_t nwords,
 	}
 
 	// ---- row basis -> word-distance basis, per element ----
+	// Q(i) = T2(128 i + d), P(i) = T3(128 i + d); |128 i + d| < 600 so every
+	// product fits int32 and the divisions are by constants.
 #pragma unroll
 	for (int e = 0; e < 4; e++) {
-		const int64_t d = (int64_t)q - (int64_t)(r0 + (uint32_t)e);
-		// Q(i) = T2(128 i + d), P(i) = T3(128 i + d), exact in int64 (|x| < 600)
-		int64_t Q0 = d * (d + 1) / 2;
-		int64_t Q1 = (d + 128) * (d + 129) / 2;
-		int64_t P[4];
+		const int d = (int)q - (int)(r0 + (uint32_t)e);
+		const int Q0 = d * (d + 1) / 2;
+		const int Q1 = (d + 128) * (d + 129) / 2;
+		int P[4];
 #pragma unroll
 		for (int i = 0; i < 4; i++) {
-			const int64_t x = d + 128 * i;
+			const int x = d + 128 * i;
 			P[i] = x * (x + 1) * (x + 2) / 6;
 		}
-		const int64_t q2 = 16384;
-		const int64_t q1 = Q1 - Q0;
-		const int64_t d1 = P[1] - P[0];
-		const int64_t d2 = P[2] - 2 * P[1] + P[0];
-		const int64_t d3 = P[3] - 3 * P[2] + 3 * P[1] - P[0];   // 128^3
+		const int q2 = 16384;
+		const int q1 = Q1 - Q0;
+		const int d1 = P[1] - P[0];
+		const int d2 = P[2] - 2 * P[1] + P[0];
+		const int d3 = 2097152;                       // 128^3
 		const uint64_t sa = acc.sa[e], sb = acc.sb[e], sc = acc.sc[e], sd = acc.sd[e];
 		out.a += sa;
-		out.b += 128ull * sb + (uint64_t)d * sa;
-		out.c += (uint64_t)q2 * sc + (uint64_t)(q1 - q2) * sb + (uint64_t)Q0 * sa;
-		out.d += (uint64_t)d3 * sd + (uint64_t)(d2 - 2 * d3) * sc +
-		    (uint64_t)(d1 - d2 + d3) * sb + (uint64_t)P[0] * sa;
+		out.b += 128ull * sb + (uint64_t)(int64_t)d * sa;
+		out.c += (uint64_t)q2 * sc + (uint64_t)(int64_t)(q1 - q2) * sb + (uint64_t)(int64_t)Q0 * sa;
+		out.d += (uint64_t)d3 * sd + (uint64_t)(int64_t)(d2 - 2 * d3) * sc +
+		    (uint64_t)(int64_t)(d1 - d2 + d3) * sb + (uint64_t)(int64_t)P[0] * sa;
 	}
 	out.a = warp_sum64(out.a);
 	out.b = warp_sum64(out.b);

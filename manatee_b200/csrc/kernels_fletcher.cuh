@@ -1,6 +1,6 @@
 // kernels_fletcher.cuh -- K1 (per-record Fletcher-4 sums) and the record scan that
-// turns them into the running stream checksum, verifies every embedded
-// drr_checksum / DRR_END checksum, or stamps them (K4 re-stamp).
+// turns them into the running stream checksum and verifies every embedded
+// drr_checksum / DRR_END checksum.
 //
 // Stream semantics restated from illumos dmu_send.c dump_record() /
 // dmu_recv.c receive_read_record() ([EXTERNAL]): the
@@ -29,8 +29,8 @@ struct RecSums {         // 144 B per record: everything the scan needs, so the
 };
 
 struct ScanResult {      // lives in device memory, mirrored to pinned host
-	Part agg;            // aggregate of the batch's record bytes (phase A)
-	Ck4 carry;           // running checksum after the batch (phase B)
+	Part agg;            // aggregate of the batch's record bytes
+	Ck4 carry;           // running checksum after the batch
 	Ck4 end_ck;          // running checksum before DRR_END, if seen
 	uint32_t bad;        // first failing record index in batch, 0xffffffff none
 	uint32_t status;     // 0 ok, else -MTZ_E*
@@ -45,73 +45,62 @@ __device__ __forceinline__ Ck4 load_ck(const uint8_t *p)   // 8-byte aligned
 	return r;
 }
 
-#define K1_THREADS 256
+#define K1_THREADS 128
 #define K1_WARPS   (K1_THREADS / 32)
 
-// One CTA per record.  body_from = 280 (VERIFY: checksum field + payload) or
-// 312 (STAMP: payload only; the 8 checksum words are folded by the chain).
-__global__ void __launch_bounds__(K1_THREADS)
+// One WARP per record (grid-stride).  A 128 KiB record is 257 rows of 512 B:
+// the warp streams them with 8 LDG.128 in flight per lane, so the per-call
+// basis conversion and the warp reduction are paid once per record.
+// body_from = 280 (VERIFY: checksum field + payload) or 312 (payload only).
+__global__ void __launch_bounds__(K1_THREADS, 5)
 k1_record_sums(const uint8_t *__restrict__ base, const mtz_rec *__restrict__ recs,
     uint32_t nrec, RecSums *__restrict__ out, uint32_t body_from)
 {
-	__shared__ Ck4 s_part[K1_WARPS];
-	__shared__ Ck4 s_head;
-	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const int lane = threadIdx.x & 31;
+	const uint32_t gw = blockIdx.x * K1_WARPS + (threadIdx.x >> 5);
+	const uint32_t nw = gridDim.x * K1_WARPS;
 
-	for (uint32_t r = blockIdx.x; r < nrec; r += gridDim.x) {
+	for (uint32_t r = gw; r < nrec; r += nw) {
 		const mtz_rec rec = recs[r];
 		const uint8_t *hdr = base + rec.off;
 		const uint8_t *body = hdr + body_from;
 		const uint32_t nwords = (DRR_HDR - body_from + rec.payload) >> 2;
 
-		const uint32_t head = (uint32_t)(((uintptr_t)body & 511u) >> 2);
-		const uint32_t rows = (head + nwords + 127u) >> 7;
-		uint32_t rpc = (rows + K1_WARPS - 1u) / K1_WARPS;
-		if (rpc > MTZ_K1_MAX_ROWS) rpc = MTZ_K1_MAX_ROWS;
-		if (rpc == 0u) rpc = 1u;
+		const Ck4 h = warp_fletcher(hdr, DRR_CKOFF / 4u, lane);
 
+		// chunks of <= MTZ_K1_MAX_ROWS rows (T3(row) must fit 32 bits); chunk
+		// boundaries sit on 512 B rows so only the first chunk has a head skip
+		const uint32_t head = (uint32_t)(((uintptr_t)body & 511u) >> 2);
+		const uint32_t first = min(nwords, MTZ_K1_MAX_ROWS * 128u - head);
 		Ck4 acc = { 0, 0, 0, 0 };
-		for (uint32_t c = (uint32_t)warp; c * rpc < rows; c += K1_WARPS) {
-			const uint64_t rw0 = (uint64_t)c * rpc * 128u;
-			const uint64_t rw1 = rw0 + (uint64_t)rpc * 128u;
-			const uint32_t w0 = rw0 > head ? (uint32_t)(rw0 - head) : 0u;
-			uint32_t w1 = rw1 > head ? (uint32_t)min((uint64_t)nwords, rw1 - head) : 0u;
-			if (w1 > w0) {
-				Ck4 p = warp_fletcher(body + 4ull * w0, w1 - w0, lane);
-				p = shift_zeros(p, (uint64_t)(nwords - w1));
-				acc.a += p.a; acc.b += p.b; acc.c += p.c; acc.d += p.d;
-			}
+		for (uint32_t w0 = 0; w0 < nwords;) {
+			const uint32_t w1 = (w0 == 0u) ? first : min(nwords, w0 + MTZ_K1_MAX_ROWS * 128u);
+			Ck4 p = warp_fletcher(body + 4ull * w0, w1 - w0, lane);
+			if (w1 != nwords) p = shift_zeros(p, (uint64_t)(nwords - w1));
+			acc.a += p.a; acc.b += p.b; acc.c += p.c; acc.d += p.d;
+			w0 = w1;
 		}
-		if (lane == 0) s_part[warp] = acc;
-		if (warp == K1_WARPS - 1) {
-			Ck4 h = warp_fletcher(hdr, DRR_CKOFF / 4u, lane);
-			if (lane == 0) s_head = h;
-		}
-		__syncthreads();
-		if (threadIdx.x == 0) {
-			Ck4 t = s_part[0];
-#pragma unroll
-			for (int w = 1; w < K1_WARPS; w++) {
-				t.a += s_part[w].a; t.b += s_part[w].b;
-				t.c += s_part[w].c; t.d += s_part[w].d;
-			}
+		if (lane == 0) {
 			RecSums o;
-			o.head = s_head; o.body = t; o.nbody = nwords; o.pad = 0;
+			o.head = h; o.body = acc; o.nbody = nwords; o.pad = 0;
 			o.type = rec.type;
 			o.emb = load_ck(hdr + DRR_CKOFF);
 			o.aux = load_ck(hdr + 8);
 			out[r] = o;
 		}
-		__syncthreads();
 	}
 }
 
 // ---------------------------------------------------------------------------
-// Record scan.  The per-record transform of the running checksum in VERIFY is
-// affine (the bytes are given), so the batch is a parallel prefix scan under
-// `concat`.  One CTA: each thread owns a contiguous run of records.
+// Record scan.  In VERIFY the per-record transform of the running checksum is
+// affine (the bytes are given), so a batch is a segmented prefix scan under
+// `concat` (segments restart at DRR_BEGIN).  Three small kernels:
+//   S1  tile aggregates            (grid = tiles, SCAN_TILE records per CTA)
+//   S2  scan of tile aggregates    (1 CTA) -> exclusive tile prefixes, batch agg
+//   S3  per-tile rescan with the carry, verify embedded/END checksums
 // ---------------------------------------------------------------------------
-#define SCAN_THREADS 1024
+#define SCAN_THREADS 256
+#define SCAN_TILE    SCAN_THREADS          // one record per thread
 
 __device__ __forceinline__ Part part_shfl_up(const Part &p, int delta)
 {
@@ -124,12 +113,12 @@ __device__ __forceinline__ Part part_shfl_up(const Part &p, int delta)
 	return r;
 }
 
-__device__ __forceinline__ Part rec_part(const RecSums &s, uint32_t type)
+__device__ __forceinline__ Part rec_part(const RecSums &s)
 {
 	Part h = { DRR_CKOFF / 4u, s.head.a, s.head.b, s.head.c, s.head.d };
 	Part b = { s.nbody, s.body.a, s.body.b, s.body.c, s.body.d };
 	Part r = concat(h, b);
-	if (type == DRR_BEGIN_T) r.n |= PART_RESET;   // checksum restarts at BEGIN
+	if (s.type == DRR_BEGIN_T) r.n |= PART_RESET;   // checksum restarts at BEGIN
 	return r;
 }
 
@@ -143,25 +132,12 @@ __device__ __forceinline__ bool ck_zero(const Ck4 &x)
 	return (x.a | x.b | x.c | x.d) == 0;
 }
 
-// phase 0: aggregate only (res->agg).  phase 1: aggregate + verify with
-// carry_in, writes res->carry / bad / status / end_ck.
-__global__ void __launch_bounds__(SCAN_THREADS)
-k_scan_verify(const RecSums *__restrict__ sums, uint32_t nrec,
-    const Ck4 *__restrict__ carry_in, ScanResult *__restrict__ res, int phase)
+// CTA-wide scan of one Part per thread; returns the exclusive prefix of this
+// thread and (in *total, valid for every thread) the CTA aggregate.
+template <int THREADS>
+__device__ __forceinline__ Part block_exclusive(const Part &mine, Part *s_warp, Part *total)
 {
-	__shared__ Part s_warp[SCAN_THREADS / 32];
-	__shared__ uint32_t s_bad;
-	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	const uint32_t per = (nrec + SCAN_THREADS - 1u) / SCAN_THREADS;
-	const uint32_t r0 = min(nrec, (uint32_t)tid * per);
-	const uint32_t r1 = min(nrec, r0 + per);
-
-	if (tid == 0) s_bad = 0xffffffffu;
-
-	Part mine = { 0, 0, 0, 0, 0 };
-	for (uint32_t r = r0; r < r1; r++) mine = concat(mine, rec_part(sums[r], sums[r].type));
-
-	// inclusive scan across the CTA under concat (left operand = earlier)
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	Part inc = mine;
 #pragma unroll
 	for (int d = 1; d < 32; d <<= 1) {
@@ -171,52 +147,87 @@ k_scan_verify(const RecSums *__restrict__ sums, uint32_t nrec,
 	if (lane == 31) s_warp[warp] = inc;
 	__syncthreads();
 	if (warp == 0) {
-		Part w = s_warp[lane];
-		Part winc = w;
+		Part w = { 0, 0, 0, 0, 0 };
+		if (lane < THREADS / 32) w = s_warp[lane];
 #pragma unroll
 		for (int d = 1; d < 32; d <<= 1) {
-			Part up = part_shfl_up(winc, d);
-			if (lane >= d) winc = concat(up, winc);
+			Part up = part_shfl_up(w, d);
+			if (lane >= d) w = concat(up, w);
 		}
-		s_warp[lane] = winc;               // inclusive over warps
+		if (lane < THREADS / 32) s_warp[lane] = w;     // inclusive over warps
 	}
 	__syncthreads();
-	// exclusive prefix of this thread
 	Part excl = { 0, 0, 0, 0, 0 };
 	if (warp > 0) excl = s_warp[warp - 1];
-	{
-		Part up = part_shfl_up(inc, 1);
-		if (lane > 0) excl = concat(excl, up);
-	}
-	if (tid == SCAN_THREADS - 1) res->agg = concat(excl, mine);
-	if (phase == 0) return;
+	Part up = part_shfl_up(inc, 1);
+	if (lane > 0) excl = concat(excl, up);
+	*total = s_warp[THREADS / 32 - 1];
+	return excl;
+}
 
-	Ck4 s = apply(*carry_in, excl);
-	uint32_t bad = 0xffffffffu;
-	for (uint32_t r = r0; r < r1; r++) {
-		const RecSums rs = sums[r];
-		if (rs.type == DRR_BEGIN_T) s.a = s.b = s.c = s.d = 0;
-		if (rs.type == DRR_END_T) {
-			if (!ck_eq(rs.aux, s) && bad == 0xffffffffu) bad = r;
-			res->end_ck = s;
-			res->end_seen = 1;
-		}
-		Part h = { DRR_CKOFF / 4u, rs.head.a, rs.head.b, rs.head.c, rs.head.d };
-		Ck4 mid = apply(s, h);
-		if (rs.type != DRR_BEGIN_T) {
-			if (!ck_zero(rs.emb) && !ck_eq(rs.emb, mid) && bad == 0xffffffffu) bad = r;
-		}
-		Part b = { rs.nbody, rs.body.a, rs.body.b, rs.body.c, rs.body.d };
-		s = apply(mid, b);
+__global__ void __launch_bounds__(SCAN_THREADS)
+k_scan_tiles(const RecSums *__restrict__ sums, uint32_t nrec, Part *__restrict__ tile_agg)
+{
+	__shared__ Part s_warp[SCAN_THREADS / 32];
+	const uint32_t r = blockIdx.x * SCAN_TILE + threadIdx.x;
+	Part mine = { 0, 0, 0, 0, 0 };
+	if (r < nrec) mine = rec_part(sums[r]);
+	Part total;
+	(void)block_exclusive<SCAN_THREADS>(mine, s_warp, &total);
+	if (threadIdx.x == 0) tile_agg[blockIdx.x] = total;
+}
+
+// single CTA: exclusive scan over the tile aggregates (looped in CTA-size steps)
+__global__ void __launch_bounds__(SCAN_THREADS)
+k_scan_spine(Part *__restrict__ tile_agg, uint32_t ntiles, ScanResult *__restrict__ res)
+{
+	__shared__ Part s_warp[SCAN_THREADS / 32];
+	Part running = { 0, 0, 0, 0, 0 };
+	for (uint32_t t0 = 0; t0 < ntiles; t0 += SCAN_THREADS) {
+		const uint32_t t = t0 + threadIdx.x;
+		Part mine = { 0, 0, 0, 0, 0 };
+		if (t < ntiles) mine = tile_agg[t];
+		Part total;
+		Part excl = block_exclusive<SCAN_THREADS>(mine, s_warp, &total);
+		if (t < ntiles) tile_agg[t] = concat(running, excl);    // exclusive prefix
+		running = concat(running, total);
+		__syncthreads();
 	}
-	if (bad != 0xffffffffu) atomicMin(&s_bad, bad);
-	__syncthreads();
-	if (tid == SCAN_THREADS - 1) {
-		// the last thread with records holds the final state; threads with an
-		// empty range carry the same prefix forward, so the last thread is right
-		res->carry = s;
-		res->bad = s_bad;
-		res->status = (s_bad != 0xffffffffu) ? (uint32_t)(-MTZ_ECKSUM) : 0u;
+	if (threadIdx.x == 0) {
+		res->agg = running;
+		res->bad = 0xffffffffu;
+	}
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS)
+k_scan_verify(const RecSums *__restrict__ sums, uint32_t nrec,
+    const Part *__restrict__ tile_prefix, const Ck4 *__restrict__ carry_in,
+    ScanResult *__restrict__ res)
+{
+	__shared__ Part s_warp[SCAN_THREADS / 32];
+	const uint32_t r = blockIdx.x * SCAN_TILE + threadIdx.x;
+	Part mine = { 0, 0, 0, 0, 0 };
+	RecSums rs;
+	rs.type = 0xffffffffu;
+	if (r < nrec) { rs = sums[r]; mine = rec_part(rs); }
+	Part total;
+	Part excl = block_exclusive<SCAN_THREADS>(mine, s_warp, &total);
+	if (r >= nrec) return;
+	Ck4 s = apply(apply(*carry_in, tile_prefix[blockIdx.x]), excl);
+	bool bad = false;
+	if (rs.type == DRR_BEGIN_T) s.a = s.b = s.c = s.d = 0;
+	if (rs.type == DRR_END_T) {
+		if (!ck_eq(rs.aux, s)) bad = true;
+		res->end_ck = s;
+		res->end_seen = 1;
+	}
+	Part h = { DRR_CKOFF / 4u, rs.head.a, rs.head.b, rs.head.c, rs.head.d };
+	Ck4 mid = apply(s, h);
+	if (rs.type != DRR_BEGIN_T && !ck_zero(rs.emb) && !ck_eq(rs.emb, mid)) bad = true;
+	if (bad) atomicMin(&res->bad, r);
+	if (r == nrec - 1u) {
+		Part b = { rs.nbody, rs.body.a, rs.body.b, rs.body.c, rs.body.d };
+		res->carry = apply(mid, b);
 	}
 }
 

@@ -21,6 +21,7 @@ struct Slot {
 	mtz_rec *h_recs = nullptr;    // pinned staging
 	size_t rec_cap = 0;
 	RecSums *d_sums = nullptr;
+	Part *d_tiles = nullptr;      // scan spine scratch
 	ScanResult *d_res = nullptr;
 	ScanResult *h_res = nullptr;  // pinned
 	cudaStream_t st = nullptr;
@@ -64,7 +65,9 @@ struct mtz_handle {
 	// device-API / deferred-verify state: one growing table of per-record sums
 	mtz::RecSums *dv_sums = nullptr;
 	size_t dv_sums_cap = 0;
+	mtz::Part *dv_tiles = nullptr;
 	size_t dv_nrec = 0, dv_in_bytes = 0;
+	uint64_t dv_first = 0;
 	mtz::ScanResult *dv_res = nullptr, *dv_hres = nullptr;
 	cudaStream_t dv_st = nullptr;
 	cudaEvent_t dv_k1a = nullptr, dv_k1b = nullptr;

@@ -168,6 +168,7 @@ static int32_t alloc_slot(mtz_handle *h, Slot &s, size_t cap, size_t rec_cap)
 	MTZ_CU(h, cudaMalloc(&s.d_recs, rec_cap * sizeof(mtz_rec)));
 	MTZ_CU(h, cudaHostAlloc(&s.h_recs, rec_cap * sizeof(mtz_rec), cudaHostAllocDefault));
 	MTZ_CU(h, cudaMalloc(&s.d_sums, rec_cap * sizeof(RecSums)));
+	MTZ_CU(h, cudaMalloc(&s.d_tiles, (rec_cap / SCAN_TILE + 2) * sizeof(Part)));
 	MTZ_CU(h, cudaMalloc(&s.d_res, sizeof(ScanResult)));
 	MTZ_CU(h, cudaHostAlloc(&s.h_res, sizeof(ScanResult), cudaHostAllocDefault));
 	MTZ_CU(h, cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking));
@@ -185,6 +186,7 @@ static void free_slot(Slot &s)
 	if (s.d_recs) cudaFree(s.d_recs);
 	if (s.h_recs) cudaFreeHost(s.h_recs);
 	if (s.d_sums) cudaFree(s.d_sums);
+	if (s.d_tiles) cudaFree(s.d_tiles);
 	if (s.d_res) cudaFree(s.d_res);
 	if (s.h_res) cudaFreeHost(s.h_res);
 	if (s.st) cudaStreamDestroy(s.st);
@@ -271,6 +273,7 @@ int32_t mtz_close(mtz_handle *h)
 	if (h->dv_k1b) cudaEventDestroy(h->dv_k1b);
 	for (auto &s : h->slots) free_slot(s);
 	if (h->dv_sums) cudaFree(h->dv_sums);
+	if (h->dv_tiles) cudaFree(h->dv_tiles);
 	if (h->dv_res) cudaFree(h->dv_res);
 	if (h->dv_hres) cudaFreeHost(h->dv_hres);
 	if (h->d_carry_in) cudaFree(h->d_carry_in);
@@ -325,7 +328,8 @@ static int32_t launch_k1(mtz_handle *h, cudaStream_t st, const uint8_t *d_in,
     const mtz_rec *d_recs, size_t nrec, RecSums *d_sums, cudaEvent_t ea, cudaEvent_t eb)
 {
 	if (nrec == 0) return MTZ_OK;
-	const unsigned grid = (unsigned)std::min<size_t>(nrec, (size_t)h->sm_count * 64);
+	const unsigned grid = (unsigned)std::min<size_t>((nrec + K1_WARPS - 1) / K1_WARPS,
+	    (size_t)h->sm_count * 5 * 8);
 	if (ea) MTZ_CU(h, cudaEventRecord(ea, st));
 	k1_record_sums<<<grid, K1_THREADS, 0, st>>>(d_in, d_recs, (uint32_t)nrec, d_sums, 280u);
 	MTZ_CU(h, cudaGetLastError());
@@ -334,13 +338,25 @@ static int32_t launch_k1(mtz_handle *h, cudaStream_t st, const uint8_t *d_in,
 	return MTZ_OK;
 }
 
+// Segmented scan of a batch's per-record sums.  phase 0: aggregate only;
+// phase 1: also verify against the running checksum in h->d_carry_in.
 static int32_t launch_scan(mtz_handle *h, cudaStream_t st, const RecSums *d_sums, size_t nrec,
-    ScanResult *d_res, int phase)
+    Part *d_tiles, ScanResult *d_res, int phase)
 {
 	MTZ_CU(h, cudaMemsetAsync(d_res, 0, sizeof(ScanResult), st));
-	k_scan_verify<<<1, SCAN_THREADS, 0, st>>>(d_sums, (uint32_t)nrec, h->d_carry_in, d_res, phase);
+	if (nrec == 0) {
+		MTZ_CU(h, cudaMemsetAsync(&d_res->bad, 0xff, sizeof(uint32_t), st));
+		MTZ_CU(h, cudaMemcpyAsync(&d_res->carry, h->d_carry_in, sizeof(Ck4), cudaMemcpyDeviceToDevice, st));
+		return MTZ_OK;
+	}
+	const unsigned ntiles = (unsigned)((nrec + SCAN_TILE - 1) / SCAN_TILE);
+	k_scan_tiles<<<ntiles, SCAN_THREADS, 0, st>>>(d_sums, (uint32_t)nrec, d_tiles);
+	k_scan_spine<<<1, SCAN_THREADS, 0, st>>>(d_tiles, ntiles, d_res);
+	if (phase == 1)
+		k_scan_verify<<<ntiles, SCAN_THREADS, 0, st>>>(d_sums, (uint32_t)nrec, d_tiles,
+		    h->d_carry_in, d_res);
 	MTZ_CU(h, cudaGetLastError());
-	count_launch(h, 1);
+	count_launch(h, phase == 1 ? 3 : 2);
 	return MTZ_OK;
 }
 
@@ -359,6 +375,9 @@ static int32_t ensure_dv_sums(mtz_handle *h, size_t need, cudaStream_t st)
 	}
 	(void)st;
 	h->dv_sums = n; h->dv_sums_cap = ncap;
+	if (h->dv_tiles) MTZ_CU(h, cudaFree(h->dv_tiles));
+	h->dv_tiles = nullptr;
+	MTZ_CU(h, cudaMalloc(&h->dv_tiles, (ncap / SCAN_TILE + 2) * sizeof(Part)));
 	return MTZ_OK;
 }
 
@@ -401,6 +420,7 @@ int32_t mtz_dev_submit(mtz_handle *h, const void *d_in, size_t in_bytes,
 	int32_t rc = ensure_dv_sums(h, nrec, st);
 	if (rc != MTZ_OK) return rc;
 	h->dv_nrec = nrec; h->dv_in_bytes = in_bytes; h->dv_st = st;
+	h->dv_first = h->records_done;
 	rc = launch_k1(h, st, (const uint8_t *)d_in, d_recs, nrec, h->dv_sums, h->dv_k1a, h->dv_k1b);
 	h->dv_timed = (rc == MTZ_OK && nrec > 0);
 	return rc;
@@ -412,7 +432,7 @@ int32_t mtz_dev_aggregate(mtz_handle *h, uint64_t agg[5])
 	if (agg == nullptr) return MTZ_EINVAL;
 	MTZ_CU(h, cudaSetDevice(h->device));
 	cudaStream_t st = h->dv_st ? h->dv_st : h->st;
-	int32_t rc = launch_scan(h, st, h->dv_sums, h->dv_nrec, h->dv_res, 0);
+	int32_t rc = launch_scan(h, st, h->dv_sums, h->dv_nrec, h->dv_tiles, h->dv_res, 0);
 	if (rc != MTZ_OK) return rc;
 	MTZ_CU(h, cudaMemcpyAsync(h->dv_hres, h->dv_res, sizeof(ScanResult), cudaMemcpyDeviceToHost, st));
 	MTZ_CU(h, cudaStreamSynchronize(st));
@@ -435,13 +455,13 @@ static int32_t account_result(mtz_handle *h, const ScanResult &r, uint64_t first
 			memcpy(h->end_ck, &r.end_ck, 32);
 		}
 	}
-	if (r.status != 0) {
+	if (r.bad != 0xffffffffu) {
 		const uint64_t bad = first_rec + r.bad;
 		{
 			std::lock_guard<std::mutex> g(h->stats_mu);
 			if (bad < h->stats.bad_record) h->stats.bad_record = bad;
 		}
-		return fail(h, -(int32_t)r.status, "stream checksum mismatch at record %llu",
+		return fail(h, MTZ_ECKSUM, "stream checksum mismatch at record %llu",
 		    (unsigned long long)bad);
 	}
 	return MTZ_OK;
@@ -461,7 +481,7 @@ int32_t mtz_dev_finish(mtz_handle *h, const uint64_t carry_in[4], const uint64_t
 		memcpy(&h->h_carry[1], carry_out_in, 32);
 		MTZ_CU(h, cudaMemcpyAsync(h->d_carry_out, &h->h_carry[1], 32, cudaMemcpyHostToDevice, st));
 	}
-	int32_t rc = launch_scan(h, st, h->dv_sums, h->dv_nrec, h->dv_res, 1);
+	int32_t rc = launch_scan(h, st, h->dv_sums, h->dv_nrec, h->dv_tiles, h->dv_res, 1);
 	if (rc != MTZ_OK) return rc;
 	MTZ_CU(h, cudaMemcpyAsync(h->dv_hres, h->dv_res, sizeof(ScanResult), cudaMemcpyDeviceToHost, st));
 	MTZ_CU(h, cudaMemcpyAsync(h->d_carry_in, &h->dv_res->carry, 32, cudaMemcpyDeviceToDevice, st));
@@ -478,8 +498,8 @@ int32_t mtz_dev_finish(mtz_handle *h, const uint64_t carry_in[4], const uint64_t
 	if (out_bytes) *out_bytes = h->dv_in_bytes;
 	if (carry) memcpy(carry, &r.carry, 32);
 	if (carry_out) memcpy(carry_out, &r.carry, 32);
-	rc = account_result(h, r, h->records_done, h->dv_nrec, h->dv_in_bytes, h->dv_in_bytes);
-	if (rc == MTZ_OK) h->records_done += h->dv_nrec;
+	rc = account_result(h, r, h->dv_first, h->dv_nrec, h->dv_in_bytes, h->dv_in_bytes);
+	if (rc == MTZ_OK) h->records_done = h->dv_first + h->dv_nrec;
 	return rc;
 }
 
@@ -544,12 +564,13 @@ static int32_t submit_batch(mtz_handle *h, Slot &s, const uint8_t *p0, size_t n0
 			if (rc != MTZ_OK) return rc;
 			rc = launch_k1(h, s.st, s.d_in, s.d_recs, nrec, h->dv_sums + h->dv_nrec, s.ev_k1a, s.ev_k1b);
 			if (rc != MTZ_OK) return rc;
+			if (h->dv_nrec == 0) h->dv_first = s.first_rec;
 			h->dv_nrec += nrec; h->dv_in_bytes += bytes; h->dv_st = h->st;
 		} else {
 			rc = launch_k1(h, s.st, s.d_in, s.d_recs, nrec, s.d_sums, s.ev_k1a, s.ev_k1b);
 			if (rc != MTZ_OK) return rc;
 			if (h->have_prev_scan) MTZ_CU(h, cudaStreamWaitEvent(s.st, h->ev_prev_scan, 0));
-			rc = launch_scan(h, s.st, s.d_sums, nrec, s.d_res, 1);
+			rc = launch_scan(h, s.st, s.d_sums, nrec, s.d_tiles, s.d_res, 1);
 			if (rc != MTZ_OK) return rc;
 			MTZ_CU(h, cudaMemcpyAsync(h->d_carry_in, &s.d_res->carry, 32, cudaMemcpyDeviceToDevice, s.st));
 			MTZ_CU(h, cudaEventRecord(h->ev_prev_scan, s.st));
