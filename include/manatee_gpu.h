@@ -98,6 +98,17 @@ typedef struct mtz_rec {
 	uint64_t resv;
 } mtz_rec;
 
+/* One codec job (32 B): a frame to decode or a logical block to encode.
+ * Offsets are relative to the src/dst base pointers of the call. */
+typedef struct mtz_job {
+	uint64_t src_off;  /* decode: BE32-framed LZ4 payload; encode: logical bytes */
+	uint64_t dst_off;  /* decode: lsize bytes out; encode: frame slot of lsize bytes */
+	uint32_t src_len;  /* decode: payload (psize) bytes; encode: unused */
+	uint32_t lsize;    /* drr_logical_size */
+	uint32_t out_len;  /* decode: lsize; encode: psize, or lsize = store raw */
+	int32_t  status;   /* MTZ_OK or MTZ_ECODEC */
+} mtz_job;
+
 /* ---- lifecycle ---- */
 int32_t     mtz_abi_version(void);
 int32_t     mtz_device_count(void);                 /* sm_100 devices visible, <0 on error */
@@ -160,6 +171,14 @@ int32_t mtz_dev_reset(mtz_handle *h);
 /* set the running checksums a slice continues from (NULL = leave) */
 int32_t mtz_set_carry(mtz_handle *h, const uint64_t carry_in[4],
     const uint64_t carry_out[4]);
+
+/* ---- kernel-level entry points: the LZ4 kernels on device-resident jobs.  The
+ * stage pipeline launches exactly these; they are exported so the parity tests
+ * and ncu can drive K2/K3 in isolation.  d_jobs is a device array. ---- */
+int32_t mtz_k_lz4_decode(mtz_handle *h, const void *d_src, void *d_dst,
+    mtz_job *d_jobs, uint32_t njobs, void *cuda_stream);
+int32_t mtz_k_lz4_encode(mtz_handle *h, const void *d_src, void *d_dst,
+    mtz_job *d_jobs, uint32_t njobs, void *cuda_stream);
 
 /* ---- synthetic-workload helpers for bench/tests (device-side generation of the
  * BASELINE.md section 3 streams by tiling a seeded host corpus) ---- */

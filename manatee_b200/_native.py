@@ -54,6 +54,7 @@ SYMBOLS = [
     "mtz_end_checksum", "mtz_host_alloc", "mtz_host_free", "mtz_process_host",
     "mtz_index_host", "mtz_dev_index", "mtz_dev_submit", "mtz_dev_aggregate",
     "mtz_dev_finish", "mtz_dev_reset", "mtz_set_carry", "mtz_synth_tile",
+    "mtz_k_lz4_decode", "mtz_k_lz4_encode",
 ]
 
 _lib = None
@@ -97,6 +98,8 @@ def lib():
     L.mtz_dev_finish.argtypes = [H, vp, vp, C.POINTER(sz), C.POINTER(u64 * 4), C.POINTER(u64 * 4)]
     L.mtz_dev_reset.argtypes = [H]
     L.mtz_set_carry.argtypes = [H, vp, vp]
+    L.mtz_k_lz4_decode.argtypes = [H, vp, vp, vp, C.c_uint32, vp]
+    L.mtz_k_lz4_encode.argtypes = [H, vp, vp, vp, C.c_uint32, vp]
     L.mtz_synth_tile.argtypes = [H, vp, sz, sz, vp, sz, u64, C.c_uint32, vp, C.POINTER(sz),
                                  C.POINTER(sz)]
     for s in SYMBOLS:

@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 #include "../../include/manatee_gpu.h"
 #include "kernels_fletcher.cuh"
+#include "kernels_lz4.cuh"
 
 namespace mtz {
 

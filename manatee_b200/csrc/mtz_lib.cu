@@ -1047,6 +1047,48 @@ int32_t mtz_event_fd(mtz_handle *h)
 	return e->efd;
 }
 
+// ---------------------------------------------------- LZ4 kernel entries ---
+static int32_t lz4_grid(mtz_handle *h, uint32_t njobs, int warps_per_sm)
+{
+	const uint32_t blocks_needed = (njobs + LZ4_WARPS - 1) / LZ4_WARPS;
+	const uint32_t cap = (uint32_t)h->sm_count * (uint32_t)(warps_per_sm / LZ4_WARPS);
+	return (int32_t)std::max(1u, std::min(blocks_needed, cap));
+}
+
+int32_t mtz_k_lz4_decode(mtz_handle *h, const void *d_src, void *d_dst, mtz_job *d_jobs,
+    uint32_t njobs, void *cuda_stream)
+{
+	CHECK_H(h);
+	if (njobs == 0) return MTZ_OK;
+	MTZ_CU(h, cudaSetDevice(h->device));
+	cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : h->st;
+	k2_lz4_decode<<<lz4_grid(h, njobs, 64), LZ4_THREADS, 0, st>>>((const uint8_t *)d_src,
+	    (uint8_t *)d_dst, d_jobs, njobs);
+	MTZ_CU(h, cudaGetLastError());
+	count_launch(h, 1);
+	return MTZ_OK;
+}
+
+int32_t mtz_k_lz4_encode(mtz_handle *h, const void *d_src, void *d_dst, mtz_job *d_jobs,
+    uint32_t njobs, void *cuda_stream)
+{
+	CHECK_H(h);
+	if (njobs == 0) return MTZ_OK;
+	MTZ_CU(h, cudaSetDevice(h->device));
+	cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : h->st;
+	const size_t smem = (size_t)LZ4_WARPS * LZ4_TABLE_WORDS * sizeof(uint32_t);
+	static bool attr_set = false;
+	if (!attr_set) {
+		MTZ_CU(h, cudaFuncSetAttribute(k3_lz4_encode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		attr_set = true;
+	}
+	k3_lz4_encode<<<lz4_grid(h, njobs, 12), LZ4_THREADS, smem, st>>>((const uint8_t *)d_src,
+	    (uint8_t *)d_dst, d_jobs, njobs);
+	MTZ_CU(h, cudaGetLastError());
+	count_launch(h, 1);
+	return MTZ_OK;
+}
+
 // ------------------------------------------------- not yet implemented ----
 int32_t mtz_dev_index(mtz_handle *h, const void *, size_t, mtz_rec *, size_t, size_t *, void *) { CHECK_H(h); return MTZ_EINVAL; }
 int32_t mtz_synth_tile(mtz_handle *h, const void *, size_t, size_t, void *, size_t, uint64_t, uint32_t, mtz_rec *, size_t *, size_t *) { CHECK_H(h); return MTZ_EINVAL; }
