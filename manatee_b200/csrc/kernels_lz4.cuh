@@ -95,6 +95,7 @@ k2_lz4_decode(const uint8_t *__restrict__ src_base, uint8_t *__restrict__ dst_ba
 	const uint32_t nw = gridDim.x * LZ4_WARPS;
 	for (uint32_t j = gw; j < njobs; j += nw) {
 		const mtz_job job = jobs[j];
+		if (job.lsize == 0u) continue;                 // not a decode job (pipeline: 1 job slot per record)
 		const int32_t st = warp_lz4_decode(src_base + job.src_off, job.src_len,
 		    dst_base + job.dst_off, job.lsize, lane);
 		if (lane == 0) {
@@ -351,6 +352,7 @@ k3_lz4_encode(const uint8_t *__restrict__ src_base, uint8_t *__restrict__ dst_ba
 	const uint32_t nw = gridDim.x * LZ4_WARPS;
 	for (uint32_t j = gw; j < njobs; j += nw) {
 		const mtz_job job = jobs[j];
+		if (job.lsize == 0u) continue;
 		const uint32_t ps = warp_zfs_lz4_compress(src_base + job.src_off, job.lsize,
 		    dst_base + job.dst_off, tab, lane);
 		__syncwarp();

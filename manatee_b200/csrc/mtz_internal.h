@@ -11,8 +11,23 @@
 #include "../../include/manatee_gpu.h"
 #include "kernels_fletcher.cuh"
 #include "kernels_lz4.cuh"
+#include "kernels_codec.cuh"
 
 namespace mtz {
+
+// device scratch of one codec batch (modes COMPRESS / DECOMPRESS / RECOMPRESS)
+struct CodecBufs {
+	size_t rec_cap = 0, scratch_cap = 0;
+	CodecRec *cr = nullptr;
+	uint64_t *vals = nullptr, *offs = nullptr, *out_offs = nullptr;
+	mtz_job *dec = nullptr, *enc = nullptr;
+	mtz_rec *out_recs = nullptr;
+	RecSums *osums = nullptr;
+	uint8_t *d_logical = nullptr, *d_enc = nullptr;
+	CodecResult *d_cres = nullptr, *h_cres = nullptr;   // h_: pinned
+	ScanResult *d_ores = nullptr, *h_ores = nullptr;    // output-chain result
+	uint64_t *d_outpos = nullptr;                       // running output offset (device)
+};
 
 struct Slot {
 	uint8_t *d_in = nullptr;      // batch bytes (input stream slice)
@@ -28,12 +43,16 @@ struct Slot {
 	cudaStream_t st = nullptr;
 	cudaEvent_t ev_start = nullptr, ev_done = nullptr;
 	cudaEvent_t ev_k1a = nullptr, ev_k1b = nullptr;
+	cudaEvent_t ev_c0 = nullptr, ev_c1 = nullptr;     // around K2+K3
 	bool busy = false;
 	size_t nrec = 0, bytes = 0, out_bytes = 0;
 	uint64_t first_rec = 0;       // stream-wide index of the batch's first record
 	uint64_t in_off = 0;          // absolute stream offset of the batch
 	uint64_t writes = 0;
-	void *codec = nullptr;        // per-slot codec scratch
+	CodecBufs cb;                 // per-slot codec scratch
+	cudaEvent_t ev_d2h = nullptr;
+	bool d2h_pending = false;
+	uint64_t lz4_dec = 0, lz4_try = 0;
 };
 
 struct Engine;                    // streaming state (rings + worker thread)
@@ -72,7 +91,11 @@ struct mtz_handle {
 	mtz::ScanResult *dv_res = nullptr, *dv_hres = nullptr;
 	cudaStream_t dv_st = nullptr;
 	cudaEvent_t dv_k1a = nullptr, dv_k1b = nullptr;
+	cudaEvent_t dv_c0 = nullptr, dv_c1 = nullptr;
 	bool dv_timed = false;
+
+	mtz::CodecBufs dv_cb;              // device-API codec scratch (sub-batched)
+	std::vector<mtz_rec> dv_hrecs;     // host copy of the device record table
 
 	mtz::Engine *eng = nullptr;        // created on first streaming call
 	std::mutex eng_mu;

@@ -176,8 +176,12 @@ static int32_t alloc_slot(mtz_handle *h, Slot &s, size_t cap, size_t rec_cap)
 	MTZ_CU(h, cudaEventCreate(&s.ev_done));
 	MTZ_CU(h, cudaEventCreate(&s.ev_k1a));
 	MTZ_CU(h, cudaEventCreate(&s.ev_k1b));
+	MTZ_CU(h, cudaEventCreate(&s.ev_c0));
+	MTZ_CU(h, cudaEventCreate(&s.ev_c1));
 	return MTZ_OK;
 }
+
+static void codec_free(CodecBufs &cb);
 
 static void free_slot(Slot &s)
 {
@@ -194,6 +198,10 @@ static void free_slot(Slot &s)
 	if (s.ev_done) cudaEventDestroy(s.ev_done);
 	if (s.ev_k1a) cudaEventDestroy(s.ev_k1a);
 	if (s.ev_k1b) cudaEventDestroy(s.ev_k1b);
+	if (s.ev_c0) cudaEventDestroy(s.ev_c0);
+	if (s.ev_c1) cudaEventDestroy(s.ev_c1);
+	if (s.ev_d2h) cudaEventDestroy(s.ev_d2h);
+	codec_free(s.cb);
 	s = Slot();
 }
 
@@ -225,9 +233,13 @@ int32_t mtz_open(const mtz_config *cfg, mtz_handle **out)
 	if (h == nullptr) return fail(nullptr, MTZ_ENOMEM, "handle allocation");
 	memset(&h->cfg, 0, sizeof h->cfg);
 	memcpy(&h->cfg, cfg, std::min((size_t)cfg->struct_size, sizeof h->cfg));
-	if (h->cfg.ring_bytes == 0) h->cfg.ring_bytes = 256ull << 20;
+	const bool codec_mode = cfg->mode == MTZ_MODE_COMPRESS || cfg->mode == MTZ_MODE_DECOMPRESS ||
+	    cfg->mode == MTZ_MODE_RECOMPRESS;
+	// the LZ4 kernels want ~1000 records in flight per batch; Fletcher alone is
+	// happy with 32 MiB batches
+	if (h->cfg.batch_bytes == 0) h->cfg.batch_bytes = codec_mode ? (128ull << 20) : (32ull << 20);
+	if (h->cfg.ring_bytes == 0) h->cfg.ring_bytes = std::max<uint64_t>(256ull << 20, 4 * h->cfg.batch_bytes);
 	if (h->cfg.out_ring_bytes == 0) h->cfg.out_ring_bytes = h->cfg.ring_bytes;
-	if (h->cfg.batch_bytes == 0) h->cfg.batch_bytes = 32ull << 20;
 	if (h->cfg.record_bytes == 0) h->cfg.record_bytes = 131072;
 	if (h->cfg.n_slots == 0) h->cfg.n_slots = 4;
 	if (h->cfg.n_slots > 16) h->cfg.n_slots = 16;
@@ -269,6 +281,9 @@ int32_t mtz_close(mtz_handle *h)
 	cudaSetDevice(h->device);
 	engine_destroy(h);
 	cudaDeviceSynchronize();
+	if (h->dv_c0) cudaEventDestroy(h->dv_c0);
+	if (h->dv_c1) cudaEventDestroy(h->dv_c1);
+	codec_free(h->dv_cb);
 	if (h->dv_k1a) cudaEventDestroy(h->dv_k1a);
 	if (h->dv_k1b) cudaEventDestroy(h->dv_k1b);
 	for (auto &s : h->slots) free_slot(s);
@@ -381,6 +396,106 @@ static int32_t ensure_dv_sums(mtz_handle *h, size_t need, cudaStream_t st)
 	return MTZ_OK;
 }
 
+// ------------------------------------------------------- codec pipeline ---
+static bool is_codec_mode(uint32_t m)
+{
+	return m == MTZ_MODE_COMPRESS || m == MTZ_MODE_DECOMPRESS || m == MTZ_MODE_RECOMPRESS;
+}
+
+static int32_t codec_alloc(mtz_handle *h, CodecBufs &cb, size_t rec_cap, size_t scratch_cap)
+{
+	cb.rec_cap = rec_cap; cb.scratch_cap = scratch_cap;
+	MTZ_CU(h, cudaMalloc(&cb.cr, rec_cap * sizeof(CodecRec)));
+	MTZ_CU(h, cudaMalloc(&cb.vals, rec_cap * sizeof(uint64_t)));
+	MTZ_CU(h, cudaMalloc(&cb.offs, rec_cap * sizeof(uint64_t)));
+	MTZ_CU(h, cudaMalloc(&cb.out_offs, rec_cap * sizeof(uint64_t)));
+	MTZ_CU(h, cudaMalloc(&cb.dec, rec_cap * sizeof(mtz_job)));
+	MTZ_CU(h, cudaMalloc(&cb.enc, rec_cap * sizeof(mtz_job)));
+	MTZ_CU(h, cudaMalloc(&cb.out_recs, rec_cap * sizeof(mtz_rec)));
+	MTZ_CU(h, cudaMalloc(&cb.osums, rec_cap * sizeof(RecSums)));
+	if (h->cfg.mode != MTZ_MODE_COMPRESS) MTZ_CU(h, cudaMalloc(&cb.d_logical, scratch_cap + 512));
+	if (h->cfg.mode != MTZ_MODE_DECOMPRESS) MTZ_CU(h, cudaMalloc(&cb.d_enc, scratch_cap + 512));
+	MTZ_CU(h, cudaMalloc(&cb.d_cres, sizeof(CodecResult)));
+	MTZ_CU(h, cudaHostAlloc(&cb.h_cres, sizeof(CodecResult), cudaHostAllocDefault));
+	MTZ_CU(h, cudaMalloc(&cb.d_ores, sizeof(ScanResult)));
+	MTZ_CU(h, cudaHostAlloc(&cb.h_ores, sizeof(ScanResult), cudaHostAllocDefault));
+	MTZ_CU(h, cudaMalloc(&cb.d_outpos, sizeof(uint64_t)));
+	MTZ_CU(h, cudaMemset(cb.d_outpos, 0, sizeof(uint64_t)));
+	return MTZ_OK;
+}
+
+static void codec_free(CodecBufs &cb)
+{
+	cudaFree(cb.cr); cudaFree(cb.vals); cudaFree(cb.offs); cudaFree(cb.out_offs);
+	cudaFree(cb.dec); cudaFree(cb.enc); cudaFree(cb.out_recs); cudaFree(cb.osums);
+	cudaFree(cb.d_logical); cudaFree(cb.d_enc); cudaFree(cb.d_cres); cudaFree(cb.d_ores);
+	cudaFree(cb.d_outpos);
+	if (cb.h_cres) cudaFreeHost(cb.h_cres);
+	if (cb.h_ores) cudaFreeHost(cb.h_ores);
+	cb = CodecBufs();
+}
+
+// start of a codec batch: output offset 0, no bad record, counters zero
+static int32_t codec_reset(mtz_handle *h, cudaStream_t st, CodecBufs &cb)
+{
+	MTZ_CU(h, cudaMemsetAsync(cb.d_outpos, 0, sizeof(uint64_t), st));
+	MTZ_CU(h, cudaMemsetAsync(cb.d_cres, 0, sizeof(CodecResult), st));
+	MTZ_CU(h, cudaMemsetAsync(&cb.d_cres->bad, 0xff, sizeof(uint32_t), st));
+	MTZ_CU(h, cudaMemsetAsync(cb.d_ores, 0, sizeof(ScanResult), st));
+	return MTZ_OK;
+}
+
+// Part 1 of the re-encoding pipeline of one (sub-)batch: plan + K2 + K3.  It
+// does not touch the running checksums, so it may run ahead of the chain.
+static int32_t codec_launch_pre(mtz_handle *h, cudaStream_t st, CodecBufs &cb, const uint8_t *d_in,
+    const mtz_rec *d_recs, size_t nrec, cudaEvent_t ea, cudaEvent_t eb)
+{
+	if (nrec == 0) return MTZ_OK;
+	if (nrec > cb.rec_cap) return fail(h, MTZ_ENOSPC, "codec batch of %zu records exceeds %zu", nrec, cb.rec_cap);
+	const uint32_t n = (uint32_t)nrec, mode = h->cfg.mode;
+	const unsigned tb = 256, gb = (n + tb - 1) / tb;
+	k_plan_need<<<gb, tb, 0, st>>>(d_recs, n, mode, cb.cr, cb.vals);
+	k_xscan_u64<<<1, XSCAN_THREADS, 0, st>>>(cb.vals, cb.offs, n, nullptr, nullptr);
+	k_plan_jobs<<<gb, tb, 0, st>>>(d_in, d_recs, n, cb.cr, cb.offs, cb.d_logical, cb.d_enc, cb.dec, cb.enc);
+	MTZ_CU(h, cudaGetLastError());
+	count_launch(h, 3);
+	if (ea) MTZ_CU(h, cudaEventRecord(ea, st));
+	if (mode != MTZ_MODE_COMPRESS) {
+		int32_t rc = mtz_k_lz4_decode(h, nullptr, nullptr, cb.dec, n, st);
+		if (rc != MTZ_OK) return rc;
+	}
+	if (mode != MTZ_MODE_DECOMPRESS) {
+		int32_t rc = mtz_k_lz4_encode(h, nullptr, nullptr, cb.enc, n, st);
+		if (rc != MTZ_OK) return rc;
+	}
+	if (eb) MTZ_CU(h, cudaEventRecord(eb, st));
+	return MTZ_OK;
+}
+
+// Part 2: layout, assemble into d_out + *cb.d_outpos (the running output offset
+// lives on the device so sub-batches chain without a host round trip), sums of
+// the output records, and the sequential stamp chain from h->d_carry_out.
+static int32_t codec_launch_post(mtz_handle *h, cudaStream_t st, CodecBufs &cb, const uint8_t *d_in,
+    const mtz_rec *d_recs, size_t nrec, uint8_t *d_out, uint32_t rec_base)
+{
+	if (nrec == 0) return MTZ_OK;
+	const uint32_t n = (uint32_t)nrec, mode = h->cfg.mode;
+	const unsigned tb = 256, gb = (n + tb - 1) / tb;
+	k_layout<<<gb, tb, 0, st>>>(d_recs, n, cb.cr, cb.dec, cb.enc, cb.vals, cb.d_cres, rec_base);
+	k_xscan_u64<<<1, XSCAN_THREADS, 0, st>>>(cb.vals, cb.out_offs, n, cb.d_outpos, cb.d_outpos);
+	const unsigned ga = (unsigned)std::min<size_t>((n + 7) / 8, (size_t)h->sm_count * 8);
+	k_assemble<<<ga, ASM_THREADS, 0, st>>>(d_in, d_recs, n, mode, cb.cr, cb.out_offs, cb.enc,
+	    cb.d_logical, cb.d_enc, d_out, cb.out_recs);
+	MTZ_CU(h, cudaGetLastError());
+	const unsigned g1 = (unsigned)std::min<size_t>((n + K1_WARPS - 1) / K1_WARPS, (size_t)h->sm_count * 40);
+	k1_record_sums<<<g1, K1_THREADS, 0, st>>>(d_out, cb.out_recs, n, cb.osums, 312u);
+	k_stamp_chain<<<1, 32, 0, st>>>(d_out, cb.out_recs, cb.osums, n, h->d_carry_out, cb.d_ores);
+	MTZ_CU(h, cudaGetLastError());
+	MTZ_CU(h, cudaMemcpyAsync(&cb.d_cres->out_bytes, cb.d_outpos, sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
+	count_launch(h, 5);
+	return MTZ_OK;
+}
+
 // ------------------------------------------------------------ device API --
 int32_t mtz_dev_reset(mtz_handle *h)
 {
@@ -413,8 +528,8 @@ int32_t mtz_dev_submit(mtz_handle *h, const void *d_in, size_t in_bytes,
 	(void)d_out; (void)out_cap;
 	if (nrec > 0xfffffff0ull) return fail(h, MTZ_EINVAL, "too many records in one batch");
 	if (((uintptr_t)d_in & 3) != 0) return fail(h, MTZ_EINVAL, "d_in must be 4-byte aligned");
-	if (h->cfg.mode != MTZ_MODE_VERIFY)
-		return fail(h, MTZ_EINVAL, "mtz_dev_submit: mode %u not supported yet", h->cfg.mode);
+	if (h->cfg.mode == MTZ_MODE_PASSTHROUGH)
+		return fail(h, MTZ_EINVAL, "mtz_dev_submit: no device path for PASSTHROUGH");
 	MTZ_CU(h, cudaSetDevice(h->device));
 	cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : h->st;
 	int32_t rc = ensure_dv_sums(h, nrec, st);
@@ -423,7 +538,49 @@ int32_t mtz_dev_submit(mtz_handle *h, const void *d_in, size_t in_bytes,
 	h->dv_first = h->records_done;
 	rc = launch_k1(h, st, (const uint8_t *)d_in, d_recs, nrec, h->dv_sums, h->dv_k1a, h->dv_k1b);
 	h->dv_timed = (rc == MTZ_OK && nrec > 0);
-	return rc;
+	if (rc != MTZ_OK || !is_codec_mode(h->cfg.mode)) return rc;
+
+	// ---- re-encoding modes: bounded-scratch sub-batches, output chained on device
+	if (d_out == nullptr) return fail(h, MTZ_EINVAL, "codec modes need d_out");
+	if (h->dv_cb.cr == nullptr) {
+		const size_t scratch = std::max<size_t>(2ull << 30, (size_t)h->cfg.batch_bytes + MAX_RECORD_BYTES);
+		rc = codec_alloc(h, h->dv_cb, 65536, scratch);
+		if (rc != MTZ_OK) return rc;
+		MTZ_CU(h, cudaEventCreate(&h->dv_c0));
+		MTZ_CU(h, cudaEventCreate(&h->dv_c1));
+	}
+	h->dv_hrecs.resize(nrec);
+	MTZ_CU(h, cudaMemcpyAsync(h->dv_hrecs.data(), d_recs, nrec * sizeof(mtz_rec), cudaMemcpyDeviceToHost, st));
+	MTZ_CU(h, cudaStreamSynchronize(st));
+	rc = codec_reset(h, st, h->dv_cb);
+	if (rc != MTZ_OK) return rc;
+	size_t need_out = 0;
+	for (size_t i = 0; i < nrec; i++)
+		need_out += DRR_HDR + std::max<size_t>(h->dv_hrecs[i].payload,
+		    h->dv_hrecs[i].type == 3 ? h->dv_hrecs[i].lsize : 0);
+	if (need_out > out_cap)
+		return fail(h, MTZ_ENOSPC, "d_out must hold the worst case of %zu bytes", need_out);
+	bool first = true;
+	for (size_t i0 = 0; i0 < nrec;) {
+		size_t i1 = i0, budget = 0;
+		while (i1 < nrec && (i1 - i0) < h->dv_cb.rec_cap) {
+			const mtz_rec &r = h->dv_hrecs[i1];
+			const size_t cost = std::max<size_t>(r.payload, r.type == 3 ? r.lsize : 0) + 64;
+			if (cost > h->dv_cb.scratch_cap) return fail(h, MTZ_ENOSPC, "record exceeds the codec scratch");
+			if (i1 > i0 && budget + cost > h->dv_cb.scratch_cap) break;
+			budget += cost; i1++;
+		}
+		rc = codec_launch_pre(h, st, h->dv_cb, (const uint8_t *)d_in, d_recs + i0, i1 - i0,
+		    first ? h->dv_c0 : nullptr, nullptr);
+		if (rc != MTZ_OK) return rc;
+		rc = codec_launch_post(h, st, h->dv_cb, (const uint8_t *)d_in, d_recs + i0, i1 - i0,
+		    (uint8_t *)d_out, (uint32_t)i0);
+		if (rc != MTZ_OK) return rc;
+		first = false;
+		i0 = i1;
+	}
+	MTZ_CU(h, cudaEventRecord(h->dv_c1, st));
+	return MTZ_OK;
 }
 
 int32_t mtz_dev_aggregate(mtz_handle *h, uint64_t agg[5])
@@ -485,7 +642,19 @@ int32_t mtz_dev_finish(mtz_handle *h, const uint64_t carry_in[4], const uint64_t
 	if (rc != MTZ_OK) return rc;
 	MTZ_CU(h, cudaMemcpyAsync(h->dv_hres, h->dv_res, sizeof(ScanResult), cudaMemcpyDeviceToHost, st));
 	MTZ_CU(h, cudaMemcpyAsync(h->d_carry_in, &h->dv_res->carry, 32, cudaMemcpyDeviceToDevice, st));
+	const bool codec = is_codec_mode(h->cfg.mode) && h->dv_cb.cr != nullptr;
+	if (codec) {
+		MTZ_CU(h, cudaMemcpyAsync(h->dv_cb.h_cres, h->dv_cb.d_cres, sizeof(CodecResult), cudaMemcpyDeviceToHost, st));
+		MTZ_CU(h, cudaMemcpyAsync(h->dv_cb.h_ores, h->dv_cb.d_ores, sizeof(ScanResult), cudaMemcpyDeviceToHost, st));
+	}
 	MTZ_CU(h, cudaStreamSynchronize(st));
+	if (codec && h->dv_nrec > 0) {
+		float cm = 0;
+		if (cudaEventElapsedTime(&cm, h->dv_c0, h->dv_c1) == cudaSuccess) {
+			std::lock_guard<std::mutex> g(h->stats_mu);
+			h->stats.codec_ms += cm;
+		}
+	}
 	if (h->dv_timed) {
 		float ms = 0;
 		if (cudaEventElapsedTime(&ms, h->dv_k1a, h->dv_k1b) == cudaSuccess) {
@@ -495,11 +664,34 @@ int32_t mtz_dev_finish(mtz_handle *h, const uint64_t carry_in[4], const uint64_t
 		h->dv_timed = false;
 	}
 	const ScanResult &r = *h->dv_hres;
-	if (out_bytes) *out_bytes = h->dv_in_bytes;
+	size_t ob = h->dv_in_bytes;
 	if (carry) memcpy(carry, &r.carry, 32);
 	if (carry_out) memcpy(carry_out, &r.carry, 32);
-	rc = account_result(h, r, h->dv_first, h->dv_nrec, h->dv_in_bytes, h->dv_in_bytes);
+	if (codec && h->dv_nrec > 0) {
+		const CodecResult &c = *h->dv_cb.h_cres;
+		ob = (size_t)c.out_bytes;
+		if (carry_out) memcpy(carry_out, &h->dv_cb.h_ores->carry, 32);
+		if (c.bad != 0xffffffffu) {
+			const uint64_t bad = h->dv_first + c.bad;
+			{
+				std::lock_guard<std::mutex> g(h->stats_mu);
+				if (bad < h->stats.bad_record) h->stats.bad_record = bad;
+			}
+			return fail(h, MTZ_ECODEC, "LZ4 frame of record %llu does not decode to drr_logical_size",
+			    (unsigned long long)bad);
+		}
+		std::lock_guard<std::mutex> g(h->stats_mu);
+		h->stats.lz4_decoded += c.n_dec;
+		h->stats.lz4_encoded += c.n_enc;
+	}
+	if (out_bytes) *out_bytes = ob;
+	rc = account_result(h, r, h->dv_first, h->dv_nrec, h->dv_in_bytes, ob);
 	if (rc == MTZ_OK) h->records_done = h->dv_first + h->dv_nrec;
+	if (rc == MTZ_OK && codec && h->dv_nrec > 0 && h->dv_cb.h_ores->end_seen) {
+		std::lock_guard<std::mutex> g(h->stats_mu);
+		h->stats.end_seen = 1;
+		memcpy(h->end_ck, &h->dv_cb.h_ores->end_ck, 32);
+	}
 	return rc;
 }
 
@@ -513,25 +705,70 @@ static int32_t ensure_slots(mtz_handle *h)
 	for (auto &s : h->slots) {
 		int32_t rc = alloc_slot(h, s, cap, rec_cap);
 		if (rc != MTZ_OK) return rc;
+		if (is_codec_mode(h->cfg.mode)) {
+			s.out_cap = cap;
+			MTZ_CU(h, cudaMalloc(&s.d_out, cap + 512));
+			MTZ_CU(h, cudaEventCreateWithFlags(&s.ev_d2h, cudaEventDisableTiming));
+			rc = codec_alloc(h, s.cb, rec_cap, cap + rec_cap * 48);
+			if (rc != MTZ_OK) return rc;
+		}
 	}
 	return MTZ_OK;
 }
 
-// Wait for a slot's batch, fold its verdict into the handle.  on_done (optional)
-// is told how many output bytes the batch produced.
+// Batch assembly shared by the bulk and the streaming paths: decides whether the
+// record whose header is `hdr` still fits the batch being cut for slot s.
+struct BatchCut { size_t cnt = 0, in_bytes = 0, budget = 0; uint64_t writes = 0; };
+
+// returns 1 accepted, 0 batch is full (cut first), <0 error (already reported)
+static int32_t batch_accept(mtz_handle *h, const Slot &s, BatchCut &bc, const uint8_t *hdr,
+    int64_t pl, uint32_t ls, uint32_t comp, uint64_t stream_off, mtz_rec *out)
+{
+	const size_t rl = DRR_HDR + (size_t)pl;
+	const bool codec = is_codec_mode(h->cfg.mode);
+	const uint32_t type = rd32(hdr);
+	size_t cost = rl;
+	if (codec) cost = DRR_HDR + std::max<size_t>((size_t)pl, ls) + 48;
+	if (cost > s.cap)
+		return fail(h, MTZ_ENOSPC, "record of %zu bytes at stream offset %llu exceeds the batch slot",
+		    cost, (unsigned long long)stream_off);
+	if (bc.cnt > 0 && (bc.budget + cost > s.cap || bc.cnt >= s.rec_cap)) return 0;
+	if (codec && type == 0) {
+		// BEGIN: the modes are only defined on the streams oracle/stream.c accepts
+		const uint64_t vi = rd64(hdr + 16);
+		const uint64_t feat = (vi >> 2) & ((1ull << 30) - 1ull);
+		const bool marked = (vi & VI_STAGE) != 0;
+		if (h->cfg.mode == MTZ_MODE_COMPRESS && ((feat & FEAT_COMPRESSED) || marked))
+			return fail(h, MTZ_EINVAL, "COMPRESS: stream is already compressed");
+		if (h->cfg.mode == MTZ_MODE_DECOMPRESS && !marked)
+			return fail(h, MTZ_EINVAL, "DECOMPRESS: stream was not produced by the COMPRESS stage");
+	}
+	mtz_rec r;
+	r.off = bc.in_bytes; r.payload = (uint32_t)pl; r.type = type;
+	r.lsize = ls; r.comp = comp; r.resv = 0;
+	*out = r;
+	bc.cnt++; bc.in_bytes += rl; bc.budget += cost;
+	if (type == 3) bc.writes++;
+	return 1;
+}
+
+// Wait for a slot's kernels, fold its verdict into the handle.
 static int32_t harvest(mtz_handle *h, Slot &s)
 {
 	if (!s.busy) return MTZ_OK;
 	MTZ_CU(h, cudaEventSynchronize(s.ev_done));
 	s.busy = false;
-	float ms = 0, k1 = 0;
+	float ms = 0, k1 = 0, cm = 0;
 	cudaEventElapsedTime(&ms, s.ev_start, s.ev_done);
+	const bool codec = is_codec_mode(h->cfg.mode);
 	const bool k1ok = s.nrec > 0 && cudaEventElapsedTime(&k1, s.ev_k1a, s.ev_k1b) == cudaSuccess;
+	const bool cok = codec && s.nrec > 0 && cudaEventElapsedTime(&cm, s.ev_c0, s.ev_c1) == cudaSuccess;
 	{
 		std::lock_guard<std::mutex> g(h->stats_mu);
 		h->stats.gpu_ms += ms;
 		h->stats.write_records += s.writes;
 		if (k1ok) { h->stats.k1_ms += k1; h->stats.k1_launches += 1; }
+		if (cok) h->stats.codec_ms += cm;
 	}
 	if (h->cfg.mode == MTZ_MODE_PASSTHROUGH || (h->cfg.flags & MTZ_FLAG_DEFER_VERIFY)) {
 		std::lock_guard<std::mutex> g(h->stats_mu);
@@ -539,7 +776,29 @@ static int32_t harvest(mtz_handle *h, Slot &s)
 		h->stats.records += s.nrec;
 		return MTZ_OK;
 	}
-	return account_result(h, *s.h_res, s.first_rec, s.nrec, s.bytes, s.out_bytes);
+	if (codec && s.nrec > 0) {
+		const CodecResult &c = *s.cb.h_cres;
+		s.out_bytes = (size_t)c.out_bytes;
+		if (c.bad != 0xffffffffu) {
+			const uint64_t bad = s.first_rec + c.bad;
+			{
+				std::lock_guard<std::mutex> g(h->stats_mu);
+				if (bad < h->stats.bad_record) h->stats.bad_record = bad;
+			}
+			return fail(h, MTZ_ECODEC, "LZ4 frame of record %llu does not decode to drr_logical_size",
+			    (unsigned long long)bad);
+		}
+		std::lock_guard<std::mutex> g(h->stats_mu);
+		h->stats.lz4_decoded += c.n_dec;
+		h->stats.lz4_encoded += c.n_enc;
+	}
+	int32_t rc = account_result(h, *s.h_res, s.first_rec, s.nrec, s.bytes, s.out_bytes);
+	if (rc == MTZ_OK && codec && s.nrec > 0 && s.cb.h_ores->end_seen) {
+		std::lock_guard<std::mutex> g(h->stats_mu);
+		h->stats.end_seen = 1;
+		memcpy(h->end_ck, &s.cb.h_ores->end_ck, 32);     // END checksum of the OUTPUT stream
+	}
+	return rc;
 }
 
 // Enqueue one batch: the bytes come from up to two host pieces (ring wrap),
@@ -557,28 +816,40 @@ static int32_t submit_batch(mtz_handle *h, Slot &s, const uint8_t *p0, size_t n0
 	if (n0) MTZ_CU(h, cudaMemcpyAsync(s.d_in, p0, n0, cudaMemcpyHostToDevice, s.st));
 	if (n1) MTZ_CU(h, cudaMemcpyAsync(s.d_in + n0, p1, n1, cudaMemcpyHostToDevice, s.st));
 	int32_t rc = MTZ_OK;
-	if (h->cfg.mode == MTZ_MODE_VERIFY) {
-		if (h->cfg.flags & MTZ_FLAG_DEFER_VERIFY) {
-			// shard mode: sums accumulate in the handle-wide table; verdict later
-			rc = ensure_dv_sums(h, h->dv_nrec + nrec, s.st);
+	if (h->cfg.mode == MTZ_MODE_VERIFY && (h->cfg.flags & MTZ_FLAG_DEFER_VERIFY)) {
+		// shard mode: sums accumulate in the handle-wide table; verdict later
+		rc = ensure_dv_sums(h, h->dv_nrec + nrec, s.st);
+		if (rc != MTZ_OK) return rc;
+		rc = launch_k1(h, s.st, s.d_in, s.d_recs, nrec, h->dv_sums + h->dv_nrec, s.ev_k1a, s.ev_k1b);
+		if (rc != MTZ_OK) return rc;
+		if (h->dv_nrec == 0) h->dv_first = s.first_rec;
+		h->dv_nrec += nrec; h->dv_in_bytes += bytes; h->dv_st = h->st;
+	} else if (h->cfg.mode != MTZ_MODE_PASSTHROUGH) {
+		// every mode verifies the INPUT stream's checksums
+		rc = launch_k1(h, s.st, s.d_in, s.d_recs, nrec, s.d_sums, s.ev_k1a, s.ev_k1b);
+		if (rc != MTZ_OK) return rc;
+		if (is_codec_mode(h->cfg.mode)) {
+			rc = codec_reset(h, s.st, s.cb);
 			if (rc != MTZ_OK) return rc;
-			rc = launch_k1(h, s.st, s.d_in, s.d_recs, nrec, h->dv_sums + h->dv_nrec, s.ev_k1a, s.ev_k1b);
+			// K2/K3 of this batch overlap the previous batch's checksum chains
+			rc = codec_launch_pre(h, s.st, s.cb, s.d_in, s.d_recs, nrec, s.ev_c0, s.ev_c1);
 			if (rc != MTZ_OK) return rc;
-			if (h->dv_nrec == 0) h->dv_first = s.first_rec;
-			h->dv_nrec += nrec; h->dv_in_bytes += bytes; h->dv_st = h->st;
-		} else {
-			rc = launch_k1(h, s.st, s.d_in, s.d_recs, nrec, s.d_sums, s.ev_k1a, s.ev_k1b);
-			if (rc != MTZ_OK) return rc;
-			if (h->have_prev_scan) MTZ_CU(h, cudaStreamWaitEvent(s.st, h->ev_prev_scan, 0));
-			rc = launch_scan(h, s.st, s.d_sums, nrec, s.d_tiles, s.d_res, 1);
-			if (rc != MTZ_OK) return rc;
-			MTZ_CU(h, cudaMemcpyAsync(h->d_carry_in, &s.d_res->carry, 32, cudaMemcpyDeviceToDevice, s.st));
-			MTZ_CU(h, cudaEventRecord(h->ev_prev_scan, s.st));
-			h->have_prev_scan = true;
-			MTZ_CU(h, cudaMemcpyAsync(s.h_res, s.d_res, sizeof(ScanResult), cudaMemcpyDeviceToHost, s.st));
 		}
+		if (h->have_prev_scan) MTZ_CU(h, cudaStreamWaitEvent(s.st, h->ev_prev_scan, 0));
+		rc = launch_scan(h, s.st, s.d_sums, nrec, s.d_tiles, s.d_res, 1);
+		if (rc != MTZ_OK) return rc;
+		MTZ_CU(h, cudaMemcpyAsync(h->d_carry_in, &s.d_res->carry, 32, cudaMemcpyDeviceToDevice, s.st));
+		if (is_codec_mode(h->cfg.mode)) {
+			rc = codec_launch_post(h, s.st, s.cb, s.d_in, s.d_recs, nrec, s.d_out, 0u);
+			if (rc != MTZ_OK) return rc;
+			MTZ_CU(h, cudaMemcpyAsync(s.cb.h_cres, s.cb.d_cres, sizeof(CodecResult), cudaMemcpyDeviceToHost, s.st));
+			MTZ_CU(h, cudaMemcpyAsync(s.cb.h_ores, s.cb.d_ores, sizeof(ScanResult), cudaMemcpyDeviceToHost, s.st));
+		}
+		MTZ_CU(h, cudaEventRecord(h->ev_prev_scan, s.st));
+		h->have_prev_scan = true;
+		MTZ_CU(h, cudaMemcpyAsync(s.h_res, s.d_res, sizeof(ScanResult), cudaMemcpyDeviceToHost, s.st));
 	}
-	if (host_out != nullptr)
+	if (host_out != nullptr && !is_codec_mode(h->cfg.mode))
 		MTZ_CU(h, cudaMemcpyAsync(host_out, s.d_in, bytes, cudaMemcpyDeviceToHost, s.st));
 	MTZ_CU(h, cudaEventRecord(s.ev_done, s.st));
 	s.busy = true;
@@ -592,60 +863,69 @@ int32_t mtz_process_host(mtz_handle *h, const void *in, size_t n, void *out, siz
 {
 	CHECK_H(h);
 	if (in == nullptr && n != 0) return MTZ_EINVAL;
-	if (h->cfg.mode != MTZ_MODE_VERIFY && h->cfg.mode != MTZ_MODE_PASSTHROUGH)
-		return fail(h, MTZ_EINVAL, "mtz_process_host: mode %u not supported yet", h->cfg.mode);
-	if (out != nullptr && out != in && out_cap < n)
+	const bool codec = is_codec_mode(h->cfg.mode);
+	if (codec && (h->cfg.flags & MTZ_FLAG_DEFER_VERIFY))
+		return fail(h, MTZ_EINVAL, "deferred verification is a VERIFY-mode feature");
+	if (!codec && out != nullptr && out != in && out_cap < n)
 		return fail(h, MTZ_ENOSPC, "output buffer smaller than the stream");
+	if (codec && out == nullptr)
+		return fail(h, MTZ_EINVAL, "codec modes need an output buffer");
 	MTZ_CU(h, cudaSetDevice(h->device));
 	int32_t rc = ensure_slots(h);
 	if (rc != MTZ_OK) return rc;
 
 	const uint8_t *src = (const uint8_t *)in;
 	const bool parse = h->cfg.mode != MTZ_MODE_PASSTHROUGH;
-	size_t off = 0;
+	size_t off = 0, out_pos = 0;
 	uint64_t b = 0;
+	// retire the batch that occupies slot s: verdict, then (codec) its output bytes
+	auto retire = [&](Slot &s) -> int32_t {
+		const bool was_busy = s.busy;
+		int32_t r = harvest(h, s);
+		if (r != MTZ_OK || !was_busy || !codec) return r;
+		if (out_pos + s.out_bytes > out_cap)
+			return fail(h, MTZ_ENOSPC, "output buffer too small (%zu needed so far)", out_pos + s.out_bytes);
+		MTZ_CU(h, cudaMemcpyAsync((uint8_t *)out + out_pos, s.d_out, s.out_bytes, cudaMemcpyDeviceToHost, s.st));
+		MTZ_CU(h, cudaStreamSynchronize(s.st));
+		out_pos += s.out_bytes;
+		return MTZ_OK;
+	};
 	while (off < n && rc == MTZ_OK) {
 		Slot &s = h->slots[b % h->slots.size()];
-		rc = harvest(h, s);
+		rc = retire(s);
 		if (rc != MTZ_OK) break;
-		size_t cnt = 0, used = 0;
-		s.writes = 0;
-		const size_t want = std::min(n - off, (size_t)h->cfg.batch_bytes);
+		BatchCut bc;
 		if (!parse) {
-			used = want;
+			bc.in_bytes = std::min(n - off, std::min((size_t)h->cfg.batch_bytes, s.cap));
 		} else {
-			size_t pos = 0;
-			while (off + pos < n) {
-				const uint8_t *hp = src + off + pos;
+			while (off + bc.in_bytes < n) {
+				const size_t at = off + bc.in_bytes;
+				const uint8_t *hp = src + at;
 				uint32_t ls, comp;
-				if (n - off - pos < DRR_HDR) { rc = fail(h, MTZ_EFORMAT, "truncated record header at offset %zu", off + pos); break; }
+				if (n - at < DRR_HDR) { rc = fail(h, MTZ_EFORMAT, "truncated record header at offset %zu", at); break; }
 				const int64_t pl = drr_payload(hp, &ls, &comp);
-				if (pl < 0) { rc = fail(h, MTZ_EFORMAT, "malformed record header at offset %zu", off + pos); break; }
-				if ((uint64_t)pl > n - off - pos - DRR_HDR) { rc = fail(h, MTZ_EFORMAT, "truncated payload at offset %zu", off + pos); break; }
-				const size_t rl = DRR_HDR + (size_t)pl;
-				if (rl > s.cap) { rc = fail(h, MTZ_ENOSPC, "record larger than a batch slot"); break; }
-				if (cnt > 0 && (pos + rl > s.cap || cnt >= s.rec_cap)) break;
-				mtz_rec r;
-				r.off = pos; r.payload = (uint32_t)pl; r.type = rd32(hp);
-				r.lsize = ls; r.comp = comp; r.resv = 0;
-				s.h_recs[cnt++] = r;
-				pos += rl;
-				if (r.type == 3) s.writes++;
-				if (pos >= want) break;
+				if (pl < 0) { rc = fail(h, MTZ_EFORMAT, "malformed record header at offset %zu", at); break; }
+				if ((uint64_t)pl > n - at - DRR_HDR) { rc = fail(h, MTZ_EFORMAT, "truncated payload at offset %zu", at); break; }
+				const int32_t a = batch_accept(h, s, bc, hp, pl, ls, comp, at, &s.h_recs[bc.cnt]);
+				if (a < 0) { rc = a; break; }
+				if (a == 0) break;
+				if (bc.budget >= (size_t)h->cfg.batch_bytes) break;
 			}
-			used = pos;
 		}
 		if (rc != MTZ_OK) break;
-		uint8_t *ho = (out != nullptr && out != in) ? (uint8_t *)out + off : nullptr;
-		rc = submit_batch(h, s, src + off, used, nullptr, 0, cnt, off, ho);
-		off += used;
+		s.writes = bc.writes;
+		uint8_t *ho = (!codec && out != nullptr && out != in) ? (uint8_t *)out + off : nullptr;
+		rc = submit_batch(h, s, src + off, bc.in_bytes, nullptr, 0, bc.cnt, off, ho);
+		off += bc.in_bytes;
 		b++;
 	}
-	for (auto &s : h->slots) {
-		int32_t r2 = harvest(h, s);
+	// drain in submission order
+	for (size_t k = 0; k < h->slots.size(); k++) {
+		Slot &s = h->slots[(b + k) % h->slots.size()];
+		int32_t r2 = retire(s);
 		if (rc == MTZ_OK) rc = r2;
 	}
-	if (out_n) *out_n = (rc == MTZ_OK) ? n : 0;
+	if (out_n) *out_n = (rc != MTZ_OK) ? 0 : (codec ? out_pos : n);
 	return rc;
 }
 
@@ -684,7 +964,7 @@ struct Engine {
 	std::thread thr;
 	int efd = -1;
 	std::vector<mtz_rec> cur;      // records of the batch being assembled
-	uint64_t cur_writes = 0;
+	BatchCut bc;
 	std::deque<InFlight> inflight;
 	uint64_t next_slot = 0;
 	std::chrono::steady_clock::time_point last_input;
@@ -727,10 +1007,11 @@ static int32_t engine_parse(Engine *e, bool *cut)
 {
 	mtz_handle *h = e->h;
 	*cut = false;
-	const size_t slot_cap = h->slots[0].cap, rec_cap = h->slots[0].rec_cap;
+	const Slot &s0 = h->slots[0];
 	if (h->cfg.mode == MTZ_MODE_PASSTHROUGH) {
-		const uint64_t lim = e->batch_begin + std::min<uint64_t>(h->cfg.batch_bytes, slot_cap);
+		const uint64_t lim = e->batch_begin + std::min<uint64_t>(h->cfg.batch_bytes, s0.cap);
 		e->parse_pos = std::min(e->in_head, lim);
+		e->bc.in_bytes = (size_t)(e->parse_pos - e->batch_begin);
 		*cut = (e->parse_pos == lim);
 		return MTZ_OK;
 	}
@@ -743,20 +1024,18 @@ static int32_t engine_parse(Engine *e, bool *cut)
 			return fail(h, MTZ_EFORMAT, "malformed record header at stream offset %llu",
 			    (unsigned long long)e->parse_pos);
 		const uint64_t rl = DRR_HDR + (uint64_t)pl;
-		if (rl > slot_cap || rl > e->in_cap)
-			return fail(h, MTZ_ENOSPC, "record of %llu bytes exceeds the batch/ring size",
+		if (rl > e->in_cap)
+			return fail(h, MTZ_ENOSPC, "record of %llu bytes exceeds the input ring",
 			    (unsigned long long)rl);
 		if (e->in_head - e->parse_pos < rl) break;                 // incomplete
-		const uint64_t bb = e->parse_pos - e->batch_begin;
-		if (!e->cur.empty() && (bb + rl > slot_cap || e->cur.size() >= rec_cap)) { *cut = true; break; }
 		mtz_rec r;
-		r.off = bb; r.payload = (uint32_t)pl; r.type = rd32(hdr);
-		r.lsize = ls; r.comp = comp; r.resv = 0;
+		const int32_t a = batch_accept(h, s0, e->bc, hdr, pl, ls, comp, e->parse_pos, &r);
+		if (a < 0) return a;
+		if (a == 0) { *cut = true; break; }
 		e->cur.push_back(r);
-		if (r.type == 3) e->cur_writes++;
 		e->parse_pos += rl;
 		if (r.type == 5) { *cut = true; break; }                  // END: ship now
-		if (e->parse_pos - e->batch_begin >= h->cfg.batch_bytes) { *cut = true; break; }
+		if (e->bc.budget >= h->cfg.batch_bytes) { *cut = true; break; }
 	}
 	return MTZ_OK;
 }
@@ -770,7 +1049,7 @@ static int32_t engine_submit(Engine *e)
 	const size_t o = (size_t)(b0 % e->in_cap);
 	const size_t n0 = std::min(n, e->in_cap - o);
 	if (!e->cur.empty()) memcpy(s.h_recs, e->cur.data(), e->cur.size() * sizeof(mtz_rec));
-	s.writes = e->cur_writes;
+	s.writes = e->bc.writes;
 	int32_t rc = submit_batch(h, s, e->in_buf + o, n0, e->in_buf, n - n0, e->cur.size(), b0, nullptr);
 	if (rc != MTZ_OK) return rc;
 	MTZ_CU(h, cudaLaunchHostFunc(s.st, engine_host_cb, e));
@@ -778,7 +1057,7 @@ static int32_t engine_submit(Engine *e)
 	e->inflight.push_back(f);
 	e->next_slot++;
 	e->batch_begin = b1;
-	e->cur.clear(); e->cur_writes = 0;
+	e->cur.clear(); e->bc = BatchCut();
 	return MTZ_OK;
 }
 
@@ -794,7 +1073,9 @@ static int32_t engine_harvest(Engine *e, std::unique_lock<std::mutex> &lk, bool 
 		if (q != cudaSuccess) return fail_cuda(h, q, "cudaEventQuery(batch)");
 		int32_t rc = harvest(h, s);
 		if (rc != MTZ_OK) return rc;
-		const size_t n = (size_t)(f.in_end - f.in_begin);
+		const bool codec = is_codec_mode(h->cfg.mode);
+		const size_t n = codec ? s.out_bytes : (size_t)(f.in_end - f.in_begin);
+		const uint8_t *dsrc = codec ? s.d_out : s.d_in;
 		if (e->own_out) {
 			// copy the batch result into the output ring (wait for room)
 			size_t done = 0;
@@ -807,7 +1088,7 @@ static int32_t engine_harvest(Engine *e, std::unique_lock<std::mutex> &lk, bool 
 				const size_t oo = (size_t)(e->out_head % e->out_cap);
 				const size_t c = std::min(std::min(room, n - done), e->out_cap - oo);
 				lk.unlock();
-				cudaError_t ce = cudaMemcpyAsync(e->out_buf + oo, s.d_in + done, c, cudaMemcpyDeviceToHost, s.st);
+				cudaError_t ce = cudaMemcpyAsync(e->out_buf + oo, dsrc + done, c, cudaMemcpyDeviceToHost, s.st);
 				if (ce == cudaSuccess) ce = cudaStreamSynchronize(s.st);
 				lk.lock();
 				if (ce != cudaSuccess) return fail_cuda(h, ce, "D2H to output ring");
@@ -879,8 +1160,6 @@ static int32_t engine_get(mtz_handle *h, Engine **out)
 {
 	std::lock_guard<std::mutex> g(h->eng_mu);
 	if (h->eng != nullptr) { *out = h->eng; return MTZ_OK; }
-	if (h->cfg.mode != MTZ_MODE_VERIFY && h->cfg.mode != MTZ_MODE_PASSTHROUGH)
-		return fail(h, MTZ_EINVAL, "streaming API: mode %u not supported yet", h->cfg.mode);
 	if (h->cfg.flags & MTZ_FLAG_DEFER_VERIFY)
 		return fail(h, MTZ_EINVAL, "streaming API cannot defer verification");
 	MTZ_CU(h, cudaSetDevice(h->device));
