@@ -59,6 +59,12 @@ static inline int
 common_len(const uint8_t *a, const uint8_t *b, const uint8_t *lim)
 {
 	const uint8_t *s = b;
+	while (b + 8 <= lim) {               /* 8 bytes at a time, same count */
+		uint64_t x, y;
+		memcpy(&x, a, 8); memcpy(&y, b, 8);
+		if (x != y) return ((int)(b - s) + (__builtin_ctzll(x ^ y) >> 3));
+		a += 8; b += 8;
+	}
 	while (b < lim && *a == *b) { a++; b++; }
 	return ((int)(b - s));
 }
@@ -80,7 +86,8 @@ static int
 lz4_encode(const uint8_t *src, int isize, uint8_t *dst, int osize, int log,
     int check_dist)
 {
-	uint32_t *table;
+	static __thread uint32_t table_mem[8192];   /* 32 KiB, covers both flavours */
+	uint32_t *table = table_mem;
 	const uint8_t *ip = src, *anchor = src;
 	const uint8_t *const iend = src + isize;
 	const uint8_t *const mflimit = iend - MFLIMIT;
@@ -90,8 +97,7 @@ lz4_encode(const uint8_t *src, int isize, uint8_t *dst, int osize, int log,
 	uint32_t fwd_h;
 	int result = 0;
 
-	table = (uint32_t *)calloc((size_t)1 << log, sizeof (uint32_t));
-	if (table == NULL) return (0);
+	memset(table, 0, sizeof (uint32_t) << log);
 
 	if (isize < MINLENGTH) goto tail;
 
@@ -198,7 +204,6 @@ tail:
 		result = (int)(op - dst);
 	}
 out:
-	free(table);
 	return (result);
 }
 

@@ -184,3 +184,28 @@ def test_mode_preconditions_like_the_oracle(oracle):
     with pytest.raises(MtzError) as ei:
         _gpu("decompress", s)
     assert ei.value.code == EINVAL
+
+
+def test_golden_fixtures_on_gpu(oracle):
+    """The committed golden vectors (tests/golden/, generated by make_golden.py)."""
+    import json
+    import os
+    from manatee_b200 import GpuSnapshotStage
+    from manatee_b200._native import MtzError
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    meta = json.load(open(os.path.join(gold, "golden.json")))
+    s = np.fromfile(os.path.join(gold, "stream_small.bin"), dtype=np.uint8)
+    c = np.fromfile(os.path.join(gold, "stream_small_lz4.bin"), dtype=np.uint8)
+    with GpuSnapshotStage("verify") as g:
+        g.process_host(s)
+        assert ["%016x" % x for x in g.end_checksum()] == meta["stream_small"]["end_cksum"]
+    got, gs, end = _gpu("compress", s)
+    assert np.array_equal(got, c)
+    assert ["%016x" % x for x in end] == meta["stream_small_lz4"]["end_cksum"]
+    back, _, _ = _gpu("decompress", c)
+    assert np.array_equal(back, s)
+    bad = np.fromfile(os.path.join(gold, "stream_small_corrupt_5.bin"), dtype=np.uint8)
+    with GpuSnapshotStage("verify") as g:
+        with pytest.raises(MtzError):
+            g.process_host(bad)
+        assert g.stats()["bad_record"] == meta["stream_small_corrupt_5"]["bad_record"]
