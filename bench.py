@@ -118,27 +118,15 @@ def make_shard(O, rank, world, nwrites, pinned_array):
     flags = (1 if rank == 0 else 0) | (2 if rank == world - 1 else 0)
     buf, ppay = O.synth_shard_fill(nwrites, RECSIZE, O.PAYLOAD_PCG, rank * nwrites, flags,
                                    out=pinned_array, nthreads=max(1, host_threads() // world))
+    from manatee_b200 import shard as SH
     state = (0, 0, 0, 0)
     carry_in = state
     for r in range(world):
         if r == rank:
             carry_in = state
             state = O.synth_shard_stamp(buf, nwrites, RECSIZE, flags, ppay, state)
-        if world > 1:
-            # int64 view of the u64 state; gloo/nccl both move int64
-            t = torch.tensor([s - (1 << 64) if s >= (1 << 63) else s for s in state],
-                             dtype=torch.int64, device="cuda")
-            dist.broadcast(t, src=r)
-            state = tuple(int(x) & ((1 << 64) - 1) for x in t.cpu().tolist())
+        state = SH.broadcast_state(state, r)
     return buf, carry_in
-
-
-def to_i64(v):
-    return [x - (1 << 64) if x >= (1 << 63) else x for x in v]
-
-
-def from_i64(v):
-    return tuple(int(x) & ((1 << 64) - 1) for x in v)
 
 
 def run_reference(args):
@@ -216,24 +204,12 @@ def run_ours(args):
     torch.cuda.synchronize()
 
     st = torch.cuda.Stream()
-    agg_t = torch.zeros(5, dtype=torch.int64, device="cuda")
 
-    def carry_from_aggs(all_aggs):
-        c = (0, 0, 0, 0)
-        for r in range(rank):
-            a = all_aggs[r]
-            if a[0] >> 63:
-                c = (0, 0, 0, 0)
-            c = O.fletcher4_apply(c, (a[0] & ((1 << 63) - 1),) + tuple(a[1:]))
-        return c
+    from manatee_b200 import shard as SH
 
     def exchange(g):
         """all-gather of the 40-byte shard aggregate; returns this rank's carry-in."""
-        agg = g.dev_aggregate()
-        agg_t.copy_(torch.tensor(to_i64(agg), dtype=torch.int64))
-        outs = [torch.zeros_like(agg_t) for _ in range(world)]
-        dist.all_gather(outs, agg_t)
-        return carry_from_aggs([from_i64(o.cpu().tolist()) for o in outs])
+        return SH.carry_before(rank, SH.all_gather_aggregates(g.dev_aggregate()))
 
     # ---------------- resident (HBM) timing: `value` ----------------
     g = GpuSnapshotStage("verify", device=local)

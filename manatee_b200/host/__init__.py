@@ -1,0 +1,19 @@
+"""Host-side mirror of the reference's peer-bootstrap pipeline surface.
+
+Node.js is not installed in this image (`node --version`: not found), so the host
+side above the C ABI is mirrored in Python with the same names, argument meaning,
+job-object fields and error behaviour as the reference modules:
+
+    backup_queue.BackupQueue     lib/backupQueue.js
+    backup_server.BackupServer   lib/backupServer.js   (POST /backup/, GET /backup/:uuid)
+    backup_sender.BackupSender   lib/backupSender.js   (_send, _getLatestSnapshot)
+    zfs_client.ZfsClient         lib/zfsClient.js      (_receive, _postRestoreRequest,
+                                                        _pollRestoreCompletion, restore)
+
+``js/`` holds the Node sources a maintainer ships; both splice the same
+``GpuSnapshotStage`` into the two ``.pipe()`` calls.
+"""
+from .backup_queue import BackupQueue  # noqa: F401
+from .backup_server import BackupServer  # noqa: F401
+from .backup_sender import BackupSender  # noqa: F401
+from .zfs_client import ZfsClient  # noqa: F401

@@ -1,0 +1,175 @@
+"""BackupSender -- mirror of lib/backupSender.js with the GPU stage in the pipe.
+
+Reference data path (lib/backupSender.js:172-179):
+    socket = net.connect(job.port, job.host)
+    zfsSend = spawn(zfsPath, ['send', '-v', '-P', snapshot])
+    zfsSend.stdout.pipe(socket)
+Here:  zfsSend.stdout -> GpuSnapshotStage(mode) -> socket   (gpu cfg absent/off:
+the legacy identity pipe, byte for byte).
+
+Kept verbatim: one _send per 'push' (no coalescing, :72-73); job.done goes
+false -> 0 -> True | 'failed' (:196, :218, :224); job.size / job.completed are the
+decimal STRINGS captured by the two stderr regexes (:125, :136, :197-212); a
+failure emits 'err' (not 'error') and sets job.err (:74-88); the POSTed `dataset`
+is ignored, the sender ships its own configured dataset (:66, :253);
+_getLatestSnapshot takes the first name matching /^\\d{13}$/ from
+`zfs list -t snapshot -H -d 1 -S name -o name <ds>` (:244-288).
+Not replicated: the crash when the socket errors before 'connect'
+(zfsSend undefined, :230-233) -- guarded instead.
+"""
+import re
+import socket
+import subprocess
+import threading
+
+from .backup_queue import BackupQueue
+
+ZFS_PROGRESS_HEADER = re.compile(r"^full\s+\S+\s+(\d+)\n.*\n*$")
+ZFS_PROGRESS_REGEX = re.compile(r"^\d\d:\d\d:\d\d\t(\d+)\t\S+\n$")
+CHUNK = 1 << 20
+
+
+class BackupSender(object):
+    def __init__(self, options):
+        assert isinstance(options, dict), "options (object) is required"
+        assert isinstance(options.get("dataset"), str), "options.dataset (string) is required"
+        assert isinstance(options.get("queue"), BackupQueue), "options.queue (object) is required"
+        assert isinstance(options.get("zfsPath"), str), "options.zfsPath (string) is required"
+        self._zfsPath = options["zfsPath"]
+        self._dataset = options["dataset"]
+        self._queue = options["queue"]
+        self._gpu = options.get("gpu") or None     # {'mode': 'verify'|'compress', 'device': 0, ...}
+        self._env = options.get("env")
+        self._listeners = {}
+        self._threads = []
+        self._queue.on("push", self._on_push)
+
+    @staticmethod
+    def start(cfg):
+        return BackupSender(cfg)
+
+    def on(self, event, fn):
+        self._listeners.setdefault(event, []).append(fn)
+        return self
+
+    def emit(self, event, *args):
+        for fn in list(self._listeners.get(event, [])):
+            fn(*args)
+
+    def join(self, timeout=None):
+        for t in list(self._threads):
+            t.join(timeout)
+
+    def _on_push(self, backupJob):
+        def cb(err):
+            if err:
+                backupJob["err"] = err
+                self.emit("err", err)
+            else:
+                self.emit("done", backupJob)
+        t = threading.Thread(target=self._send, args=(backupJob, cb), daemon=True)
+        self._threads.append(t)
+        t.start()
+
+    # -- lib/backupSender.js:244-288
+    def _getLatestSnapshot(self):
+        cmd = "zfs list -t snapshot -H -d 1 -S name -o name " + self._dataset
+        p = subprocess.run(cmd, shell=True, capture_output=True, text=True, env=self._env)
+        if p.returncode != 0:
+            raise RuntimeError("Command failed: %s\n%s" % (cmd, p.stderr))
+        for line in p.stdout.split("\n"):
+            parts = line.split("@")
+            if len(parts) > 1 and re.match(r"^\d{13}$", parts[1]):
+                return line
+        raise RuntimeError("no snapshots found")
+
+    def _make_stage(self):
+        if not self._gpu or self._gpu.get("mode", "off") == "off":
+            return None
+        from ..stage import GpuSnapshotStage          # the product: fails loudly without the .so/GPU
+        g = self._gpu
+        return GpuSnapshotStage(g["mode"], device=g.get("device", 0),
+                                ring_bytes=g.get("ringBytes", 0), batch_bytes=g.get("batchBytes", 0),
+                                out_ring_bytes=g.get("outRingBytes", 0), n_slots=g.get("slots", 0))
+
+    # -- lib/backupSender.js:154-242
+    def _send(self, backupJob, callback):
+        sock = zfsSend = stage = None
+        try:
+            snapshot = self._getLatestSnapshot()
+            sock = socket.create_connection((backupJob["host"], int(backupJob["port"])))
+            zfsSend = subprocess.Popen([self._zfsPath, "send", "-v", "-P", snapshot],
+                                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=self._env)
+            backupJob["size"] = None
+            backupJob["done"] = 0
+            last_msg = [""]
+
+            def stderr_reader():
+                for raw in iter(zfsSend.stderr.readline, b""):
+                    data = raw.decode(errors="replace")
+                    # zfs prints "full ...\nsize ...\n" as one write; mimic that grouping
+                    if data.startswith("full") and not ZFS_PROGRESS_HEADER.match(data):
+                        nxt = zfsSend.stderr.readline().decode(errors="replace")
+                        data += nxt
+                    m = ZFS_PROGRESS_HEADER.match(data)
+                    if m:
+                        backupJob["size"] = m.group(1)
+                    else:
+                        m = ZFS_PROGRESS_REGEX.match(data)
+                        if m:
+                            backupJob["completed"] = m.group(1)
+                    last_msg[0] = data
+            te = threading.Thread(target=stderr_reader, daemon=True)
+            te.start()
+
+            stage = self._make_stage()
+            pump_err = []
+            if stage is None:
+                while True:                                   # stdout.pipe(socket)
+                    buf = zfsSend.stdout.read(CHUNK)
+                    if not buf:
+                        break
+                    sock.sendall(buf)
+            else:
+                def drain():
+                    try:
+                        while True:
+                            b = stage.read(CHUNK)
+                            if b is None:
+                                break
+                            sock.sendall(b)
+                    except Exception as e:                    # noqa: BLE001
+                        pump_err.append(e)
+                td = threading.Thread(target=drain, daemon=True)
+                td.start()
+                try:
+                    while True:                               # stdout.pipe(stage)
+                        buf = zfsSend.stdout.read(CHUNK)
+                        if not buf:
+                            break
+                        stage.write(buf)
+                    stage.flush()
+                except Exception as e:                        # noqa: BLE001
+                    pump_err.append(e)
+                td.join()
+                backupJob["gpu"] = stage.stats()              # additive field
+            code = zfsSend.wait()
+            te.join(2)
+            if pump_err:
+                raise pump_err[0]
+            if code != 0:
+                backupJob["done"] = "failed"
+                raise RuntimeError("zfs send: %s %d" % (last_msg[0], code))
+            sock.shutdown(socket.SHUT_WR)
+            backupJob["done"] = True
+            callback(None)
+        except Exception as e:                                # noqa: BLE001
+            backupJob["done"] = "failed"
+            if zfsSend is not None and zfsSend.poll() is None:
+                zfsSend.terminate()                           # SIGTERM, lib/backupSender.js:233
+            callback(e)
+        finally:
+            if stage is not None:
+                stage.close()
+            if sock is not None:
+                sock.close()

@@ -1,0 +1,175 @@
+"""ZfsClient (receive half) -- mirror of lib/zfsClient.js:_receive and helpers.
+
+Reference data path (lib/zfsClient.js:793-794, 823-832):
+    zfsRecv = spawn(zfsPath, ['recv', '-v', '-u', dataset])
+    server = net.createServer(); server.on('connection', socket.pipe(zfsRecv.stdin))
+    server.listen(zfsPort, zfsHost, 1)
+Here:  socket -> GpuSnapshotStage(mode) -> zfsRecv.stdin.
+
+Kept: POST {host, port, dataset} to <serverUrl>/backup (:638-668); poll the job
+every pollInterval ms, `done === true` ends it, `done === 'failed'` or any HTTP
+error is an error, anything else (false, 0) means in progress (:685-754); the last
+polled job is kept in _restoreObject for the status server (:722); on any error
+the `zfs recv` child is SIGKILLed (:867-876); restore(serverUrl, cb(err, oldDataset)).
+The dataset isolate/mount/snapshot steps of restore() (:115-207) are metadata
+operations outside the bulk-data path and stay with the caller.
+"""
+import json
+import socket
+import subprocess
+import threading
+import time
+import urllib.error
+import urllib.request
+
+CHUNK = 1 << 20
+
+
+class ZfsClient(object):
+    def __init__(self, options):
+        assert isinstance(options, dict), "options (object) is required"
+        for k, t in (("dataset", str), ("dbUser", str), ("mountpoint", str), ("pollInterval", int),
+                     ("zfsHost", str), ("zfsPath", str), ("zfsPort", int)):
+            assert isinstance(options.get(k), t), "options.%s (%s) is required" % (k, t.__name__)
+        self._dataset = options["dataset"]
+        self._mountpoint = options["mountpoint"]
+        self._dbUser = options["dbUser"]
+        self._pollInterval = options["pollInterval"]
+        self._restoreObject = None
+        self._zfsHost = options["zfsHost"]
+        self._zfsPort = options["zfsPort"]
+        self._zfsPath = options["zfsPath"]
+        self._gpu = options.get("gpu") or None
+        self._env = options.get("env")
+
+    # -- lib/zfsClient.js:115 (bulk-data part only)
+    def restore(self, serverUrl, callback):
+        try:
+            self._receive(self._dataset, serverUrl, self._pollInterval)
+        except Exception as e:                                # noqa: BLE001
+            return callback(e, None)
+        return callback(None, None)
+
+    def _make_stage(self):
+        if not self._gpu or self._gpu.get("mode", "off") == "off":
+            return None
+        from ..stage import GpuSnapshotStage
+        g = self._gpu
+        return GpuSnapshotStage(g["mode"], device=g.get("device", 0),
+                                ring_bytes=g.get("ringBytes", 0), batch_bytes=g.get("batchBytes", 0),
+                                out_ring_bytes=g.get("outRingBytes", 0), n_slots=g.get("slots", 0))
+
+    # -- lib/zfsClient.js:638-668
+    def _postRestoreRequest(self, serverUrl):
+        body = json.dumps({"host": self._zfsHost, "port": self._zfsPort,
+                           "dataset": self._dataset}).encode()
+        req = urllib.request.Request(serverUrl.rstrip("/") + "/backup", data=body,
+                                     headers={"Content-Type": "application/json"})
+        try:
+            with urllib.request.urlopen(req, timeout=30) as r:
+                obj = json.loads(r.read().decode())
+        except (urllib.error.URLError, OSError) as e:
+            raise RuntimeError("Posting restore request failed: %s" % e)
+        return obj.get("jobPath")
+
+    # -- lib/zfsClient.js:685-754
+    def _pollRestoreCompletion(self, serverUrl, pollInterval, jobPath, abort):
+        while True:
+            time.sleep(pollInterval / 1000.0)
+            if abort.is_set():
+                raise RuntimeError("receive pipe failed")
+            try:
+                with urllib.request.urlopen(serverUrl.rstrip("/") + jobPath, timeout=30) as r:
+                    obj = json.loads(r.read().decode())
+            except urllib.error.HTTPError as e:
+                raise RuntimeError("error getting restore job status: %d %s" % (e.code, e.read().decode()))
+            except (urllib.error.URLError, OSError) as e:
+                raise RuntimeError("error getting restore job status: %s" % e)
+            self._restoreObject = obj
+            if obj.get("done") is True:
+                return obj
+            if obj.get("done") == "failed":
+                raise RuntimeError("restore job failed")
+
+    # -- lib/zfsClient.js:765-886
+    def _receive(self, dataset, serverUrl, pollInterval):
+        zfsRecv = subprocess.Popen([self._zfsPath, "recv", "-v", "-u", dataset],
+                                   stdin=subprocess.PIPE, stdout=subprocess.PIPE,
+                                   stderr=subprocess.PIPE, env=self._env)
+        server = socket.socket(socket.AF_INET, socket.SOCK_STREAM)
+        server.setsockopt(socket.SOL_SOCKET, socket.SO_REUSEADDR, 1)
+        abort = threading.Event()
+        pipe_err = []
+        stage_box = []
+
+        def serve():
+            conn = None
+            stage = None
+            try:
+                conn, _ = server.accept()
+                stage = self._make_stage()
+                stage_box.append(stage)
+                if stage is None:
+                    while True:                               # socket.pipe(zfsRecv.stdin)
+                        buf = conn.recv(CHUNK)
+                        if not buf:
+                            break
+                        zfsRecv.stdin.write(buf)
+                else:
+                    def drain():
+                        try:
+                            while True:
+                                b = stage.read(CHUNK)
+                                if b is None:
+                                    break
+                                zfsRecv.stdin.write(b)
+                        except Exception as e:                # noqa: BLE001
+                            pipe_err.append(e)
+                    td = threading.Thread(target=drain, daemon=True)
+                    td.start()
+                    try:
+                        while True:
+                            buf = conn.recv(CHUNK)
+                            if not buf:
+                                break
+                            stage.write(buf)
+                        stage.flush()
+                    except Exception as e:                    # noqa: BLE001
+                        pipe_err.append(e)
+                    td.join()
+                zfsRecv.stdin.close()
+            except Exception as e:                            # noqa: BLE001
+                pipe_err.append(e)
+            finally:
+                if pipe_err:
+                    abort.set()
+                if stage is not None:
+                    self._gpuStats = stage.stats()
+                    stage.close()
+                if conn is not None:
+                    conn.close()
+
+        try:
+            server.bind((self._zfsHost, self._zfsPort))
+            server.listen(1)                                  # backlog 1, lib/zfsClient.js:832
+            ts = threading.Thread(target=serve, daemon=True)
+            ts.start()
+            jobPath = self._postRestoreRequest(serverUrl)
+            self._pollRestoreCompletion(serverUrl, pollInterval, jobPath, abort)
+            ts.join(60)
+            if pipe_err:
+                raise pipe_err[0]
+            code = zfsRecv.wait(60)
+            if code != 0:
+                raise RuntimeError("zfs recv: %s %d" % (zfsRecv.stderr.read().decode(errors="replace"), code))
+        except Exception:
+            try:
+                zfsRecv.kill()                                # SIGKILL, lib/zfsClient.js:873
+            except OSError:
+                pass
+            raise
+        finally:
+            try:
+                server.close()
+            except OSError:
+                pass

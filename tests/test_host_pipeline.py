@@ -1,0 +1,183 @@
+"""Host logic of the peer-bootstrap path (mirror of lib/backupServer.js,
+lib/backupQueue.js, lib/backupSender.js, lib/zfsClient.js) with a fake `zfs`
+selected through the reference's own zfsPath knob.  CPU tests run the legacy
+identity pipe (gpu off == reference behaviour); the gpu-marked ones put the stage
+in the pipe: VERIFY on both sides, and COMPRESS on the sender / DECOMPRESS on the
+receiver with transport identity end to end."""
+import hashlib
+import json
+import os
+import socket
+import stat
+import sys
+import threading
+import time
+import urllib.error
+import urllib.request
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+@pytest.fixture()
+def fakezfs(tmp_path, oracle):
+    """dir with an executable `zfs`, a seeded stream file and the env to use them"""
+    z = tmp_path / "bin"
+    z.mkdir()
+    zfs = z / "zfs"
+    zfs.write_text("#!/bin/sh\nexec %s %s \"$@\"\n" % (sys.executable, os.path.join(ROOT, "tools", "fake_zfs.py")))
+    zfs.chmod(zfs.stat().st_mode | stat.S_IEXEC)
+    stream = oracle.synth_stream(40, recsize=131072, kind=oracle.PAYLOAD_PGPAGE)
+    sp = tmp_path / "stream.bin"
+    stream.tofile(str(sp))
+    env = dict(os.environ)
+    env["PATH"] = str(z) + os.pathsep + env.get("PATH", "")
+    env["FAKE_ZFS_STREAM"] = str(sp)
+    env["FAKE_ZFS_RECV_OUT"] = str(tmp_path / "recv.out")
+    return {"zfs": str(zfs), "env": env, "stream": stream, "recv_out": str(tmp_path / "recv.out")}
+
+
+def _run_restore(fakezfs, sender_gpu=None, recv_gpu=None, env_extra=None):
+    from manatee_b200.host import BackupSender, BackupServer, ZfsClient
+    env = dict(fakezfs["env"])
+    env.update(env_extra or {})
+    srv = BackupServer.start({"log": None, "port": 0, "host": "127.0.0.1"})
+    sender = BackupSender.start({"log": None, "dataset": "zones/x/data/manatee", "zfsPath": fakezfs["zfs"],
+                                 "queue": srv.getQueue(), "gpu": sender_gpu, "env": env})
+    events = []
+    sender.on("err", lambda e: events.append(("err", e)))
+    sender.on("done", lambda j: events.append(("done", j)))
+    cli = ZfsClient({"log": None, "dataset": "zones/y/data/manatee", "dbUser": "postgres",
+                     "mountpoint": "/manatee/pg", "pollInterval": 50, "zfsHost": "127.0.0.1",
+                     "zfsPath": fakezfs["zfs"], "zfsPort": _free_port(), "gpu": recv_gpu, "env": env})
+    res = {}
+    cli.restore("http://127.0.0.1:%d" % srv.port, lambda err, old: res.update(err=err, old=old))
+    sender.join(10)
+    srv.close()
+    return res, cli, events
+
+
+def test_rest_surface(fakezfs):
+    from manatee_b200.host import BackupServer
+    srv = BackupServer.start({"log": None, "port": 0, "host": "127.0.0.1"})
+    base = "http://127.0.0.1:%d" % srv.port
+    try:
+        pushed = []
+        srv.getQueue().on("push", pushed.append)
+        req = urllib.request.Request(base + "/backup/", data=json.dumps(
+            {"host": "10.0.0.9", "port": 1234, "dataset": "zones/a/b"}).encode(),
+            headers={"Content-Type": "application/json"})
+        obj = json.loads(urllib.request.urlopen(req).read())
+        assert set(obj) == {"jobid", "jobPath"} and obj["jobPath"] == "/backup/" + obj["jobid"]
+        time.sleep(0.05)
+        assert pushed and pushed[0]["done"] is False and pushed[0]["dataset"] == "zones/a/b"
+        job = json.loads(urllib.request.urlopen(base + obj["jobPath"]).read())
+        assert job["uuid"] == obj["jobid"] and job["host"] == "10.0.0.9" and job["port"] == 1234
+        # missing parameter -> 409 MissingParameter (lib/backupServer.js:135-138)
+        bad = urllib.request.Request(base + "/backup/", data=json.dumps({"host": "h", "port": 1}).encode(),
+                                     headers={"Content-Type": "application/json"})
+        with pytest.raises(urllib.error.HTTPError) as ei:
+            urllib.request.urlopen(bad)
+        assert ei.value.code == 409 and json.loads(ei.value.read())["code"] == "MissingParameter"
+        with pytest.raises(urllib.error.HTTPError) as ei:
+            urllib.request.urlopen(base + "/backup/00000000-0000-0000-0000-000000000000")
+        assert ei.value.code == 404
+        # job.err -> 500 InternalError; the sender mutates the same object the server serialises
+        pushed[0]["err"] = RuntimeError("zfs send: boom 1")
+        with pytest.raises(urllib.error.HTTPError) as ei:
+            urllib.request.urlopen(base + obj["jobPath"])
+        assert ei.value.code == 500 and "boom" in json.loads(ei.value.read())["message"]
+    finally:
+        srv.close()
+
+
+def test_queue_never_evicts():
+    from manatee_b200.host import BackupQueue
+    q = BackupQueue({"log": None})
+    seen = []
+    q.on("push", seen.append)
+    for i in range(3):
+        q.push({"uuid": "u%d" % i})
+    assert [j["uuid"] for j in seen] == ["u0", "u1", "u2"]
+    assert q.get("u1", lambda j: j)["uuid"] == "u1"
+    assert q.get("nope", lambda j: j) is None
+    assert q.get("u0", lambda j: j) is not None          # still there: pop() is never called
+
+
+def test_legacy_identity_pipe_end_to_end(fakezfs):
+    """gpu off == the reference: bytes into `zfs recv` == bytes out of `zfs send`."""
+    res, cli, events = _run_restore(fakezfs)
+    assert res["err"] is None, res
+    digest, n = open(fakezfs["recv_out"]).read().split()
+    s = fakezfs["stream"]
+    assert int(n) == s.size and digest == hashlib.sha256(s.tobytes()).hexdigest()
+    job = cli._restoreObject
+    assert job["done"] is True
+    assert job["size"] == str(s.size) and job["completed"] == str(s.size)     # strings, like the regex captures
+    assert events and events[0][0] == "done"
+
+
+def test_latest_snapshot_selection_and_failures(fakezfs):
+    from manatee_b200.host import BackupQueue, BackupSender
+    snd = BackupSender.start({"log": None, "dataset": "zones/x/data/manatee", "zfsPath": fakezfs["zfs"],
+                              "queue": BackupQueue({}), "env": fakezfs["env"]})
+    assert snd._getLatestSnapshot() == "zones/x/data/manatee@1405378955344"   # 13 digits, operator snapshot skipped
+    env = dict(fakezfs["env"]); env["FAKE_ZFS_NO_SNAPSHOTS"] = "1"
+    snd2 = BackupSender.start({"log": None, "dataset": "d", "zfsPath": fakezfs["zfs"],
+                               "queue": BackupQueue({}), "env": env})
+    with pytest.raises(RuntimeError, match="no snapshots found"):
+        snd2._getLatestSnapshot()
+    # zfs send exiting non-zero => job.done == 'failed', 'err' event, receiver errors out
+    res, cli, events = _run_restore(fakezfs, env_extra={"FAKE_ZFS_SEND_FAIL_AT": str(3 << 20)})
+    assert res["err"] is not None
+    assert events and events[0][0] == "err"
+
+
+@pytest.mark.gpu
+def test_gpu_verify_stage_in_both_pipes(fakezfs):
+    res, cli, events = _run_restore(fakezfs, sender_gpu={"mode": "verify", "batchBytes": 2 << 20, "ringBytes": 16 << 20},
+                                    recv_gpu={"mode": "verify", "batchBytes": 2 << 20, "ringBytes": 16 << 20})
+    assert res["err"] is None, res
+    digest, n = open(fakezfs["recv_out"]).read().split()
+    s = fakezfs["stream"]
+    assert int(n) == s.size and digest == hashlib.sha256(s.tobytes()).hexdigest()
+    assert cli._restoreObject["done"] is True
+    assert cli._restoreObject["gpu"]["records"] == 43 and cli._gpuStats["records"] == 43
+
+
+@pytest.mark.gpu
+def test_gpu_compress_on_the_wire_identity_at_zfs_recv(fakezfs):
+    """COMPRESS in the sender, DECOMPRESS in the receiver: fewer bytes on the TCP leg,
+    `zfs recv` sees exactly the bytes `zfs send` produced."""
+    cfg = {"batchBytes": 4 << 20, "ringBytes": 32 << 20, "outRingBytes": 32 << 20}
+    res, cli, events = _run_restore(fakezfs, sender_gpu=dict(cfg, mode="compress"),
+                                    recv_gpu=dict(cfg, mode="decompress"))
+    assert res["err"] is None, res
+    digest, n = open(fakezfs["recv_out"]).read().split()
+    s = fakezfs["stream"]
+    assert int(n) == s.size and digest == hashlib.sha256(s.tobytes()).hexdigest()
+    g = cli._restoreObject["gpu"]
+    assert g["lz4_encoded"] == 40 and g["bytes_out"] < g["bytes_in"] // 2
+    assert cli._gpuStats["lz4_decoded"] == 40
+
+
+@pytest.mark.gpu
+def test_gpu_corrupt_stream_fails_the_job(fakezfs, tmp_path):
+    s = fakezfs["stream"].copy()
+    s[5_000_000] ^= 1
+    p = tmp_path / "bad.bin"
+    s.tofile(str(p))
+    res, cli, events = _run_restore(fakezfs, sender_gpu={"mode": "verify", "batchBytes": 1 << 20, "ringBytes": 8 << 20},
+                                    env_extra={"FAKE_ZFS_STREAM": str(p)})
+    assert res["err"] is not None                    # receiver's poll sees done == 'failed' / 500
+    assert events and events[0][0] == "err" and "checksum" in str(events[0][1])
