@@ -1,0 +1,115 @@
+/*
+ * gpuSnapshotStage.js -- the stream.Transform that is spliced into manatee's
+ * two pipes:
+ *
+ *     zfsSend.stdout.pipe(stage).pipe(socket)      // lib/backupSender.js:179
+ *     socket.pipe(stage).pipe(zfsRecv.stdin)       // lib/zfsClient.js:826
+ *
+ * All work happens in libmanatee_gpu.so on the GPU; this file only moves Buffers
+ * between Node's stream machinery and the library's pinned rings.  There is no
+ * JS/CPU fallback: if the addon cannot be loaded or no B200 is present, creating
+ * a stage throws, and the caller's `gpu.mode` must be 'off' to get the legacy
+ * identity pipe.
+ *
+ * Written against the N-API addon in ../src/binding.cc.  Not executed in this
+ * repository (no Node.js in the build image); manatee_b200/stage.py is the
+ * mirror that the test-suite runs.
+ */
+var stream = require('stream');
+var util = require('util');
+var fs = require('fs');
+
+var MODES = { verify: 0, compress: 1, decompress: 2, recompress: 3, passthrough: 4 };
+
+function GpuSnapshotStage(options) {
+    if (!(this instanceof GpuSnapshotStage)) {
+        return (new GpuSnapshotStage(options));
+    }
+    options = options || {};
+    stream.Transform.call(this, { highWaterMark: options.highWaterMark || (4 << 20) });
+    this._addon = require('../build/Release/manatee_gpu.node');
+    this._h = this._addon.open({
+        mode: MODES[options.mode || 'verify'],
+        device: options.device || 0,
+        ringBytes: options.ringBytes || 0,
+        outRingBytes: options.outRingBytes || 0,
+        batchBytes: options.batchBytes || 0,
+        slots: options.slots || 0
+    });
+    this._pending = null;      // {chunk, off, cb} waiting for ring space
+    this._flushCb = null;
+    this._closed = false;
+    var self = this;
+    // wake-up source: the library's eventfd becomes readable when output, EOF or an
+    // error is pending.  fs.createReadStream on the fd keeps this on the event loop.
+    this._efd = fs.createReadStream(null, { fd: this._addon.eventFd(this._h), highWaterMark: 8,
+                                            autoClose: false });
+    this._efd.on('data', function () { self._drain(); });
+}
+util.inherits(GpuSnapshotStage, stream.Transform);
+
+GpuSnapshotStage.prototype._fail = function (err) {
+    // sticky failure -> destroy(err) -> sender: job.done='failed', emit 'err'
+    // (lib/backupSender.js:74-88, 218); receiver: _receive cb(err) -> SIGKILL zfs recv
+    // (lib/zfsClient.js:867-876)
+    this._cleanup();
+    this.destroy(err);
+};
+
+GpuSnapshotStage.prototype._cleanup = function () {
+    if (this._closed) { return; }
+    this._closed = true;
+    try { this._efd.destroy(); } catch (e) {}
+    try { this._addon.close(this._h); } catch (e) {}
+};
+
+GpuSnapshotStage.prototype._feed = function () {
+    var p = this._pending;
+    if (!p) { return; }
+    try {
+        while (p.off < p.chunk.length) {
+            var n = this._addon.write(this._h, p.chunk.slice(p.off));
+            if (n === 0) { return; }            // ring full: retried from _drain()
+            p.off += n;
+        }
+    } catch (e) { return (this._fail(e)); }
+    this._pending = null;
+    p.cb();
+};
+
+GpuSnapshotStage.prototype._transform = function (chunk, enc, cb) {
+    this._pending = { chunk: chunk, off: 0, cb: cb };
+    this._feed();
+    this._drain();
+};
+
+GpuSnapshotStage.prototype._drain = function () {
+    if (this._closed) { return; }
+    try {
+        for (;;) {
+            var ab = this._addon.peek(this._h);
+            if (ab === null) { break; }
+            if (ab === 'eof') {
+                var fcb = this._flushCb;
+                this._flushCb = null;
+                this.stats = this._addon.stats(this._h);
+                this._cleanup();
+                if (fcb) { fcb(); }
+                return;
+            }
+            // copy out of the pinned ring before releasing the slice
+            var buf = Buffer.from(Buffer.from(ab));
+            this._addon.consume(this._h, buf.length);
+            this.push(buf);
+        }
+    } catch (e) { return (this._fail(e)); }
+    this._feed();
+};
+
+GpuSnapshotStage.prototype._flush = function (cb) {
+    this._flushCb = cb;
+    try { this._addon.flush(this._h); } catch (e) { return (this._fail(e)); }
+    this._drain();
+};
+
+module.exports = GpuSnapshotStage;

@@ -1,0 +1,207 @@
+// binding.cc -- thin N-API addon over the C ABI of libmanatee_gpu.so
+// (include/manatee_gpu.h).  It adds NO logic: every export is one mtz_* call.
+//
+// NOT COMPILED IN THIS REPOSITORY'S CI: the build image has no Node.js and no
+// node_api.h (`node --version`: not found).  It is the binding a maintainer adds
+// to manatee; tests/ drive the same C ABI through ctypes instead.
+//
+// JS surface (used by js/lib/gpuSnapshotStage.js):
+//   open({mode, device, ringBytes, outRingBytes, batchBytes, slots}) -> handle (external)
+//   acquire(handle, want)          -> ArrayBuffer over the PINNED input ring slice (zero copy) | null
+//   commit(handle, n)
+//   write(handle, Buffer)          -> bytes accepted (non-blocking; 0 == ring full)
+//   flush(handle)
+//   peek(handle)                   -> ArrayBuffer over the pinned output slice | null | 'eof'
+//   consume(handle, n)
+//   eventFd(handle)                -> fd for uv_poll (readable when output / error / EOF is pending)
+//   stats(handle) -> {bytesIn, bytesOut, records, ...}; endChecksum(handle) -> [4 x BigInt]
+//   close(handle)
+// Every failing call throws Error(mtz_last_error) with .code = MTZ_E* so the stage
+// can destroy(err), which the sender maps to job.done='failed' (lib/backupSender.js:218).
+#include <node_api.h>
+#include <string.h>
+#include "../../include/manatee_gpu.h"
+
+#define NAPI_OK(call) do { if ((call) != napi_ok) { napi_throw_error(env, NULL, #call); return NULL; } } while (0)
+
+static napi_value throw_mtz(napi_env env, mtz_handle *h, int32_t rc)
+{
+	char code[16];
+	snprintf(code, sizeof code, "%d", rc);
+	const char *msg = mtz_last_error(h);
+	napi_throw_error(env, code, (msg && *msg) ? msg : mtz_strerror(rc));
+	return NULL;
+}
+
+static mtz_handle *get_handle(napi_env env, napi_value v)
+{
+	void *p = NULL;
+	if (napi_get_value_external(env, v, &p) != napi_ok) return NULL;
+	return (mtz_handle *)p;
+}
+
+static uint64_t get_u64_prop(napi_env env, napi_value obj, const char *name)
+{
+	napi_value v; bool has = false; double d = 0;
+	if (napi_has_named_property(env, obj, name, &has) != napi_ok || !has) return 0;
+	napi_get_named_property(env, obj, name, &v);
+	napi_get_value_double(env, v, &d);
+	return (uint64_t)d;
+}
+
+static napi_value Open(napi_env env, napi_callback_info info)
+{
+	size_t argc = 1; napi_value argv[1];
+	NAPI_OK(napi_get_cb_info(env, info, &argc, argv, NULL, NULL));
+	mtz_config cfg; memset(&cfg, 0, sizeof cfg);
+	cfg.struct_size = sizeof cfg;
+	cfg.mode = (uint32_t)get_u64_prop(env, argv[0], "mode");
+	cfg.device = (int32_t)get_u64_prop(env, argv[0], "device");
+	cfg.ring_bytes = get_u64_prop(env, argv[0], "ringBytes");
+	cfg.out_ring_bytes = get_u64_prop(env, argv[0], "outRingBytes");
+	cfg.batch_bytes = get_u64_prop(env, argv[0], "batchBytes");
+	cfg.n_slots = (uint32_t)get_u64_prop(env, argv[0], "slots");
+	mtz_handle *h = NULL;
+	int32_t rc = mtz_open(&cfg, &h);
+	if (rc != MTZ_OK) return throw_mtz(env, NULL, rc);
+	napi_value ext;
+	NAPI_OK(napi_create_external(env, h, NULL, NULL, &ext));
+	return ext;
+}
+
+static void noop_finalize(napi_env, void *, void *) {}
+
+static napi_value Acquire(napi_env env, napi_callback_info info)
+{
+	size_t argc = 2; napi_value argv[2];
+	NAPI_OK(napi_get_cb_info(env, info, &argc, argv, NULL, NULL));
+	mtz_handle *h = get_handle(env, argv[0]);
+	uint32_t want = 0; napi_get_value_uint32(env, argv[1], &want);
+	void *p = NULL; size_t got = 0;
+	int32_t rc = mtz_ring_acquire(h, want, &p, &got);
+	napi_value out;
+	if (rc == MTZ_EAGAIN) { napi_get_null(env, &out); return out; }
+	if (rc != MTZ_OK) return throw_mtz(env, h, rc);
+	// library-owned pinned memory: external ArrayBuffer with a no-op finalizer
+	NAPI_OK(napi_create_external_arraybuffer(env, p, got, noop_finalize, NULL, &out));
+	return out;
+}
+
+static napi_value Commit(napi_env env, napi_callback_info info)
+{
+	size_t argc = 2; napi_value argv[2];
+	NAPI_OK(napi_get_cb_info(env, info, &argc, argv, NULL, NULL));
+	mtz_handle *h = get_handle(env, argv[0]);
+	uint32_t n = 0; napi_get_value_uint32(env, argv[1], &n);
+	int32_t rc = mtz_ring_commit(h, n);
+	if (rc != MTZ_OK) return throw_mtz(env, h, rc);
+	return NULL;
+}
+
+static napi_value Write(napi_env env, napi_callback_info info)
+{
+	size_t argc = 2; napi_value argv[2];
+	NAPI_OK(napi_get_cb_info(env, info, &argc, argv, NULL, NULL));
+	mtz_handle *h = get_handle(env, argv[0]);
+	void *data = NULL; size_t len = 0;
+	NAPI_OK(napi_get_buffer_info(env, argv[1], &data, &len));
+	// non-blocking: the event loop must never stall (SURVEY.md 8b "Threading")
+	size_t done = 0;
+	while (done < len) {
+		void *p = NULL; size_t got = 0;
+		int32_t rc = mtz_ring_acquire(h, len - done, &p, &got);
+		if (rc == MTZ_EAGAIN) break;
+		if (rc != MTZ_OK) return throw_mtz(env, h, rc);
+		memcpy(p, (const char *)data + done, got);
+		rc = mtz_ring_commit(h, got);
+		if (rc != MTZ_OK) return throw_mtz(env, h, rc);
+		done += got;
+	}
+	napi_value out; napi_create_double(env, (double)done, &out);
+	return out;
+}
+
+static napi_value Flush(napi_env env, napi_callback_info info)
+{
+	size_t argc = 1; napi_value argv[1];
+	NAPI_OK(napi_get_cb_info(env, info, &argc, argv, NULL, NULL));
+	mtz_handle *h = get_handle(env, argv[0]);
+	int32_t rc = mtz_flush(h);
+	if (rc != MTZ_OK) return throw_mtz(env, h, rc);
+	return NULL;
+}
+
+static napi_value Peek(napi_env env, napi_callback_info info)
+{
+	size_t argc = 1; napi_value argv[1];
+	NAPI_OK(napi_get_cb_info(env, info, &argc, argv, NULL, NULL));
+	mtz_handle *h = get_handle(env, argv[0]);
+	const void *p = NULL; size_t n = 0;
+	int32_t rc = mtz_out_peek(h, &p, &n);
+	napi_value out;
+	if (rc == MTZ_EAGAIN) { napi_get_null(env, &out); return out; }
+	if (rc == MTZ_EOF) { napi_create_string_utf8(env, "eof", 3, &out); return out; }
+	if (rc != MTZ_OK) return throw_mtz(env, h, rc);
+	NAPI_OK(napi_create_external_arraybuffer(env, (void *)p, n, noop_finalize, NULL, &out));
+	return out;
+}
+
+static napi_value Consume(napi_env env, napi_callback_info info)
+{
+	size_t argc = 2; napi_value argv[2];
+	NAPI_OK(napi_get_cb_info(env, info, &argc, argv, NULL, NULL));
+	mtz_handle *h = get_handle(env, argv[0]);
+	uint32_t n = 0; napi_get_value_uint32(env, argv[1], &n);
+	int32_t rc = mtz_out_consume(h, n);
+	if (rc != MTZ_OK) return throw_mtz(env, h, rc);
+	return NULL;
+}
+
+static napi_value EventFd(napi_env env, napi_callback_info info)
+{
+	size_t argc = 1; napi_value argv[1];
+	NAPI_OK(napi_get_cb_info(env, info, &argc, argv, NULL, NULL));
+	mtz_handle *h = get_handle(env, argv[0]);
+	napi_value out; napi_create_int32(env, mtz_event_fd(h), &out);
+	return out;
+}
+
+static napi_value Stats(napi_env env, napi_callback_info info)
+{
+	size_t argc = 1; napi_value argv[1];
+	NAPI_OK(napi_get_cb_info(env, info, &argc, argv, NULL, NULL));
+	mtz_handle *h = get_handle(env, argv[0]);
+	mtz_stats st;
+	int32_t rc = mtz_get_stats(h, &st);
+	if (rc != MTZ_OK) return throw_mtz(env, h, rc);
+	napi_value o, v; napi_create_object(env, &o);
+#define PUT(name, field) napi_create_double(env, (double)st.field, &v); napi_set_named_property(env, o, name, v)
+	PUT("bytesIn", bytes_in); PUT("bytesOut", bytes_out); PUT("records", records);
+	PUT("writeRecords", write_records); PUT("lz4Decoded", lz4_decoded); PUT("lz4Encoded", lz4_encoded);
+	PUT("batches", batches); PUT("gpuMs", gpu_ms); PUT("kernelLaunches", kernel_launches);
+#undef PUT
+	return o;
+}
+
+static napi_value Close(napi_env env, napi_callback_info info)
+{
+	size_t argc = 1; napi_value argv[1];
+	NAPI_OK(napi_get_cb_info(env, info, &argc, argv, NULL, NULL));
+	mtz_close(get_handle(env, argv[0]));
+	return NULL;
+}
+
+static napi_value Init(napi_env env, napi_value exports)
+{
+	napi_property_descriptor d[] = {
+		{"open", 0, Open, 0, 0, 0, napi_default, 0}, {"acquire", 0, Acquire, 0, 0, 0, napi_default, 0},
+		{"commit", 0, Commit, 0, 0, 0, napi_default, 0}, {"write", 0, Write, 0, 0, 0, napi_default, 0},
+		{"flush", 0, Flush, 0, 0, 0, napi_default, 0}, {"peek", 0, Peek, 0, 0, 0, napi_default, 0},
+		{"consume", 0, Consume, 0, 0, 0, napi_default, 0}, {"eventFd", 0, EventFd, 0, 0, 0, napi_default, 0},
+		{"stats", 0, Stats, 0, 0, 0, napi_default, 0}, {"close", 0, Close, 0, 0, 0, napi_default, 0},
+	};
+	napi_define_properties(env, exports, sizeof d / sizeof d[0], d);
+	return exports;
+}
+
+NAPI_MODULE(manatee_gpu, Init)
