@@ -121,7 +121,7 @@ __device__ __forceinline__ uint32_t ld32u(const uint8_t *p)
 	const uintptr_t a = (uintptr_t)p;
 	const uint32_t *w = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
 	const uint32_t sh = (uint32_t)(a & 3u) * 8u;
-	return __funnelshift_r(w[0], w[1], sh);
+	return __funnelshift_r(__ldg(w), __ldg(w + 1), sh);       // source is read-only while encoding
 }
 
 // sum_{i<x} ((67+i)>>6): distance covered by the first x search attempts
@@ -131,19 +131,148 @@ __device__ __forceinline__ uint32_t skip_dist(uint32_t x)
 	return 64u * (q * (q - 1u) / 2u) + q * r - 3u;
 }
 
-template <int LOG, bool DIST> struct Lz4Tab;
-template <> struct Lz4Tab<12, true> {          // isize >= 64 KiB + 11: u32 positions
+// ---- hash tables (shared memory, one per warp) ----------------------------
+struct TabU32 {                                 // 4096 x u32: any block size
 	uint32_t *t;
+	static constexpr int LOG = 12;
+	__device__ __forceinline__ void clear(int lane) const {
+		for (int i = lane; i < 4096; i += 32) t[i] = 0;
+	}
 	__device__ __forceinline__ uint32_t get(uint32_t h) const { return t[h]; }
 	__device__ __forceinline__ void set(uint32_t h, uint32_t v) const { t[h] = v; }
 };
-template <> struct Lz4Tab<13, false> {         // small blocks: u16 positions, 8192 slots
+struct TabU16 {                                 // 8192 x u16: blocks below 64 KiB + 11
 	uint32_t *t;
+	static constexpr int LOG = 13;
+	__device__ __forceinline__ void clear(int lane) const {
+		for (int i = lane; i < 4096; i += 32) t[i] = 0;
+	}
 	__device__ __forceinline__ uint32_t get(uint32_t h) const { return reinterpret_cast<uint16_t *>(t)[h]; }
 	__device__ __forceinline__ void set(uint32_t h, uint32_t v) const { reinterpret_cast<uint16_t *>(t)[h] = (uint16_t)v; }
 };
+struct Tab17 {                                  // 4096 x 17 bit: blocks up to 128 KiB in 8.5 KiB
+	uint32_t *t;                                // [0,2048) u16 pairs, [2048,2176) bit 16 of each slot
+	static constexpr int LOG = 12;
+	__device__ __forceinline__ void clear(int lane) const {
+		for (int i = lane; i < 2176; i += 32) t[i] = 0;
+	}
+	__device__ __forceinline__ uint32_t get(uint32_t h) const {
+		const uint32_t lo = reinterpret_cast<uint16_t *>(t)[h];
+		const uint32_t hi = (t[2048u + (h >> 5)] >> (h & 31u)) & 1u;
+		return lo | (hi << 16);
+	}
+	__device__ __forceinline__ void set(uint32_t h, uint32_t v) const {
+		reinterpret_cast<uint16_t *>(t)[h] = (uint16_t)v;
+		if (v >> 16) atomicOr(&t[2048u + (h >> 5)], 1u << (h & 31u));
+		else atomicAnd(&t[2048u + (h >> 5)], ~(1u << (h & 31u)));
+	}
+};
 
-#define LZ4_TABLE_WORDS 4096                    // 16 KiB of shared memory per warp
+#define LZ4_TAB_BIG_WORDS     4096u             // TabU32 / TabU16: 16 KiB
+#define LZ4_TAB_COMPACT_WORDS 2176u             // Tab17: 8.5 KiB
+
+// ---- sliding window of the source in shared memory ------------------------
+// The matcher reads the source at the scan front (sequential) and at recent
+// candidates (mostly a few KiB back).  A per-warp ring of LZ4_WIN bytes, filled
+// ahead of the scan with cp.async (16 B per lane, 512 B per fill), turns those
+// reads into ~30-cycle shared-memory loads; anything older falls back to global.
+// Measured on B200 (profiles/r1_k3_encode.md): K3 is bound by dependent
+// instruction / shared-memory latency at low occupancy, not by source-read
+// latency, so the window costs more (shared memory -> fewer warps, residency
+// checks -> more instructions) than it saves.  LZ4_WIN = 0 compiles it out; the
+// code stays for experiments with larger dictionaries.
+#ifndef LZ4_WIN
+#define LZ4_WIN 0u
+#endif
+#define LZ4_AHEAD 3072u
+
+struct SrcWin {
+	const uint8_t *g;          // source (global)
+	const uint8_t *ga;         // g rounded down to 16 B; sx = x + skew indexes it
+	uint32_t *ring;            // LZ4_WIN bytes of shared memory
+	uint32_t skew, issued, ready, limit;   // skewed coordinates; issued/ready multiples of 512
+	int lane;
+
+#if LZ4_WIN == 0
+	// no ring: keep the scan front warm in L2 instead (the record is streamed
+	// from HBM exactly once; without this every new line costs a DRAM round trip)
+	uint32_t pf_hi, pf_lim;
+	__device__ __forceinline__ void init(const uint8_t *src, uint32_t isize, uint32_t *, int ln)
+	{
+		g = src; lane = ln; pf_hi = 0; pf_lim = isize;
+	}
+	__device__ __forceinline__ void prefetch(uint32_t x_hi)
+	{
+		const uint32_t want = min(pf_lim, x_hi);
+		if (want > pf_hi) {
+			const uint32_t x = pf_hi + 128u * (uint32_t)lane;
+			if (x < want) asm volatile("prefetch.global.L2 [%0];" :: "l"(g + x));
+			pf_hi = min(want, pf_hi + 4096u);
+		}
+	}
+	__device__ __forceinline__ void ensure(uint32_t) {}
+	__device__ __forceinline__ uint32_t rd32(uint32_t x) const { return ld32u(g + x); }
+	__device__ __forceinline__ uint32_t rd8(uint32_t x) const { return g[x]; }
+#else
+	__device__ __forceinline__ void init(const uint8_t *src, uint32_t isize, uint32_t *r, int ln)
+	{
+		g = src; ring = r; lane = ln;
+		skew = (uint32_t)((uintptr_t)src & 15u);
+		ga = src - skew;
+		limit = ((skew + isize + 15u) & ~15u) + 16u;
+		issued = ready = 0;
+	}
+	__device__ __forceinline__ void fill_one()
+	{
+		const uint32_t sx = issued + 16u * (uint32_t)lane;
+		if (sx < limit) {
+			const uint32_t dst = (uint32_t)__cvta_generic_to_shared(
+			    reinterpret_cast<uint8_t *>(ring) + (sx & (LZ4_WIN - 1u)));
+			asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(ga + sx) : "memory");
+		}
+		issued += 512u;
+	}
+	// request bytes up to source position x_hi (non-blocking)
+	__device__ __forceinline__ void prefetch(uint32_t x_hi)
+	{
+		const uint32_t want = min(limit, skew + x_hi);
+		bool any = false;
+		while (issued < want && issued - ready < LZ4_WIN - 512u) { fill_one(); any = true; }
+		if (any) asm volatile("cp.async.commit_group;" ::: "memory");
+	}
+	// make [.., x_hi) resident if the ring can hold it (blocking)
+	__device__ __forceinline__ void ensure(uint32_t x_hi)
+	{
+		const uint32_t want = min(limit, skew + x_hi);
+		if (want <= ready) return;
+		prefetch(x_hi);
+		asm volatile("cp.async.wait_all;" ::: "memory");
+		__syncwarp();
+		ready = issued;
+	}
+	__device__ __forceinline__ bool resident(uint32_t sx, uint32_t n) const
+	{
+		const uint32_t lo = issued > LZ4_WIN ? issued - LZ4_WIN : 0u;
+		return sx >= lo && sx + n <= ready;
+	}
+	__device__ __forceinline__ uint32_t rd32(uint32_t x) const
+	{
+		const uint32_t sx = x + skew;
+		if (resident(sx, 4u)) {
+			const uint32_t i = sx & (LZ4_WIN - 1u);
+			const uint32_t w0 = ring[i >> 2], w1 = ring[((i >> 2) + 1u) & (LZ4_WIN / 4u - 1u)];
+			return __funnelshift_r(w0, w1, (i & 3u) * 8u);
+		}
+		return ld32u(g + x);
+	}
+	__device__ __forceinline__ uint32_t rd8(uint32_t x) const
+	{
+		const uint32_t sx = x + skew;
+		if (resident(sx, 1u)) return reinterpret_cast<const uint8_t *>(ring)[sx & (LZ4_WIN - 1u)];
+		return g[x];
+	}
+#endif
+};
 
 // cooperative store of a 255-run length extension (value = len - 15 already)
 __device__ __forceinline__ uint32_t put_len_ext(uint8_t *dst, uint32_t op, uint32_t v, int lane)
@@ -155,13 +284,17 @@ __device__ __forceinline__ uint32_t put_len_ext(uint8_t *dst, uint32_t op, uint3
 }
 
 // returns the LZ4 block size, or 0 when it does not fit in osize
-template <int LOG, bool DIST>
+template <class TAB, bool DIST>
 __device__ __forceinline__ uint32_t warp_lz4_encode(const uint8_t *__restrict__ src,
-    uint32_t isize, uint8_t *__restrict__ dst, uint32_t osize, uint32_t *tabmem, int lane)
+    uint32_t isize, uint8_t *__restrict__ dst, uint32_t osize, uint32_t *tabmem,
+    uint32_t *ringmem, int lane)
 {
-	Lz4Tab<LOG, DIST> tab; tab.t = tabmem;
+	constexpr int LOG = TAB::LOG;
+	TAB tab; tab.t = tabmem;
+	SrcWin win; win.init(src, isize, ringmem, lane);
 	const uint32_t lanebit = 1u << lane, lower = lanebit - 1u;
-	for (int i = lane; i < LZ4_TABLE_WORDS; i += 32) tabmem[i] = 0;
+	tab.clear(lane);
+	win.prefetch(LZ4_AHEAD);
 	__syncwarp();
 
 	uint32_t ip = 0, anchor = 0, op = 0;
@@ -180,18 +313,21 @@ __device__ __forceinline__ uint32_t warp_lz4_encode(const uint8_t *__restrict__ 
 				const uint32_t p = start + skip_dist(a);
 				const uint32_t step = (67u + a) >> 6;
 				const bool valid = (p + step <= mflimit);
+				// positions of this round end below start + skip_dist(a0 + 32) + 4
+				win.ensure(min(iend, start + skip_dist(a0 + 32u) + 8u));
 				uint32_t h = 0xffffffffu - (uint32_t)lane, cand = 0, v = 0;
 				if (valid) {
-					v = ld32u(src + p);
+					v = win.rd32(p);
 					h = (v * 2654435761u) >> (32 - LOG);
 				}
-				const uint32_t same = __match_any_sync(0xffffffffu, h) & lower;
+				const uint32_t all_same = __match_any_sync(0xffffffffu, h);
+				const uint32_t same = all_same & lower;
 				const int from = same ? (31 - __clz((int)same)) : lane;
 				const uint32_t fwd = __shfl_sync(0xffffffffu, p, from);
 				bool hit = false;
 				if (valid) {
 					cand = same ? fwd : tab.get(h);
-					if (!DIST || cand + LZ4_MAXDIST >= p) hit = (ld32u(src + cand) == v);
+					if (!DIST || cand + LZ4_MAXDIST >= p) hit = (win.rd32(cand) == v);
 				}
 				const uint32_t hits = __ballot_sync(0xffffffffu, hit);
 				const uint32_t inval = __ballot_sync(0xffffffffu, !valid);
@@ -201,7 +337,6 @@ __device__ __forceinline__ uint32_t warp_lz4_encode(const uint8_t *__restrict__ 
 				// commit table updates of lanes <= F (the last equal-hash lane wins)
 				{
 					const uint32_t upto = (F >= 31) ? 0xffffffffu : ((2u << F) - 1u);
-					const uint32_t all_same = __match_any_sync(0xffffffffu, h);
 					const uint32_t later = all_same & ~(lanebit | lower) & upto;
 					if ((lanebit & upto) && later == 0u) tab.set(h, p);
 				}
@@ -211,6 +346,7 @@ __device__ __forceinline__ uint32_t warp_lz4_encode(const uint8_t *__restrict__ 
 					ref = __shfl_sync(0xffffffffu, cand, F);
 					break;
 				}
+				win.prefetch(start + skip_dist(a0 + 64u) + LZ4_AHEAD);
 			}
 			if (to_tail) break;
 
@@ -218,7 +354,7 @@ __device__ __forceinline__ uint32_t warp_lz4_encode(const uint8_t *__restrict__ 
 			for (;;) {
 				const uint32_t k = (uint32_t)lane + 1u;
 				bool eq = false;
-				if (ip >= anchor + k && ref >= k) eq = (src[ip - k] == src[ref - k]);
+				if (ip >= anchor + k && ref >= k) eq = (win.rd8(ip - k) == win.rd8(ref - k));
 				const uint32_t ne = ~__ballot_sync(0xffffffffu, eq);
 				const uint32_t n = ne ? (uint32_t)(__ffs((int)ne) - 1) : 32u;
 				ip -= n; ref -= n;
@@ -236,7 +372,7 @@ __device__ __forceinline__ uint32_t warp_lz4_encode(const uint8_t *__restrict__ 
 			} else {
 				tokval = litlen << 4;
 			}
-			for (uint32_t i = (uint32_t)lane; i < litlen; i += 32u) dst[op + i] = src[anchor + i];
+			for (uint32_t i = (uint32_t)lane; i < litlen; i += 32u) dst[op + i] = (uint8_t)win.rd8(anchor + i);
 			op += litlen;
 
 			// ------------------------------- one or more back-to-back matches --
@@ -250,11 +386,12 @@ __device__ __forceinline__ uint32_t warp_lz4_encode(const uint8_t *__restrict__ 
 				anchor = ip;
 				// common prefix of src+ref and src+ip, ip bounded by matchlimit
 				for (;;) {
+					win.ensure(min(iend, ip + 132u));
 					const uint32_t o = 4u * (uint32_t)lane;
 					const uint32_t room = (ip + o < matchlimit) ? (matchlimit - ip - o) : 0u;
 					uint32_t n = 0;
 					if (room) {
-						const uint32_t x = ld32u(src + ip + o) ^ ld32u(src + ref + o);
+						const uint32_t x = win.rd32(ip + o) ^ win.rd32(ref + o);
 						n = x ? (uint32_t)((__ffs((int)x) - 1) >> 3) : 4u;
 						if (n > room) n = room;
 					}
@@ -263,6 +400,7 @@ __device__ __forceinline__ uint32_t warp_lz4_encode(const uint8_t *__restrict__ 
 					const uint32_t adv = (Fp < 32) ? (4u * (uint32_t)Fp + __shfl_sync(0xffffffffu, n, Fp & 31)) : 128u;
 					ip += adv; ref += adv;
 					if (Fp < 32) break;
+					win.prefetch(ip + 128u + LZ4_AHEAD);
 				}
 				uint32_t mlen = ip - anchor;
 				if (op + (1u + LZ4_LASTLITERALS) + (mlen >> 8) > osize) return 0u;
@@ -278,21 +416,250 @@ __device__ __forceinline__ uint32_t warp_lz4_encode(const uint8_t *__restrict__ 
 
 				// insert ip-2, then probe ip for an immediate follow-on match
 				{
-					const uint32_t h2 = (ld32u(src + ip - 2) * 2654435761u) >> (32 - LOG);
+					win.ensure(min(iend, ip + 8u));
+					const uint32_t h2 = (win.rd32(ip - 2u) * 2654435761u) >> (32 - LOG);
 					if (lane == 0) tab.set(h2, ip - 2u);
 					__syncwarp();
-					const uint32_t v = ld32u(src + ip);
+					const uint32_t v = win.rd32(ip);
 					const uint32_t h = (v * 2654435761u) >> (32 - LOG);
 					ref = tab.get(h);
 					__syncwarp();
 					if (lane == 0) tab.set(h, ip);
 					__syncwarp();
-					if ((!DIST || ref + LZ4_MAXDIST >= ip) && ld32u(src + ref) == v) {
+					if ((!DIST || ref + LZ4_MAXDIST >= ip) && win.rd32(ref) == v) {
 						token = op++;
 						tokval = 0;
 						continue;
 					}
 				}
+				break;
+			}
+			if (to_tail) break;
+			anchor = ip++;
+			win.prefetch(ip + LZ4_AHEAD);
+		}
+	}
+	// ---------------------------------------------------- last literals --
+	{
+		const uint32_t last = iend - anchor;
+		if (op + last + 1u + ((last + 255u - 15u) / 255u) > osize) return 0u;
+		if (last >= 15u) {
+			if (lane == 0) dst[op] = (uint8_t)(15u << 4);
+			op = put_len_ext(dst, op + 1u, last - 15u, lane);
+		} else {
+			if (lane == 0) dst[op] = (uint8_t)(last << 4);
+			op += 1u;
+		}
+		for (uint32_t i = (uint32_t)lane; i < last; i += 32u) dst[op + i] = src[anchor + i];
+		op += last;
+	}
+	return op;
+}
+
+// ---------------------------------------------------------------------------
+// v3 of the same bit-exact matcher with the dependent global round trips of one
+// LZ4 sequence merged from seven to three (profiles/r1_k3_encode.md: K3 is bound
+// by latency chains at <= 24 warps/SM, not by bandwidth):
+//   trip A  candidate gather of a search round (positions come preloaded)
+//   trip B  catch-up bytes + first 32 literals + first match-extension round
+//   trip C  follow-on probe + its extension round + next search round's positions
+// The 6 bytes around the match end that the table inserts hash come out of the
+// extension round's registers by shuffle.
+struct ExtRound {            // one 128-byte extension round held in registers
+	uint32_t wa, wb;         // words at ip0 + 4*lane and ref0 + 4*lane (0 when not loaded)
+};
+
+__device__ __forceinline__ ExtRound ext_load(const uint8_t *src, uint32_t ip0, uint32_t ref0,
+    uint32_t iend, int lane)
+{
+	ExtRound e; e.wa = 0; e.wb = 0;
+	const uint32_t o = 4u * (uint32_t)lane;
+	if (ip0 + o + 4u <= iend) { e.wa = ld32u(src + ip0 + o); e.wb = ld32u(src + ref0 + o); }
+	return e;
+}
+
+__device__ __forceinline__ uint32_t extract32(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t off)
+{
+	return (off < 4u) ? __funnelshift_r(w0, w1, off * 8u) : __funnelshift_r(w1, w2, (off - 4u) * 8u);
+}
+
+template <class TAB, bool DIST>
+__device__ __forceinline__ uint32_t warp_lz4_encode3(const uint8_t *__restrict__ src,
+    uint32_t isize, uint8_t *__restrict__ dst, uint32_t osize, uint32_t *tabmem, int lane)
+{
+	constexpr int LOG = TAB::LOG;
+	TAB tab; tab.t = tabmem;
+	const uint32_t lanebit = 1u << lane, lower = lanebit - 1u;
+	tab.clear(lane);
+	__syncwarp();
+
+	uint32_t ip = 0, anchor = 0, op = 0;
+	const uint32_t iend = isize;
+	if (isize >= (uint32_t)LZ4_MINLENGTH) {
+		const uint32_t mflimit = iend - LZ4_MFLIMIT;
+		const uint32_t matchlimit = iend - LZ4_LASTLITERALS;
+		ip = 1;
+		bool have_pre = false;         // vpre holds rd32(start + lane) for the next search
+		uint32_t vpre = 0;
+		for (;;) {
+			// ------------------------------------------------ search (trip A per round)
+			uint32_t ref = 0;
+			bool to_tail = false;
+			const uint32_t start = ip;
+			for (uint32_t a0 = 0;; a0 += 32u) {
+				const uint32_t a = a0 + (uint32_t)lane;
+				const uint32_t p = start + skip_dist(a);
+				const uint32_t step = (67u + a) >> 6;
+				const bool valid = (p + step <= mflimit);
+				uint32_t h = 0xffffffffu - (uint32_t)lane, cand = 0, v = 0;
+				if (valid) {
+					v = (a0 == 0u && have_pre) ? vpre : ld32u(src + p);
+					h = (v * 2654435761u) >> (32 - LOG);
+				}
+				const uint32_t all_same = __match_any_sync(0xffffffffu, h);
+				const uint32_t same = all_same & lower;
+				const int from = same ? (31 - __clz((int)same)) : lane;
+				const uint32_t fwd = __shfl_sync(0xffffffffu, p, from);
+				bool hit = false;
+				if (valid) {
+					cand = same ? fwd : tab.get(h);
+					if (!DIST || cand + LZ4_MAXDIST >= p) hit = (ld32u(src + cand) == v);
+				}
+				const uint32_t hits = __ballot_sync(0xffffffffu, hit);
+				const uint32_t inval = __ballot_sync(0xffffffffu, !valid);
+				const int F = hits ? (__ffs((int)hits) - 1) : 32;
+				const int I = inval ? (__ffs((int)inval) - 1) : 32;
+				if (I < F) { to_tail = true; break; }
+				{
+					const uint32_t upto = (F >= 31) ? 0xffffffffu : ((2u << F) - 1u);
+					const uint32_t later = all_same & ~(lanebit | lower) & upto;
+					if ((lanebit & upto) && later == 0u) tab.set(h, p);
+				}
+				__syncwarp();
+				if (F < 32) {
+					ip = __shfl_sync(0xffffffffu, p, F);
+					ref = __shfl_sync(0xffffffffu, cand, F);
+					break;
+				}
+			}
+			have_pre = false;
+			if (to_tail) break;
+
+			// ------------------------------------------------ trip B: issue everything
+			// that depends only on (ip, ref) before consuming any of it
+			const uint32_t k = (uint32_t)lane + 1u;
+			const bool cu_ok = (ip >= anchor + k && ref >= k);
+			uint32_t ca = 0, cb = 1;
+			if (cu_ok) { ca = src[ip - k]; cb = src[ref - k]; }
+			uint32_t lit0 = 0;
+			if (anchor + (uint32_t)lane < ip) lit0 = src[anchor + (uint32_t)lane];
+			ExtRound er = ext_load(src, ip, ref, iend, lane);   // lane 0 = the 4 matched bytes
+
+			// catch up (first 32 candidates from the preloaded bytes)
+			const uint32_t ip_pre = ip, ref_pre = ref;
+			{
+				const uint32_t ne = ~__ballot_sync(0xffffffffu, cu_ok && ca == cb);
+				uint32_t n = ne ? (uint32_t)(__ffs((int)ne) - 1) : 32u;
+				ip -= n; ref -= n;
+				while (n == 32u) {
+					bool eq = false;
+					if (ip >= anchor + k && ref >= k) eq = (src[ip - k] == src[ref - k]);
+					const uint32_t ne2 = ~__ballot_sync(0xffffffffu, eq);
+					n = ne2 ? (uint32_t)(__ffs((int)ne2) - 1) : 32u;
+					ip -= n; ref -= n;
+				}
+			}
+
+			// ---------------------------------------------- literals --
+			const uint32_t litlen = ip - anchor;
+			uint32_t token = op++;
+			if (op + litlen + (2u + 1u + LZ4_LASTLITERALS) + (litlen >> 8) > osize) return 0u;
+			uint32_t tokval;
+			if (litlen >= 15u) {
+				tokval = 15u << 4;
+				op = put_len_ext(dst, op, litlen - 15u, lane);
+			} else {
+				tokval = litlen << 4;
+			}
+			if ((uint32_t)lane < litlen) dst[op + (uint32_t)lane] = (uint8_t)lit0;
+			for (uint32_t i = 32u + (uint32_t)lane; i < litlen; i += 32u) dst[op + i] = src[anchor + i];
+			op += litlen;
+
+			// ------------------------------- one or more back-to-back matches --
+			uint32_t ext_ip = ip_pre, ext_ref = ref_pre;     // where round `er` starts
+			for (;;) {
+				if (lane == 0) {
+					dst[op] = (uint8_t)((ip - ref) & 0xffu);
+					dst[op + 1] = (uint8_t)((ip - ref) >> 8);
+				}
+				op += 2;
+				anchor = ip + LZ4_MINMATCH;
+				// extension: rounds of 128 bytes from (ext_ip, ext_ref); round 0 preloaded
+				uint32_t prev31 = 0, v_end = 0, v_m2 = 0;
+				for (;;) {
+					const uint32_t o = 4u * (uint32_t)lane;
+					const uint32_t room = (ext_ip + o < matchlimit) ? (matchlimit - ext_ip - o) : 0u;
+					uint32_t n = 0;
+					if (room) {
+						const uint32_t x = er.wa ^ er.wb;
+						n = x ? (uint32_t)((__ffs((int)x) - 1) >> 3) : 4u;
+						if (n > room) n = room;
+					}
+					const uint32_t part = __ballot_sync(0xffffffffu, n < 4u);
+					if (part) {
+						const int Fp = __ffs((int)part) - 1;
+						const uint32_t nf = __shfl_sync(0xffffffffu, n, Fp);
+						ip = ext_ip + 4u * (uint32_t)Fp + nf;
+						// bytes [ip-2, ip+4) from the registers of lanes Fp-1, Fp, Fp+1
+						const uint32_t w1 = __shfl_sync(0xffffffffu, er.wa, Fp);
+						uint32_t w0 = __shfl_sync(0xffffffffu, er.wa, (Fp + 31) & 31);
+						uint32_t w2 = __shfl_sync(0xffffffffu, er.wa, (Fp + 1) & 31);
+						if (Fp == 0) w0 = prev31;
+						if (Fp == 31 && nf > 0u) w2 = (ip + 4u <= iend) ? ld32u(src + ext_ip + 128u) : 0u;
+						v_m2 = extract32(w0, w1, w2, nf + 2u);
+						v_end = extract32(w0, w1, w2, nf + 4u);
+						break;
+					}
+					prev31 = __shfl_sync(0xffffffffu, er.wa, 31);
+					ext_ip += 128u; ext_ref += 128u;
+					er = ext_load(src, ext_ip, ext_ref, iend, lane);
+				}
+				uint32_t mlen = ip - anchor;
+				if (op + (1u + LZ4_LASTLITERALS) + (mlen >> 8) > osize) return 0u;
+				if (mlen >= 15u) {
+					tokval += 15u;
+					op = put_len_ext(dst, op, mlen - 15u, lane);
+				} else {
+					tokval += mlen;
+				}
+				if (lane == 0) dst[token] = (uint8_t)tokval;
+
+				if (ip > mflimit) { anchor = ip; to_tail = true; break; }
+
+				// insert ip-2, then probe ip (trip C carries the probe, its extension
+				// round and the next search round's positions)
+				const uint32_t h2 = (v_m2 * 2654435761u) >> (32 - LOG);
+				if (lane == 0) tab.set(h2, ip - 2u);
+				__syncwarp();
+				const uint32_t hh = (v_end * 2654435761u) >> (32 - LOG);
+				const uint32_t pref = tab.get(hh);
+				__syncwarp();
+				if (lane == 0) tab.set(hh, ip);
+				__syncwarp();
+				const uint32_t np = ip + 1u + (uint32_t)lane;          // next search, step 1
+				uint32_t vn = 0;
+				if (np + 1u <= mflimit) vn = ld32u(src + np);
+				ExtRound e2 = ext_load(src, ip, pref, iend, lane);
+				const bool probe_hit = (!DIST || pref + LZ4_MAXDIST >= ip) &&
+				    (__shfl_sync(0xffffffffu, e2.wb, 0) == v_end);
+				if (probe_hit) {
+					ref = pref;
+					token = op++;
+					tokval = 0;
+					er = e2; ext_ip = ip; ext_ref = ref;
+					continue;
+				}
+				vpre = vn; have_pre = true;
 				break;
 			}
 			if (to_tail) break;
@@ -316,18 +683,42 @@ __device__ __forceinline__ uint32_t warp_lz4_encode(const uint8_t *__restrict__ 
 	return op;
 }
 
+#ifndef LZ4_ENC_V3
+#define LZ4_ENC_V3 1
+#endif
+
 // zio_compress_data(LZ4) + 512 B sector rounding.  out_len = psize (frame
-// stored at dst) or lsize (store raw: dst content is scratch).
+// stored at dst) or lsize (store raw: dst content is scratch).  COMPACT: the
+// launch reserved only the 8.5 KiB table (every block is 64 KiB+11 .. 128 KiB).
+template <bool COMPACT>
 __device__ __forceinline__ uint32_t warp_zfs_lz4_compress(const uint8_t *__restrict__ src,
-    uint32_t lsize, uint8_t *__restrict__ dst, uint32_t *tabmem, int lane)
+    uint32_t lsize, uint8_t *__restrict__ dst, uint32_t *tabmem, uint32_t *ringmem, int lane)
 {
 	const uint32_t d_len = lsize - (lsize >> 3);
 	if (lsize < 1024u || lsize > (16u << 20) || d_len < 4u) return lsize;
 	uint32_t blk;
-	if (lsize < (uint32_t)LZ4_64KLIMIT)
-		blk = warp_lz4_encode<13, false>(src, lsize, dst + 4, d_len - 4u, tabmem, lane);
+#if LZ4_ENC_V3
+	(void)ringmem;
+	if (COMPACT)
+		blk = warp_lz4_encode3<Tab17, true>(src, lsize, dst + 4, d_len - 4u, tabmem, lane);
+	else if (lsize < (uint32_t)LZ4_64KLIMIT)
+		blk = warp_lz4_encode3<TabU16, false>(src, lsize, dst + 4, d_len - 4u, tabmem, lane);
 	else
-		blk = warp_lz4_encode<12, true>(src, lsize, dst + 4, d_len - 4u, tabmem, lane);
+		blk = warp_lz4_encode3<TabU32, true>(src, lsize, dst + 4, d_len - 4u, tabmem, lane);
+#else
+	if (COMPACT)
+		blk = warp_lz4_encode<Tab17, true>(src, lsize, dst + 4, d_len - 4u, tabmem, ringmem, lane);
+	else if (lsize < (uint32_t)LZ4_64KLIMIT)
+		blk = warp_lz4_encode<TabU16, false>(src, lsize, dst + 4, d_len - 4u, tabmem, ringmem, lane);
+	else
+		blk = warp_lz4_encode<TabU32, true>(src, lsize, dst + 4, d_len - 4u, tabmem, ringmem, lane);
+#endif
+	// every exit of the encoder: nothing may still land in the ring once the
+	// warp moves on to its next record
+#if LZ4_WIN != 0
+	asm volatile("cp.async.wait_all;" ::: "memory");
+#endif
+	__syncwarp();
 	if (blk == 0u) return lsize;
 	const uint32_t c_len = blk + 4u;
 	if (c_len > d_len) return lsize;
@@ -341,20 +732,31 @@ __device__ __forceinline__ uint32_t warp_zfs_lz4_compress(const uint8_t *__restr
 	return psize;
 }
 
+// per-warp shared memory: [table | ring]
+template <bool COMPACT>
 __global__ void __launch_bounds__(LZ4_THREADS)
 k3_lz4_encode(const uint8_t *__restrict__ src_base, uint8_t *__restrict__ dst_base,
     mtz_job *__restrict__ jobs, uint32_t njobs)
 {
-	extern __shared__ uint32_t s_tab[];               // LZ4_WARPS x 16 KiB
+	extern __shared__ uint4 s_dyn[];
+	constexpr uint32_t TABW = COMPACT ? LZ4_TAB_COMPACT_WORDS : LZ4_TAB_BIG_WORDS;
+	constexpr uint32_t PERW = TABW + LZ4_WIN / 4u;
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	uint32_t *tab = s_tab + warp * LZ4_TABLE_WORDS;
+	uint32_t *tab = reinterpret_cast<uint32_t *>(s_dyn) + warp * PERW;
+	uint32_t *ring = tab + TABW;
 	const uint32_t gw = blockIdx.x * LZ4_WARPS + (uint32_t)warp;
 	const uint32_t nw = gridDim.x * LZ4_WARPS;
 	for (uint32_t j = gw; j < njobs; j += nw) {
 		const mtz_job job = jobs[j];
 		if (job.lsize == 0u) continue;
-		const uint32_t ps = warp_zfs_lz4_compress(src_base + job.src_off, job.lsize,
-		    dst_base + job.dst_off, tab, lane);
+		// a compact launch is only made when the host saw nothing but 128 KiB-class
+		// blocks; anything else it might meet is stored raw (never wrong, only bigger)
+		uint32_t ps;
+		if (COMPACT && (job.lsize < (uint32_t)LZ4_64KLIMIT || job.lsize > 131072u))
+			ps = job.lsize;
+		else
+			ps = warp_zfs_lz4_compress<COMPACT>(src_base + job.src_off, job.lsize,
+			    dst_base + job.dst_off, tab, ring, lane);
 		__syncwarp();
 		if (lane == 0) { jobs[j].out_len = ps; jobs[j].status = MTZ_OK; }
 	}

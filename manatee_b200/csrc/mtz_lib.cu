@@ -447,8 +447,20 @@ static int32_t codec_reset(mtz_handle *h, cudaStream_t st, CodecBufs &cb)
 
 // Part 1 of the re-encoding pipeline of one (sub-)batch: plan + K2 + K3.  It
 // does not touch the running checksums, so it may run ahead of the chain.
+static int32_t launch_k3(mtz_handle *h, cudaStream_t st, const void *d_src, void *d_dst,
+    mtz_job *d_jobs, uint32_t njobs, bool compact);
+
+// true when every DRR_WRITE of the table has a 128 KiB-class logical size
+static bool all_compact_blocks(const mtz_rec *recs, size_t n)
+{
+	for (size_t i = 0; i < n; i++)
+		if (recs[i].type == 3 && (recs[i].lsize < (uint32_t)LZ4_64KLIMIT || recs[i].lsize > 131072u))
+			return false;
+	return true;
+}
+
 static int32_t codec_launch_pre(mtz_handle *h, cudaStream_t st, CodecBufs &cb, const uint8_t *d_in,
-    const mtz_rec *d_recs, size_t nrec, cudaEvent_t ea, cudaEvent_t eb)
+    const mtz_rec *d_recs, size_t nrec, cudaEvent_t ea, cudaEvent_t eb, bool compact)
 {
 	if (nrec == 0) return MTZ_OK;
 	if (nrec > cb.rec_cap) return fail(h, MTZ_ENOSPC, "codec batch of %zu records exceeds %zu", nrec, cb.rec_cap);
@@ -465,7 +477,7 @@ static int32_t codec_launch_pre(mtz_handle *h, cudaStream_t st, CodecBufs &cb, c
 		if (rc != MTZ_OK) return rc;
 	}
 	if (mode != MTZ_MODE_DECOMPRESS) {
-		int32_t rc = mtz_k_lz4_encode(h, nullptr, nullptr, cb.enc, n, st);
+		int32_t rc = launch_k3(h, st, nullptr, nullptr, cb.enc, n, compact);
 		if (rc != MTZ_OK) return rc;
 	}
 	if (eb) MTZ_CU(h, cudaEventRecord(eb, st));
@@ -571,7 +583,7 @@ int32_t mtz_dev_submit(mtz_handle *h, const void *d_in, size_t in_bytes,
 			budget += cost; i1++;
 		}
 		rc = codec_launch_pre(h, st, h->dv_cb, (const uint8_t *)d_in, d_recs + i0, i1 - i0,
-		    first ? h->dv_c0 : nullptr, nullptr);
+		    first ? h->dv_c0 : nullptr, nullptr, all_compact_blocks(h->dv_hrecs.data() + i0, i1 - i0));
 		if (rc != MTZ_OK) return rc;
 		rc = codec_launch_post(h, st, h->dv_cb, (const uint8_t *)d_in, d_recs + i0, i1 - i0,
 		    (uint8_t *)d_out, (uint32_t)i0);
@@ -832,7 +844,8 @@ static int32_t submit_batch(mtz_handle *h, Slot &s, const uint8_t *p0, size_t n0
 			rc = codec_reset(h, s.st, s.cb);
 			if (rc != MTZ_OK) return rc;
 			// K2/K3 of this batch overlap the previous batch's checksum chains
-			rc = codec_launch_pre(h, s.st, s.cb, s.d_in, s.d_recs, nrec, s.ev_c0, s.ev_c1);
+			rc = codec_launch_pre(h, s.st, s.cb, s.d_in, s.d_recs, nrec, s.ev_c0, s.ev_c1,
+			    all_compact_blocks(s.h_recs, nrec));
 			if (rc != MTZ_OK) return rc;
 		}
 		if (h->have_prev_scan) MTZ_CU(h, cudaStreamWaitEvent(s.st, h->ev_prev_scan, 0));
@@ -1348,6 +1361,31 @@ int32_t mtz_k_lz4_decode(mtz_handle *h, const void *d_src, void *d_dst, mtz_job 
 	return MTZ_OK;
 }
 
+// compact = every block is 64 KiB+11 .. 128 KiB: 8.5 KiB tables, more warps per SM
+static int32_t launch_k3(mtz_handle *h, cudaStream_t st, const void *d_src, void *d_dst,
+    mtz_job *d_jobs, uint32_t njobs, bool compact)
+{
+	const size_t tabw = compact ? LZ4_TAB_COMPACT_WORDS : LZ4_TAB_BIG_WORDS;
+	const size_t smem = (size_t)LZ4_WARPS * (tabw + LZ4_WIN / 4) * sizeof(uint32_t);
+	static bool attr_set = false;
+	if (!attr_set) {
+		MTZ_CU(h, cudaFuncSetAttribute(k3_lz4_encode<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+		    (int)((size_t)LZ4_WARPS * (LZ4_TAB_COMPACT_WORDS + LZ4_WIN / 4) * 4)));
+		MTZ_CU(h, cudaFuncSetAttribute(k3_lz4_encode<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+		    (int)((size_t)LZ4_WARPS * (LZ4_TAB_BIG_WORDS + LZ4_WIN / 4) * 4)));
+		attr_set = true;
+	}
+	const int blocks_per_sm = (int)((227u * 1024u) / (smem + 1024));
+	const int grid = lz4_grid(h, njobs, blocks_per_sm * LZ4_WARPS);
+	if (compact)
+		k3_lz4_encode<true><<<grid, LZ4_THREADS, smem, st>>>((const uint8_t *)d_src, (uint8_t *)d_dst, d_jobs, njobs);
+	else
+		k3_lz4_encode<false><<<grid, LZ4_THREADS, smem, st>>>((const uint8_t *)d_src, (uint8_t *)d_dst, d_jobs, njobs);
+	MTZ_CU(h, cudaGetLastError());
+	count_launch(h, 1);
+	return MTZ_OK;
+}
+
 int32_t mtz_k_lz4_encode(mtz_handle *h, const void *d_src, void *d_dst, mtz_job *d_jobs,
     uint32_t njobs, void *cuda_stream)
 {
@@ -1355,17 +1393,7 @@ int32_t mtz_k_lz4_encode(mtz_handle *h, const void *d_src, void *d_dst, mtz_job 
 	if (njobs == 0) return MTZ_OK;
 	MTZ_CU(h, cudaSetDevice(h->device));
 	cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : h->st;
-	const size_t smem = (size_t)LZ4_WARPS * LZ4_TABLE_WORDS * sizeof(uint32_t);
-	static bool attr_set = false;
-	if (!attr_set) {
-		MTZ_CU(h, cudaFuncSetAttribute(k3_lz4_encode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-		attr_set = true;
-	}
-	k3_lz4_encode<<<lz4_grid(h, njobs, 12), LZ4_THREADS, smem, st>>>((const uint8_t *)d_src,
-	    (uint8_t *)d_dst, d_jobs, njobs);
-	MTZ_CU(h, cudaGetLastError());
-	count_launch(h, 1);
-	return MTZ_OK;
+	return launch_k3(h, st, d_src, d_dst, d_jobs, njobs, false);
 }
 
 // ------------------------------------------------- not yet implemented ----
