@@ -152,9 +152,10 @@ int32_t mtz_process_host(mtz_handle *h, const void *in, size_t n, void *out,
 /* host-side DRR parse: fills recs[] for whole records in [buf, buf+n) */
 int32_t mtz_index_host(const void *buf, size_t n, mtz_rec *recs, size_t cap,
     size_t *nrec, size_t *consumed);
-/* GPU-side DRR parse of a resident stream (speculative strided header walk) */
+/* GPU-side DRR parse of a resident stream (speculative strided header walk):
+ * fills d_recs (device) for the whole records in [d_in, d_in+n); synchronises. */
 int32_t mtz_dev_index(mtz_handle *h, const void *d_in, size_t n, mtz_rec *d_recs,
-    size_t cap, size_t *nrec, void *cuda_stream);
+    size_t cap, size_t *nrec, size_t *consumed, void *cuda_stream);
 /* enqueue one batch on cuda_stream (NULL = handle's stream).  Phase A computes
  * per-record Fletcher partials (+ codec work) and the batch aggregate. */
 int32_t mtz_dev_submit(mtz_handle *h, const void *d_in, size_t in_bytes,
@@ -179,12 +180,6 @@ int32_t mtz_k_lz4_decode(mtz_handle *h, const void *d_src, void *d_dst,
     mtz_job *d_jobs, uint32_t njobs, void *cuda_stream);
 int32_t mtz_k_lz4_encode(mtz_handle *h, const void *d_src, void *d_dst,
     mtz_job *d_jobs, uint32_t njobs, void *cuda_stream);
-
-/* ---- synthetic-workload helpers for bench/tests (device-side generation of the
- * BASELINE.md section 3 streams by tiling a seeded host corpus) ---- */
-int32_t mtz_synth_tile(mtz_handle *h, const void *d_corpus, size_t corpus_bytes,
-    size_t corpus_records, void *d_stream, size_t cap, uint64_t nwrites,
-    uint32_t recsize, mtz_rec *d_recs, size_t *out_bytes, size_t *nrec);
 
 #ifdef __cplusplus
 }

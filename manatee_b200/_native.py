@@ -53,7 +53,7 @@ SYMBOLS = [
     "mtz_out_peek", "mtz_out_consume", "mtz_read", "mtz_event_fd", "mtz_get_stats",
     "mtz_end_checksum", "mtz_host_alloc", "mtz_host_free", "mtz_process_host",
     "mtz_index_host", "mtz_dev_index", "mtz_dev_submit", "mtz_dev_aggregate",
-    "mtz_dev_finish", "mtz_dev_reset", "mtz_set_carry", "mtz_synth_tile",
+    "mtz_dev_finish", "mtz_dev_reset", "mtz_set_carry",
     "mtz_k_lz4_decode", "mtz_k_lz4_encode",
 ]
 
@@ -92,7 +92,7 @@ def lib():
     L.mtz_host_free.argtypes = [vp]
     L.mtz_process_host.argtypes = [H, vp, sz, vp, sz, C.POINTER(sz)]
     L.mtz_index_host.argtypes = [vp, sz, vp, sz, C.POINTER(sz), C.POINTER(sz)]
-    L.mtz_dev_index.argtypes = [H, vp, sz, vp, sz, C.POINTER(sz), vp]
+    L.mtz_dev_index.argtypes = [H, vp, sz, vp, sz, C.POINTER(sz), C.POINTER(sz), vp]
     L.mtz_dev_submit.argtypes = [H, vp, sz, vp, sz, vp, sz, vp]
     L.mtz_dev_aggregate.argtypes = [H, C.POINTER(u64 * 5)]
     L.mtz_dev_finish.argtypes = [H, vp, vp, C.POINTER(sz), C.POINTER(u64 * 4), C.POINTER(u64 * 4)]
@@ -100,8 +100,6 @@ def lib():
     L.mtz_set_carry.argtypes = [H, vp, vp]
     L.mtz_k_lz4_decode.argtypes = [H, vp, vp, vp, C.c_uint32, vp]
     L.mtz_k_lz4_encode.argtypes = [H, vp, vp, vp, C.c_uint32, vp]
-    L.mtz_synth_tile.argtypes = [H, vp, sz, sz, vp, sz, u64, C.c_uint32, vp, C.POINTER(sz),
-                                 C.POINTER(sz)]
     for s in SYMBOLS:
         getattr(L, s).restype = getattr(L, s).restype if s in (
             "mtz_last_error", "mtz_strerror") else i32

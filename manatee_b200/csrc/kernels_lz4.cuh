@@ -334,6 +334,7 @@ __device__ __forceinline__ uint32_t warp_lz4_encode(const uint8_t *__restrict__ 
 				const int F = hits ? (__ffs((int)hits) - 1) : 32;
 				const int I = inval ? (__ffs((int)inval) - 1) : 32;
 				if (I < F) { to_tail = true; break; }
+				__syncwarp();
 				// commit table updates of lanes <= F (the last equal-hash lane wins)
 				{
 					const uint32_t upto = (F >= 31) ? 0xffffffffu : ((2u << F) - 1u);
@@ -530,6 +531,7 @@ __device__ __forceinline__ uint32_t warp_lz4_encode3(const uint8_t *__restrict__
 				const int F = hits ? (__ffs((int)hits) - 1) : 32;
 				const int I = inval ? (__ffs((int)inval) - 1) : 32;
 				if (I < F) { to_tail = true; break; }
+				__syncwarp();                   // every lane's table read precedes the commits
 				{
 					const uint32_t upto = (F >= 31) ? 0xffffffffu : ((2u << F) - 1u);
 					const uint32_t later = all_same & ~(lanebit | lower) & upto;

@@ -12,6 +12,7 @@
 #include "kernels_fletcher.cuh"
 #include "kernels_lz4.cuh"
 #include "kernels_codec.cuh"
+#include "kernels_index.cuh"
 
 namespace mtz {
 
@@ -96,6 +97,8 @@ struct mtz_handle {
 
 	mtz::CodecBufs dv_cb;              // device-API codec scratch (sub-batched)
 	std::vector<mtz_rec> dv_hrecs;     // host copy of the device record table
+
+	mtz::IndexResult *d_ires = nullptr, *h_ires = nullptr;
 
 	mtz::Engine *eng = nullptr;        // created on first streaming call
 	std::mutex eng_mu;

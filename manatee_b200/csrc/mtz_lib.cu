@@ -284,6 +284,8 @@ int32_t mtz_close(mtz_handle *h)
 	if (h->dv_c0) cudaEventDestroy(h->dv_c0);
 	if (h->dv_c1) cudaEventDestroy(h->dv_c1);
 	codec_free(h->dv_cb);
+	if (h->d_ires) cudaFree(h->d_ires);
+	if (h->h_ires) cudaFreeHost(h->h_ires);
 	if (h->dv_k1a) cudaEventDestroy(h->dv_k1a);
 	if (h->dv_k1b) cudaEventDestroy(h->dv_k1b);
 	for (auto &s : h->slots) free_slot(s);
@@ -1396,8 +1398,31 @@ int32_t mtz_k_lz4_encode(mtz_handle *h, const void *d_src, void *d_dst, mtz_job 
 	return launch_k3(h, st, d_src, d_dst, d_jobs, njobs, false);
 }
 
-// ------------------------------------------------- not yet implemented ----
-int32_t mtz_dev_index(mtz_handle *h, const void *, size_t, mtz_rec *, size_t, size_t *, void *) { CHECK_H(h); return MTZ_EINVAL; }
-int32_t mtz_synth_tile(mtz_handle *h, const void *, size_t, size_t, void *, size_t, uint64_t, uint32_t, mtz_rec *, size_t *, size_t *) { CHECK_H(h); return MTZ_EINVAL; }
+// ------------------------------------------------------- GPU-side parse ---
+int32_t mtz_dev_index(mtz_handle *h, const void *d_in, size_t n, mtz_rec *d_recs, size_t cap,
+    size_t *nrec, size_t *consumed, void *cuda_stream)
+{
+	CHECK_H(h);
+	if (d_in == nullptr || d_recs == nullptr) return MTZ_EINVAL;
+	if (((uintptr_t)d_in & 3) != 0) return fail(h, MTZ_EINVAL, "d_in must be 4-byte aligned");
+	MTZ_CU(h, cudaSetDevice(h->device));
+	cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : h->st;
+	if (h->d_ires == nullptr) {
+		MTZ_CU(h, cudaMalloc(&h->d_ires, sizeof(IndexResult)));
+		MTZ_CU(h, cudaHostAlloc(&h->h_ires, sizeof(IndexResult), cudaHostAllocDefault));
+	}
+	k_index<<<1, INDEX_THREADS, 0, st>>>((const uint8_t *)d_in, (uint64_t)n, d_recs, (uint64_t)cap, h->d_ires);
+	MTZ_CU(h, cudaGetLastError());
+	count_launch(h, 1);
+	MTZ_CU(h, cudaMemcpyAsync(h->h_ires, h->d_ires, sizeof(IndexResult), cudaMemcpyDeviceToHost, st));
+	MTZ_CU(h, cudaStreamSynchronize(st));
+	if (nrec) *nrec = (size_t)h->h_ires->nrec;
+	if (consumed) *consumed = (size_t)h->h_ires->consumed;
+	if (h->h_ires->status == MTZ_EFORMAT)
+		return fail(h, MTZ_EFORMAT, "malformed record header at stream offset %llu",
+		    (unsigned long long)h->h_ires->consumed);
+	if (h->h_ires->status == MTZ_ENOSPC) return MTZ_ENOSPC;     // not sticky: caller may retry bigger
+	return MTZ_OK;
+}
 
 } // extern "C"

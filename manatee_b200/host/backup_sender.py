@@ -40,6 +40,12 @@ class BackupSender(object):
         self._queue = options["queue"]
         self._gpu = options.get("gpu") or None     # {'mode': 'verify'|'compress', 'device': 0, ...}
         self._env = options.get("env")
+        # SURVEY.md 8f f1 (additive, default off == reference behaviour): requests that
+        # arrive within coalesceMs of each other share ONE zfs send + ONE stage pass,
+        # the processed stream is teed to every requester's socket.
+        self._coalesceMs = int(options.get("coalesceMs", 0) or 0)
+        self._pending = []
+        self._pend_lock = threading.Lock()
         self._listeners = {}
         self._threads = []
         self._queue.on("push", self._on_push)
@@ -60,16 +66,35 @@ class BackupSender(object):
         for t in list(self._threads):
             t.join(timeout)
 
-    def _on_push(self, backupJob):
+    def _job_cb(self, backupJob):
         def cb(err):
             if err:
                 backupJob["err"] = err
                 self.emit("err", err)
             else:
                 self.emit("done", backupJob)
-        t = threading.Thread(target=self._send, args=(backupJob, cb), daemon=True)
-        self._threads.append(t)
-        t.start()
+        return cb
+
+    def _on_push(self, backupJob):
+        if self._coalesceMs <= 0:
+            t = threading.Thread(target=self._send, args=(backupJob, self._job_cb(backupJob)),
+                                 daemon=True)
+            self._threads.append(t)
+            t.start()
+            return
+        with self._pend_lock:
+            self._pending.append(backupJob)
+            first = len(self._pending) == 1
+        if first:
+            def fire():
+                import time
+                time.sleep(self._coalesceMs / 1000.0)
+                with self._pend_lock:
+                    jobs, self._pending = self._pending, []
+                self._send_group(jobs)
+            t = threading.Thread(target=fire, daemon=True)
+            self._threads.append(t)
+            t.start()
 
     # -- lib/backupSender.js:244-288
     def _getLatestSnapshot(self):
@@ -92,12 +117,70 @@ class BackupSender(object):
                                 ring_bytes=g.get("ringBytes", 0), batch_bytes=g.get("batchBytes", 0),
                                 out_ring_bytes=g.get("outRingBytes", 0), n_slots=g.get("slots", 0))
 
+    def _send_group(self, jobs):
+        """One zfs send + one stage pass teed to every job's socket (coalesced restore)."""
+        class Tee(object):
+            def __init__(self, socks):
+                self.socks = socks
+
+            def sendall(self, b):
+                for j, s_ in list(self.socks.items()):
+                    try:
+                        s_.sendall(b)
+                    except OSError as e:
+                        jobs_by_id[j]["done"] = "failed"
+                        self_cb[j](e)
+                        del self.socks[j]
+                if not self.socks:
+                    raise OSError("every coalesced receiver went away")
+
+            def shutdown(self, how):
+                for s_ in self.socks.values():
+                    try:
+                        s_.shutdown(how)
+                    except OSError:
+                        pass
+
+            def close(self):
+                for s_ in self.socks.values():
+                    s_.close()
+
+        jobs_by_id = {id(j): j for j in jobs}
+        self_cb = {id(j): self._job_cb(j) for j in jobs}
+        socks = {}
+        for j in jobs:
+            try:
+                socks[id(j)] = socket.create_connection((j["host"], int(j["port"])))
+            except OSError as e:
+                j["done"] = "failed"
+                self_cb[id(j)](e)
+        if not socks:
+            return
+        live = [jobs_by_id[k] for k in socks]
+        lead = dict(live[0])                       # progress fields are mirrored to every job
+
+        class Shared(dict):
+            def __setitem__(self_, k, v):
+                dict.__setitem__(self_, k, v)
+                for j in live:
+                    if j.get("done") != "failed" or k != "done":
+                        j[k] = v
+        shared = Shared(lead)
+
+        def cb(err):
+            for j in live:
+                if j.get("done") == "failed" and not err:
+                    continue
+                self_cb[id(j)](err)
+        self._send(shared, cb, sock=Tee(socks))
+
     # -- lib/backupSender.js:154-242
-    def _send(self, backupJob, callback):
-        sock = zfsSend = stage = None
+    def _send(self, backupJob, callback, sock=None):
+        zfsSend = stage = None
         try:
             snapshot = self._getLatestSnapshot()
-            sock = socket.create_connection((backupJob["host"], int(backupJob["port"])))
+            if sock is None:
+                sock = socket.create_connection((backupJob["host"], int(backupJob["port"])))
             zfsSend = subprocess.Popen([self._zfsPath, "send", "-v", "-P", snapshot],
                                        stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=self._env)
             backupJob["size"] = None

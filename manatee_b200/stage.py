@@ -127,6 +127,14 @@ class GpuSnapshotStage(object):
         self._check(self._L.mtz_dev_submit(self._h, d_in_ptr, in_bytes, d_recs_ptr, nrec,
                                            d_out_ptr or None, out_cap, cuda_stream or None))
 
+    def dev_index(self, d_in_ptr, nbytes, d_recs_ptr, cap, cuda_stream=0):
+        """GPU-side DRR parse of a resident stream -> (nrec, consumed_bytes)."""
+        nrec = C.c_size_t(0)
+        used = C.c_size_t(0)
+        self._check(self._L.mtz_dev_index(self._h, d_in_ptr, nbytes, d_recs_ptr, cap, C.byref(nrec),
+                                          C.byref(used), cuda_stream or None))
+        return nrec.value, used.value
+
     def dev_aggregate(self):
         agg = (C.c_uint64 * 5)()
         self._check(self._L.mtz_dev_aggregate(self._h, C.byref(agg)))

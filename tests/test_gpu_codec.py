@@ -209,3 +209,81 @@ def test_golden_fixtures_on_gpu(oracle):
         with pytest.raises(MtzError):
             g.process_host(bad)
         assert g.stats()["bad_record"] == meta["stream_small_corrupt_5"]["bad_record"]
+
+
+def _all_types_stream(oracle, seed=7):
+    """A stream exercising every DRR record type and odd sizes (the oracle generator only
+    emits BEGIN/OBJECT/WRITE/END): built by hand, stamped by the oracle."""
+    rng = np.random.default_rng(seed)
+
+    def hdr(t, f=None):
+        f = f or {}
+        h = np.zeros(312, dtype=np.uint8)
+        h[0:4] = np.array([t], dtype=np.uint32).view(np.uint8)
+        for off, (val, width) in f.items():
+            h[off:off + width] = np.array([val], dtype={4: np.uint32, 8: np.uint64}[width]).view(np.uint8)
+        return h
+
+    parts = []
+    b = hdr(0, {8: (0x2F5bacbac, 8), 16: (1 | (0x4 << 2), 8), 4: (24, 4)})
+    parts += [b, rng.integers(0, 256, 24, dtype=np.uint8)]                       # BEGIN with a 24-byte payload
+    parts += [hdr(1, {8: (8, 8), 28: (13, 4)}), rng.integers(0, 256, 16, dtype=np.uint8)]   # OBJECT bonus 13 -> 16
+    parts += [hdr(2, {8: (9, 8), 16: (100, 8)})]                               # FREEOBJECTS
+    for k, ls in enumerate([512, 1024, 4096, 131072, 16384, 2 << 20]):
+        pay = oracle.gen_payload(oracle.PAYLOAD_PGPAGE if k % 2 == 0 else oracle.PAYLOAD_PCG, 50 + k, ls)
+        w = hdr(3, {8: (8, 8), 24: (k * (1 << 21), 8), 32: (ls, 8)})
+        w[48] = 7
+        parts += [w, pay]
+        if k == 2:
+            parts += [hdr(4, {8: (8, 8), 16: (1 << 30, 8), 24: (4096, 8)})]   # FREE
+            parts += [hdr(7, {8: (8, 8), 16: (520, 8)}), rng.integers(0, 256, 520, dtype=np.uint8)]  # SPILL
+        if k == 4:
+            parts += [hdr(6, {8: (8, 8), 16: (0, 8), 24: (4096, 8)})]          # WRITE_BYREF
+            e = hdr(8, {8: (8, 8), 16: (0, 8), 24: (512, 8), 48: (512, 4), 52: (21, 4)})
+            parts += [e, rng.integers(0, 256, 24, dtype=np.uint8)]               # WRITE_EMBEDDED psize 21 -> 24
+    parts += [hdr(5)]
+    s = np.concatenate(parts)
+    rc, _ = oracle.stream_restamp(s)
+    assert rc == 0 and oracle.stream_verify(s)[0] == 0
+    return s
+
+
+def test_every_record_type_all_modes(oracle):
+    from manatee_b200 import GpuSnapshotStage
+    s = _all_types_stream(oracle)
+    rc, st = oracle.stream_verify(s)
+    with GpuSnapshotStage("verify", batch_bytes=1 << 20) as g:
+        g.process_host(s)
+        assert g.end_checksum() == st.end_cksum.tuple() and g.stats()["records"] == st.records
+    rc, want, st = oracle.stream_compress(s)
+    assert rc == 0
+    got, gs, end = _gpu("compress", s, batch_bytes=1 << 20)
+    assert np.array_equal(got, want) and end == st.end_cksum.tuple()
+    back, _, _ = _gpu("decompress", got)
+    assert np.array_equal(back, s)
+    rc, want_r, _ = oracle.stream_recompress(got)
+    got_r, _, _ = _gpu("recompress", got)
+    assert np.array_equal(got_r, want_r)
+
+
+def test_empty_and_tiny_streams(oracle):
+    from manatee_b200 import GpuSnapshotStage
+    empty = np.zeros(0, dtype=np.uint8)
+    for mode in ("verify", "compress"):
+        with GpuSnapshotStage(mode) as g:
+            out = np.zeros(1024, dtype=np.uint8)
+            assert g.process_host(empty, out) == 0
+    s = oracle.synth_stream(0)                      # BEGIN, OBJECT, END only
+    got, gs, end = _gpu("compress", s)
+    rc, want, st = oracle.stream_compress(s)
+    assert np.array_equal(got, want) and gs["records"] == 3
+
+
+def test_sixteen_mib_record(oracle):
+    """largest ZFS block: K1 chunk loop (T3 weights overflow guard) and the u32-table encoder"""
+    s = oracle.synth_stream(2, recsize=16 << 20, kind=oracle.PAYLOAD_PGPAGE)
+    rc, want, st = oracle.stream_compress(s)
+    got, gs, end = _gpu("compress", s, batch_bytes=8 << 20)
+    assert np.array_equal(got, want) and end == st.end_cksum.tuple()
+    back, _, _ = _gpu("decompress", got, cap=s.size + (1 << 20), batch_bytes=8 << 20)
+    assert np.array_equal(back, s)

@@ -183,3 +183,38 @@ def test_deferred_shard_verify_via_host_path(oracle):
         assert g1.stats()["bad_record"] + 31 == st.bad_record
     finally:
         g0.close(); g1.close()
+
+
+def test_gpu_side_parse_matches_host_parser(oracle):
+    """mtz_dev_index (speculative strided header walk in HBM) == mtz_index_host."""
+    import torch
+    from manatee_b200 import GpuSnapshotStage, index_host
+    from manatee_b200.stage import REC_DTYPE
+    raw = oracle.synth_stream(300, recsize=16384, kind=oracle.PAYLOAD_PGPAGE)
+    rc, comp, _ = oracle.stream_compress(raw)              # variable-length records
+    two = np.concatenate([oracle.synth_stream(5, recsize=512), raw])
+    for s in (raw, comp, two, raw[:-1000], oracle.synth_stream(0)):
+        want, used = index_host(s)
+        d = torch.from_numpy(s.copy()).cuda()
+        d_recs = torch.zeros((len(want) + 8) * 32, dtype=torch.uint8, device="cuda")
+        with GpuSnapshotStage("verify") as g:
+            n, got_used = g.dev_index(d.data_ptr(), s.size, d_recs.data_ptr(), len(want) + 8)
+            got = d_recs.cpu().numpy().view(REC_DTYPE)[:n]
+            assert n == len(want) and got_used == used
+            for f in ("off", "payload", "type", "lsize", "comp"):
+                assert np.array_equal(got[f], want[f]), f
+            # the GPU-built table drives the verify path end to end
+            if s is raw:
+                g.dev_submit(d.data_ptr(), used, d_recs.data_ptr(), n)
+                g.dev_finish()
+                assert g.end_checksum() == oracle.stream_verify(raw)[1].end_cksum.tuple()
+    bad = raw.copy()
+    cnt, offs = oracle.stream_index(bad)
+    bad[int(offs[40])] = 0x77                                  # unknown drr_type
+    from manatee_b200._native import MtzError, EFORMAT
+    d = torch.from_numpy(bad).cuda()
+    d_recs = torch.zeros(400 * 32, dtype=torch.uint8, device="cuda")
+    with GpuSnapshotStage("verify") as g:
+        with pytest.raises(MtzError) as ei:
+            g.dev_index(d.data_ptr(), bad.size, d_recs.data_ptr(), 400)
+        assert ei.value.code == EFORMAT

@@ -181,3 +181,39 @@ def test_gpu_corrupt_stream_fails_the_job(fakezfs, tmp_path):
                                     env_extra={"FAKE_ZFS_STREAM": str(p)})
     assert res["err"] is not None                    # receiver's poll sees done == 'failed' / 500
     assert events and events[0][0] == "err" and "checksum" in str(events[0][1])
+
+
+def test_coalesced_restores_share_one_send(fakezfs, tmp_path):
+    """two peers asking within the window get the same bytes from ONE
+    `zfs send` (the reference would run two).  Default (coalesceMs absent) stays per-job."""
+    from manatee_b200.host import BackupSender, BackupServer, ZfsClient
+    env = dict(fakezfs["env"])
+    counter = tmp_path / "sends"
+    env["FAKE_ZFS_SEND_COUNT"] = str(counter)
+    srv = BackupServer.start({"log": None, "port": 0, "host": "127.0.0.1"})
+    sender = BackupSender.start({"log": None, "dataset": "zones/x/data/manatee", "zfsPath": fakezfs["zfs"],
+                                 "queue": srv.getQueue(), "env": env, "coalesceMs": 300})
+    outs, results, threads = [], [], []
+    for k in range(2):
+        e2 = dict(env); e2["FAKE_ZFS_RECV_OUT"] = str(tmp_path / ("recv%d.out" % k))
+        outs.append(e2["FAKE_ZFS_RECV_OUT"])
+        cli = ZfsClient({"log": None, "dataset": "zones/y%d/data/manatee" % k, "dbUser": "postgres",
+                         "mountpoint": "/manatee/pg", "pollInterval": 50, "zfsHost": "127.0.0.1",
+                         "zfsPath": fakezfs["zfs"], "zfsPort": _free_port(), "env": e2})
+        res = {}
+        results.append((res, cli))
+        t = threading.Thread(target=cli.restore, args=("http://127.0.0.1:%d" % srv.port,
+                                                       lambda err, old, res=res: res.update(err=err)))
+        threads.append(t)
+        t.start()
+    for t in threads:
+        t.join(60)
+    sender.join(10)
+    srv.close()
+    want = hashlib.sha256(fakezfs["stream"].tobytes()).hexdigest()
+    for (res, cli), o in zip(results, outs):
+        assert res.get("err") is None, res
+        digest, n = open(o).read().split()
+        assert digest == want and int(n) == fakezfs["stream"].size
+        assert cli._restoreObject["done"] is True
+    assert open(str(counter)).read().count("send") == 1, "coalesced requests must share one zfs send"

@@ -36,7 +36,15 @@ def _worker(rank, world, port, q):
         aggs = SH.all_gather_aggregates(tuple(agg))
         mine = SH.carry_before(rank, aggs)
         end = SH.carry_before(world, aggs)
-        q.put((rank, mine == carry_in, end == state, buf.tobytes()))
+        # fan-out: every rank ends up having streamed the WHOLE stream in shard order
+        import hashlib
+        import torch
+        from manatee_b200 import fanout as FO
+        sizes = FO.shard_sizes(buf.size)
+        h = hashlib.sha256()
+        got = FO.broadcast_shards(torch.from_numpy(buf.copy()), sizes,
+                                  lambda src, t: h.update(t.numpy().tobytes()))
+        q.put((rank, mine == carry_in, end == state, buf.tobytes(), h.hexdigest(), got, sizes))
     finally:
         dist.destroy_process_group()
 
@@ -56,6 +64,10 @@ def test_two_rank_shard_exchange_matches_single_stream():
         assert p.exitcode == 0
     assert all(r[1] for r in res), "carry derived from the all-gather != generator's running checksum"
     assert all(r[2] for r in res)
+    import hashlib
+    full = hashlib.sha256(res[0][3] + res[1][3]).hexdigest()
+    assert res[0][4] == full and res[1][4] == full, "fan-out did not deliver the whole stream to every rank"
+    assert res[0][5] == len(res[1][3]) and res[1][5] == len(res[0][3])
     whole = np.frombuffer(res[0][3] + res[1][3], dtype=np.uint8)
     assert np.array_equal(whole, O.synth_stream(24, recsize=8192, kind=O.PAYLOAD_PCG))
     assert O.stream_verify(whole)[0] == 0

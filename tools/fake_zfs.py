@@ -27,6 +27,9 @@ def main():
         return 0
     if a[0] == "send":
         snap = a[-1]
+        if os.environ.get("FAKE_ZFS_SEND_COUNT"):
+            with open(os.environ["FAKE_ZFS_SEND_COUNT"], "a") as f:
+                f.write("send\n")
         path = os.environ["FAKE_ZFS_STREAM"]
         size = os.path.getsize(path)
         sys.stderr.write("full\t%s\t%d\nsize\t%d\n" % (snap, size, size))
