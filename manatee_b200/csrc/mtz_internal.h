@@ -95,7 +95,9 @@ struct mtz_handle {
 	cudaEvent_t dv_c0 = nullptr, dv_c1 = nullptr;
 	bool dv_timed = false;
 
-	mtz::CodecBufs dv_cb;              // device-API codec scratch (sub-batched)
+	mtz::CodecBufs dv_cb, dv_cb2;      // device-API codec scratch (sub-batched, double-buffered)
+	cudaStream_t st_post = nullptr;    // layout/assemble/stamp of sub-batch k under K2/K3 of k+1
+	cudaEvent_t ev_pre[2] = {nullptr, nullptr}, ev_post[2] = {nullptr, nullptr};
 	std::vector<mtz_rec> dv_hrecs;     // host copy of the device record table
 
 	mtz::IndexResult *d_ires = nullptr, *h_ires = nullptr;
