@@ -386,7 +386,16 @@ def run_ours(args):
 
         def consume(src, t):            # stand-in for the egress writer of this GPU's peer
             touched[0] += int(t.numel())
-        FO.broadcast_shards(d_stream[:shard.size], sizes, consume, recv)      # warm-up (NCCL setup)
+        # warm-up pass doubles as the correctness check: every rank must have streamed the
+        # same bytes (wrap-around int64 sum of the whole stream, compared across ranks)
+        acc = torch.zeros(1, dtype=torch.int64, device="cuda")
+
+        def consume_check(src, t):
+            acc.add_(t[:(t.numel() // 8) * 8].view(torch.int64).sum())
+        FO.broadcast_shards(d_stream[:shard.size], sizes, consume_check, recv)
+        accs = [torch.zeros_like(acc) for _ in range(world)]
+        dist.all_gather(accs, acc)
+        assert all(int(a.item()) == int(accs[0].item()) for a in accs), "fan-out delivered different bytes"
         f0 = torch.cuda.Event(enable_timing=True); f1 = torch.cuda.Event(enable_timing=True)
         dist.barrier(); torch.cuda.synchronize()
         f0.record()
@@ -447,6 +456,51 @@ def run_ours(args):
                        "verdict crosses back"}
         ge.close()
 
+    # ---------------- streaming-ring API (what the Node Transform binds), N=1 ----------------
+    ring = None
+    if not args.no_e2e and world == 1:
+        import ctypes as C
+        L = N.lib()
+        gr = GpuSnapshotStage("verify", device=local, ring_bytes=1 << 30, batch_bytes=64 << 20, n_slots=4)
+        sample = shard[:min(shard.size, 4 << 30)]
+        # cut the sample at a record boundary so the stream ends cleanly
+        cutrec = int(np.searchsorted(recs["off"], sample.size, side="right")) - 1
+        sample = shard[:int(recs["off"][cutrec])]
+        perr = []
+
+        def producer():
+            try:
+                step = 8 << 20
+                for o in range(0, sample.size, step):
+                    gr.write(sample[o:o + step])
+                gr.flush()
+            except Exception as e:              # noqa: BLE001
+                perr.append(e)
+        t0 = time.perf_counter()
+        th = threading.Thread(target=producer)
+        th.start()
+        got = 0
+        p, n = C.c_void_p(), C.c_size_t()
+        while True:                             # zero-copy consumer: peek / consume
+            rc = L.mtz_out_peek(gr._h, C.byref(p), C.byref(n))
+            if rc == N.OK:
+                got += n.value
+                L.mtz_out_consume(gr._h, n.value)
+            elif rc == N.EOF:
+                break
+            elif rc == N.EAGAIN:
+                time.sleep(0.0002)
+            else:
+                break
+        th.join()
+        dt = time.perf_counter() - t0
+        ok = (not perr) and got == sample.size
+        ring = {"value": round(sample.size / GIB / dt, 3), "unit": "GiB/s", "ok": bool(ok),
+                "sample_gib": round(sample.size / GIB, 2),
+                "call": "mtz_write (8 MiB chunks, one producer thread memcpy into the pinned ring) -> "
+                        "engine thread -> mtz_out_peek/consume; bound by the single host memcpy thread"}
+        gr.close()
+
     # ---------------- CPU baseline (rank 0, N=1) ----------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -501,6 +555,7 @@ def run_ours(args):
                          "algorithmic_bytes_per_launch": alg_bytes,
                          "k1_ms": round(k1_ms, 4)},
             "cpu_baseline": cpu,
+            "e2e_stream_api": ring,
             "fanout": fan,
             "clocks": clk,
             "end_checksum": ["%016x" % x for x in (end_ck or ())],

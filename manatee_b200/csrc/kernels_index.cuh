@@ -10,6 +10,7 @@
 // the host parser drr_payload() in mtz_lib.cu.
 #pragma once
 #include <stdint.h>
+#include <cooperative_groups.h>
 #include "../../include/manatee_gpu.h"
 
 namespace mtz {
@@ -61,62 +62,88 @@ __device__ __forceinline__ int64_t dev_drr_payload(const uint8_t *h, uint32_t *l
 }
 
 #define INDEX_THREADS 1024
+#define INDEX_Q       4                 // speculative records per thread and round
+#define INDEX_CTA_SLOTS (INDEX_THREADS * INDEX_Q)
+
+// Grid-wide (cooperative launch, one CTA per SM): in every round all CTAs parse
+// the headers of one window of gridDim.x * 4096 guessed record starts; the first
+// slot that breaks the guess is found with ONE packed 64-bit atomicMin
+//     key = slot << 40 | code << 38 | record_length
+// and one grid barrier.  A send stream is a handful of runs of equal-length
+// records, so a 64 GiB stream is indexed in a few rounds.
+struct IndexShared {
+	unsigned long long key[3];          // round-robin so a reset never races a reader
+};
 
 __global__ void __launch_bounds__(INDEX_THREADS)
 k_index(const uint8_t *__restrict__ base, uint64_t n, mtz_rec *__restrict__ recs, uint64_t cap,
-    IndexResult *__restrict__ res)
+    IndexResult *__restrict__ res, IndexShared *__restrict__ sh)
 {
-	__shared__ uint32_t s_first;       // first thread whose record breaks the stride guess
-	__shared__ uint64_t s_rl;          // its record length
-	__shared__ int32_t s_code;         // 0 continue, 1 stop (incomplete tail), <0 error
+	cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+	__shared__ unsigned long long s_key;
 	uint64_t cur = 0, count = 0, S = 0;
 	const uint32_t t = threadIdx.x;
+	const uint32_t window = gridDim.x * INDEX_CTA_SLOTS;
 	int32_t status = MTZ_OK;
-	for (;;) {
-		if (t == 0) { s_first = 0xffffffffu; s_code = 0; s_rl = 0; }
+	for (uint32_t round = 0;; round++) {
+		if (t == 0) s_key = ~0ull;
+		if (blockIdx.x == 0 && t == 0) sh->key[(round + 1u) % 3u] = ~0ull;
 		__syncthreads();
-		const uint64_t off = cur + (uint64_t)t * S;
-		// with S == 0 (first record, or after a zero-length guess) only thread 0 is meaningful
-		const bool active = (S != 0ull || t == 0u) && off < n;
-		uint64_t rl = 0;
-		int32_t code = 0;
-		mtz_rec r; r.off = off; r.payload = 0; r.type = 0; r.lsize = 0; r.comp = 0; r.resv = 0;
-		if (active) {
-			if (n - off < 312ull) code = 1;                    // incomplete header: stop here
+		mtz_rec r[INDEX_Q];
+		unsigned long long mykey = ~0ull;
+#pragma unroll
+		for (int q = 0; q < INDEX_Q; q++) {
+			const uint32_t j = blockIdx.x * INDEX_CTA_SLOTS + t + (uint32_t)q * INDEX_THREADS;
+			const uint64_t off = cur + (uint64_t)j * S;
+			const bool active = (S != 0ull || j == 0u) && off < n;
+			uint64_t rl = 0; uint32_t code = 0;            // 0 ok, 1 stop (tail), 2 malformed
+			r[q].off = off; r[q].payload = 0; r[q].type = 0; r[q].lsize = 0; r[q].comp = 0; r[q].resv = 0;
+			if (!active) code = 1;
+			else if (n - off < 312ull) code = 1;
 			else {
 				uint32_t ls, comp;
 				const int64_t pl = dev_drr_payload(base + off, &ls, &comp);
-				if (pl < 0) code = MTZ_EFORMAT;
-				else if ((uint64_t)pl > n - off - 312ull) code = 1;   // incomplete payload
+				if (pl < 0) code = 2;
+				else if ((uint64_t)pl > n - off - 312ull) code = 1;
 				else {
 					rl = 312ull + (uint64_t)pl;
-					r.payload = (uint32_t)pl; r.type = ld_u32(base + off); r.lsize = ls; r.comp = comp;
+					r[q].payload = (uint32_t)pl; r[q].type = ld_u32(base + off);
+					r[q].lsize = ls; r[q].comp = comp;
 				}
 			}
+			// with S == 0 only slot 0 is a real guess: every other slot "breaks"
+			if (code != 0u || rl != S) {
+				const unsigned long long k = ((unsigned long long)j << 40) |
+				    ((unsigned long long)code << 38) | (unsigned long long)rl;
+				if (k < mykey) mykey = k;
+			}
 		}
-		// a thread ends the confirmed prefix if it is inactive, failed, or its length != S
-		const bool breaks = !active || code != 0 || rl != S;
-		if (breaks) atomicMin(&s_first, t);
+		if (mykey != ~0ull) atomicMin(&s_key, mykey);
 		__syncthreads();
-		const uint32_t m = s_first;                // threads 0..m sit on true record starts
-		if (t == m) { s_code = active ? code : 1; s_rl = rl; }
-		__syncthreads();
-		const int32_t mcode = (m == 0xffffffffu) ? 0 : s_code;
-		// accepted records: 0..m-1 always; m too when it parsed cleanly
-		const uint32_t nacc = (m == 0xffffffffu) ? INDEX_THREADS : (m + ((mcode == 0) ? 1u : 0u));
+		if (t == 0 && s_key != ~0ull) atomicMin(&sh->key[round % 3u], s_key);
+		grid.sync();
+		const unsigned long long key = *((volatile unsigned long long *)&sh->key[round % 3u]);
+		const bool none = (key == ~0ull);
+		const uint32_t m = (uint32_t)(key >> 40);
+		const uint32_t mcode = none ? 0u : (uint32_t)((key >> 38) & 3u);
+		const uint64_t mrl = key & ((1ull << 38) - 1ull);
+		const uint32_t nacc = none ? window : (m + ((mcode == 0u) ? 1u : 0u));
 		if (count + nacc > cap) { status = MTZ_ENOSPC; break; }
-		if (t < nacc) recs[count + t] = r;
+#pragma unroll
+		for (int q = 0; q < INDEX_Q; q++) {
+			const uint32_t j = blockIdx.x * INDEX_CTA_SLOTS + t + (uint32_t)q * INDEX_THREADS;
+			if (j < nacc) recs[count + j] = r[q];
+		}
 		count += nacc;
-		if (m == 0xffffffffu) { cur += (uint64_t)INDEX_THREADS * S; }
+		if (none) cur += (uint64_t)window * S;
 		else {
 			cur += (uint64_t)m * S;
-			if (mcode == 0) { cur += s_rl; S = s_rl; }
-			else { if (mcode < 0) status = mcode; break; }      // tail or malformed: done
+			if (mcode == 0u) { cur += mrl; S = mrl; }
+			else { if (mcode == 2u) status = MTZ_EFORMAT; break; }
 		}
 		if (cur >= n) break;
-		__syncthreads();
 	}
-	if (t == 0) { res->nrec = count; res->consumed = cur; res->status = status; }
+	if (blockIdx.x == 0 && t == 0) { res->nrec = count; res->consumed = cur; res->status = status; }
 }
 
 } // namespace mtz

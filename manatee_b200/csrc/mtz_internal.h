@@ -101,6 +101,7 @@ struct mtz_handle {
 	std::vector<mtz_rec> dv_hrecs;     // host copy of the device record table
 
 	mtz::IndexResult *d_ires = nullptr, *h_ires = nullptr;
+	mtz::IndexShared *d_ishared = nullptr;
 
 	mtz::Engine *eng = nullptr;        // created on first streaming call
 	std::mutex eng_mu;

@@ -296,6 +296,7 @@ int32_t mtz_close(mtz_handle *h)
 		if (h->ev_post[i]) cudaEventDestroy(h->ev_post[i]);
 	}
 	if (h->d_ires) cudaFree(h->d_ires);
+	if (h->d_ishared) cudaFree(h->d_ishared);
 	if (h->h_ires) cudaFreeHost(h->h_ires);
 	if (h->dv_k1a) cudaEventDestroy(h->dv_k1a);
 	if (h->dv_k1b) cudaEventDestroy(h->dv_k1b);
@@ -1449,9 +1450,20 @@ int32_t mtz_dev_index(mtz_handle *h, const void *d_in, size_t n, mtz_rec *d_recs
 	if (h->d_ires == nullptr) {
 		MTZ_CU(h, cudaMalloc(&h->d_ires, sizeof(IndexResult)));
 		MTZ_CU(h, cudaHostAlloc(&h->h_ires, sizeof(IndexResult), cudaHostAllocDefault));
+		MTZ_CU(h, cudaMalloc(&h->d_ishared, sizeof(IndexShared)));
 	}
-	k_index<<<1, INDEX_THREADS, 0, st>>>((const uint8_t *)d_in, (uint64_t)n, d_recs, (uint64_t)cap, h->d_ires);
-	MTZ_CU(h, cudaGetLastError());
+	MTZ_CU(h, cudaMemsetAsync(h->d_ishared, 0xff, sizeof(IndexShared), st));
+	{
+		// cooperative launch: one CTA per SM (1024 threads x 64 regs fill the register file)
+		const uint8_t *a0 = (const uint8_t *)d_in;
+		uint64_t a1 = (uint64_t)n, a3 = (uint64_t)cap;
+		mtz_rec *a2 = d_recs;
+		IndexResult *a4 = h->d_ires;
+		IndexShared *a5 = h->d_ishared;
+		void *args[] = { &a0, &a1, &a2, &a3, &a4, &a5 };
+		MTZ_CU(h, cudaLaunchCooperativeKernel((void *)k_index, dim3((unsigned)h->sm_count),
+		    dim3(INDEX_THREADS), args, 0, st));
+	}
 	count_launch(h, 1);
 	MTZ_CU(h, cudaMemcpyAsync(h->h_ires, h->d_ires, sizeof(IndexResult), cudaMemcpyDeviceToHost, st));
 	MTZ_CU(h, cudaStreamSynchronize(st));
