@@ -9,6 +9,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <algorithm>
 #include "mtz_internal.h"
 
@@ -1415,6 +1416,15 @@ static int32_t launch_k3(mtz_handle *h, cudaStream_t st, const void *d_src, void
 		    (int)((size_t)LZ4_WARPS * (LZ4_TAB_COMPACT_WORDS + LZ4_WIN / 4) * 4)));
 		MTZ_CU(h, cudaFuncSetAttribute(k3_lz4_encode<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
 		    (int)((size_t)LZ4_WARPS * (LZ4_TAB_BIG_WORDS + LZ4_WIN / 4) * 4)));
+		// all of the unified L1/shared array as shared memory: K3 is bound by records in
+		// flight (24 tables of 8.5 KiB per SM), measured 62 vs 46 GiB/s at a 75 % carve-out
+		// (profiles/r1_k3_encode.md).  MTZ_K3_CARVEOUT overrides for experiments.
+		{
+			const char *e = getenv("MTZ_K3_CARVEOUT");
+			const int pct = e ? atoi(e) : 100;
+			MTZ_CU(h, cudaFuncSetAttribute(k3_lz4_encode<true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+			MTZ_CU(h, cudaFuncSetAttribute(k3_lz4_encode<false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+		}
 		attr_set = true;
 	}
 	const int blocks_per_sm = (int)((227u * 1024u) / (smem + 1024));
