@@ -287,3 +287,61 @@ def test_sixteen_mib_record(oracle):
     assert np.array_equal(got, want) and end == st.end_cksum.tuple()
     back, _, _ = _gpu("decompress", got, cap=s.size + (1 << 20), batch_bytes=8 << 20)
     assert np.array_equal(back, s)
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3, 4])
+def test_randomized_streams_all_modes(oracle, seed):
+    """Seeded fuzz: random record mix / sizes / payload kinds / batch sizes; every mode must
+    reproduce the oracle bit for bit, and DECOMPRESS(COMPRESS(x)) == x."""
+    from manatee_b200 import GpuSnapshotStage
+    rng = np.random.default_rng(1000 + seed)
+
+    def u(h, off, val, width):
+        h[off:off + width] = np.array([val], dtype={4: np.uint32, 8: np.uint64}[width]).view(np.uint8)
+
+    parts = []
+    b = np.zeros(312, dtype=np.uint8)
+    u(b, 8, 0x2F5bacbac, 8); u(b, 16, 1 | (0x4 << 2), 8)
+    parts.append(b)
+    for k in range(int(rng.integers(20, 60))):
+        kind = int(rng.integers(0, 10))
+        h = np.zeros(312, dtype=np.uint8)
+        if kind <= 5:                                   # DRR_WRITE, sizes 512 B .. 256 KiB
+            ls = int(rng.choice([512, 1024, 2048, 8192, 16384, 65536, 131072, 262144]))
+            pk = int(rng.integers(0, 3))
+            pay = oracle.gen_payload([oracle.PAYLOAD_PGPAGE, oracle.PAYLOAD_PCG, oracle.PAYLOAD_ZERO][pk],
+                                     int(rng.integers(0, 1 << 20)), ls)
+            if pk == 0 and rng.integers(0, 2):
+                pay = pay.copy(); pay[ls // 3:] = rng.integers(0, 256, ls - ls // 3, dtype=np.uint8)
+            u(h, 0, 3, 4); u(h, 8, 8, 8); u(h, 24, k << 18, 8); u(h, 32, ls, 8); h[48] = 7
+            parts += [h, pay]
+        elif kind == 6:
+            u(h, 0, 1, 4); bl = int(rng.integers(0, 300)); u(h, 28, bl, 4)
+            parts += [h, rng.integers(0, 256, (bl + 7) & ~7, dtype=np.uint8)]
+        elif kind == 7:
+            u(h, 0, 4, 4); u(h, 8, 8, 8); u(h, 16, k << 20, 8); u(h, 24, 4096, 8)
+            parts.append(h)
+        elif kind == 8:
+            u(h, 0, 7, 4); ln = int(rng.integers(1, 64)) * 8; u(h, 16, ln, 8)
+            parts += [h, rng.integers(0, 256, ln, dtype=np.uint8)]
+        else:
+            u(h, 0, 2, 4); u(h, 8, k, 8); u(h, 16, 5, 8)
+            parts.append(h)
+    e = np.zeros(312, dtype=np.uint8); u(e, 0, 5, 4)
+    parts.append(e)
+    s = np.concatenate(parts)
+    assert oracle.stream_restamp(s)[0] == 0
+    rc, vst = oracle.stream_verify(s)
+    assert rc == 0
+    batch = int(rng.choice([1 << 19, 1 << 20, 3 << 20, 0]))
+    with GpuSnapshotStage("verify", batch_bytes=batch) as g:
+        g.process_host(s)
+        assert g.end_checksum() == vst.end_cksum.tuple()
+    rc, want_c, cst = oracle.stream_compress(s)
+    got_c, gs, end = _gpu("compress", s, batch_bytes=batch, n_slots=int(rng.integers(1, 5)))
+    assert np.array_equal(got_c, want_c) and end == cst.end_cksum.tuple()
+    got_d, _, _ = _gpu("decompress", got_c, cap=s.size + (1 << 20), batch_bytes=batch)
+    assert np.array_equal(got_d, s)
+    rc, want_r, _ = oracle.stream_recompress(got_c)
+    got_r, _, _ = _gpu("recompress", got_c, cap=s.size + (1 << 20), batch_bytes=batch)
+    assert np.array_equal(got_r, want_r)
