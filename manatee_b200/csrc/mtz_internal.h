@@ -99,6 +99,10 @@ struct mtz_handle {
 	cudaStream_t st_post = nullptr;    // layout/assemble/stamp of sub-batch k under K2/K3 of k+1
 	cudaEvent_t ev_pre[2] = {nullptr, nullptr}, ev_post[2] = {nullptr, nullptr};
 	std::vector<mtz_rec> dv_hrecs;     // host copy of the device record table
+	mtz_rec *dv_all_orecs = nullptr;   // shard mode: output table / sums of the whole submit
+	mtz::RecSums *dv_all_osums = nullptr;
+	size_t dv_all_cap = 0;
+	uint8_t *dv_out = nullptr;
 
 	mtz::IndexResult *d_ires = nullptr, *h_ires = nullptr;
 	mtz::IndexShared *d_ishared = nullptr;

@@ -296,6 +296,8 @@ int32_t mtz_close(mtz_handle *h)
 		if (h->ev_pre[i]) cudaEventDestroy(h->ev_pre[i]);
 		if (h->ev_post[i]) cudaEventDestroy(h->ev_post[i]);
 	}
+	if (h->dv_all_orecs) cudaFree(h->dv_all_orecs);
+	if (h->dv_all_osums) cudaFree(h->dv_all_osums);
 	if (h->d_ires) cudaFree(h->d_ires);
 	if (h->d_ishared) cudaFree(h->d_ishared);
 	if (h->h_ires) cudaFreeHost(h->h_ires);
@@ -503,20 +505,26 @@ static int32_t codec_launch_pre(mtz_handle *h, cudaStream_t st, CodecBufs &cb, c
 // lives on the device so sub-batches chain without a host round trip), sums of
 // the output records, and the sequential stamp chain from h->d_carry_out.
 static int32_t codec_launch_post(mtz_handle *h, cudaStream_t st, CodecBufs &cb, const uint8_t *d_in,
-    const mtz_rec *d_recs, size_t nrec, uint8_t *d_out, uint32_t rec_base)
+    const mtz_rec *d_recs, size_t nrec, uint8_t *d_out, uint32_t rec_base,
+    mtz_rec *all_orecs = nullptr, RecSums *all_osums = nullptr)
 {
 	if (nrec == 0) return MTZ_OK;
+	// shard mode: output record table / sums are kept for the whole submit and the
+	// stamp chain runs later (mtz_dev_finish) from the previous shard's checksum
+	mtz_rec *orecs = all_orecs ? all_orecs + rec_base : cb.out_recs;
+	RecSums *osums = all_osums ? all_osums + rec_base : cb.osums;
 	const uint32_t n = (uint32_t)nrec, mode = h->cfg.mode;
 	const unsigned tb = 256, gb = (n + tb - 1) / tb;
 	k_layout<<<gb, tb, 0, st>>>(d_recs, n, cb.cr, cb.dec, cb.enc, cb.vals, cb.d_cres, rec_base);
 	k_xscan_u64<<<1, XSCAN_THREADS, 0, st>>>(cb.vals, cb.out_offs, n, cb.d_outpos, cb.d_outpos);
 	const unsigned ga = (unsigned)std::min<size_t>((n + 7) / 8, (size_t)h->sm_count * 8);
 	k_assemble<<<ga, ASM_THREADS, 0, st>>>(d_in, d_recs, n, mode, cb.cr, cb.out_offs, cb.enc,
-	    cb.d_logical, cb.d_enc, d_out, cb.out_recs);
+	    cb.d_logical, cb.d_enc, d_out, orecs);
 	MTZ_CU(h, cudaGetLastError());
 	const unsigned g1 = (unsigned)std::min<size_t>((n + K1_WARPS - 1) / K1_WARPS, (size_t)h->sm_count * 40);
-	k1_record_sums<<<g1, K1_THREADS, 0, st>>>(d_out, cb.out_recs, n, cb.osums, 312u);
-	k_stamp_chain<<<1, 32, 0, st>>>(d_out, cb.out_recs, cb.osums, n, h->d_carry_out, cb.d_ores);
+	k1_record_sums<<<g1, K1_THREADS, 0, st>>>(d_out, orecs, n, osums, 312u);
+	if (all_osums == nullptr)
+		k_stamp_chain<<<1, 32, 0, st>>>(d_out, orecs, osums, n, h->d_carry_out, cb.d_ores);
 	MTZ_CU(h, cudaGetLastError());
 	MTZ_CU(h, cudaMemcpyAsync(&cb.d_cres->out_bytes, cb.d_outpos, sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
 	count_launch(h, 5);
@@ -603,6 +611,16 @@ int32_t mtz_dev_submit(mtz_handle *h, const void *d_in, size_t in_bytes,
 		    h->dv_hrecs[i].type == 3 ? h->dv_hrecs[i].lsize : 0);
 	if (need_out > out_cap)
 		return fail(h, MTZ_ENOSPC, "d_out must hold the worst case of %zu bytes", need_out);
+	const bool defer = (h->cfg.flags & MTZ_FLAG_DEFER_VERIFY) != 0;
+	if (defer && nrec > h->dv_all_cap) {
+		if (h->dv_all_orecs) MTZ_CU(h, cudaFree(h->dv_all_orecs));
+		if (h->dv_all_osums) MTZ_CU(h, cudaFree(h->dv_all_osums));
+		h->dv_all_orecs = nullptr; h->dv_all_osums = nullptr;
+		h->dv_all_cap = nrec + nrec / 8 + 64;
+		MTZ_CU(h, cudaMalloc(&h->dv_all_orecs, h->dv_all_cap * sizeof(mtz_rec)));
+		MTZ_CU(h, cudaMalloc(&h->dv_all_osums, h->dv_all_cap * sizeof(RecSums)));
+	}
+	h->dv_out = (uint8_t *)d_out;
 	MTZ_CU(h, cudaEventRecord(h->dv_c0, st));
 	MTZ_CU(h, cudaEventRecord(h->ev_pre[0], st));              // orders codec_reset before any post
 	MTZ_CU(h, cudaStreamWaitEvent(h->st_post, h->ev_pre[0], 0));
@@ -626,7 +644,8 @@ int32_t mtz_dev_submit(mtz_handle *h, const void *d_in, size_t in_bytes,
 		MTZ_CU(h, cudaEventRecord(h->ev_pre[b], st));
 		MTZ_CU(h, cudaStreamWaitEvent(h->st_post, h->ev_pre[b], 0));
 		rc = codec_launch_post(h, h->st_post, cb, (const uint8_t *)d_in, d_recs + i0, i1 - i0,
-		    (uint8_t *)d_out, (uint32_t)i0);
+		    (uint8_t *)d_out, (uint32_t)i0, defer ? h->dv_all_orecs : nullptr,
+		    defer ? h->dv_all_osums : nullptr);
 		if (rc != MTZ_OK) return rc;
 		MTZ_CU(h, cudaEventRecord(h->ev_post[b], h->st_post));
 		used[b] = true;
@@ -698,6 +717,14 @@ int32_t mtz_dev_finish(mtz_handle *h, const uint64_t carry_in[4], const uint64_t
 	MTZ_CU(h, cudaMemcpyAsync(h->dv_hres, h->dv_res, sizeof(ScanResult), cudaMemcpyDeviceToHost, st));
 	MTZ_CU(h, cudaMemcpyAsync(h->d_carry_in, &h->dv_res->carry, 32, cudaMemcpyDeviceToDevice, st));
 	const bool codec = is_codec_mode(h->cfg.mode) && h->dv_cb.cr != nullptr;
+	if (codec && (h->cfg.flags & MTZ_FLAG_DEFER_VERIFY) && h->dv_nrec > 0) {
+		// shard mode: the stamp chain of the whole shard, from the checksum the previous
+		// shard's output ended with (carry_out_in, uploaded above)
+		k_stamp_chain<<<1, 32, 0, st>>>(h->dv_out, h->dv_all_orecs, h->dv_all_osums,
+		    (uint32_t)h->dv_nrec, h->d_carry_out, h->dv_cb.d_ores);
+		MTZ_CU(h, cudaGetLastError());
+		count_launch(h, 1);
+	}
 	if (codec) {
 		MTZ_CU(h, cudaMemcpyAsync(h->dv_cb.h_cres, h->dv_cb.d_cres, sizeof(CodecResult), cudaMemcpyDeviceToHost, st));
 		MTZ_CU(h, cudaMemcpyAsync(h->dv_cb.h_ores, h->dv_cb.d_ores, sizeof(ScanResult), cudaMemcpyDeviceToHost, st));

@@ -345,3 +345,42 @@ def test_randomized_streams_all_modes(oracle, seed):
     rc, want_r, _ = oracle.stream_recompress(got_c)
     got_r, _, _ = _gpu("recompress", got_c, cap=s.size + (1 << 20), batch_bytes=batch)
     assert np.array_equal(got_r, want_r)
+
+
+def test_codec_shards_with_deferred_chain(oracle):
+    """Record-index sharding of RECOMPRESS (what two ranks do): K2/K3/assemble per shard in
+    any order, input verdict after the 40-byte aggregate exchange, output stamp chain hopping
+    shard to shard with the 32-byte checksum.  Concatenated output == oracle on the whole."""
+    import torch
+    from manatee_b200 import GpuSnapshotStage, index_host
+    from manatee_b200 import shard as SH
+    from manatee_b200._native import FLAG_DEFER_VERIFY
+    s = _mixed_stream(oracle, n=48)
+    rc, c, _ = oracle.stream_compress(s)
+    rc, want, st = oracle.stream_recompress(c)
+    recs, used = index_host(c)
+    cut = 23
+    cut_off = int(recs["off"][cut])
+    shards = [(0, cut_off, recs[:cut].copy()), (cut_off, c.size - cut_off, recs[cut:].copy())]
+    shards[1][2]["off"] -= cut_off
+    d_in = torch.from_numpy(c).cuda()
+    stages, outs, aggs = [], [], []
+    for (o, n, r) in reversed(shards):                      # submit order is irrelevant
+        g = GpuSnapshotStage("recompress", flags=FLAG_DEFER_VERIFY)
+        d_r = torch.from_numpy(r.view(np.uint8).copy()).cuda()
+        d_o = torch.zeros(int(r["lsize"].sum()) + 312 * len(r) + (1 << 20), dtype=torch.uint8, device="cuda")
+        g.dev_submit(d_in.data_ptr() + o, n, d_r.data_ptr(), len(r), d_o.data_ptr(), d_o.numel())
+        stages.insert(0, g); outs.insert(0, (d_o, d_r)); aggs.insert(0, g.dev_aggregate())
+    try:
+        carry_out = (0, 0, 0, 0)
+        pieces = []
+        for k, g in enumerate(stages):
+            ob, _, carry_out = g.dev_finish(carry_in=SH.carry_before(k, aggs), carry_out_in=carry_out)
+            pieces.append(outs[k][0][:ob].cpu().numpy())
+        got = np.concatenate(pieces)
+        assert np.array_equal(got, want)
+        assert carry_out == oracle.fletcher4(want)
+        assert stages[1].end_checksum() == st.end_cksum.tuple()
+    finally:
+        for g in stages:
+            g.close()
