@@ -77,9 +77,9 @@ class ClockSampler(object):
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -90,7 +90,12 @@ class ClockSampler(object):
             self.proc.kill()
         sm, mx, reasons, pw = [], [], set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        rows = [r for (ts, r) in self.rows if t0 is None or (t0 - 0.02 <= ts <= t1 + 0.05)]
+        scope = "timed region"
+        if len(rows) < 2:             # region shorter than the sampler's period: use the whole
+            rows = [r for (ts, r) in self.rows]      # loaded window (warm-up + timed steps)
+            scope = "warm-up + timed region"
+        for r in rows:
             if len(r) < 9:
                 continue
             try:
@@ -103,7 +108,7 @@ class ClockSampler(object):
         return {"sm_mhz": statistics.median(sm) if sm else None,
                 "sm_max_mhz": max(mx) if mx else None,
                 "power_w_max": max(pw) if pw else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "scope": scope, "reasons": sorted(reasons)}
 
 
 def cpu_quota():
@@ -331,6 +336,9 @@ def run_ours(args):
 
     d_recs_gpu = torch.empty((len(recs) + 16) * 32, dtype=torch.uint8, device="cuda")
 
+    agg_t = torch.zeros(5, dtype=torch.int64, device="cuda")
+    all_t = torch.zeros(5 * world, dtype=torch.int64, device="cuda")
+
     def step_resident():
         # the DRR record table is rebuilt ON THE GPU every step (K4 parse half): nothing but
         # the stream bytes is assumed to be resident when the timed region starts
@@ -339,10 +347,19 @@ def run_ours(args):
         assert n_idx == len(recs) and used_idx == shard.size
         g.dev_submit(d_stream.data_ptr(), shard.size, d_recs_gpu.data_ptr(), n_idx,
                      cuda_stream=st.cuda_stream)
-        c = exchange(g) if world > 1 else (0, 0, 0, 0)
-        _, carry, _ = g.dev_finish(carry_in=c)
+        if world == 1:
+            _, carry, _ = g.dev_finish(carry_in=(0, 0, 0, 0))
+            return carry
+        # shard exchange without a host round trip: aggregate -> NCCL all-gather -> carry fold
+        # -> verify, all ordered on one CUDA stream; the only sync is the verdict read
+        with torch.cuda.stream(st):
+            g.dev_aggregate_async(agg_t.data_ptr())
+            dist.all_gather_into_tensor(all_t, agg_t)
+            _, carry, _ = g.dev_finish_gathered(all_t.data_ptr(), rank)
         return carry
 
+    clocks = ClockSampler(local)
+    clocks.start()                      # before warm-up: nvidia-smi needs ~100 ms to start
     for _ in range(args.warmup):
         carry = step_resident()
     if world > 1:
@@ -352,11 +369,10 @@ def run_ours(args):
     e0 = torch.cuda.Event(enable_timing=True)
     e1 = torch.cuda.Event(enable_timing=True)
     s0 = g.stats()
-    clocks = ClockSampler(local)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    clocks.start()
+    t_wall0 = time.time()
     e0.record(st)
     for _ in range(args.steps):
         carry = step_resident()
@@ -365,7 +381,7 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
     ms_total = e0.elapsed_time(e1)
-    clk = clocks.stop()
+    clk = clocks.stop(t_wall0, time.time())
     s1 = g.stats()
     t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
     if world > 1:

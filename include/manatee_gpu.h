@@ -168,6 +168,14 @@ int32_t mtz_dev_aggregate(mtz_handle *h, uint64_t agg[5]);
 int32_t mtz_dev_finish(mtz_handle *h, const uint64_t carry_in[4],
     const uint64_t carry_out_in[4], size_t *out_bytes, uint64_t carry[4],
     uint64_t carry_out[4]);
+/* stream-ordered form of the same exchange (no host round trip): the aggregate is
+ * written to d_agg (5 x u64, device), the caller all-gathers it on the same CUDA
+ * stream (NCCL), and hands the gathered table (world x 5 x u64, device) back; the
+ * carry-in is folded from the aggregates of ranks < rank on the GPU. */
+int32_t mtz_dev_aggregate_async(mtz_handle *h, void *d_agg);
+int32_t mtz_dev_finish_gathered(mtz_handle *h, const void *d_all_aggs, uint32_t rank,
+    const uint64_t carry_out_in[4], size_t *out_bytes, uint64_t carry[4],
+    uint64_t carry_out[4]);
 int32_t mtz_dev_reset(mtz_handle *h);
 /* set the running checksums a slice continues from (NULL = leave) */
 int32_t mtz_set_carry(mtz_handle *h, const uint64_t carry_in[4],

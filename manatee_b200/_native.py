@@ -53,7 +53,7 @@ SYMBOLS = [
     "mtz_out_peek", "mtz_out_consume", "mtz_read", "mtz_event_fd", "mtz_get_stats",
     "mtz_end_checksum", "mtz_host_alloc", "mtz_host_free", "mtz_process_host",
     "mtz_index_host", "mtz_dev_index", "mtz_dev_submit", "mtz_dev_aggregate",
-    "mtz_dev_finish", "mtz_dev_reset", "mtz_set_carry",
+    "mtz_dev_finish", "mtz_dev_reset", "mtz_dev_aggregate_async", "mtz_dev_finish_gathered", "mtz_set_carry",
     "mtz_k_lz4_decode", "mtz_k_lz4_encode",
 ]
 
@@ -97,6 +97,9 @@ def lib():
     L.mtz_dev_aggregate.argtypes = [H, C.POINTER(u64 * 5)]
     L.mtz_dev_finish.argtypes = [H, vp, vp, C.POINTER(sz), C.POINTER(u64 * 4), C.POINTER(u64 * 4)]
     L.mtz_dev_reset.argtypes = [H]
+    L.mtz_dev_aggregate_async.argtypes = [H, vp]
+    L.mtz_dev_finish_gathered.argtypes = [H, vp, C.c_uint32, vp, C.POINTER(sz), C.POINTER(u64 * 4),
+                                          C.POINTER(u64 * 4)]
     L.mtz_set_carry.argtypes = [H, vp, vp]
     L.mtz_k_lz4_decode.argtypes = [H, vp, vp, vp, C.c_uint32, vp]
     L.mtz_k_lz4_encode.argtypes = [H, vp, vp, vp, C.c_uint32, vp]

@@ -231,4 +231,13 @@ k_scan_verify(const RecSums *__restrict__ sums, uint32_t nrec,
 	}
 }
 
+// carry-in of shard `rank` = fold of the aggregates of all earlier shards (device-side
+// twin of manatee_b200/shard.py::carry_before)
+__global__ void k_fold_carry(const Part *__restrict__ aggs, uint32_t rank, Ck4 *__restrict__ carry)
+{
+	Ck4 s = { 0, 0, 0, 0 };
+	for (uint32_t r = 0; r < rank; r++) s = apply(s, aggs[r]);
+	*carry = s;
+}
+
 } // namespace mtz

@@ -171,109 +171,6 @@ struct Tab17 {                                  // 4096 x 17 bit: blocks up to 1
 #define LZ4_TAB_BIG_WORDS     4096u             // TabU32 / TabU16: 16 KiB
 #define LZ4_TAB_COMPACT_WORDS 2176u             // Tab17: 8.5 KiB
 
-// ---- sliding window of the source in shared memory ------------------------
-// The matcher reads the source at the scan front (sequential) and at recent
-// candidates (mostly a few KiB back).  A per-warp ring of LZ4_WIN bytes, filled
-// ahead of the scan with cp.async (16 B per lane, 512 B per fill), turns those
-// reads into ~30-cycle shared-memory loads; anything older falls back to global.
-// Measured on B200 (profiles/r1_k3_encode.md): K3 is bound by dependent
-// instruction / shared-memory latency at low occupancy, not by source-read
-// latency, so the window costs more (shared memory -> fewer warps, residency
-// checks -> more instructions) than it saves.  LZ4_WIN = 0 compiles it out; the
-// code stays for experiments with larger dictionaries.
-#ifndef LZ4_WIN
-#define LZ4_WIN 0u
-#endif
-#define LZ4_AHEAD 3072u
-
-struct SrcWin {
-	const uint8_t *g;          // source (global)
-	const uint8_t *ga;         // g rounded down to 16 B; sx = x + skew indexes it
-	uint32_t *ring;            // LZ4_WIN bytes of shared memory
-	uint32_t skew, issued, ready, limit;   // skewed coordinates; issued/ready multiples of 512
-	int lane;
-
-#if LZ4_WIN == 0
-	// no ring: keep the scan front warm in L2 instead (the record is streamed
-	// from HBM exactly once; without this every new line costs a DRAM round trip)
-	uint32_t pf_hi, pf_lim;
-	__device__ __forceinline__ void init(const uint8_t *src, uint32_t isize, uint32_t *, int ln)
-	{
-		g = src; lane = ln; pf_hi = 0; pf_lim = isize;
-	}
-	__device__ __forceinline__ void prefetch(uint32_t x_hi)
-	{
-		const uint32_t want = min(pf_lim, x_hi);
-		if (want > pf_hi) {
-			const uint32_t x = pf_hi + 128u * (uint32_t)lane;
-			if (x < want) asm volatile("prefetch.global.L2 [%0];" :: "l"(g + x));
-			pf_hi = min(want, pf_hi + 4096u);
-		}
-	}
-	__device__ __forceinline__ void ensure(uint32_t) {}
-	__device__ __forceinline__ uint32_t rd32(uint32_t x) const { return ld32u(g + x); }
-	__device__ __forceinline__ uint32_t rd8(uint32_t x) const { return g[x]; }
-#else
-	__device__ __forceinline__ void init(const uint8_t *src, uint32_t isize, uint32_t *r, int ln)
-	{
-		g = src; ring = r; lane = ln;
-		skew = (uint32_t)((uintptr_t)src & 15u);
-		ga = src - skew;
-		limit = ((skew + isize + 15u) & ~15u) + 16u;
-		issued = ready = 0;
-	}
-	__device__ __forceinline__ void fill_one()
-	{
-		const uint32_t sx = issued + 16u * (uint32_t)lane;
-		if (sx < limit) {
-			const uint32_t dst = (uint32_t)__cvta_generic_to_shared(
-			    reinterpret_cast<uint8_t *>(ring) + (sx & (LZ4_WIN - 1u)));
-			asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(ga + sx) : "memory");
-		}
-		issued += 512u;
-	}
-	// request bytes up to source position x_hi (non-blocking)
-	__device__ __forceinline__ void prefetch(uint32_t x_hi)
-	{
-		const uint32_t want = min(limit, skew + x_hi);
-		bool any = false;
-		while (issued < want && issued - ready < LZ4_WIN - 512u) { fill_one(); any = true; }
-		if (any) asm volatile("cp.async.commit_group;" ::: "memory");
-	}
-	// make [.., x_hi) resident if the ring can hold it (blocking)
-	__device__ __forceinline__ void ensure(uint32_t x_hi)
-	{
-		const uint32_t want = min(limit, skew + x_hi);
-		if (want <= ready) return;
-		prefetch(x_hi);
-		asm volatile("cp.async.wait_all;" ::: "memory");
-		__syncwarp();
-		ready = issued;
-	}
-	__device__ __forceinline__ bool resident(uint32_t sx, uint32_t n) const
-	{
-		const uint32_t lo = issued > LZ4_WIN ? issued - LZ4_WIN : 0u;
-		return sx >= lo && sx + n <= ready;
-	}
-	__device__ __forceinline__ uint32_t rd32(uint32_t x) const
-	{
-		const uint32_t sx = x + skew;
-		if (resident(sx, 4u)) {
-			const uint32_t i = sx & (LZ4_WIN - 1u);
-			const uint32_t w0 = ring[i >> 2], w1 = ring[((i >> 2) + 1u) & (LZ4_WIN / 4u - 1u)];
-			return __funnelshift_r(w0, w1, (i & 3u) * 8u);
-		}
-		return ld32u(g + x);
-	}
-	__device__ __forceinline__ uint32_t rd8(uint32_t x) const
-	{
-		const uint32_t sx = x + skew;
-		if (resident(sx, 1u)) return reinterpret_cast<const uint8_t *>(ring)[sx & (LZ4_WIN - 1u)];
-		return g[x];
-	}
-#endif
-};
-
 // cooperative store of a 255-run length extension (value = len - 15 already)
 __device__ __forceinline__ uint32_t put_len_ext(uint8_t *dst, uint32_t op, uint32_t v, int lane)
 {
@@ -283,184 +180,10 @@ __device__ __forceinline__ uint32_t put_len_ext(uint8_t *dst, uint32_t op, uint3
 	return op + n255 + 1u;
 }
 
-// returns the LZ4 block size, or 0 when it does not fit in osize
-template <class TAB, bool DIST>
-__device__ __forceinline__ uint32_t warp_lz4_encode(const uint8_t *__restrict__ src,
-    uint32_t isize, uint8_t *__restrict__ dst, uint32_t osize, uint32_t *tabmem,
-    uint32_t *ringmem, int lane)
-{
-	constexpr int LOG = TAB::LOG;
-	TAB tab; tab.t = tabmem;
-	SrcWin win; win.init(src, isize, ringmem, lane);
-	const uint32_t lanebit = 1u << lane, lower = lanebit - 1u;
-	tab.clear(lane);
-	win.prefetch(LZ4_AHEAD);
-	__syncwarp();
-
-	uint32_t ip = 0, anchor = 0, op = 0;
-	const uint32_t iend = isize;
-	if (isize >= (uint32_t)LZ4_MINLENGTH) {
-		const uint32_t mflimit = iend - LZ4_MFLIMIT;
-		const uint32_t matchlimit = iend - LZ4_LASTLITERALS;
-		ip = 1;                                         // slot of position 0 is already 0
-		for (;;) {
-			// ------------------------------------------------ search --
-			uint32_t ref = 0;
-			bool to_tail = false;
-			const uint32_t start = ip;
-			for (uint32_t a0 = 0;; a0 += 32u) {
-				const uint32_t a = a0 + (uint32_t)lane;
-				const uint32_t p = start + skip_dist(a);
-				const uint32_t step = (67u + a) >> 6;
-				const bool valid = (p + step <= mflimit);
-				// positions of this round end below start + skip_dist(a0 + 32) + 4
-				win.ensure(min(iend, start + skip_dist(a0 + 32u) + 8u));
-				uint32_t h = 0xffffffffu - (uint32_t)lane, cand = 0, v = 0;
-				if (valid) {
-					v = win.rd32(p);
-					h = (v * 2654435761u) >> (32 - LOG);
-				}
-				const uint32_t all_same = __match_any_sync(0xffffffffu, h);
-				const uint32_t same = all_same & lower;
-				const int from = same ? (31 - __clz((int)same)) : lane;
-				const uint32_t fwd = __shfl_sync(0xffffffffu, p, from);
-				bool hit = false;
-				if (valid) {
-					cand = same ? fwd : tab.get(h);
-					if (!DIST || cand + LZ4_MAXDIST >= p) hit = (win.rd32(cand) == v);
-				}
-				const uint32_t hits = __ballot_sync(0xffffffffu, hit);
-				const uint32_t inval = __ballot_sync(0xffffffffu, !valid);
-				const int F = hits ? (__ffs((int)hits) - 1) : 32;
-				const int I = inval ? (__ffs((int)inval) - 1) : 32;
-				if (I < F) { to_tail = true; break; }
-				__syncwarp();
-				// commit table updates of lanes <= F (the last equal-hash lane wins)
-				{
-					const uint32_t upto = (F >= 31) ? 0xffffffffu : ((2u << F) - 1u);
-					const uint32_t later = all_same & ~(lanebit | lower) & upto;
-					if ((lanebit & upto) && later == 0u) tab.set(h, p);
-				}
-				__syncwarp();
-				if (F < 32) {
-					ip = __shfl_sync(0xffffffffu, p, F);
-					ref = __shfl_sync(0xffffffffu, cand, F);
-					break;
-				}
-				win.prefetch(start + skip_dist(a0 + 64u) + LZ4_AHEAD);
-			}
-			if (to_tail) break;
-
-			// ---------------------------------------------- catch up --
-			for (;;) {
-				const uint32_t k = (uint32_t)lane + 1u;
-				bool eq = false;
-				if (ip >= anchor + k && ref >= k) eq = (win.rd8(ip - k) == win.rd8(ref - k));
-				const uint32_t ne = ~__ballot_sync(0xffffffffu, eq);
-				const uint32_t n = ne ? (uint32_t)(__ffs((int)ne) - 1) : 32u;
-				ip -= n; ref -= n;
-				if (n < 32u) break;
-			}
-
-			// ---------------------------------------------- literals --
-			const uint32_t litlen = ip - anchor;
-			uint32_t token = op++;
-			if (op + litlen + (2u + 1u + LZ4_LASTLITERALS) + (litlen >> 8) > osize) return 0u;
-			uint32_t tokval;
-			if (litlen >= 15u) {
-				tokval = 15u << 4;
-				op = put_len_ext(dst, op, litlen - 15u, lane);
-			} else {
-				tokval = litlen << 4;
-			}
-			for (uint32_t i = (uint32_t)lane; i < litlen; i += 32u) dst[op + i] = (uint8_t)win.rd8(anchor + i);
-			op += litlen;
-
-			// ------------------------------- one or more back-to-back matches --
-			for (;;) {
-				if (lane == 0) {
-					dst[op] = (uint8_t)((ip - ref) & 0xffu);
-					dst[op + 1] = (uint8_t)((ip - ref) >> 8);
-				}
-				op += 2;
-				ip += LZ4_MINMATCH; ref += LZ4_MINMATCH;
-				anchor = ip;
-				// common prefix of src+ref and src+ip, ip bounded by matchlimit
-				for (;;) {
-					win.ensure(min(iend, ip + 132u));
-					const uint32_t o = 4u * (uint32_t)lane;
-					const uint32_t room = (ip + o < matchlimit) ? (matchlimit - ip - o) : 0u;
-					uint32_t n = 0;
-					if (room) {
-						const uint32_t x = win.rd32(ip + o) ^ win.rd32(ref + o);
-						n = x ? (uint32_t)((__ffs((int)x) - 1) >> 3) : 4u;
-						if (n > room) n = room;
-					}
-					const uint32_t part = __ballot_sync(0xffffffffu, n < 4u);
-					const int Fp = part ? (__ffs((int)part) - 1) : 32;
-					const uint32_t adv = (Fp < 32) ? (4u * (uint32_t)Fp + __shfl_sync(0xffffffffu, n, Fp & 31)) : 128u;
-					ip += adv; ref += adv;
-					if (Fp < 32) break;
-					win.prefetch(ip + 128u + LZ4_AHEAD);
-				}
-				uint32_t mlen = ip - anchor;
-				if (op + (1u + LZ4_LASTLITERALS) + (mlen >> 8) > osize) return 0u;
-				if (mlen >= 15u) {
-					tokval += 15u;
-					op = put_len_ext(dst, op, mlen - 15u, lane);
-				} else {
-					tokval += mlen;
-				}
-				if (lane == 0) dst[token] = (uint8_t)tokval;
-
-				if (ip > mflimit) { anchor = ip; to_tail = true; break; }
-
-				// insert ip-2, then probe ip for an immediate follow-on match
-				{
-					win.ensure(min(iend, ip + 8u));
-					const uint32_t h2 = (win.rd32(ip - 2u) * 2654435761u) >> (32 - LOG);
-					if (lane == 0) tab.set(h2, ip - 2u);
-					__syncwarp();
-					const uint32_t v = win.rd32(ip);
-					const uint32_t h = (v * 2654435761u) >> (32 - LOG);
-					ref = tab.get(h);
-					__syncwarp();
-					if (lane == 0) tab.set(h, ip);
-					__syncwarp();
-					if ((!DIST || ref + LZ4_MAXDIST >= ip) && win.rd32(ref) == v) {
-						token = op++;
-						tokval = 0;
-						continue;
-					}
-				}
-				break;
-			}
-			if (to_tail) break;
-			anchor = ip++;
-			win.prefetch(ip + LZ4_AHEAD);
-		}
-	}
-	// ---------------------------------------------------- last literals --
-	{
-		const uint32_t last = iend - anchor;
-		if (op + last + 1u + ((last + 255u - 15u) / 255u) > osize) return 0u;
-		if (last >= 15u) {
-			if (lane == 0) dst[op] = (uint8_t)(15u << 4);
-			op = put_len_ext(dst, op + 1u, last - 15u, lane);
-		} else {
-			if (lane == 0) dst[op] = (uint8_t)(last << 4);
-			op += 1u;
-		}
-		for (uint32_t i = (uint32_t)lane; i < last; i += 32u) dst[op + i] = src[anchor + i];
-		op += last;
-	}
-	return op;
-}
-
 // ---------------------------------------------------------------------------
-// v3 of the same bit-exact matcher with the dependent global round trips of one
-// LZ4 sequence merged from seven to three (profiles/r1_k3_encode.md: K3 is bound
-// by latency chains at <= 24 warps/SM, not by bandwidth):
+// The matcher.  One LZ4 sequence costs three dependent global round trips (an
+// earlier version needed seven; profiles/r1_k3_encode.md: K3 is bound by latency
+// chains at <= 24 warps/SM, not by bandwidth):
 //   trip A  candidate gather of a search round (positions come preloaded)
 //   trip B  catch-up bytes + first 32 literals + first match-extension round
 //   trip C  follow-on probe + its extension round + next search round's positions
@@ -685,41 +408,22 @@ __device__ __forceinline__ uint32_t warp_lz4_encode3(const uint8_t *__restrict__
 	return op;
 }
 
-#ifndef LZ4_ENC_V3
-#define LZ4_ENC_V3 1
-#endif
-
 // zio_compress_data(LZ4) + 512 B sector rounding.  out_len = psize (frame
 // stored at dst) or lsize (store raw: dst content is scratch).  COMPACT: the
 // launch reserved only the 8.5 KiB table (every block is 64 KiB+11 .. 128 KiB).
 template <bool COMPACT>
 __device__ __forceinline__ uint32_t warp_zfs_lz4_compress(const uint8_t *__restrict__ src,
-    uint32_t lsize, uint8_t *__restrict__ dst, uint32_t *tabmem, uint32_t *ringmem, int lane)
+    uint32_t lsize, uint8_t *__restrict__ dst, uint32_t *tabmem, int lane)
 {
 	const uint32_t d_len = lsize - (lsize >> 3);
 	if (lsize < 1024u || lsize > (16u << 20) || d_len < 4u) return lsize;
 	uint32_t blk;
-#if LZ4_ENC_V3
-	(void)ringmem;
 	if (COMPACT)
 		blk = warp_lz4_encode3<Tab17, true>(src, lsize, dst + 4, d_len - 4u, tabmem, lane);
 	else if (lsize < (uint32_t)LZ4_64KLIMIT)
 		blk = warp_lz4_encode3<TabU16, false>(src, lsize, dst + 4, d_len - 4u, tabmem, lane);
 	else
 		blk = warp_lz4_encode3<TabU32, true>(src, lsize, dst + 4, d_len - 4u, tabmem, lane);
-#else
-	if (COMPACT)
-		blk = warp_lz4_encode<Tab17, true>(src, lsize, dst + 4, d_len - 4u, tabmem, ringmem, lane);
-	else if (lsize < (uint32_t)LZ4_64KLIMIT)
-		blk = warp_lz4_encode<TabU16, false>(src, lsize, dst + 4, d_len - 4u, tabmem, ringmem, lane);
-	else
-		blk = warp_lz4_encode<TabU32, true>(src, lsize, dst + 4, d_len - 4u, tabmem, ringmem, lane);
-#endif
-	// every exit of the encoder: nothing may still land in the ring once the
-	// warp moves on to its next record
-#if LZ4_WIN != 0
-	asm volatile("cp.async.wait_all;" ::: "memory");
-#endif
 	__syncwarp();
 	if (blk == 0u) return lsize;
 	const uint32_t c_len = blk + 4u;
@@ -734,7 +438,7 @@ __device__ __forceinline__ uint32_t warp_zfs_lz4_compress(const uint8_t *__restr
 	return psize;
 }
 
-// per-warp shared memory: [table | ring]
+// per-warp shared memory: the hash table
 template <bool COMPACT>
 __global__ void __launch_bounds__(LZ4_THREADS)
 k3_lz4_encode(const uint8_t *__restrict__ src_base, uint8_t *__restrict__ dst_base,
@@ -742,10 +446,9 @@ k3_lz4_encode(const uint8_t *__restrict__ src_base, uint8_t *__restrict__ dst_ba
 {
 	extern __shared__ uint4 s_dyn[];
 	constexpr uint32_t TABW = COMPACT ? LZ4_TAB_COMPACT_WORDS : LZ4_TAB_BIG_WORDS;
-	constexpr uint32_t PERW = TABW + LZ4_WIN / 4u;
+	constexpr uint32_t PERW = TABW;
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	uint32_t *tab = reinterpret_cast<uint32_t *>(s_dyn) + warp * PERW;
-	uint32_t *ring = tab + TABW;
 	const uint32_t gw = blockIdx.x * LZ4_WARPS + (uint32_t)warp;
 	const uint32_t nw = gridDim.x * LZ4_WARPS;
 	for (uint32_t j = gw; j < njobs; j += nw) {
@@ -758,7 +461,7 @@ k3_lz4_encode(const uint8_t *__restrict__ src_base, uint8_t *__restrict__ dst_ba
 			ps = job.lsize;
 		else
 			ps = warp_zfs_lz4_compress<COMPACT>(src_base + job.src_off, job.lsize,
-			    dst_base + job.dst_off, tab, ring, lane);
+			    dst_base + job.dst_off, tab, lane);
 		__syncwarp();
 		if (lane == 0) { jobs[j].out_len = ps; jobs[j].status = MTZ_OK; }
 	}

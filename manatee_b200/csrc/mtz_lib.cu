@@ -698,12 +698,47 @@ static int32_t account_result(mtz_handle *h, const ScanResult &r, uint64_t first
 	return MTZ_OK;
 }
 
+int32_t mtz_dev_aggregate_async(mtz_handle *h, void *d_agg)
+{
+	CHECK_H(h);
+	if (d_agg == nullptr) return MTZ_EINVAL;
+	MTZ_CU(h, cudaSetDevice(h->device));
+	cudaStream_t st = h->dv_st ? h->dv_st : h->st;
+	int32_t rc = launch_scan(h, st, h->dv_sums, h->dv_nrec, h->dv_tiles, h->dv_res, 0);
+	if (rc != MTZ_OK) return rc;
+	MTZ_CU(h, cudaMemcpyAsync(d_agg, &h->dv_res->agg, sizeof(Part), cudaMemcpyDeviceToDevice, st));
+	return MTZ_OK;
+}
+
+static int32_t dev_finish_impl(mtz_handle *h, const uint64_t carry_in[4], const void *d_all_aggs,
+    uint32_t rank, const uint64_t carry_out_in[4], size_t *out_bytes, uint64_t carry[4],
+    uint64_t carry_out[4]);
+
 int32_t mtz_dev_finish(mtz_handle *h, const uint64_t carry_in[4], const uint64_t carry_out_in[4],
     size_t *out_bytes, uint64_t carry[4], uint64_t carry_out[4])
+{
+	return dev_finish_impl(h, carry_in, nullptr, 0, carry_out_in, out_bytes, carry, carry_out);
+}
+
+int32_t mtz_dev_finish_gathered(mtz_handle *h, const void *d_all_aggs, uint32_t rank,
+    const uint64_t carry_out_in[4], size_t *out_bytes, uint64_t carry[4], uint64_t carry_out[4])
+{
+	if (d_all_aggs == nullptr) return MTZ_EINVAL;
+	return dev_finish_impl(h, nullptr, d_all_aggs, rank, carry_out_in, out_bytes, carry, carry_out);
+}
+
+static int32_t dev_finish_impl(mtz_handle *h, const uint64_t carry_in[4], const void *d_all_aggs,
+    uint32_t rank, const uint64_t carry_out_in[4], size_t *out_bytes, uint64_t carry[4],
+    uint64_t carry_out[4])
 {
 	CHECK_H(h);
 	MTZ_CU(h, cudaSetDevice(h->device));
 	cudaStream_t st = h->dv_st ? h->dv_st : h->st;
+	if (d_all_aggs != nullptr) {
+		k_fold_carry<<<1, 1, 0, st>>>((const Part *)d_all_aggs, rank, h->d_carry_in);
+		MTZ_CU(h, cudaGetLastError());
+		count_launch(h, 1);
+	}
 	if (carry_in != nullptr) {
 		memcpy(&h->h_carry[0], carry_in, 32);
 		MTZ_CU(h, cudaMemcpyAsync(h->d_carry_in, &h->h_carry[0], 32, cudaMemcpyHostToDevice, st));
@@ -1436,13 +1471,13 @@ static int32_t launch_k3(mtz_handle *h, cudaStream_t st, const void *d_src, void
     mtz_job *d_jobs, uint32_t njobs, bool compact)
 {
 	const size_t tabw = compact ? LZ4_TAB_COMPACT_WORDS : LZ4_TAB_BIG_WORDS;
-	const size_t smem = (size_t)LZ4_WARPS * (tabw + LZ4_WIN / 4) * sizeof(uint32_t);
+	const size_t smem = (size_t)LZ4_WARPS * tabw * sizeof(uint32_t);
 	static bool attr_set = false;
 	if (!attr_set) {
 		MTZ_CU(h, cudaFuncSetAttribute(k3_lz4_encode<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-		    (int)((size_t)LZ4_WARPS * (LZ4_TAB_COMPACT_WORDS + LZ4_WIN / 4) * 4)));
+		    (int)((size_t)LZ4_WARPS * LZ4_TAB_COMPACT_WORDS * 4)));
 		MTZ_CU(h, cudaFuncSetAttribute(k3_lz4_encode<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-		    (int)((size_t)LZ4_WARPS * (LZ4_TAB_BIG_WORDS + LZ4_WIN / 4) * 4)));
+		    (int)((size_t)LZ4_WARPS * LZ4_TAB_BIG_WORDS * 4)));
 		// all of the unified L1/shared array as shared memory: K3 is bound by records in
 		// flight (24 tables of 8.5 KiB per SM), measured 62 vs 46 GiB/s at a 75 % carve-out
 		// (profiles/r1_k3_encode.md).  MTZ_K3_CARVEOUT overrides for experiments.

@@ -140,6 +140,18 @@ class GpuSnapshotStage(object):
         self._check(self._L.mtz_dev_aggregate(self._h, C.byref(agg)))
         return tuple(int(x) for x in agg)
 
+    def dev_aggregate_async(self, d_agg_ptr):
+        self._check(self._L.mtz_dev_aggregate_async(self._h, d_agg_ptr))
+
+    def dev_finish_gathered(self, d_all_aggs_ptr, rank, carry_out_in=None):
+        ob = C.c_size_t(0)
+        c1 = (C.c_uint64 * 4)()
+        c2 = (C.c_uint64 * 4)()
+        co = (C.c_uint64 * 4)(*carry_out_in) if carry_out_in is not None else None
+        self._check(self._L.mtz_dev_finish_gathered(self._h, d_all_aggs_ptr, rank, co, C.byref(ob),
+                                                    C.byref(c1), C.byref(c2)))
+        return ob.value, tuple(int(x) for x in c1), tuple(int(x) for x in c2)
+
     def dev_finish(self, carry_in=None, carry_out_in=None):
         ob = C.c_size_t(0)
         c1 = (C.c_uint64 * 4)()

@@ -218,3 +218,50 @@ def test_gpu_side_parse_matches_host_parser(oracle):
         with pytest.raises(MtzError) as ei:
             g.dev_index(d.data_ptr(), bad.size, d_recs.data_ptr(), 400)
         assert ei.value.code == EFORMAT
+
+
+def test_stream_ordered_shard_exchange(oracle):
+    """mtz_dev_aggregate_async + mtz_dev_finish_gathered: the shard carry is folded on the GPU
+    from the gathered aggregates (what NCCL all-gather delivers), no host round trip."""
+    import torch
+    from manatee_b200 import index_host
+    s = oracle.synth_stream(60, recsize=131072, kind=oracle.PAYLOAD_PCG)
+    rc, st = oracle.stream_verify(s)
+    recs, used = index_host(s)
+    cuts = [0, 17, 41, len(recs)]
+    d = torch.from_numpy(s).cuda()
+    stages, tabs = [], []
+    aggs = torch.zeros(3 * 5, dtype=torch.int64, device="cuda")
+    for k in range(3):
+        r = recs[cuts[k]:cuts[k + 1]].copy()
+        o = int(r["off"][0])
+        n = (int(recs["off"][cuts[k + 1]]) if cuts[k + 1] < len(recs) else s.size) - o
+        r["off"] -= o
+        t = torch.from_numpy(r.view(np.uint8).copy()).cuda()
+        g = _stage()
+        g.dev_submit(d.data_ptr() + o, n, t.data_ptr(), len(r))
+        g.dev_aggregate_async(aggs[5 * k:].data_ptr())
+        stages.append(g); tabs.append(t)
+    try:
+        carries = []
+        for k, g in enumerate(stages):
+            _, c, _ = g.dev_finish_gathered(aggs.data_ptr(), k)
+            carries.append(c)
+        assert carries[-1] == oracle.fletcher4(s)
+        assert carries[0] == oracle.fletcher4(s[:int(recs["off"][17])])
+        assert stages[2].end_checksum() == st.end_cksum.tuple()
+        # corruption in shard 1 is reported there, with the shard-local record index
+        bad = s.copy(); bad[int(recs["off"][20]) + 312 + 5] ^= 8
+        d2 = torch.from_numpy(bad).cuda()
+        from manatee_b200._native import MtzError
+        g = _stage()
+        r = recs[17:41].copy(); o = int(r["off"][0]); r["off"] -= o
+        t = torch.from_numpy(r.view(np.uint8).copy()).cuda()
+        g.dev_submit(d2.data_ptr() + o, int(recs["off"][41]) - o, t.data_ptr(), len(r))
+        with pytest.raises(MtzError):
+            g.dev_finish_gathered(aggs.data_ptr(), 1)
+        assert g.stats()["bad_record"] == 4          # record 21 of the stream = index 4 of the shard
+        g.close()
+    finally:
+        for g in stages:
+            g.close()
