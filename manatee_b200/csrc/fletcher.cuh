@@ -181,12 +181,15 @@ __device__ __forceinline__ Ck4 warp_fletcher(const uint8_t *p0, uint32_t nwords,
 		// ---- full middle rows j = 1 .. NR-2, four loads in flight ----
 		uint32_t j = 1u;
 		const uint32_t jend = NR - 1u;
-		for (; j + 8u <= jend; j += 8u) {
-			uint4 v[8];
+#ifndef K1_UNROLL
+#define K1_UNROLL 12
+#endif
+		for (; j + K1_UNROLL <= jend; j += K1_UNROLL) {
+			uint4 v[K1_UNROLL];
 #pragma unroll
-			for (int u = 0; u < 8; u++) v[u] = ldg_stream(rowp + 32u * (j + (uint32_t)u));
+			for (int u = 0; u < K1_UNROLL; u++) v[u] = ldg_stream(rowp + 32u * (j + (uint32_t)u));
 #pragma unroll
-			for (int u = 0; u < 8; u++) {
+			for (int u = 0; u < K1_UNROLL; u++) {
 				t3 -= t2; t2 -= m; m -= 1u; acc.add(v[u], m, t2, t3);
 			}
 		}

@@ -361,7 +361,7 @@ static int32_t launch_k1(mtz_handle *h, cudaStream_t st, const uint8_t *d_in,
 {
 	if (nrec == 0) return MTZ_OK;
 	const unsigned grid = (unsigned)std::min<size_t>((nrec + K1_WARPS - 1) / K1_WARPS,
-	    (size_t)h->sm_count * 5 * 8);
+	    (size_t)h->sm_count * K1_MINBLOCKS * 8);
 	if (ea) MTZ_CU(h, cudaEventRecord(ea, st));
 	k1_record_sums<<<grid, K1_THREADS, 0, st>>>(d_in, d_recs, (uint32_t)nrec, d_sums, 280u);
 	MTZ_CU(h, cudaGetLastError());
