@@ -359,9 +359,21 @@ def run_ours(args):
         return carry
 
     clocks = ClockSampler(local)
-    clocks.start()                      # before warm-up: nvidia-smi needs ~100 ms to start
-    for _ in range(args.warmup):
+    if rank == 0:
+        clocks.start()                  # before warm-up: nvidia-smi needs >100 ms to start
+    warm_done = 0
+    t_w = time.time()
+    # W warm-up steps, plus (untimed) extra ones until the clock sampler is delivering rows, so
+    # that the short timed region is actually covered by samples
+    while True:
         carry = step_resident()
+        warm_done += 1
+        live = torch.tensor([1 if (rank != 0 or clocks.proc is None or len(clocks.rows) >= 2 or
+                                   time.time() - t_w > 2.0) else 0], device="cuda")
+        if world > 1:
+            dist.all_reduce(live, op=dist.ReduceOp.MIN)
+        if warm_done >= args.warmup and int(live.item()) == 1:
+            break
     if world > 1:
         # the stamped stream is the oracle's: the carry-in we derived on the GPU must
         # equal the generator's running checksum at the shard boundary
@@ -381,7 +393,7 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
     ms_total = e0.elapsed_time(e1)
-    clk = clocks.stop(t_wall0, time.time())
+    clk = clocks.stop(t_wall0, time.time()) if rank == 0 else None
     s1 = g.stats()
     t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -549,7 +561,7 @@ def run_ours(args):
             pass
         line = {
             "metric": "snapshot_stream_gibs", "value": round(value, 3), "unit": "GiB/s",
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "warmup_done": warm_done,
             "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u32->u64 (mod 2^64)", "data": "synthetic",
             "config": {
