@@ -108,11 +108,17 @@ class BackupSender(object):
                 return line
         raise RuntimeError("no snapshots found")
 
-    def _make_stage(self):
+    def _make_stage(self, backupJob=None):
         if not self._gpu or self._gpu.get("mode", "off") == "off":
             return None
         from ..stage import GpuSnapshotStage          # the product: fails loudly without the .so/GPU
-        g = self._gpu
+        g = dict(self._gpu)
+        # capability negotiation: only a receiver that asked for the
+        # stage-compressed wire gets it; everybody else gets the raw (verified) stream
+        if g["mode"] == "compress" and (backupJob is None or backupJob.get("accept") != "lz4-stage-v1"):
+            g["mode"] = "verify"
+        if backupJob is not None:
+            backupJob["wire"] = "lz4-stage-v1" if g["mode"] == "compress" else "raw"
         return GpuSnapshotStage(g["mode"], device=g.get("device", 0),
                                 ring_bytes=g.get("ringBytes", 0), batch_bytes=g.get("batchBytes", 0),
                                 out_ring_bytes=g.get("outRingBytes", 0), n_slots=g.get("slots", 0))
@@ -205,7 +211,7 @@ class BackupSender(object):
             te = threading.Thread(target=stderr_reader, daemon=True)
             te.start()
 
-            stage = self._make_stage()
+            stage = self._make_stage(backupJob)
             pump_err = []
             if stage is None:
                 while True:                                   # stdout.pipe(socket)

@@ -102,6 +102,8 @@ class BackupServer(object):
                                             "message": "host, dataset, and port parameters required"})
                 job = {"uuid": str(uuidlib.uuid4()), "host": params["host"], "port": params["port"],
                        "dataset": params["dataset"], "done": False}
+                if params.get("accept"):
+                    job["accept"] = params["accept"]      # wire capability of the receiver (f2)
                 self._send(200, {"jobid": job["uuid"], "jobPath": "/backup/" + job["uuid"]})
                 queue.push(job)
 

@@ -61,8 +61,13 @@ class ZfsClient(object):
 
     # -- lib/zfsClient.js:638-668
     def _postRestoreRequest(self, serverUrl):
-        body = json.dumps({"host": self._zfsHost, "port": self._zfsPort,
-                           "dataset": self._dataset}).encode()
+        req_body = {"host": self._zfsHost, "port": self._zfsPort, "dataset": self._dataset}
+        # advertise what this receiver's stage can undo.  A
+        # reference backupserver ignores unknown fields (lib/backupServer.js:134-146), a
+        # reference receiver never sends this, so mixed-version shards stay on the raw wire.
+        if self._gpu and self._gpu.get("mode") == "decompress":
+            req_body["accept"] = "lz4-stage-v1"
+        body = json.dumps(req_body).encode()
         req = urllib.request.Request(serverUrl.rstrip("/") + "/backup", data=body,
                                      headers={"Content-Type": "application/json"})
         try:

@@ -217,3 +217,31 @@ def test_coalesced_restores_share_one_send(fakezfs, tmp_path):
         assert digest == want and int(n) == fakezfs["stream"].size
         assert cli._restoreObject["done"] is True
     assert open(str(counter)).read().count("send") == 1, "coalesced requests must share one zfs send"
+
+
+@pytest.mark.gpu
+def test_gpu_sender_compress_falls_back_for_plain_receiver(fakezfs):
+    """Mixed versions (f2): a receiver that did not ask for the compressed wire gets the raw,
+    verified stream even from a sender configured to compress."""
+    cfg = {"batchBytes": 4 << 20, "ringBytes": 32 << 20, "outRingBytes": 32 << 20}
+    res, cli, events = _run_restore(fakezfs, sender_gpu=dict(cfg, mode="compress"), recv_gpu=None)
+    assert res["err"] is None, res
+    digest, n = open(fakezfs["recv_out"]).read().split()
+    s = fakezfs["stream"]
+    assert int(n) == s.size and digest == hashlib.sha256(s.tobytes()).hexdigest()
+    assert cli._restoreObject["wire"] == "raw" and cli._restoreObject["gpu"]["lz4_encoded"] == 0
+    # and the negotiated case advertises it in the job object
+    res, cli, events = _run_restore(fakezfs, sender_gpu=dict(cfg, mode="compress"),
+                                    recv_gpu=dict(cfg, mode="decompress"))
+    assert res["err"] is None and cli._restoreObject["wire"] == "lz4-stage-v1"
+
+
+@pytest.mark.gpu
+def test_verify_process_host_copy_out(oracle):
+    """VERIFY with a separate output buffer: the bytes come back from HBM (D2H), identical."""
+    from manatee_b200 import GpuSnapshotStage
+    s = oracle.synth_stream(20, recsize=65536, kind=oracle.PAYLOAD_PCG)
+    out = np.zeros(s.size + 100, dtype=np.uint8)
+    with GpuSnapshotStage("verify", batch_bytes=1 << 20) as g:
+        n = g.process_host(s, out)
+        assert n == s.size and np.array_equal(out[:n], s)
