@@ -51,9 +51,6 @@ struct Slot {
 	uint64_t in_off = 0;          // absolute stream offset of the batch
 	uint64_t writes = 0;
 	CodecBufs cb;                 // per-slot codec scratch
-	cudaEvent_t ev_d2h = nullptr;
-	bool d2h_pending = false;
-	uint64_t lz4_dec = 0, lz4_try = 0;
 };
 
 struct Engine;                    // streaming state (rings + worker thread)
@@ -81,7 +78,6 @@ struct mtz_handle {
 	cudaEvent_t ev_prev_scan = nullptr;
 	bool have_prev_scan = false;
 	uint64_t records_done = 0;
-	uint64_t batch_seq = 0;
 
 	// device-API / deferred-verify state: one growing table of per-record sums
 	mtz::RecSums *dv_sums = nullptr;

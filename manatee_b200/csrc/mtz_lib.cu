@@ -201,7 +201,6 @@ static void free_slot(Slot &s)
 	if (s.ev_k1b) cudaEventDestroy(s.ev_k1b);
 	if (s.ev_c0) cudaEventDestroy(s.ev_c0);
 	if (s.ev_c1) cudaEventDestroy(s.ev_c1);
-	if (s.ev_d2h) cudaEventDestroy(s.ev_d2h);
 	codec_free(s.cb);
 	s = Slot();
 }
@@ -825,7 +824,6 @@ static int32_t ensure_slots(mtz_handle *h)
 		if (is_codec_mode(h->cfg.mode)) {
 			s.out_cap = cap;
 			MTZ_CU(h, cudaMalloc(&s.d_out, cap + 512));
-			MTZ_CU(h, cudaEventCreateWithFlags(&s.ev_d2h, cudaEventDisableTiming));
 			rc = codec_alloc(h, s.cb, rec_cap, cap + rec_cap * 48);
 			if (rc != MTZ_OK) return rc;
 		}
@@ -971,7 +969,6 @@ static int32_t submit_batch(mtz_handle *h, Slot &s, const uint8_t *p0, size_t n0
 		MTZ_CU(h, cudaMemcpyAsync(host_out, s.d_in, bytes, cudaMemcpyDeviceToHost, s.st));
 	MTZ_CU(h, cudaEventRecord(s.ev_done, s.st));
 	s.busy = true;
-	h->batch_seq++;
 	return MTZ_OK;
 }
 
