@@ -93,6 +93,8 @@ struct mtz_handle {
 
 	mtz::CodecBufs dv_cb, dv_cb2;      // device-API codec scratch (sub-batched, double-buffered)
 	cudaStream_t st_post = nullptr;    // layout/assemble/stamp of sub-batch k under K2/K3 of k+1
+	cudaStream_t st_dec = nullptr;     // plan + K2 of sub-batch k+1 under K3 of k
+	cudaEvent_t ev_dec[2] = {nullptr, nullptr};
 	cudaEvent_t ev_pre[2] = {nullptr, nullptr}, ev_post[2] = {nullptr, nullptr};
 	std::vector<mtz_rec> dv_hrecs;     // host copy of the device record table
 	mtz_rec *dv_all_orecs = nullptr;   // shard mode: output table / sums of the whole submit

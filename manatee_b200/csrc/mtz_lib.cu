@@ -291,7 +291,9 @@ int32_t mtz_close(mtz_handle *h)
 	}
 	codec_free(h->dv_cb);
 	if (h->st_post) cudaStreamDestroy(h->st_post);
+	if (h->st_dec) cudaStreamDestroy(h->st_dec);
 	for (int i = 0; i < 2; i++) {
+		if (h->ev_dec[i]) cudaEventDestroy(h->ev_dec[i]);
 		if (h->ev_pre[i]) cudaEventDestroy(h->ev_pre[i]);
 		if (h->ev_post[i]) cudaEventDestroy(h->ev_post[i]);
 	}
@@ -475,8 +477,26 @@ static bool all_compact_blocks(const mtz_rec *recs, size_t n)
 	return true;
 }
 
+static int32_t codec_launch_dec(mtz_handle *h, cudaStream_t st, CodecBufs &cb, const uint8_t *d_in,
+    const mtz_rec *d_recs, size_t nrec);
+static int32_t codec_launch_enc(mtz_handle *h, cudaStream_t st, CodecBufs &cb, size_t nrec, bool compact);
+
 static int32_t codec_launch_pre(mtz_handle *h, cudaStream_t st, CodecBufs &cb, const uint8_t *d_in,
     const mtz_rec *d_recs, size_t nrec, cudaEvent_t ea, cudaEvent_t eb, bool compact)
+{
+	if (nrec == 0) return MTZ_OK;
+	if (ea) MTZ_CU(h, cudaEventRecord(ea, st));
+	int32_t rc = codec_launch_dec(h, st, cb, d_in, d_recs, nrec);
+	if (rc != MTZ_OK) return rc;
+	rc = codec_launch_enc(h, st, cb, nrec, compact);
+	if (rc != MTZ_OK) return rc;
+	if (eb) MTZ_CU(h, cudaEventRecord(eb, st));
+	return MTZ_OK;
+}
+
+// plan + K2 (decode) of one (sub-)batch
+static int32_t codec_launch_dec(mtz_handle *h, cudaStream_t st, CodecBufs &cb, const uint8_t *d_in,
+    const mtz_rec *d_recs, size_t nrec)
 {
 	if (nrec == 0) return MTZ_OK;
 	if (nrec > cb.rec_cap) return fail(h, MTZ_ENOSPC, "codec batch of %zu records exceeds %zu", nrec, cb.rec_cap);
@@ -487,17 +507,18 @@ static int32_t codec_launch_pre(mtz_handle *h, cudaStream_t st, CodecBufs &cb, c
 	k_plan_jobs<<<gb, tb, 0, st>>>(d_in, d_recs, n, cb.cr, cb.offs, cb.d_logical, cb.d_enc, cb.dec, cb.enc);
 	MTZ_CU(h, cudaGetLastError());
 	count_launch(h, 3);
-	if (ea) MTZ_CU(h, cudaEventRecord(ea, st));
 	if (mode != MTZ_MODE_COMPRESS) {
 		int32_t rc = mtz_k_lz4_decode(h, nullptr, nullptr, cb.dec, n, st);
 		if (rc != MTZ_OK) return rc;
 	}
-	if (mode != MTZ_MODE_DECOMPRESS) {
-		int32_t rc = launch_k3(h, st, nullptr, nullptr, cb.enc, n, compact);
-		if (rc != MTZ_OK) return rc;
-	}
-	if (eb) MTZ_CU(h, cudaEventRecord(eb, st));
 	return MTZ_OK;
+}
+
+// K3 (encode) of one (sub-)batch
+static int32_t codec_launch_enc(mtz_handle *h, cudaStream_t st, CodecBufs &cb, size_t nrec, bool compact)
+{
+	if (nrec == 0 || h->cfg.mode == MTZ_MODE_DECOMPRESS) return MTZ_OK;
+	return launch_k3(h, st, nullptr, nullptr, cb.enc, (uint32_t)nrec, compact);
 }
 
 // Part 2: layout, assemble into d_out + *cb.d_outpos (the running output offset
@@ -594,7 +615,9 @@ int32_t mtz_dev_submit(mtz_handle *h, const void *d_in, size_t in_bytes,
 		MTZ_CU(h, cudaEventCreate(&h->dv_c0));
 		MTZ_CU(h, cudaEventCreate(&h->dv_c1));
 		MTZ_CU(h, cudaStreamCreateWithFlags(&h->st_post, cudaStreamNonBlocking));
+		MTZ_CU(h, cudaStreamCreateWithFlags(&h->st_dec, cudaStreamNonBlocking));
 		for (int i = 0; i < 2; i++) {
+			MTZ_CU(h, cudaEventCreateWithFlags(&h->ev_dec[i], cudaEventDisableTiming));
 			MTZ_CU(h, cudaEventCreateWithFlags(&h->ev_pre[i], cudaEventDisableTiming));
 			MTZ_CU(h, cudaEventCreateWithFlags(&h->ev_post[i], cudaEventDisableTiming));
 		}
@@ -636,9 +659,15 @@ int32_t mtz_dev_submit(mtz_handle *h, const void *d_in, size_t in_bytes,
 			budget += cost; i1++;
 		}
 		const int b = (int)(k & 1);
-		if (used[b]) MTZ_CU(h, cudaStreamWaitEvent(st, h->ev_post[b], 0));   // scratch set free again
-		rc = codec_launch_pre(h, st, cb, (const uint8_t *)d_in, d_recs + i0, i1 - i0, nullptr, nullptr,
-		    all_compact_blocks(h->dv_hrecs.data() + i0, i1 - i0));
+		// decode stream: plan + K2 of sub-batch k run under K3 of sub-batch k-1 (K2 needs no
+		// shared memory and K3 leaves 40 warp slots per SM empty)
+		if (used[b]) MTZ_CU(h, cudaStreamWaitEvent(h->st_dec, h->ev_post[b], 0));   // scratch set free again
+		else MTZ_CU(h, cudaStreamWaitEvent(h->st_dec, h->ev_pre[0], 0));           // after codec_reset
+		rc = codec_launch_dec(h, h->st_dec, cb, (const uint8_t *)d_in, d_recs + i0, i1 - i0);
+		if (rc != MTZ_OK) return rc;
+		MTZ_CU(h, cudaEventRecord(h->ev_dec[b], h->st_dec));
+		MTZ_CU(h, cudaStreamWaitEvent(st, h->ev_dec[b], 0));
+		rc = codec_launch_enc(h, st, cb, i1 - i0, all_compact_blocks(h->dv_hrecs.data() + i0, i1 - i0));
 		if (rc != MTZ_OK) return rc;
 		MTZ_CU(h, cudaEventRecord(h->ev_pre[b], st));
 		MTZ_CU(h, cudaStreamWaitEvent(h->st_post, h->ev_pre[b], 0));
