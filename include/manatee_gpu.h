@@ -63,9 +63,9 @@ typedef struct mtz_config {
 	int32_t  device;        /* CUDA ordinal */
 	uint32_t mode;          /* MTZ_MODE_* */
 	uint32_t flags;         /* MTZ_FLAG_* */
-	uint64_t ring_bytes;    /* pinned input ring (0 = 256 MiB) */
+	uint64_t ring_bytes;    /* pinned input ring (0 = max(256 MiB, 2 x batch_bytes)) */
 	uint64_t out_ring_bytes;/* pinned output ring, codec modes (0 = ring_bytes) */
-	uint64_t batch_bytes;   /* target bytes per GPU batch (0 = 32 MiB) */
+	uint64_t batch_bytes;   /* target bytes per GPU batch (0 = 32 MiB; 256 MiB in codec modes) */
 	uint32_t record_bytes;  /* expected recordsize hint (0 = 131072) */
 	uint32_t n_slots;       /* batches in flight (0 = 4) */
 } mtz_config;
