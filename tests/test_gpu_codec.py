@@ -384,3 +384,51 @@ def test_codec_shards_with_deferred_chain(oracle):
     finally:
         for g in stages:
             g.close()
+
+
+def test_size_independent_properties_at_2gib(oracle):
+    """Properties that need no oracle pass over the data (so they scale to BASELINE sizes;
+    bench.py checks the same ones at 16 GiB / 64 GiB): END checksum of a GPU-compressed stream
+    verifies on the GPU; DECOMPRESS(COMPRESS(x)) == x; RECOMPRESS is idempotent; one flipped
+    bit anywhere is reported at the record that follows it."""
+    import torch
+    from manatee_b200 import GpuSnapshotStage, index_host
+    from manatee_b200._native import MtzError, ECKSUM
+    nw = (2 << 30) // 131384
+    s = oracle.synth_stream(nw, kind=oracle.PAYLOAD_PGPAGE)
+    recs, used = index_host(s)
+    d_in = torch.from_numpy(s).cuda()
+    d_recs = torch.from_numpy(recs.view(np.uint8).copy()).cuda()
+    d_c = torch.empty(s.size + (1 << 20), dtype=torch.uint8, device="cuda")
+    with GpuSnapshotStage("compress") as g:
+        g.dev_submit(d_in.data_ptr(), s.size, d_recs.data_ptr(), len(recs), d_c.data_ptr(), d_c.numel())
+        nc, _, _ = g.dev_finish()
+        end_c = g.end_checksum()
+        assert g.stats()["lz4_encoded"] == nw and nc < s.size // 2
+    # verify the compressed stream with a GPU-built table
+    d_rc = torch.empty((len(recs) + 16) * 32, dtype=torch.uint8, device="cuda")
+    with GpuSnapshotStage("verify") as g:
+        n_idx, used_c = g.dev_index(d_c.data_ptr(), nc, d_rc.data_ptr(), len(recs) + 16)
+        assert n_idx == len(recs) and used_c == nc
+        g.dev_submit(d_c.data_ptr(), nc, d_rc.data_ptr(), n_idx)
+        g.dev_finish()
+        assert g.end_checksum() == end_c
+    # recompress: idempotent; decompress: identity
+    d_o = torch.empty(s.size + (1 << 20), dtype=torch.uint8, device="cuda")
+    with GpuSnapshotStage("recompress") as g:
+        g.dev_submit(d_c.data_ptr(), nc, d_rc.data_ptr(), n_idx, d_o.data_ptr(), d_o.numel())
+        nr, _, _ = g.dev_finish()
+        assert nr == nc and torch.equal(d_o[:nr], d_c[:nc])
+    with GpuSnapshotStage("decompress") as g:
+        g.dev_submit(d_c.data_ptr(), nc, d_rc.data_ptr(), n_idx, d_o.data_ptr(), d_o.numel())
+        nd, _, _ = g.dev_finish()
+        assert nd == s.size and torch.equal(d_o[:nd], d_in[:s.size])
+    # one flipped bit in record k's payload -> ECKSUM at record k+1
+    kbad = 9000
+    pos = int(recs["off"][kbad]) + 312 + 77777
+    d_in[pos] ^= 0x20
+    with GpuSnapshotStage("verify") as g:
+        g.dev_submit(d_in.data_ptr(), s.size, d_recs.data_ptr(), len(recs))
+        with pytest.raises(MtzError) as ei:
+            g.dev_finish()
+        assert ei.value.code == ECKSUM and g.stats()["bad_record"] == kbad + 1
