@@ -50,6 +50,7 @@ def parse_args():
     ap.add_argument("--recompress-gib", type=float, default=64.0,
                     help="logical GiB of the configs[2] RECOMPRESS side measurement (N=1 only, 0 = skip)")
     ap.add_argument("--recompress-steps", type=int, default=3)
+    ap.add_argument("--recsize", type=int, default=131072, help="DRR_WRITE logical size (dataset recordsize)")
     return ap.parse_args()
 
 
@@ -606,7 +607,10 @@ def run_ours(args):
 
 
 def main():
+    global RECSIZE, REC_BYTES
     args = parse_args()
+    RECSIZE = args.recsize
+    REC_BYTES = 312 + RECSIZE
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)

@@ -94,6 +94,10 @@ __host__ __device__ __forceinline__ Ck4 fold_cksum_words(Ck4 s, const Ck4 &v)
 
 #ifdef __CUDACC__
 
+#ifndef K1_UNROLL
+#define K1_UNROLL 12          // LDG.128 in flight per lane (profiles/r1_verify_k1.md)
+#endif
+
 __device__ __forceinline__ uint4 ldg_stream(const uint4 *p)
 {
 	uint4 r;
@@ -181,9 +185,6 @@ __device__ __forceinline__ Ck4 warp_fletcher(const uint8_t *p0, uint32_t nwords,
 		// ---- full middle rows j = 1 .. NR-2, four loads in flight ----
 		uint32_t j = 1u;
 		const uint32_t jend = NR - 1u;
-#ifndef K1_UNROLL
-#define K1_UNROLL 12
-#endif
 		for (; j + K1_UNROLL <= jend; j += K1_UNROLL) {
 			uint4 v[K1_UNROLL];
 #pragma unroll
@@ -251,6 +252,137 @@ __device__ __forceinline__ Ck4 warp_fletcher(const uint8_t *p0, uint32_t nwords,
 	out.c = warp_sum64(out.c);
 	out.d = warp_sum64(out.d);
 	return out;
+}
+
+// ---------------------------------------------------------------------------
+// Group form of the same computation: G = 8, 16 or 32 lanes own one segment
+// (rows of 16*G bytes), so a warp works on 32/G small records at once and the
+// fixed cost per record (basis conversion, reduction) is shared.  Everything is
+// identical to warp_fletcher with 128 replaced by RW = 4*G words per row; the
+// shuffles of the final reduction stay inside the group (xor masks < G).
+template <int G>
+__device__ __forceinline__ Ck4 group_fletcher(const uint8_t *p0, uint32_t nwords, int gl)
+{
+	constexpr uint32_t RW = 4u * G;                 // words per row
+	constexpr uint32_t RB = 16u * G;                // bytes per row
+	Ck4 out = { 0, 0, 0, 0 };
+	RowAcc acc; acc.zero();
+	uint32_t q = 1;
+	if (nwords != 0u) {
+		const uintptr_t a0 = (uintptr_t)p0;
+		const uintptr_t abase = a0 & ~(uintptr_t)(RB - 1u);
+		const uint32_t head = (uint32_t)((a0 - abase) >> 2);
+		const uint32_t E = head + nwords;
+		const uint32_t NR = (E + RW - 1u) / RW;
+		q = E - RW * (NR - 1u);                      // 1..RW words in the last row
+		const uint4 *rowp = reinterpret_cast<const uint4 *>(abase) + gl;
+		const uint32_t r0 = 4u * (uint32_t)gl;
+		uint32_t m = NR - 1u;
+		uint32_t t2 = (m * (m + 1u)) >> 1;
+		uint32_t t3 = (uint32_t)(((uint64_t)m * (m + 1u) * (m + 2u)) / 6u);
+		{
+			uint4 v = make_uint4(0, 0, 0, 0);
+			const uint32_t lim = (NR == 1u) ? q : RW;
+			if (r0 + 4u > head && r0 < lim) {
+				v = ldg_stream(rowp);
+				if (r0 + 0u < head || r0 + 0u >= lim) v.x = 0;
+				if (r0 + 1u < head || r0 + 1u >= lim) v.y = 0;
+				if (r0 + 2u < head || r0 + 2u >= lim) v.z = 0;
+				if (r0 + 3u < head || r0 + 3u >= lim) v.w = 0;
+			}
+			acc.add(v, m, t2, t3);
+		}
+		if (NR > 1u) {
+			uint32_t j = 1u;
+			const uint32_t jend = NR - 1u;
+			for (; j + K1_UNROLL <= jend; j += K1_UNROLL) {
+				uint4 v[K1_UNROLL];
+#pragma unroll
+				for (int u = 0; u < K1_UNROLL; u++) v[u] = ldg_stream(rowp + (uint32_t)G * (j + (uint32_t)u));
+#pragma unroll
+				for (int u = 0; u < K1_UNROLL; u++) {
+					t3 -= t2; t2 -= m; m -= 1u; acc.add(v[u], m, t2, t3);
+				}
+			}
+			for (; j + 4u <= jend; j += 4u) {
+				uint4 v0 = ldg_stream(rowp + (uint32_t)G * (j + 0u));
+				uint4 v1 = ldg_stream(rowp + (uint32_t)G * (j + 1u));
+				uint4 v2 = ldg_stream(rowp + (uint32_t)G * (j + 2u));
+				uint4 v3 = ldg_stream(rowp + (uint32_t)G * (j + 3u));
+				t3 -= t2; t2 -= m; m -= 1u; acc.add(v0, m, t2, t3);
+				t3 -= t2; t2 -= m; m -= 1u; acc.add(v1, m, t2, t3);
+				t3 -= t2; t2 -= m; m -= 1u; acc.add(v2, m, t2, t3);
+				t3 -= t2; t2 -= m; m -= 1u; acc.add(v3, m, t2, t3);
+			}
+			for (; j < jend; j++) {
+				uint4 v = ldg_stream(rowp + (uint32_t)G * j);
+				t3 -= t2; t2 -= m; m -= 1u; acc.add(v, m, t2, t3);
+			}
+			{
+				uint4 v = make_uint4(0, 0, 0, 0);
+				if (r0 < q) {
+					v = ldg_stream(rowp + (uint32_t)G * jend);
+					if (r0 + 1u >= q) v.y = 0;
+					if (r0 + 2u >= q) v.z = 0;
+					if (r0 + 3u >= q) v.w = 0;
+				}
+				acc.add(v, 0u, 0u, 0u);
+			}
+		}
+	}
+	// row basis -> word-distance basis: k = RW * m + d
+#pragma unroll
+	for (int e = 0; e < 4; e++) {
+		const int d = (int)q - (int)(4u * (uint32_t)gl + (uint32_t)e);
+		const int Q0 = d * (d + 1) / 2;
+		const int Q1 = (d + (int)RW) * (d + (int)RW + 1) / 2;
+		int P[4];
+#pragma unroll
+		for (int i = 0; i < 4; i++) {
+			const int x = d + (int)RW * i;
+			P[i] = x * (x + 1) * (x + 2) / 6;
+		}
+		const int q2 = (int)(RW * RW);
+		const int q1 = Q1 - Q0;
+		const int d1 = P[1] - P[0];
+		const int d2 = P[2] - 2 * P[1] + P[0];
+		const int d3 = (int)(RW * RW * RW);
+		const uint64_t sa = acc.sa[e], sb = acc.sb[e], sc = acc.sc[e], sd = acc.sd[e];
+		out.a += sa;
+		out.b += (uint64_t)RW * sb + (uint64_t)(int64_t)d * sa;
+		out.c += (uint64_t)q2 * sc + (uint64_t)(int64_t)(q1 - q2) * sb + (uint64_t)(int64_t)Q0 * sa;
+		out.d += (uint64_t)d3 * sd + (uint64_t)(int64_t)(d2 - 2 * d3) * sc +
+		    (uint64_t)(int64_t)(d1 - d2 + d3) * sb + (uint64_t)(int64_t)P[0] * sa;
+	}
+#pragma unroll
+	for (int mk = G / 2; mk > 0; mk >>= 1) {
+		out.a += shfl_xor64(out.a, mk); out.b += shfl_xor64(out.b, mk);
+		out.c += shfl_xor64(out.c, mk); out.d += shfl_xor64(out.d, mk);
+	}
+	return out;
+}
+
+// sums of the 70 header words [0,280) computed directly (k = 70 - index is tiny, so
+// the products are plain 64-bit): the group's lanes take words gl, gl+G, ...
+template <int G>
+__device__ __forceinline__ Ck4 group_head70(const uint8_t *hdr, int gl)
+{
+	Ck4 o = { 0, 0, 0, 0 };
+	const uint32_t *w = reinterpret_cast<const uint32_t *>(hdr);
+	for (uint32_t i = (uint32_t)gl; i < 70u; i += (uint32_t)G) {
+		const uint64_t v = w[i];
+		const uint64_t k = 70u - i;
+		o.a += v;
+		o.b += k * v;
+		o.c += (k * (k + 1u) / 2u) * v;
+		o.d += (k * (k + 1u) * (k + 2u) / 6u) * v;
+	}
+#pragma unroll
+	for (int mk = G / 2; mk > 0; mk >>= 1) {
+		o.a += shfl_xor64(o.a, mk); o.b += shfl_xor64(o.b, mk);
+		o.c += shfl_xor64(o.c, mk); o.d += shfl_xor64(o.d, mk);
+	}
+	return o;
 }
 
 // sums of a chunk followed by z zero words (moves the chunk's reference point)

@@ -96,6 +96,59 @@ k1_record_sums(const uint8_t *__restrict__ base, const mtz_rec *__restrict__ rec
 	}
 }
 
+// Small-record form: G lanes per record, 32/G records per warp.  Chosen by the host
+// from the batch's average record size (a 128 KiB stream keeps G = 32).
+template <int G>
+__global__ void __launch_bounds__(K1_THREADS, K1_MINBLOCKS)
+k1_record_sums_g(const uint8_t *__restrict__ base, const mtz_rec *__restrict__ recs,
+    uint32_t nrec, RecSums *__restrict__ out, uint32_t body_from)
+{
+	constexpr uint32_t GPW = 32u / G;                      // groups per warp
+	const int lane = threadIdx.x & 31;
+	const int gl = lane & (G - 1);
+	const uint32_t gid = (blockIdx.x * K1_WARPS + (threadIdx.x >> 5)) * GPW + (uint32_t)(lane / G);
+	const uint32_t ngroups = gridDim.x * K1_WARPS * GPW;
+	// all lanes of a warp iterate together (shuffles inside): pad the trip count
+	const uint32_t iters = (nrec + ngroups - 1u) / ngroups;
+	for (uint32_t it = 0; it < iters; it++) {
+		const uint32_t r = gid + it * ngroups;
+		const bool live = r < nrec;
+		mtz_rec rec; rec.off = 0; rec.payload = 0; rec.type = 0; rec.lsize = 0; rec.comp = 0; rec.resv = 0;
+		if (live) rec = recs[r];
+		const uint8_t *hdr = base + rec.off;
+		const uint8_t *body = hdr + body_from;
+		const uint32_t nwords = live ? ((DRR_HDR - body_from + rec.payload) >> 2) : 0u;
+		Ck4 h = { 0, 0, 0, 0 };
+		if (live) h = group_head70<G>(hdr, gl); else (void)group_head70<G>(base, gl);
+		// chunks of <= MTZ_K1_MAX_ROWS rows of 16*G bytes
+		constexpr uint32_t RW = 4u * G;
+		const uint32_t headw = (uint32_t)(((uintptr_t)body & (16u * G - 1u)) >> 2);
+		const uint32_t first = min(nwords, MTZ_K1_MAX_ROWS * RW - headw);
+		Ck4 acc = { 0, 0, 0, 0 };
+		uint32_t w0 = 0;
+		// every group runs the same number of group_fletcher calls as the slowest one
+		const uint32_t my_chunks = (nwords == 0u) ? 1u : 1u + (nwords - first + MTZ_K1_MAX_ROWS * RW - 1u) / (MTZ_K1_MAX_ROWS * RW);
+		uint32_t max_chunks = my_chunks;
+#pragma unroll
+		for (int mk = 16; mk > 0; mk >>= 1) max_chunks = max(max_chunks, __shfl_xor_sync(0xffffffffu, max_chunks, mk));
+		for (uint32_t c = 0; c < max_chunks; c++) {
+			const uint32_t w1 = (w0 >= nwords) ? nwords : ((c == 0u) ? first : min(nwords, w0 + MTZ_K1_MAX_ROWS * RW));
+			Ck4 p = group_fletcher<G>(body + 4ull * w0, w1 - w0, gl);
+			if (w1 != nwords) p = shift_zeros(p, (uint64_t)(nwords - w1));
+			acc.a += p.a; acc.b += p.b; acc.c += p.c; acc.d += p.d;
+			w0 = w1;
+		}
+		if (live && gl == 0) {
+			RecSums o;
+			o.head = h; o.body = acc; o.nbody = nwords; o.pad = 0;
+			o.type = rec.type;
+			o.emb = load_ck(hdr + DRR_CKOFF);
+			o.aux = load_ck(hdr + 8);
+			out[r] = o;
+		}
+	}
+}
+
 // ---------------------------------------------------------------------------
 // Record scan.  In VERIFY the per-record transform of the running checksum is
 // affine (the bytes are given), so a batch is a segmented prefix scan under

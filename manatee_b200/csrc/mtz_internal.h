@@ -28,6 +28,7 @@ struct CodecBufs {
 	CodecResult *d_cres = nullptr, *h_cres = nullptr;   // h_: pinned
 	ScanResult *d_ores = nullptr, *h_ores = nullptr;    // output-chain result
 	uint64_t *d_outpos = nullptr;                       // running output offset (device)
+	size_t avg_out_rec = 128u << 10;                    // K1 lane-group choice for the output records
 };
 
 struct Slot {

@@ -357,15 +357,31 @@ static inline void count_launch(mtz_handle *h, uint64_t n)
 	h->stats.kernel_launches += n;
 }
 
+// lanes per record by average record size: small records share a warp
+static void launch_k1_kernel(mtz_handle *h, cudaStream_t st, const uint8_t *d_in, const mtz_rec *d_recs,
+    size_t nrec, RecSums *d_sums, uint32_t body_from, size_t avg_rec)
+{
+	const size_t cap = (size_t)h->sm_count * K1_MINBLOCKS * 8;
+	if (avg_rec >= (96u << 10)) {
+		const unsigned grid = (unsigned)std::min<size_t>((nrec + K1_WARPS - 1) / K1_WARPS, cap);
+		k1_record_sums<<<grid, K1_THREADS, 0, st>>>(d_in, d_recs, (uint32_t)nrec, d_sums, body_from);
+	} else if (avg_rec >= (24u << 10)) {
+		const unsigned grid = (unsigned)std::min<size_t>((nrec + K1_WARPS * 2 - 1) / (K1_WARPS * 2), cap);
+		k1_record_sums_g<16><<<grid, K1_THREADS, 0, st>>>(d_in, d_recs, (uint32_t)nrec, d_sums, body_from);
+	} else {
+		const unsigned grid = (unsigned)std::min<size_t>((nrec + K1_WARPS * 4 - 1) / (K1_WARPS * 4), cap);
+		k1_record_sums_g<8><<<grid, K1_THREADS, 0, st>>>(d_in, d_recs, (uint32_t)nrec, d_sums, body_from);
+	}
+}
+
 // K1 over a batch: per-record Fletcher-4 sums into d_sums[0..nrec)
 static int32_t launch_k1(mtz_handle *h, cudaStream_t st, const uint8_t *d_in,
-    const mtz_rec *d_recs, size_t nrec, RecSums *d_sums, cudaEvent_t ea, cudaEvent_t eb)
+    const mtz_rec *d_recs, size_t nrec, RecSums *d_sums, cudaEvent_t ea, cudaEvent_t eb,
+    size_t avg_rec = (128u << 10))
 {
 	if (nrec == 0) return MTZ_OK;
-	const unsigned grid = (unsigned)std::min<size_t>((nrec + K1_WARPS - 1) / K1_WARPS,
-	    (size_t)h->sm_count * K1_MINBLOCKS * 8);
 	if (ea) MTZ_CU(h, cudaEventRecord(ea, st));
-	k1_record_sums<<<grid, K1_THREADS, 0, st>>>(d_in, d_recs, (uint32_t)nrec, d_sums, 280u);
+	launch_k1_kernel(h, st, d_in, d_recs, nrec, d_sums, 280u, avg_rec);
 	MTZ_CU(h, cudaGetLastError());
 	if (eb) MTZ_CU(h, cudaEventRecord(eb, st));
 	count_launch(h, 1);
@@ -542,8 +558,8 @@ static int32_t codec_launch_post(mtz_handle *h, cudaStream_t st, CodecBufs &cb, 
 	k_assemble<<<ga, ASM_THREADS, 0, st>>>(d_in, d_recs, n, mode, cb.cr, cb.out_offs, cb.enc,
 	    cb.d_logical, cb.d_enc, d_out, orecs);
 	MTZ_CU(h, cudaGetLastError());
-	const unsigned g1 = (unsigned)std::min<size_t>((n + K1_WARPS - 1) / K1_WARPS, (size_t)h->sm_count * 40);
-	k1_record_sums<<<g1, K1_THREADS, 0, st>>>(d_out, orecs, n, osums, 312u);
+	// output records of a codec batch are smaller than the logical size: decide by the input's
+	launch_k1_kernel(h, st, d_out, orecs, n, osums, 312u, cb.avg_out_rec);
 	if (all_osums == nullptr)
 		k_stamp_chain<<<1, 32, 0, st>>>(d_out, orecs, osums, n, h->d_carry_out, cb.d_ores);
 	MTZ_CU(h, cudaGetLastError());
@@ -592,7 +608,8 @@ int32_t mtz_dev_submit(mtz_handle *h, const void *d_in, size_t in_bytes,
 	if (rc != MTZ_OK) return rc;
 	h->dv_nrec = nrec; h->dv_in_bytes = in_bytes; h->dv_st = st;
 	h->dv_first = h->records_done;
-	rc = launch_k1(h, st, (const uint8_t *)d_in, d_recs, nrec, h->dv_sums, h->dv_k1a, h->dv_k1b);
+	rc = launch_k1(h, st, (const uint8_t *)d_in, d_recs, nrec, h->dv_sums, h->dv_k1a, h->dv_k1b,
+	    nrec ? in_bytes / nrec : 0);
 	h->dv_timed = (rc == MTZ_OK && nrec > 0);
 	if (rc != MTZ_OK || !is_codec_mode(h->cfg.mode)) return rc;
 
@@ -965,13 +982,15 @@ static int32_t submit_batch(mtz_handle *h, Slot &s, const uint8_t *p0, size_t n0
 		// shard mode: sums accumulate in the handle-wide table; verdict later
 		rc = ensure_dv_sums(h, h->dv_nrec + nrec, s.st);
 		if (rc != MTZ_OK) return rc;
-		rc = launch_k1(h, s.st, s.d_in, s.d_recs, nrec, h->dv_sums + h->dv_nrec, s.ev_k1a, s.ev_k1b);
+		rc = launch_k1(h, s.st, s.d_in, s.d_recs, nrec, h->dv_sums + h->dv_nrec, s.ev_k1a, s.ev_k1b,
+		    nrec ? bytes / nrec : 0);
 		if (rc != MTZ_OK) return rc;
 		if (h->dv_nrec == 0) h->dv_first = s.first_rec;
 		h->dv_nrec += nrec; h->dv_in_bytes += bytes; h->dv_st = h->st;
 	} else if (h->cfg.mode != MTZ_MODE_PASSTHROUGH) {
 		// every mode verifies the INPUT stream's checksums
-		rc = launch_k1(h, s.st, s.d_in, s.d_recs, nrec, s.d_sums, s.ev_k1a, s.ev_k1b);
+		rc = launch_k1(h, s.st, s.d_in, s.d_recs, nrec, s.d_sums, s.ev_k1a, s.ev_k1b,
+		    nrec ? bytes / nrec : 0);
 		if (rc != MTZ_OK) return rc;
 		if (is_codec_mode(h->cfg.mode)) {
 			rc = codec_reset(h, s.st, s.cb);
