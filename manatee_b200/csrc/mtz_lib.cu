@@ -368,9 +368,12 @@ static void launch_k1_kernel(mtz_handle *h, cudaStream_t st, const uint8_t *d_in
 	} else if (avg_rec >= (24u << 10)) {
 		const unsigned grid = (unsigned)std::min<size_t>((nrec + K1_WARPS * 2 - 1) / (K1_WARPS * 2), cap);
 		k1_record_sums_g<16><<<grid, K1_THREADS, 0, st>>>(d_in, d_recs, (uint32_t)nrec, d_sums, body_from);
-	} else {
+	} else if (avg_rec >= (12u << 10)) {
 		const unsigned grid = (unsigned)std::min<size_t>((nrec + K1_WARPS * 4 - 1) / (K1_WARPS * 4), cap);
 		k1_record_sums_g<8><<<grid, K1_THREADS, 0, st>>>(d_in, d_recs, (uint32_t)nrec, d_sums, body_from);
+	} else {
+		const unsigned grid = (unsigned)std::min<size_t>((nrec + K1_WARPS * 8 - 1) / (K1_WARPS * 8), cap);
+		k1_record_sums_g<4><<<grid, K1_THREADS, 0, st>>>(d_in, d_recs, (uint32_t)nrec, d_sums, body_from);
 	}
 }
 
