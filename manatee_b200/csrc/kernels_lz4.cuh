@@ -50,7 +50,9 @@ __device__ __forceinline__ int32_t warp_lz4_decode(const uint8_t *__restrict__ s
 			} while (s == 255u);
 		}
 		if (len > iend - ip || len > lsize - op) return MTZ_ECODEC;
-		for (uint32_t i = (uint32_t)lane; i < len; i += 32u) dst[op + i] = in[ip + i];
+		if ((uint32_t)lane < len) dst[op + (uint32_t)lane] = in[ip + (uint32_t)lane];
+		if (len > 32u)
+			for (uint32_t i = 32u + (uint32_t)lane; i < len; i += 32u) dst[op + i] = in[ip + i];
 		ip += len; op += len;
 		if (ip == iend) break;                         // last sequence: literals only
 
@@ -72,10 +74,19 @@ __device__ __forceinline__ int32_t warp_lz4_decode(const uint8_t *__restrict__ s
 		__syncwarp();                                  // earlier stores -> these loads
 		const uint8_t *ref = dst + (op - off);
 		if (off >= ml) {
-			for (uint32_t i = (uint32_t)lane; i < ml; i += 32u) dst[op + i] = ref[i];
+			if ((uint32_t)lane < ml) dst[op + (uint32_t)lane] = ref[lane];
+			if (ml > 32u)
+				for (uint32_t i = 32u + (uint32_t)lane; i < ml; i += 32u) dst[op + i] = ref[i];
 		} else {
-			// overlapping match: the source is periodic with period `off`
-			for (uint32_t i = (uint32_t)lane; i < ml; i += 32u) dst[op + i] = ref[i % off];
+			// overlapping match: the source is periodic with period `off`; i % off is kept
+			// incrementally (one division per match instead of one per byte)
+			uint32_t r = (uint32_t)lane % off;
+			const uint32_t stp = 32u % off;
+			for (uint32_t i = (uint32_t)lane; i < ml; i += 32u) {
+				dst[op + i] = ref[r];
+				r += stp;
+				if (r >= off) r -= off;
+			}
 		}
 		op += ml;
 	}
