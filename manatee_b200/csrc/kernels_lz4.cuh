@@ -151,6 +151,10 @@ struct TabU32 {                                 // 4096 x u32: any block size
 	}
 	__device__ __forceinline__ uint32_t get(uint32_t h) const { return t[h]; }
 	__device__ __forceinline__ void set(uint32_t h, uint32_t v) const { t[h] = v; }
+	// slot used as a scratch mark while its value is held in a register (see search)
+	__device__ __forceinline__ void tag(uint32_t h, uint32_t v) const { t[h] = v; }
+	__device__ __forceinline__ uint32_t tagval(uint32_t h) const { return t[h]; }
+	__device__ __forceinline__ void untag(uint32_t h, uint32_t old) const { t[h] = old; }
 };
 struct TabU16 {                                 // 8192 x u16: blocks below 64 KiB + 11
 	uint32_t *t;
@@ -160,6 +164,9 @@ struct TabU16 {                                 // 8192 x u16: blocks below 64 K
 	}
 	__device__ __forceinline__ uint32_t get(uint32_t h) const { return reinterpret_cast<uint16_t *>(t)[h]; }
 	__device__ __forceinline__ void set(uint32_t h, uint32_t v) const { reinterpret_cast<uint16_t *>(t)[h] = (uint16_t)v; }
+	__device__ __forceinline__ void tag(uint32_t h, uint32_t v) const { reinterpret_cast<uint16_t *>(t)[h] = (uint16_t)v; }
+	__device__ __forceinline__ uint32_t tagval(uint32_t h) const { return reinterpret_cast<uint16_t *>(t)[h]; }
+	__device__ __forceinline__ void untag(uint32_t h, uint32_t old) const { reinterpret_cast<uint16_t *>(t)[h] = (uint16_t)old; }
 };
 struct Tab17 {                                  // 4096 x 17 bit: blocks up to 128 KiB in 8.5 KiB
 	uint32_t *t;                                // [0,2048) u16 pairs, [2048,2176) bit 16 of each slot
@@ -177,6 +184,10 @@ struct Tab17 {                                  // 4096 x 17 bit: blocks up to 1
 		if (v >> 16) atomicOr(&t[2048u + (h >> 5)], 1u << (h & 31u));
 		else atomicAnd(&t[2048u + (h >> 5)], ~(1u << (h & 31u)));
 	}
+	// only the low half is used as the mark; bit 16 of the slot stays in the bitmap
+	__device__ __forceinline__ void tag(uint32_t h, uint32_t v) const { reinterpret_cast<uint16_t *>(t)[h] = (uint16_t)v; }
+	__device__ __forceinline__ uint32_t tagval(uint32_t h) const { return reinterpret_cast<uint16_t *>(t)[h]; }
+	__device__ __forceinline__ void untag(uint32_t h, uint32_t old) const { reinterpret_cast<uint16_t *>(t)[h] = (uint16_t)old; }
 };
 
 #define LZ4_TAB_BIG_WORDS     4096u             // TabU32 / TabU16: 16 KiB
@@ -251,22 +262,47 @@ __device__ __forceinline__ uint32_t warp_lz4_encode3(const uint8_t *__restrict__
 					v = (a0 == 0u && have_pre) ? vpre : ld32u(src + p);
 					h = (v * 2654435761u) >> (32 - LOG);
 				}
-				const uint32_t all_same = __match_any_sync(0xffffffffu, h);
-				const uint32_t same = all_same & lower;
-				const int from = same ? (31 - __clz((int)same)) : lane;
-				const uint32_t fwd = __shfl_sync(0xffffffffu, p, from);
-				bool hit = false;
-				if (valid) {
-					cand = same ? fwd : tab.get(h);
-					if (!DIST || cand + LZ4_MAXDIST >= p) hit = (ld32u(src + cand) == v);
-				}
-				const uint32_t hits = __ballot_sync(0xffffffffu, hit);
-				const uint32_t inval = __ballot_sync(0xffffffffu, !valid);
-				const int F = hits ? (__ffs((int)hits) - 1) : 32;
-				const int I = inval ? (__ffs((int)inval) - 1) : 32;
-				if (I < F) { to_tail = true; break; }
-				__syncwarp();                   // every lane's table read precedes the commits
-				{
+				// Do two lanes of this round hash to the same slot?  __match_any_sync answers
+				// that but costs ~365 cycles on B200 when all 32 values differ (the common
+				// case; tools/micro/match_any.cu).  Cheaper: every lane already holds its
+				// slot's value, so mark the slots with lane ids (~100 cycles) and look back.
+				uint32_t oldv = 0;
+				if (valid) oldv = tab.get(h);
+				__syncwarp();
+				if (valid) tab.tag(h, (uint32_t)lane);
+				__syncwarp();
+				const bool clash = valid && (tab.tagval(h) != (uint32_t)lane);
+				int F, I;
+				if (!__any_sync(0xffffffffu, clash)) {
+					// all slots distinct: no in-round forwarding, every lane owns its slot
+					bool hit = false;
+					cand = oldv;
+					if (valid && (!DIST || cand + LZ4_MAXDIST >= p)) hit = (ld32u(src + cand) == v);
+					const uint32_t hits = __ballot_sync(0xffffffffu, hit);
+					const uint32_t inval = __ballot_sync(0xffffffffu, !valid);
+					F = hits ? (__ffs((int)hits) - 1) : 32;
+					I = inval ? (__ffs((int)inval) - 1) : 32;
+					if (I < F) { to_tail = true; break; }      // table is not used after this
+					if (valid) {
+						if (lane <= F) tab.set(h, p); else tab.untag(h, oldv);
+					}
+				} else {
+					if (valid) tab.untag(h, oldv);
+					__syncwarp();
+					const uint32_t all_same = __match_any_sync(0xffffffffu, h);
+					const uint32_t same = all_same & lower;
+					const int from = same ? (31 - __clz((int)same)) : lane;
+					const uint32_t fwd = __shfl_sync(0xffffffffu, p, from);
+					bool hit = false;
+					if (valid) {
+						cand = same ? fwd : oldv;
+						if (!DIST || cand + LZ4_MAXDIST >= p) hit = (ld32u(src + cand) == v);
+					}
+					const uint32_t hits = __ballot_sync(0xffffffffu, hit);
+					const uint32_t inval = __ballot_sync(0xffffffffu, !valid);
+					F = hits ? (__ffs((int)hits) - 1) : 32;
+					I = inval ? (__ffs((int)inval) - 1) : 32;
+					if (I < F) { to_tail = true; break; }
 					const uint32_t upto = (F >= 31) ? 0xffffffffu : ((2u << F) - 1u);
 					const uint32_t later = all_same & ~(lanebit | lower) & upto;
 					if ((lanebit & upto) && later == 0u) tab.set(h, p);
