@@ -151,6 +151,7 @@ struct TabU32 {                                 // 4096 x u32: any block size
 	}
 	__device__ __forceinline__ uint32_t get(uint32_t h) const { return t[h]; }
 	__device__ __forceinline__ void set(uint32_t h, uint32_t v) const { t[h] = v; }
+	__device__ __forceinline__ void set_from(uint32_t h, uint32_t v, uint32_t) const { t[h] = v; }
 	// slot used as a scratch mark while its value is held in a register (see search)
 	__device__ __forceinline__ void tag(uint32_t h, uint32_t v) const { t[h] = v; }
 	__device__ __forceinline__ uint32_t tagval(uint32_t h) const { return t[h]; }
@@ -164,6 +165,7 @@ struct TabU16 {                                 // 8192 x u16: blocks below 64 K
 	}
 	__device__ __forceinline__ uint32_t get(uint32_t h) const { return reinterpret_cast<uint16_t *>(t)[h]; }
 	__device__ __forceinline__ void set(uint32_t h, uint32_t v) const { reinterpret_cast<uint16_t *>(t)[h] = (uint16_t)v; }
+	__device__ __forceinline__ void set_from(uint32_t h, uint32_t v, uint32_t) const { reinterpret_cast<uint16_t *>(t)[h] = (uint16_t)v; }
 	__device__ __forceinline__ void tag(uint32_t h, uint32_t v) const { reinterpret_cast<uint16_t *>(t)[h] = (uint16_t)v; }
 	__device__ __forceinline__ uint32_t tagval(uint32_t h) const { return reinterpret_cast<uint16_t *>(t)[h]; }
 	__device__ __forceinline__ void untag(uint32_t h, uint32_t old) const { reinterpret_cast<uint16_t *>(t)[h] = (uint16_t)old; }
@@ -179,10 +181,15 @@ struct Tab17 {                                  // 4096 x 17 bit: blocks up to 1
 		const uint32_t hi = (t[2048u + (h >> 5)] >> (h & 31u)) & 1u;
 		return lo | (hi << 16);
 	}
-	__device__ __forceinline__ void set(uint32_t h, uint32_t v) const {
+	// bit 16 of a slot flips at most once per record (positions cross 64 KiB once): only
+	// then is the ~100-cycle shared-memory atomic paid
+	__device__ __forceinline__ void set_from(uint32_t h, uint32_t v, uint32_t old) const {
 		reinterpret_cast<uint16_t *>(t)[h] = (uint16_t)v;
-		if (v >> 16) atomicOr(&t[2048u + (h >> 5)], 1u << (h & 31u));
-		else atomicAnd(&t[2048u + (h >> 5)], ~(1u << (h & 31u)));
+		if (((v ^ old) >> 16) & 1u) atomicXor(&t[2048u + (h >> 5)], 1u << (h & 31u));
+	}
+	__device__ __forceinline__ void set(uint32_t h, uint32_t v) const {
+		const uint32_t oldhi = (t[2048u + (h >> 5)] >> (h & 31u)) & 1u;
+		set_from(h, v, oldhi << 16);
 	}
 	// only the low half is used as the mark; bit 16 of the slot stays in the bitmap
 	__device__ __forceinline__ void tag(uint32_t h, uint32_t v) const { reinterpret_cast<uint16_t *>(t)[h] = (uint16_t)v; }
@@ -284,7 +291,7 @@ __device__ __forceinline__ uint32_t warp_lz4_encode3(const uint8_t *__restrict__
 					I = inval ? (__ffs((int)inval) - 1) : 32;
 					if (I < F) { to_tail = true; break; }      // table is not used after this
 					if (valid) {
-						if (lane <= F) tab.set(h, p); else tab.untag(h, oldv);
+						if (lane <= F) tab.set_from(h, p, oldv); else tab.untag(h, oldv);
 					}
 				} else {
 					if (valid) tab.untag(h, oldv);
@@ -305,7 +312,7 @@ __device__ __forceinline__ uint32_t warp_lz4_encode3(const uint8_t *__restrict__
 					if (I < F) { to_tail = true; break; }
 					const uint32_t upto = (F >= 31) ? 0xffffffffu : ((2u << F) - 1u);
 					const uint32_t later = all_same & ~(lanebit | lower) & upto;
-					if ((lanebit & upto) && later == 0u) tab.set(h, p);
+					if ((lanebit & upto) && later == 0u) tab.set_from(h, p, oldv);
 				}
 				__syncwarp();
 				if (F < 32) {
@@ -416,7 +423,7 @@ __device__ __forceinline__ uint32_t warp_lz4_encode3(const uint8_t *__restrict__
 				const uint32_t hh = (v_end * 2654435761u) >> (32 - LOG);
 				const uint32_t pref = tab.get(hh);
 				__syncwarp();
-				if (lane == 0) tab.set(hh, ip);
+				if (lane == 0) tab.set_from(hh, ip, pref);
 				__syncwarp();
 				const uint32_t np = ip + 1u + (uint32_t)lane;          // next search, step 1
 				uint32_t vn = 0;
