@@ -10,6 +10,9 @@
 #pragma once
 #include <stdint.h>
 #include <cuda_runtime.h>
+#ifdef LZ4_PROF
+#include <cstdio>
+#endif
 #include "../../include/manatee_gpu.h"
 
 namespace mtz {
@@ -135,6 +138,13 @@ __device__ __forceinline__ uint32_t ld32u(const uint8_t *p)
 	return __funnelshift_r(__ldg(w), __ldg(w + 1), sh);       // source is read-only while encoding
 }
 
+// unaligned u32 at byte offset x of a 4-byte aligned base (32-bit index math only)
+__device__ __forceinline__ uint32_t ld32x(const uint32_t *__restrict__ base4, uint32_t x)
+{
+	const uint32_t i = x >> 2;
+	return __funnelshift_r(__ldg(base4 + i), __ldg(base4 + i + 1u), (x & 3u) * 8u);
+}
+
 // sum_{i<x} ((67+i)>>6): distance covered by the first x search attempts
 __device__ __forceinline__ uint32_t skip_dist(uint32_t x)
 {
@@ -236,11 +246,24 @@ __device__ __forceinline__ uint32_t extract32(uint32_t w0, uint32_t w1, uint32_t
 	return (off < 4u) ? __funnelshift_r(w0, w1, off * 8u) : __funnelshift_r(w1, w2, (off - 4u) * 8u);
 }
 
+#ifdef LZ4_PROF
+// clock64 phase profile (compile with -DLZ4_PROF): cycles per phase, printed by one warp
+#define PROF_DECL long long pt = clock64(), p_search = 0, p_b = 0, p_ext = 0, p_post = 0; unsigned n_seq = 0, n_round = 0, n_follow = 0;
+#define PROF_LAP(acc) { const long long now_ = clock64(); acc += now_ - pt; pt = now_; }
+#else
+#define PROF_DECL
+#define PROF_LAP(acc)
+#endif
+
 template <class TAB, bool DIST>
 __device__ __forceinline__ uint32_t warp_lz4_encode3(const uint8_t *__restrict__ src,
     uint32_t isize, uint8_t *__restrict__ dst, uint32_t osize, uint32_t *tabmem, int lane)
 {
 	constexpr int LOG = TAB::LOG;
+	PROF_DECL
+	const uint32_t mis = (uint32_t)((uintptr_t)src & 3u);
+	const uint32_t *base4 = reinterpret_cast<const uint32_t *>(src - mis);
+#define LDS32(pos) ld32x(base4, (pos) + mis)
 	TAB tab; tab.t = tabmem;
 	const uint32_t lanebit = 1u << lane, lower = lanebit - 1u;
 	tab.clear(lane);
@@ -260,13 +283,18 @@ __device__ __forceinline__ uint32_t warp_lz4_encode3(const uint8_t *__restrict__
 			bool to_tail = false;
 			const uint32_t start = ip;
 			for (uint32_t a0 = 0;; a0 += 32u) {
-				const uint32_t a = a0 + (uint32_t)lane;
-				const uint32_t p = start + skip_dist(a);
-				const uint32_t step = (67u + a) >> 6;
+				uint32_t p, step;
+				if (a0 == 0u) {                              // attempts 0..31: step 1, p = start + lane
+					p = start + (uint32_t)lane; step = 1u;
+				} else {
+					const uint32_t a = a0 + (uint32_t)lane;
+					p = start + skip_dist(a);
+					step = (67u + a) >> 6;
+				}
 				const bool valid = (p + step <= mflimit);
 				uint32_t h = 0xffffffffu - (uint32_t)lane, cand = 0, v = 0;
 				if (valid) {
-					v = (a0 == 0u && have_pre) ? vpre : ld32u(src + p);
+					v = (a0 == 0u && have_pre) ? vpre : LDS32(p);
 					h = (v * 2654435761u) >> (32 - LOG);
 				}
 				// Do two lanes of this round hash to the same slot?  __match_any_sync answers
@@ -284,7 +312,7 @@ __device__ __forceinline__ uint32_t warp_lz4_encode3(const uint8_t *__restrict__
 					// all slots distinct: no in-round forwarding, every lane owns its slot
 					bool hit = false;
 					cand = oldv;
-					if (valid && (!DIST || cand + LZ4_MAXDIST >= p)) hit = (ld32u(src + cand) == v);
+					if (valid && (!DIST || cand + LZ4_MAXDIST >= p)) hit = (LDS32(cand) == v);
 					const uint32_t hits = __ballot_sync(0xffffffffu, hit);
 					const uint32_t inval = __ballot_sync(0xffffffffu, !valid);
 					F = hits ? (__ffs((int)hits) - 1) : 32;
@@ -303,7 +331,7 @@ __device__ __forceinline__ uint32_t warp_lz4_encode3(const uint8_t *__restrict__
 					bool hit = false;
 					if (valid) {
 						cand = same ? fwd : oldv;
-						if (!DIST || cand + LZ4_MAXDIST >= p) hit = (ld32u(src + cand) == v);
+						if (!DIST || cand + LZ4_MAXDIST >= p) hit = (LDS32(cand) == v);
 					}
 					const uint32_t hits = __ballot_sync(0xffffffffu, hit);
 					const uint32_t inval = __ballot_sync(0xffffffffu, !valid);
@@ -322,7 +350,11 @@ __device__ __forceinline__ uint32_t warp_lz4_encode3(const uint8_t *__restrict__
 				}
 			}
 			have_pre = false;
+			PROF_LAP(p_search)
 			if (to_tail) break;
+#ifdef LZ4_PROF
+			n_seq++;
+#endif
 
 			// ------------------------------------------------ trip B: issue everything
 			// that depends only on (ip, ref) before consuming any of it
@@ -364,6 +396,7 @@ __device__ __forceinline__ uint32_t warp_lz4_encode3(const uint8_t *__restrict__
 			for (uint32_t i = 32u + (uint32_t)lane; i < litlen; i += 32u) dst[op + i] = src[anchor + i];
 			op += litlen;
 
+			PROF_LAP(p_b)
 			// ------------------------------- one or more back-to-back matches --
 			uint32_t ext_ip = ip_pre, ext_ref = ref_pre;     // where round `er` starts
 			for (;;) {
@@ -394,7 +427,7 @@ __device__ __forceinline__ uint32_t warp_lz4_encode3(const uint8_t *__restrict__
 						uint32_t w0 = __shfl_sync(0xffffffffu, er.wa, (Fp + 31) & 31);
 						uint32_t w2 = __shfl_sync(0xffffffffu, er.wa, (Fp + 1) & 31);
 						if (Fp == 0) w0 = prev31;
-						if (Fp == 31 && nf > 0u) w2 = (ip + 4u <= iend) ? ld32u(src + ext_ip + 128u) : 0u;
+						if (Fp == 31 && nf > 0u) w2 = (ip + 4u <= iend) ? LDS32(ext_ip + 128u) : 0u;
 						v_m2 = extract32(w0, w1, w2, nf + 2u);
 						v_end = extract32(w0, w1, w2, nf + 4u);
 						break;
@@ -412,6 +445,7 @@ __device__ __forceinline__ uint32_t warp_lz4_encode3(const uint8_t *__restrict__
 					tokval += mlen;
 				}
 				if (lane == 0) dst[token] = (uint8_t)tokval;
+				PROF_LAP(p_ext)
 
 				if (ip > mflimit) { anchor = ip; to_tail = true; break; }
 
@@ -427,11 +461,15 @@ __device__ __forceinline__ uint32_t warp_lz4_encode3(const uint8_t *__restrict__
 				__syncwarp();
 				const uint32_t np = ip + 1u + (uint32_t)lane;          // next search, step 1
 				uint32_t vn = 0;
-				if (np + 1u <= mflimit) vn = ld32u(src + np);
+				if (np + 1u <= mflimit) vn = LDS32(np);
 				ExtRound e2 = ext_load(src, ip, pref, iend, lane);
 				const bool probe_hit = (!DIST || pref + LZ4_MAXDIST >= ip) &&
 				    (__shfl_sync(0xffffffffu, e2.wb, 0) == v_end);
+				PROF_LAP(p_post)
 				if (probe_hit) {
+#ifdef LZ4_PROF
+					n_follow++;
+#endif
 					ref = pref;
 					token = op++;
 					tokval = 0;
@@ -459,6 +497,13 @@ __device__ __forceinline__ uint32_t warp_lz4_encode3(const uint8_t *__restrict__
 		for (uint32_t i = (uint32_t)lane; i < last; i += 32u) dst[op + i] = src[anchor + i];
 		op += last;
 	}
+#ifdef LZ4_PROF
+	if (lane == 0 && blockIdx.x == 7 && (threadIdx.x >> 5) == 1 && n_seq > 100)
+		printf("K3PROF seq=%u follow=%u per-seq cycles: search %lld  B(loads+catchup+literals) %lld  ext+emit %lld  post(probe) %lld  total %lld\n",
+		    n_seq, n_follow, p_search / n_seq, p_b / n_seq, p_ext / n_seq, p_post / n_seq,
+		    (p_search + p_b + p_ext + p_post) / n_seq);
+#endif
+#undef LDS32
 	return op;
 }
 
