@@ -11,16 +11,31 @@ every pollInterval ms, `done === true` ends it, `done === 'failed'` or any HTTP
 error is an error, anything else (false, 0) means in progress (:685-754); the last
 polled job is kept in _restoreObject for the status server (:722); on any error
 the `zfs recv` child is SIGKILLed (:867-876); restore(serverUrl, cb(err, oldDataset)).
-The dataset isolate/mount/snapshot steps of restore() (:115-207) are metadata
-operations outside the bulk-data path and stay with the caller.
+
+Dataset lifecycle around the receive, same order and same
+zfs(1M) invocations as the reference:
+    restore()         :115-207  isolateDataset('autorebuild') -> _receive ->
+                                canmount=noauto -> mountpoint -> inherit snapdir ->
+                                mount -> snapshotDataset; callback(err, oldDataset)
+                                (oldDataset is reported on failure too)
+    isolateDataset()  :514-624  exists? -> canmount=off -> mounted must be "no" ->
+                                inherit mountpoint -> rename -p to
+                                <parent>/isolated/<prefix>-<ISO time>
+    snapshotDataset() :214-221  <dataset>@<epoch ms>
+Additive (never read by the reference): _restoreObject['gpuRecv'] = receiver stage stats
+(the sender's are the job's own 'gpu' field).
 """
+import datetime
 import json
+import os
 import socket
 import subprocess
 import threading
 import time
 import urllib.error
 import urllib.request
+
+from . import zfs_cmd
 
 CHUNK = 1 << 20
 
@@ -32,6 +47,7 @@ class ZfsClient(object):
                      ("zfsHost", str), ("zfsPath", str), ("zfsPort", int)):
             assert isinstance(options.get(k), t), "options.%s (%s) is required" % (k, t.__name__)
         self._dataset = options["dataset"]
+        self._parentDataset = os.path.dirname(self._dataset)      # lib/zfsClient.js:75
         self._mountpoint = options["mountpoint"]
         self._dbUser = options["dbUser"]
         self._pollInterval = options["pollInterval"]
@@ -41,14 +57,60 @@ class ZfsClient(object):
         self._zfsPath = options["zfsPath"]
         self._gpu = options.get("gpu") or None
         self._env = options.get("env")
+        self._gpuStats = None
+        # metadata commands: the reference hard-codes /sbin/zfs with an empty environment
+        # (lib/common.js:156-157); `zfsBin`/`zfsEnv` exist so tests can point at a fake
+        self._zfsBin = options.get("zfsBin") or zfs_cmd.ZFS_BIN
+        self._zfsEnv = options.get("zfsEnv") or {}
 
-    # -- lib/zfsClient.js:115 (bulk-data part only)
+    def _z(self, **kw):
+        kw["zfs"] = self._zfsBin
+        kw["env"] = self._zfsEnv
+        return kw
+
+    # -- lib/zfsClient.js:115-207
     def restore(self, serverUrl, callback):
+        oldDataset = None
         try:
+            # move the existing dataset (if any) out of the way, keep its new name
+            oldDataset = self.isolateDataset({"prefix": "autorebuild"})
             self._receive(self._dataset, serverUrl, self._pollInterval)
+            # manatee mounts/unmounts the dataset itself
+            zfs_cmd.zfsSet(self._z(dataset=self._dataset, property="canmount", value="noauto"))
+            zfs_cmd.zfsSet(self._z(dataset=self._dataset, property="mountpoint", value=self._mountpoint))
+            zfs_cmd.zfsInherit(self._z(dataset=self._dataset, property="snapdir"))
+            zfs_cmd.zfsMount(self._z(dataset=self._dataset))
+            self.snapshotDataset()
         except Exception as e:                                # noqa: BLE001
-            return callback(e, None)
-        return callback(None, None)
+            err = RuntimeError('receiving snapshot from "%s": %s' % (serverUrl, e))
+            err.__cause__ = e
+            return callback(err, oldDataset)
+        return callback(None, oldDataset)
+
+    # -- lib/zfsClient.js:214-221
+    def snapshotDataset(self):
+        zfs_cmd.zfsSnapshot(self._z(dataset=self._dataset, snapshot=str(int(time.time() * 1000))))
+
+    # -- lib/zfsClient.js:514-624 -> isolated name, or None when there was nothing to isolate
+    def isolateDataset(self, opts):
+        assert isinstance(opts, dict) and isinstance(opts.get("prefix"), str), "opts.prefix (string) is required"
+        dataset = self._dataset
+        now = datetime.datetime.now(datetime.timezone.utc)
+        iso = now.strftime("%Y-%m-%dT%H:%M:%S.") + "%03dZ" % (now.microsecond // 1000)   # Date#toISOString
+        isolatedName = "/".join([self._parentDataset, "isolated", opts["prefix"] + "-" + iso])
+        try:
+            if not zfs_cmd.zfsExists(self._z(dataset=dataset)):
+                return None
+            # canmount=off implicitly unmounts; fails if the dataset is busy
+            zfs_cmd.zfsSet(self._z(dataset=dataset, property="canmount", value="off"))
+            value = zfs_cmd.zfsGet(self._z(dataset=dataset, property="mounted"))
+            if value != "no":
+                raise zfs_cmd.ZfsError('wanted "no" but found "%s" for property "mounted"' % value)
+            zfs_cmd.zfsInherit(self._z(dataset=dataset, property="mountpoint"))
+            zfs_cmd.zfsRename(self._z(dataset=dataset, target=isolatedName, parents=True))
+        except zfs_cmd.ZfsError as e:
+            raise zfs_cmd.ZfsError('preserving dataset "%s": %s' % (dataset, e), cause=e)
+        return isolatedName
 
     def _make_stage(self):
         if not self._gpu or self._gpu.get("mode", "off") == "off":
@@ -162,6 +224,8 @@ class ZfsClient(object):
             jobPath = self._postRestoreRequest(serverUrl)
             self._pollRestoreCompletion(serverUrl, pollInterval, jobPath, abort)
             ts.join(60)
+            if self._gpuStats is not None and isinstance(self._restoreObject, dict):
+                self._restoreObject["gpuRecv"] = self._gpuStats   # additive field
             if pipe_err:
                 raise pipe_err[0]
             code = zfsRecv.wait(60)

@@ -44,7 +44,9 @@ def fakezfs(tmp_path, oracle):
     env["PATH"] = str(z) + os.pathsep + env.get("PATH", "")
     env["FAKE_ZFS_STREAM"] = str(sp)
     env["FAKE_ZFS_RECV_OUT"] = str(tmp_path / "recv.out")
-    return {"zfs": str(zfs), "env": env, "stream": stream, "recv_out": str(tmp_path / "recv.out")}
+    env["FAKE_ZFS_STATE"] = str(tmp_path / "pool.json")      # dataset lifecycle model (8f f3/f4)
+    return {"zfs": str(zfs), "env": env, "stream": stream, "recv_out": str(tmp_path / "recv.out"),
+            "state": str(tmp_path / "pool.json")}
 
 
 def _run_restore(fakezfs, sender_gpu=None, recv_gpu=None, env_extra=None):
@@ -59,7 +61,8 @@ def _run_restore(fakezfs, sender_gpu=None, recv_gpu=None, env_extra=None):
     sender.on("done", lambda j: events.append(("done", j)))
     cli = ZfsClient({"log": None, "dataset": "zones/y/data/manatee", "dbUser": "postgres",
                      "mountpoint": "/manatee/pg", "pollInterval": 50, "zfsHost": "127.0.0.1",
-                     "zfsPath": fakezfs["zfs"], "zfsPort": _free_port(), "gpu": recv_gpu, "env": env})
+                     "zfsPath": fakezfs["zfs"], "zfsPort": _free_port(), "gpu": recv_gpu, "env": env,
+                     "zfsBin": fakezfs["zfs"], "zfsEnv": env})
     res = {}
     cli.restore("http://127.0.0.1:%d" % srv.port, lambda err, old: res.update(err=err, old=old))
     sender.join(10)
@@ -199,7 +202,8 @@ def test_coalesced_restores_share_one_send(fakezfs, tmp_path):
         outs.append(e2["FAKE_ZFS_RECV_OUT"])
         cli = ZfsClient({"log": None, "dataset": "zones/y%d/data/manatee" % k, "dbUser": "postgres",
                          "mountpoint": "/manatee/pg", "pollInterval": 50, "zfsHost": "127.0.0.1",
-                         "zfsPath": fakezfs["zfs"], "zfsPort": _free_port(), "env": e2})
+                         "zfsPath": fakezfs["zfs"], "zfsPort": _free_port(), "env": e2,
+                         "zfsBin": fakezfs["zfs"], "zfsEnv": e2})
         res = {}
         results.append((res, cli))
         t = threading.Thread(target=cli.restore, args=("http://127.0.0.1:%d" % srv.port,

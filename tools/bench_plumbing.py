@@ -43,7 +43,7 @@ def main():
                                   "queue": srv.getQueue(), "gpu": sg, "env": env})
         cli = ZfsClient({"log": None, "dataset": "zones/y/data/manatee", "dbUser": "postgres",
                          "mountpoint": "/m", "pollInterval": 100, "zfsHost": "127.0.0.1", "zfsPath": zfs,
-                         "zfsPort": free_port(), "gpu": rg, "env": env})
+                         "zfsPort": free_port(), "gpu": rg, "env": env, "zfsBin": zfs, "zfsEnv": env})
         res = {}
         t0 = time.perf_counter()
         cli.restore("http://127.0.0.1:%d" % srv.port, lambda err, old: res.update(err=err))
