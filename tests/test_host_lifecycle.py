@@ -344,7 +344,7 @@ def test_sender_ships_the_snapshotters_newest_and_gc_cannot_take_it_mid_send(poo
     for k in range(3):
         s.createSnapshot(str(1405378955000 + k))
     pool.z("snapshot", ds + "@zzz-operator")
-    srv, sender = _serve(pool, env_extra={"FAKE_ZFS_SEND_DELAY": "0.3"})
+    srv, sender = _serve(pool, env_extra={"FAKE_ZFS_SEND_DELAY": "1.5"})
     cli = _client(pool)
     res = {}
     t = threading.Thread(target=cli.restore, args=("http://127.0.0.1:%d" % srv.port,
