@@ -223,6 +223,75 @@ def test_coalesced_restores_share_one_send(fakezfs, tmp_path):
     assert open(str(counter)).read().count("send") == 1, "coalesced requests must share one zfs send"
 
 
+class _IdentityStageDouble(object):
+    """TEST DOUBLE with GpuSnapshotStage's streaming surface (write/flush/read/stats/close).
+    It only lets the CPU suite walk the host threading around a stage (drain threads, job
+    fields, negotiation); the product has no such thing -- the real stage needs a B200."""
+    made = []
+
+    def __init__(self, mode="verify", **kw):
+        import collections
+        self.mode, self.q, self.cv, self.eof, self.n = mode, collections.deque(), threading.Condition(), False, 0
+        _IdentityStageDouble.made.append(self)
+
+    def write(self, chunk, block=True):
+        with self.cv:
+            self.q.append(bytes(chunk)); self.n += len(chunk); self.cv.notify_all()
+
+    def flush(self):
+        with self.cv:
+            self.eof = True; self.cv.notify_all()
+
+    def read(self, cap=1 << 20, block=True):
+        with self.cv:
+            while not self.q and not self.eof:
+                self.cv.wait(0.05)
+            if self.q:
+                b = self.q.popleft()
+                if len(b) > cap:
+                    self.q.appendleft(b[cap:]); b = b[:cap]
+                return b
+            return None
+
+    def stats(self):
+        return {"bytes_in": self.n, "bytes_out": self.n, "lz4_encoded": 0, "mode": self.mode}
+
+    def close(self):
+        pass
+
+
+def test_host_threading_around_a_stage_cpu(fakezfs, monkeypatch):
+    """The host code paths the gpu-marked tests take (stage in both pipes, job.gpu / gpuRecv,
+    wire negotiation, a second restore isolating the first one's dataset), with the stage
+    replaced by an identity double so that they also run where there is no GPU."""
+    import manatee_b200.stage as stage_mod
+    monkeypatch.setattr(stage_mod, "GpuSnapshotStage", _IdentityStageDouble)
+    _IdentityStageDouble.made = []
+    s = fakezfs["stream"]
+    want = hashlib.sha256(s.tobytes()).hexdigest()
+    res, cli, events = _run_restore(fakezfs, sender_gpu={"mode": "verify"}, recv_gpu={"mode": "verify"})
+    assert res["err"] is None and res["old"] is None, res
+    digest, n = open(fakezfs["recv_out"]).read().split()
+    assert digest == want and int(n) == s.size
+    assert [m.mode for m in _IdentityStageDouble.made] == ["verify", "verify"]
+    job = cli._restoreObject
+    assert job["done"] is True and job["wire"] == "raw"
+    assert job["gpu"]["bytes_in"] == s.size and job["gpuRecv"]["bytes_out"] == s.size
+    assert events and events[-1][0] == "done"
+    # compress sender + plain receiver -> the sender's stage is opened in verify mode
+    _IdentityStageDouble.made = []
+    res, cli, events = _run_restore(fakezfs, sender_gpu={"mode": "compress"}, recv_gpu=None)
+    assert res["err"] is None and res["old"].startswith("zones/y/data/isolated/autorebuild-")
+    assert [m.mode for m in _IdentityStageDouble.made] == ["verify"] and cli._restoreObject["wire"] == "raw"
+    assert "gpuRecv" not in cli._restoreObject
+    # negotiated
+    _IdentityStageDouble.made = []
+    res, cli, events = _run_restore(fakezfs, sender_gpu={"mode": "compress"}, recv_gpu={"mode": "decompress"})
+    assert res["err"] is None
+    assert sorted(m.mode for m in _IdentityStageDouble.made) == ["compress", "decompress"]
+    assert cli._restoreObject["wire"] == "lz4-stage-v1"
+
+
 @pytest.mark.gpu
 def test_gpu_sender_compress_falls_back_for_plain_receiver(fakezfs):
     """Mixed versions (f2): a receiver that did not ask for the compressed wire gets the raw,

@@ -1,9 +1,13 @@
 #!/bin/bash
-# usage: tools/gpurun_retry.sh <timeout> '<command>'   -- retries while the pod is busy
+# usage: tools/gpurun_retry.sh <timeout> '<command>'
+# Retries ONLY when gpurun answers exit code 3 (no box/slot free: nothing charged, nothing ran).
+# Every other outcome -- including "transient"/lost-box verdicts, which count as strikes -- is
+# printed in full and returned: never retry those blindly, read the verdict first.
 for i in $(seq 1 20); do
-  out=$(gpurun --timeout "$1" -- "$2" 2>&1)
-  if echo "$out" | grep -q "status=transient"; then sleep 90; continue; fi
+  out=$(/usr/local/graft/bin/gpurun --timeout "$1" -- "$2" 2>&1)
+  rc=$?
+  if [ "$rc" = "3" ]; then sleep 90; continue; fi
   echo "$out" | grep -v "^\[gpurun\] sending"
-  exit 0
+  exit $rc
 done
 echo "gave up: pod busy"; exit 3
