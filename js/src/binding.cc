@@ -1,9 +1,10 @@
 // binding.cc -- thin N-API addon over the C ABI of libmanatee_gpu.so
 // (include/manatee_gpu.h).  It adds NO logic: every export is one mtz_* call.
 //
-// NOT COMPILED IN THIS REPOSITORY'S CI: the build image has no Node.js and no
-// node_api.h (`node --version`: not found).  It is the binding a maintainer adds
-// to manatee; tests/ drive the same C ABI through ctypes instead.
+// NOT BUILT INTO AN ADDON HERE: the build image has no Node.js and no node_api.h
+// (`node --version`: not found).  tests/test_abi.py type-checks this file against
+// include/manatee_gpu.h with a stub of the N-API declarations (tests/stubs/node_api.h,
+// `g++ -fsyntax-only`); tests/ drive the same C ABI through ctypes instead.
 //
 // JS surface (used by js/lib/gpuSnapshotStage.js):
 //   open({mode, device, ringBytes, outRingBytes, batchBytes, slots}) -> handle (external)
@@ -19,6 +20,7 @@
 // Every failing call throws Error(mtz_last_error) with .code = MTZ_E* so the stage
 // can destroy(err), which the sender maps to job.done='failed' (lib/backupSender.js:218).
 #include <node_api.h>
+#include <stdio.h>
 #include <string.h>
 #include "../../include/manatee_gpu.h"
 
@@ -183,6 +185,23 @@ static napi_value Stats(napi_env env, napi_callback_info info)
 	return o;
 }
 
+static napi_value EndChecksum(napi_env env, napi_callback_info info)
+{
+	size_t argc = 1; napi_value argv[1];
+	NAPI_OK(napi_get_cb_info(env, info, &argc, argv, NULL, NULL));
+	mtz_handle *h = get_handle(env, argv[0]);
+	uint64_t ck[4] = { 0, 0, 0, 0 };
+	int32_t rc = mtz_end_checksum(h, ck);
+	if (rc != MTZ_OK) return throw_mtz(env, h, rc);
+	napi_value arr, v;
+	NAPI_OK(napi_create_array_with_length(env, 4, &arr));
+	for (uint32_t i = 0; i < 4; i++) {
+		NAPI_OK(napi_create_bigint_uint64(env, ck[i], &v));   // 64-bit words do not fit a double
+		NAPI_OK(napi_set_element(env, arr, i, v));
+	}
+	return arr;
+}
+
 static napi_value Close(napi_env env, napi_callback_info info)
 {
 	size_t argc = 1; napi_value argv[1];
@@ -199,6 +218,7 @@ static napi_value Init(napi_env env, napi_value exports)
 		{"flush", 0, Flush, 0, 0, 0, napi_default, 0}, {"peek", 0, Peek, 0, 0, 0, napi_default, 0},
 		{"consume", 0, Consume, 0, 0, 0, napi_default, 0}, {"eventFd", 0, EventFd, 0, 0, 0, napi_default, 0},
 		{"stats", 0, Stats, 0, 0, 0, napi_default, 0}, {"close", 0, Close, 0, 0, 0, napi_default, 0},
+		{"endChecksum", 0, EndChecksum, 0, 0, 0, napi_default, 0},
 	};
 	napi_define_properties(env, exports, sizeof d / sizeof d[0], d);
 	return exports;

@@ -70,3 +70,31 @@ def test_host_index_matches_oracle(native, oracle):
     # truncated tail: only whole records are reported
     recs2, used2 = index_host(s[:-100])
     assert len(recs2) == cnt - 1 and used2 == int(offs[-1])
+
+
+def test_napi_binding_type_checks_against_the_header():
+    """js/src/binding.cc is what a manatee maintainer compiles; Node is absent here, so the
+    least we can do is type-check it against include/manatee_gpu.h with a stub of the N-API
+    declarations, and check that the JS wrapper only calls exports the binding defines."""
+    import re
+    import shutil
+    import subprocess
+    if shutil.which("g++") is None:
+        pytest.skip("no g++")
+    src = os.path.join(ROOT, "js", "src", "binding.cc")
+    r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-Wall", "-Wextra", "-Werror",
+                        "-I" + os.path.join(ROOT, "tests", "stubs"), src],
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 0, r.stderr
+    text = open(src).read()
+    exported = set(re.findall(r'\{"(\w+)", 0, \w+, 0, 0, 0, napi_default, 0\}', text))
+    assert {"open", "write", "flush", "peek", "consume", "eventFd", "stats", "close", "acquire", "commit",
+            "endChecksum"} <= exported
+    js = open(os.path.join(ROOT, "js", "lib", "gpuSnapshotStage.js")).read()
+    used = set(re.findall(r"this\._addon\.(\w+)\(", js))
+    assert used and used <= exported, used - exported
+    # every C entry point the binding calls is declared in the public header
+    called = set(re.findall(r"\b(mtz_[a-z_0-9]+)\(", text))
+    header = open(os.path.join(ROOT, "include", "manatee_gpu.h")).read()
+    for fn in called:
+        assert re.search(r"\b%s\(" % fn, header), fn
