@@ -61,6 +61,11 @@ def lib():
         L.orc_fletcher4_incremental.argtypes = [vp, sz, C.POINTER(Cksum)]
         L.orc_fletcher4_native.argtypes = [vp, sz, C.POINTER(Cksum)]
         L.orc_fletcher4_partial.argtypes = [vp, sz, C.POINTER(Partial)]
+        L.orc_fletcher4_partial_simd.argtypes = [vp, sz, C.POINTER(Partial), i32]
+        L.orc_fletcher4_simd_lanes.argtypes = [i32]
+        L.orc_fletcher4_simd_lanes.restype = i32
+        L.orc_mt_set_lanes.argtypes = [i32]
+        L.orc_mt_set_lanes.restype = i32
         L.orc_fletcher4_apply.argtypes = [C.POINTER(Cksum), C.POINTER(Partial)]
         L.orc_partial_concat.argtypes = [C.POINTER(Partial)] * 3
         L.orc_tri2.argtypes = [u64]; L.orc_tri2.restype = u64
@@ -254,6 +259,23 @@ def gen_payload(kind, recidx, length):
     dst = np.empty(length, dtype=np.uint8)
     lib().orc_gen_payload(kind, recidx, _ptr(dst), length)
     return dst
+
+
+def fletcher4_partial_simd(buf, lanes=-1):
+    """lane-parallel form (baseline only); lanes: -1 best, 0 scalar, 4 avx2, 8 avx512f"""
+    a = _u8(buf)
+    p = Partial()
+    lib().orc_fletcher4_partial_simd(_ptr(a), a.size, C.byref(p), lanes)
+    return p.tuple()
+
+
+def simd_lanes(force=-1):
+    return lib().orc_fletcher4_simd_lanes(force)
+
+
+def mt_set_lanes(lanes):
+    """Fletcher-4 flavour of mt_verify / mt_recompress; returns the lanes in use"""
+    return lib().orc_mt_set_lanes(lanes)
 
 
 def mt_verify(stream, nthreads):

@@ -267,7 +267,16 @@ orc_lz4_decompress_block(const uint8_t *src, int isize, uint8_t *dst,
 		}
 		len += MINMATCH;
 		if (len > (unsigned)(oend - op)) return (-1);
-		while (len--) *op++ = *ref++;      /* overlap-safe byte copy */
+		if (off >= len) {                  /* disjoint: one block copy */
+			memcpy(op, ref, len);
+			op += len;
+		} else if (off >= 8) {             /* overlapping, period >= 8: 8-byte steps */
+			uint8_t *const e = op + len;
+			while (op + 8 <= e) { memcpy(op, ref, 8); op += 8; ref += 8; }
+			while (op < e) *op++ = *ref++;
+		} else {
+			while (len--) *op++ = *ref++;  /* short period: byte order matters */
+		}
 	}
 	return ((int)(op - dst));
 }

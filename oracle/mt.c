@@ -2,10 +2,11 @@
  * mt.c -- ORACLE (test infrastructure; see mtz_oracle.h header).
  *
  * Record-parallel CPU drivers used ONLY as the reported CPU baseline
- * (bench.py cpu_baseline / --impl reference): the same
- * scalar Fletcher-4 and ZFS-LZ4 restatements as the single-thread oracle,
- * spread over pthreads by record index, with the O(records) sequential
- * checksum chain done on one thread.  This is what the arithmetic that today
+ * (bench.py cpu_baseline / --impl reference): the
+ * ZFS-LZ4 restatement of the single-thread oracle and Fletcher-4 in the
+ * lane-parallel form ZFS itself uses on x86 (fletcher4_simd.c; the scalar
+ * definition is selectable), spread over pthreads by record index, with the
+ * O(records) sequential checksum chain done on one thread.  This is what the arithmetic that today
  * runs inside `zfs send` / `zfs recv` (lib/backupSender.js:177,
  * lib/zfsClient.js:793) costs on the box's host cores.
  */
@@ -26,6 +27,20 @@ now_s(void)
 static inline uint32_t g32(const uint8_t *p) { uint32_t v; memcpy(&v, p, 4); return (v); }
 static inline uint64_t g64(const uint8_t *p) { uint64_t v; memcpy(&v, p, 8); return (v); }
 static inline void p64(uint8_t *p, uint64_t v) { memcpy(p, &v, 8); }
+
+/*
+ * Fletcher-4 flavour of the payload sums: -1 = the widest vector form the
+ * CPU has (what ZFS itself would pick), 0 = the scalar definition, 4 / 8 =
+ * AVX2 / AVX-512F lanes.  See fletcher4_simd.c.
+ */
+static int g_lanes = -1;
+
+int
+orc_mt_set_lanes(int lanes)
+{
+	g_lanes = lanes;
+	return (orc_fletcher4_simd_lanes(lanes));
+}
 
 typedef struct {
 	const uint8_t *in;
@@ -56,7 +71,7 @@ mt_worker(void *v)
 		uint32_t type = g32(h);
 
 		if (a->mode == 0) {
-			orc_fletcher4_partial(pay, (size_t)pl, &a->ppay[i]);
+			orc_fletcher4_partial_simd(pay, (size_t)pl, &a->ppay[i], g_lanes);
 			continue;
 		}
 		{
@@ -96,7 +111,7 @@ mt_worker(void *v)
 			} else {
 				memcpy(op, pay, (size_t)pl);
 			}
-			orc_fletcher4_partial(op, (size_t)a->opl[i], &a->ppay[i]);
+			orc_fletcher4_partial_simd(op, (size_t)a->opl[i], &a->ppay[i], g_lanes);
 		}
 	}
 	free(tmp);

@@ -47,6 +47,9 @@ void orc_fletcher4_incremental(const void *buf, size_t size, orc_cksum_t *ck);
 void orc_fletcher4_native(const void *buf, size_t size, orc_cksum_t *ck);
 void orc_fletcher4_partial(const void *buf, size_t size, orc_partial_t *p);
 void orc_fletcher4_apply(orc_cksum_t *state, const orc_partial_t *p);
+/* fletcher4_simd.c: lane-parallel form for the CPU baseline (0/4/8 lanes, <0 = best) */
+int orc_fletcher4_simd_lanes(int force);
+void orc_fletcher4_partial_simd(const void *buf, size_t size, orc_partial_t *p, int lanes);
 void orc_partial_concat(const orc_partial_t *x, const orc_partial_t *y,
     orc_partial_t *out);
 uint64_t orc_tri2(uint64_t n);   /* n(n+1)/2 mod 2^64, exact */
@@ -137,6 +140,7 @@ int orc_synth_shard_stamp(uint8_t *out, uint64_t nwrites, uint32_t recsize,
 /* ---- multi-threaded CPU baseline drivers (bench.py --impl reference) ---- */
 /* record-parallel Fletcher-4 verify: per-record partials on nthreads, then
  * the O(records) combine; returns ORC_OK/ORC_ECKSUM, seconds in *secs */
+int orc_mt_set_lanes(int lanes);          /* -1 best, 0 scalar, 4 avx2, 8 avx512f; returns lanes in use */
 int orc_mt_verify(const uint8_t *in, size_t n, int nthreads, double *secs,
     orc_stream_stats_t *st);
 int orc_mt_recompress(const uint8_t *in, size_t n, uint8_t *out, size_t cap,

@@ -132,6 +132,57 @@ def test_lz4_blocks_against_liblz4(oracle, liblz4):
         assert n3 == p.size and np.array_equal(o3, p)
 
 
+def test_lz4_overlapping_match_periods(oracle, liblz4):
+    """every copy flavour of the decoder (disjoint block copy, period >= 8 in 8-byte steps,
+    short period byte by byte) against liblz4, for every period 1..40 at several lengths"""
+    for period in range(1, 41):
+        for total in (period + 5, 100, 1000, 4099):
+            if total <= period + 12:
+                continue
+            unit = (np.arange(period, dtype=np.uint32) * 37 + period).astype(np.uint8)
+            p = np.tile(unit, total // period + 1)[:total].copy()
+            for blk in (oracle.lz4_compress_block(p),):
+                out = np.empty(total + 8, dtype=np.uint8)
+                assert liblz4.LZ4_decompress_safe(blk.ctypes.data, out.ctypes.data, blk.size, total) == total
+                n, o = oracle.lz4_decompress_block(blk, total)
+                assert n == total and np.array_equal(o, p) and np.array_equal(out[:total], p)
+            buf = np.empty(total + 64, dtype=np.uint8)
+            m = liblz4.LZ4_compress_default(p.ctypes.data, buf.ctypes.data, total, buf.size)
+            n, o = oracle.lz4_decompress_block(buf[:m], total)
+            assert n == total and np.array_equal(o, p)
+
+
+def test_fletcher4_lane_parallel_form_equals_the_definition(oracle):
+    """the CPU baseline's vector Fletcher-4 (how ZFS itself computes it on x86) is checked
+    against the scalar definition: every lane width the CPU has, ragged sizes, unaligned
+    starts, all-ones words (carry out of every 32-bit column)"""
+    rng = np.random.default_rng(11)
+    widths = sorted({0, oracle.simd_lanes(4), oracle.simd_lanes(8), oracle.simd_lanes(-1)})
+    for n in [0, 4, 8, 12, 16, 28, 32, 36, 60, 64, 68, 100, 4096, 131072 + 32, (1 << 20) + 4]:
+        for off in (0, 1, 2, 3):
+            for fill in ("rand", "ones"):
+                buf = rng.integers(0, 256, n + off, dtype=np.uint8)[off:]
+                if fill == "ones":
+                    buf = buf.copy(); buf[:] = 255
+                want = oracle.fletcher4_partial(buf)
+                for lanes in widths + [-1]:
+                    assert oracle.fletcher4_partial_simd(buf, lanes) == want, (n, off, fill, lanes)
+    # a long all-ones buffer wraps the 64-bit sums many times
+    big = np.full(100000 * 4, 255, dtype=np.uint8)
+    assert oracle.fletcher4_partial_simd(big, -1) == oracle.fletcher4_partial(big)
+    # and the threaded baseline gives the same verdict / END checksum with either flavour
+    s = oracle.synth_stream(40, recsize=131072, kind=oracle.PAYLOAD_PCG)
+    res = []
+    for lanes in (0, -1):
+        oracle.mt_set_lanes(lanes)
+        rc, secs, st = oracle.mt_verify(s, 3)
+        res.append((rc, st.records, tuple(st.end_cksum.w)))
+    oracle.mt_set_lanes(-1)
+    assert res[0] == res[1] and res[0][0] == 0
+    bad = s.copy(); bad[5 * 131384 + 1000] ^= 1
+    assert oracle.mt_verify(bad, 3)[0] != 0
+
+
 def test_lz4_hand_made_edge_blocks(oracle):
     # literal-only block
     n, o = oracle.lz4_decompress_block(bytes([0x50]) + b"hello", 5)
