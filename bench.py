@@ -629,6 +629,13 @@ def main():
     args = parse_args()
     RECSIZE = args.recsize
     REC_BYTES = 312 + RECSIZE
+    if RECSIZE != 131072 and args.recompress_gib:
+        # BASELINE configs[2] is defined on 128 KiB records; the small-recordsize sweeps are
+        # VERIFY-only (a 64 GiB codec workload of millions of tiny records took the GPU box
+        # down in round 1 -- not reproduced yet, so it is not run implicitly)
+        print("note: --recsize %d: recompress workload skipped (pass it alone with --recsize 131072)"
+              % RECSIZE, file=sys.stderr)
+        args.recompress_gib = 0
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)
