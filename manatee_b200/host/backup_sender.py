@@ -108,17 +108,26 @@ class BackupSender(object):
                 return line
         raise RuntimeError("no snapshots found")
 
+    def _decide_wire(self, jobs):
+        """Capability negotiation, settled BEFORE any socket is opened so a
+        receiver that looks at the job on connect sees it: the stage-compressed wire is used
+        only when this sender compresses AND every requester of this send advertised
+        `accept: "lz4-stage-v1"`; everybody else gets the raw (verified) stream.  With the gpu
+        stage off the job object is left exactly as the reference has it (no `wire` field)."""
+        if not self._gpu or self._gpu.get("mode", "off") == "off":
+            return
+        compress = self._gpu["mode"] == "compress" and \
+            all(j.get("accept") == "lz4-stage-v1" for j in jobs)
+        for j in jobs:
+            j["wire"] = "lz4-stage-v1" if compress else "raw"
+
     def _make_stage(self, backupJob=None):
         if not self._gpu or self._gpu.get("mode", "off") == "off":
             return None
         from ..stage import GpuSnapshotStage          # the product: fails loudly without the .so/GPU
         g = dict(self._gpu)
-        # capability negotiation: only a receiver that asked for the
-        # stage-compressed wire gets it; everybody else gets the raw (verified) stream
-        if g["mode"] == "compress" and (backupJob is None or backupJob.get("accept") != "lz4-stage-v1"):
+        if g["mode"] == "compress" and (backupJob is None or backupJob.get("wire") != "lz4-stage-v1"):
             g["mode"] = "verify"
-        if backupJob is not None:
-            backupJob["wire"] = "lz4-stage-v1" if g["mode"] == "compress" else "raw"
         return GpuSnapshotStage(g["mode"], device=g.get("device", 0),
                                 ring_bytes=g.get("ringBytes", 0), batch_bytes=g.get("batchBytes", 0),
                                 out_ring_bytes=g.get("outRingBytes", 0), n_slots=g.get("slots", 0))
@@ -153,6 +162,7 @@ class BackupSender(object):
 
         jobs_by_id = {id(j): j for j in jobs}
         self_cb = {id(j): self._job_cb(j) for j in jobs}
+        self._decide_wire(jobs)
         socks = {}
         for j in jobs:
             try:
@@ -186,6 +196,7 @@ class BackupSender(object):
         try:
             snapshot = self._getLatestSnapshot()
             if sock is None:
+                self._decide_wire([backupJob])
                 sock = socket.create_connection((backupJob["host"], int(backupJob["port"])))
             zfsSend = subprocess.Popen([self._zfsPath, "send", "-v", "-P", snapshot],
                                        stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=self._env)

@@ -112,14 +112,29 @@ class ZfsClient(object):
             raise zfs_cmd.ZfsError('preserving dataset "%s": %s' % (dataset, e), cause=e)
         return isolatedName
 
-    def _make_stage(self):
+    def _make_stage(self, mode=None):
         if not self._gpu or self._gpu.get("mode", "off") == "off":
             return None
         from ..stage import GpuSnapshotStage
         g = self._gpu
-        return GpuSnapshotStage(g["mode"], device=g.get("device", 0),
+        return GpuSnapshotStage(mode or g["mode"], device=g.get("device", 0),
                                 ring_bytes=g.get("ringBytes", 0), batch_bytes=g.get("batchBytes", 0),
                                 out_ring_bytes=g.get("outRingBytes", 0), n_slots=g.get("slots", 0))
+
+    def _wire_mode(self, serverUrl, jobPath):
+        """Which stage to put in the pipe for THIS job.  A receiver configured
+        to `decompress` only does so when the sender committed to the stage-compressed wire
+        (`job.wire == "lz4-stage-v1"`, set before it connects); a reference sender, or a GPU
+        sender that is not compressing, ships a raw stream and the stage just verifies it."""
+        mode = self._gpu["mode"]
+        if mode != "decompress":
+            return mode
+        try:
+            with urllib.request.urlopen(serverUrl.rstrip("/") + jobPath, timeout=30) as r:
+                obj = json.loads(r.read().decode())
+        except (urllib.error.URLError, OSError, ValueError):
+            obj = {}
+        return "decompress" if obj.get("wire") == "lz4-stage-v1" else "verify"
 
     # -- lib/zfsClient.js:638-668
     def _postRestoreRequest(self, serverUrl):
@@ -168,13 +183,19 @@ class ZfsClient(object):
         abort = threading.Event()
         pipe_err = []
         stage_box = []
+        job_box = []
+        posted = threading.Event()
 
         def serve():
             conn = None
             stage = None
             try:
                 conn, _ = server.accept()
-                stage = self._make_stage()
+                if self._gpu and self._gpu.get("mode", "off") != "off":
+                    # the sender connects only after our POST was queued; wait for its answer
+                    if not posted.wait(30):
+                        raise RuntimeError("no jobPath for the incoming connection")
+                    stage = self._make_stage(self._wire_mode(serverUrl, job_box[0]))
                 stage_box.append(stage)
                 if stage is None:
                     while True:                               # socket.pipe(zfsRecv.stdin)
@@ -222,6 +243,8 @@ class ZfsClient(object):
             ts = threading.Thread(target=serve, daemon=True)
             ts.start()
             jobPath = self._postRestoreRequest(serverUrl)
+            job_box.append(jobPath)
+            posted.set()
             self._pollRestoreCompletion(serverUrl, pollInterval, jobPath, abort)
             ts.join(60)
             if self._gpuStats is not None and isinstance(self._restoreObject, dict):

@@ -290,6 +290,18 @@ def test_host_threading_around_a_stage_cpu(fakezfs, monkeypatch):
     assert res["err"] is None
     assert sorted(m.mode for m in _IdentityStageDouble.made) == ["compress", "decompress"]
     assert cli._restoreObject["wire"] == "lz4-stage-v1"
+    # mixed versions, the other way round: a reference sender (no stage, no `wire` field) and a
+    # receiver configured to decompress -> the raw stream is verified, not rejected
+    _IdentityStageDouble.made = []
+    res, cli, events = _run_restore(fakezfs, sender_gpu=None, recv_gpu={"mode": "decompress"})
+    assert res["err"] is None, res
+    assert [m.mode for m in _IdentityStageDouble.made] == ["verify"]
+    assert "wire" not in cli._restoreObject and cli._restoreObject["gpuRecv"]["bytes_in"] == s.size
+    # a verifying (non-compressing) GPU sender and a decompress receiver
+    _IdentityStageDouble.made = []
+    res, cli, events = _run_restore(fakezfs, sender_gpu={"mode": "verify"}, recv_gpu={"mode": "decompress"})
+    assert res["err"] is None and cli._restoreObject["wire"] == "raw"
+    assert [m.mode for m in _IdentityStageDouble.made] == ["verify", "verify"]
 
 
 @pytest.mark.gpu
@@ -307,6 +319,21 @@ def test_gpu_sender_compress_falls_back_for_plain_receiver(fakezfs):
     res, cli, events = _run_restore(fakezfs, sender_gpu=dict(cfg, mode="compress"),
                                     recv_gpu=dict(cfg, mode="decompress"))
     assert res["err"] is None and cli._restoreObject["wire"] == "lz4-stage-v1"
+
+
+@pytest.mark.gpu
+def test_gpu_decompress_receiver_with_reference_sender(fakezfs):
+    """Mixed versions (f2), other direction: the sender is the reference (identity pipe, no
+    `wire` in the job); a receiver configured to decompress must verify the raw stream and
+    hand it to zfs recv unchanged instead of failing on the missing stage marker."""
+    cfg = {"batchBytes": 4 << 20, "ringBytes": 32 << 20, "outRingBytes": 32 << 20}
+    res, cli, events = _run_restore(fakezfs, sender_gpu=None, recv_gpu=dict(cfg, mode="decompress"))
+    assert res["err"] is None, res
+    digest, n = open(fakezfs["recv_out"]).read().split()
+    s = fakezfs["stream"]
+    assert int(n) == s.size and digest == hashlib.sha256(s.tobytes()).hexdigest()
+    assert "wire" not in cli._restoreObject
+    assert cli._restoreObject["gpuRecv"]["lz4_decoded"] == 0 and cli._restoreObject["gpuRecv"]["records"] > 0
 
 
 @pytest.mark.gpu
