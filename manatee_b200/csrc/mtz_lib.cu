@@ -105,24 +105,28 @@ static inline uint64_t rd64(const uint8_t *p) { uint64_t v; memcpy(&v, p, 8); re
 // restated from sys/zfs_ioctl.h DRR_*_PAYLOAD_SIZE ([EXTERNAL]).
 static int64_t drr_payload(const uint8_t *h, uint32_t *lsize, uint32_t *comp)
 {
+	// Every record of a send stream starts 8-byte aligned (dump_bytes()/receive_read() keep
+	// lengths at multiples of 8); the kernels rely on it for their 64-bit header loads, so a
+	// payload length that would break it is a format error here, never a misaligned access.
 	const uint32_t type = rd32(h);
 	*lsize = 0; *comp = 0;
 	switch (type) {
 	case 0: /* BEGIN */
 		if (rd64(h + 8) != 0x2F5bacbacULL) return -1;
+		if (rd32(h + 4) & 7u) return -1;
 		return (int64_t)rd32(h + 4);
 	case 1: /* OBJECT */
 		return (int64_t)(((uint64_t)rd32(h + 28) + 7) & ~7ull);
 	case 3: { /* WRITE */
 		const uint64_t ls = rd64(h + 32);
 		const uint64_t l = h[50] ? rd64(h + 96) : ls;
-		if (l > (1ull << 30) || (l & 3) || ls > (1ull << 30)) return -1;
+		if (l > (1ull << 30) || (l & 7) || ls > (1ull << 30)) return -1;
 		*lsize = (uint32_t)ls; *comp = h[50];
 		return (int64_t)l;
 	}
 	case 7: { /* SPILL */
 		const uint64_t l = rd64(h + 16);
-		if (l > (1ull << 30) || (l & 3)) return -1;
+		if (l > (1ull << 30) || (l & 7)) return -1;
 		return (int64_t)l;
 	}
 	case 8: /* WRITE_EMBEDDED */

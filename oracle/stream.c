@@ -60,18 +60,19 @@ orc_drr_payload_len(const uint8_t *h)
 	switch (type) {
 	case ORC_DRR_BEGIN:
 		if (g64(h + OFF_BEGIN_MAGIC) != ORC_BEGIN_MAGIC) return (-1);
+		if (g32(h + 4) & 7) return (-1);   /* records stay 8-byte aligned */
 		return ((int64_t)g32(h + 4));
 	case ORC_DRR_OBJECT:
 		return ((int64_t)RUP8((uint64_t)g32(h + OFF_OBJ_BONUSLEN)));
 	case ORC_DRR_WRITE: {
 		uint64_t l = h[OFF_WR_COMP] ? g64(h + OFF_WR_CSIZE) :
 		    g64(h + OFF_WR_LSIZE);
-		if (l > ((uint64_t)1 << 30) || (l & 3)) return (-1);
+		if (l > ((uint64_t)1 << 30) || (l & 7)) return (-1);
 		return ((int64_t)l);
 	}
 	case ORC_DRR_SPILL: {
 		uint64_t l = g64(h + OFF_SPILL_LEN);
-		if (l > ((uint64_t)1 << 30) || (l & 3)) return (-1);
+		if (l > ((uint64_t)1 << 30) || (l & 7)) return (-1);
 		return ((int64_t)l);
 	}
 	case ORC_DRR_WRITE_EMBEDDED:

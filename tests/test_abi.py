@@ -100,3 +100,33 @@ def test_napi_binding_type_checks_against_the_header():
     header = open(os.path.join(ROOT, "include", "manatee_gpu.h")).read()
     for fn in called:
         assert re.search(r"\b%s\(" % fn, header), fn
+
+
+def test_record_alignment_is_part_of_the_format(native, oracle):
+    """Records of a send stream are 8-byte aligned; the kernels use 64-bit header loads.  A
+    length that would break that (WRITE/SPILL/BEGIN payload not a multiple of 8) is a format
+    error in the host parser and in the oracle alike -- never a misaligned device access."""
+    import numpy as np
+    from manatee_b200 import index_host
+    from manatee_b200 import _native as N
+
+    def hdr(t, fields):
+        h = np.zeros(312, dtype=np.uint8)
+        h[0:4] = np.array([t], dtype=np.uint32).view(np.uint8)
+        for off, (val, width) in fields.items():
+            h[off:off + width] = np.array([val], dtype={4: np.uint32, 8: np.uint64}[width]).view(np.uint8)
+        return h
+
+    begin = hdr(0, {8: (0x2F5bacbac, 8), 16: (1, 8)})
+    end = hdr(5, {})
+    ok = np.concatenate([begin, hdr(7, {8: (8, 8), 16: (520, 8)}), np.zeros(520, np.uint8), end])
+    assert len(index_host(ok)[0]) == 3 and oracle.stream_index(ok)[0] == 3
+    for bad in (
+        np.concatenate([begin, hdr(7, {8: (8, 8), 16: (516, 8)}), np.zeros(516, np.uint8), end]),   # SPILL 4 mod 8
+        np.concatenate([begin, hdr(3, {8: (8, 8), 32: (1028, 8)}), np.zeros(1028, np.uint8), end]),  # WRITE 4 mod 8
+        np.concatenate([hdr(0, {8: (0x2F5bacbac, 8), 16: (1, 8), 4: (12, 4)}), np.zeros(12, np.uint8), end]),
+    ):
+        with pytest.raises(N.MtzError) as ei:
+            index_host(bad)
+        assert ei.value.code == N.EFORMAT
+        assert oracle.stream_index(bad)[0] == oracle.EFORMAT
