@@ -109,7 +109,11 @@ typedef struct mtz_job {
 	int32_t  status;   /* MTZ_OK or MTZ_ECODEC */
 } mtz_job;
 
-/* ---- lifecycle ---- */
+/* ---- lifecycle ----
+ * One handle per spliced pipe, i.e. per `zfs send` child on the sender
+ * (spawn at lib/backupSender.js:177) or per `zfs recv` child on the receiver
+ * (spawn at lib/zfsClient.js:793); opened when the child is spawned, closed when
+ * the pipe ends or fails. */
 int32_t     mtz_abi_version(void);
 int32_t     mtz_device_count(void);                 /* sm_100 devices visible, <0 on error */
 int32_t     mtz_open(const mtz_config *cfg, mtz_handle **out);
@@ -135,20 +139,31 @@ int32_t mtz_read(mtz_handle *h, void *buf, size_t cap, size_t *got, int32_t bloc
  * addon's uv_poll_t / napi_threadsafe_function wake-up source */
 int32_t mtz_event_fd(mtz_handle *h);
 
+/* counters for the job object the sender publishes through GET /backup/:uuid
+ * (lib/backupServer.js:100-131 serialises the same object the sender mutates,
+ * lib/backupSender.js:197-212): additive `job.gpu`, never read by the reference */
 int32_t mtz_get_stats(mtz_handle *h, mtz_stats *st);
 /* running Fletcher-4 of the OUTPUT stream before DRR_END (== drr_end.drr_checksum) */
 int32_t mtz_end_checksum(mtz_handle *h, uint64_t out[4]);
 
 /* ---- bulk host API: a whole stream (or a whole-record slice of one) already in
  * host memory; internally pipelined H2D -> kernels -> D2H over n_slots streams.
- * in/out should come from mtz_host_alloc (pinned) for full PCIe rate. ---- */
+ * in/out should come from mtz_host_alloc (pinned) for full PCIe rate.  Same
+ * bytes-in / bytes-out contract as the two pipes above for a caller that holds the
+ * stream in memory instead of a socket (bench.py's `e2e`, the shard drivers). ---- */
 int32_t mtz_host_alloc(size_t bytes, void **ptr);
 int32_t mtz_host_free(void *ptr);
 int32_t mtz_process_host(mtz_handle *h, const void *in, size_t n, void *out,
     size_t out_cap, size_t *out_n);
 
 /* ---- device-resident API (HBM in, HBM out): multi-GPU shards and kernel timing.
- * Pointers are CUDA device pointers passed as integers-in-void*. ---- */
+ * Pointers are CUDA device pointers passed as integers-in-void*.  The reference
+ * serves N concurrent peers with N independent sends of the same snapshot
+ * (one `_send` per 'push', lib/backupSender.js:72-73); here one stream is cut by
+ * record index across GPUs and the only exchange is the 40-byte aggregate below
+ * (SURVEY.md 8e).  The arithmetic itself replaces what the host OS's ZFS does
+ * inside `zfs send` / `zfs recv` ([EXTERNAL] dmu_send.c dump_record(),
+ * dmu_recv.c receive_read_record(), zfs_fletcher.c, lz4.c). ---- */
 /* host-side DRR parse: fills recs[] for whole records in [buf, buf+n) */
 int32_t mtz_index_host(const void *buf, size_t n, mtz_rec *recs, size_t cap,
     size_t *nrec, size_t *consumed);
