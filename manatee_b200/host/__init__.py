@@ -10,6 +10,8 @@ job-object fields and error behaviour as the reference modules:
     zfs_client.ZfsClient         lib/zfsClient.js      (_receive, _postRestoreRequest,
                                                         _pollRestoreCompletion, restore,
                                                         isolateDataset, snapshotDataset)
+    backupserver (module main)   backupserver.js       (-f <config>, same config file shape)
+    snapshotter  (module main)   snapshotter.js        (-f <config>)
     zfs_cmd                      lib/common.js         (zfsSet/Get/Inherit/Rename/Mount/...)
     snap_shotter.SnapShotter     lib/snapShotter.js    (8f f3: snapshot cadence + GC)
     status_server.StatusServer   lib/statusServer.js   (8f f4: GET /restore, /ping)

@@ -57,7 +57,14 @@ def pool(tmp_path, oracle):
             assert r.returncode == 0, r.stderr
         return r
     p.z = z_
-    p.state = lambda: json.load(open(env["FAKE_ZFS_STATE"]))
+    def state_():
+        import fcntl
+        with open(env["FAKE_ZFS_STATE"], "a+") as f:     # the fake rewrites it under the same lock
+            fcntl.flock(f, fcntl.LOCK_EX)
+            f.seek(0)
+            raw = f.read()
+        return json.loads(raw) if raw.strip() else {"datasets": {}, "held": [], "clock": 0}
+    p.state = state_
     p.opts = lambda **kw: dict(kw, zfs=p.zfs, env=env)
     return p
 
@@ -370,3 +377,63 @@ def test_sender_ships_the_snapshotters_newest_and_gc_cannot_take_it_mid_send(poo
     assert newest not in pool.state()["held"]
     s.createSnapshot("1405378955005")
     assert s._cleanupOnce() is None and s.lastCleanup["deleted"] == [newest]  # released after the send
+
+
+# ------------------------------------------------------------------ daemon entry points
+def _spawn(module, cfg_path, env):
+    p = subprocess.Popen([sys.executable, "-m", module, "-f", cfg_path], cwd=ROOT, env=env,
+                         stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    line = p.stdout.readline()                       # one JSON line once it is up
+    return p, (json.loads(line) if line.strip() else None)
+
+
+def test_backupserver_entry_point_serves_a_restore(pool):
+    """backupserver.js mirror: `-f <config>` with the reference's config shape
+    (test/etc/backupserver.json) starts REST server + sender on one queue."""
+    cfg = {"backupServerCfg": {"port": 0, "host": "127.0.0.1"},
+           "backupSenderCfg": {"zfsPath": pool.zfs, "dataset": "zones/x/data/manatee", "env": pool.env}}
+    path = str(pool.tmp / "backupserver.json")
+    json.dump(cfg, open(path, "w"))
+    env = dict(os.environ, **pool.env)
+    p, hello = _spawn("manatee_b200.host.backupserver", path, env)
+    try:
+        assert hello and hello["name"] == "manatee-backupserver" and hello["port"] > 0, p.stderr.read()
+        cli = _client(pool)
+        res = {}
+        cli.restore("http://127.0.0.1:%d" % hello["port"], lambda err, old: res.update(err=err, old=old))
+        assert res["err"] is None, res
+        digest, n = open(pool.env["FAKE_ZFS_RECV_OUT"]).read().split()
+        assert digest == hashlib.sha256(pool.stream.tobytes()).hexdigest()
+        assert cli._restoreObject["done"] is True and "gpu" not in cli._restoreObject    # gpu key absent: legacy
+    finally:
+        p.terminate(); p.wait(10)
+    # unreadable configuration is fatal, like process.abort() in the reference
+    bad = str(pool.tmp / "broken.json")
+    open(bad, "w").write("{ not json")
+    r = subprocess.run([sys.executable, "-m", "manatee_b200.host.backupserver", "-f", bad], cwd=ROOT, env=env,
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=60)
+    assert r.returncode == 134 and "Unable to read/parse configuration file" in r.stderr
+
+
+def test_snapshotter_entry_point(pool):
+    ds = "zones/x/data/manatee"
+    pool.z("create", ds)
+    cfg = {"dataset": ds, "pollInterval": 50, "snapshotNumber": 3, "zfsBin": pool.zfs, "zfsEnv": pool.env}
+    path = str(pool.tmp / "snapshotter.json")
+    json.dump(cfg, open(path, "w"))
+    p, hello = _spawn("manatee_b200.host.snapshotter", path, dict(os.environ, **pool.env))
+    try:
+        assert hello and hello["dataset"] == ds, p.stderr.read()
+        t_end = time.time() + 30
+        seen_max = 0
+        while time.time() < t_end:
+            n = len(_snaps(pool, ds))
+            seen_max = max(seen_max, n)
+            if seen_max >= 4 and n <= 4:             # retention has had to delete something
+                break
+            time.sleep(0.1)
+        assert seen_max >= 3
+    finally:
+        p.terminate(); p.wait(10)
+    names = _snaps(pool, ds)
+    assert names and all(re.match(r"^\d{13}$", n) for n in names) and len(names) <= 6
