@@ -17,7 +17,6 @@
  */
 var stream = require('stream');
 var util = require('util');
-var fs = require('fs');
 
 var MODES = { verify: 0, compress: 1, decompress: 2, recompress: 3, passthrough: 4 };
 
@@ -40,11 +39,10 @@ function GpuSnapshotStage(options) {
     this._flushCb = null;
     this._closed = false;
     var self = this;
-    // wake-up source: the library's eventfd becomes readable when output, EOF or an
-    // error is pending.  fs.createReadStream on the fd keeps this on the event loop.
-    this._efd = fs.createReadStream(null, { fd: this._addon.eventFd(this._h), highWaterMark: 8,
-                                            autoClose: false });
-    this._efd.on('data', function () { self._drain(); });
+    // wake-up source: the addon poll(2)s the library's eventfd on a native thread and calls
+    // this function on the event loop (napi_threadsafe_function) whenever output, EOF or an
+    // error is pending -- the loop neither blocks nor busy-polls.
+    this._watch = this._addon.watch(this._h, function () { self._drain(); });
 }
 util.inherits(GpuSnapshotStage, stream.Transform);
 
@@ -59,7 +57,7 @@ GpuSnapshotStage.prototype._fail = function (err) {
 GpuSnapshotStage.prototype._cleanup = function () {
     if (this._closed) { return; }
     this._closed = true;
-    try { this._efd.destroy(); } catch (e) {}
+    try { this._addon.unwatch(this._watch); } catch (e) {}   // joins the poll thread first
     try { this._addon.close(this._h); } catch (e) {}
 };
 

@@ -1,10 +1,12 @@
 // binding.cc -- thin N-API addon over the C ABI of libmanatee_gpu.so
 // (include/manatee_gpu.h).  It adds NO logic: every export is one mtz_* call.
 //
-// NOT BUILT INTO AN ADDON HERE: the build image has no Node.js and no node_api.h
-// (`node --version`: not found).  tests/test_abi.py type-checks this file against
-// include/manatee_gpu.h with a stub of the N-API declarations (tests/stubs/node_api.h,
-// `g++ -fsyntax-only`); tests/ drive the same C ABI through ctypes instead.
+// NOT BUILT INTO A NODE ADDON HERE: the build image has no Node.js and no node_api.h
+// (`node --version`: not found).  The test-suite compiles this very file against a stub of
+// the N-API declarations (tests/stubs/node_api.h), links it with a miniature in-process
+// N-API (tests/stubs/napi_mock.cc) and executes it through tests/stubs/napi_harness.cc --
+// on the CPU with an in-memory stand-in of the library, on a B200 with the real one
+// (tests/test_zz_napi_harness.py).
 //
 // JS surface (used by js/lib/gpuSnapshotStage.js):
 //   open({mode, device, ringBytes, outRingBytes, batchBytes, slots}) -> handle (external)
@@ -14,14 +16,22 @@
 //   flush(handle)
 //   peek(handle)                   -> ArrayBuffer over the pinned output slice | null | 'eof'
 //   consume(handle, n)
-//   eventFd(handle)                -> fd for uv_poll (readable when output / error / EOF is pending)
+//   eventFd(handle)                -> the library's eventfd (readable when output / error / EOF is pending)
+//   watch(handle, fn)              -> watcher (external): a small native thread poll(2)s that fd and
+//                                     calls fn() ON THE EVENT LOOP through a napi_threadsafe_function,
+//                                     so the loop never blocks and never busy-polls
+//   unwatch(watcher)               -> stops and joins the thread (call before close)
 //   stats(handle) -> {bytesIn, bytesOut, records, ...}; endChecksum(handle) -> [4 x BigInt]
 //   close(handle)
 // Every failing call throws Error(mtz_last_error) with .code = MTZ_E* so the stage
 // can destroy(err), which the sender maps to job.done='failed' (lib/backupSender.js:218).
 #include <node_api.h>
+#include <poll.h>
 #include <stdio.h>
 #include <string.h>
+#include <sys/eventfd.h>
+#include <unistd.h>
+#include <thread>
 #include "../../include/manatee_gpu.h"
 
 #define NAPI_OK(call) do { if ((call) != napi_ok) { napi_throw_error(env, NULL, #call); return NULL; } } while (0)
@@ -168,6 +178,79 @@ static napi_value EventFd(napi_env env, napi_callback_info info)
 	return out;
 }
 
+// ---- wake-up path: library eventfd -> native poll thread -> threadsafe function -> JS ----
+struct Watcher {
+	napi_threadsafe_function tsfn = NULL;
+	std::thread th;
+	int efd = -1;      // the library's eventfd (owned by the handle)
+	int stop_fd = -1;  // ours: written by unwatch()
+};
+
+static void watcher_main(Watcher *w)
+{
+	struct pollfd fds[2];
+	fds[0].fd = w->efd; fds[0].events = POLLIN;
+	fds[1].fd = w->stop_fd; fds[1].events = POLLIN;
+	for (;;) {
+		fds[0].revents = fds[1].revents = 0;
+		if (poll(fds, 2, -1) < 0) continue;                       // EINTR
+		if (fds[1].revents) break;
+		if (fds[0].revents & (POLLERR | POLLHUP | POLLNVAL)) break;
+		if (fds[0].revents & POLLIN) {
+			uint64_t v;
+			if (read(w->efd, &v, sizeof v) < 0) { /* raced with another reader: fine */ }
+			// default call_js: invokes the JS function with no arguments on the loop thread
+			napi_call_threadsafe_function(w->tsfn, NULL, napi_tsfn_nonblocking);
+		}
+	}
+	napi_release_threadsafe_function(w->tsfn, napi_tsfn_release);
+}
+
+static napi_value Watch(napi_env env, napi_callback_info info)
+{
+	size_t argc = 2; napi_value argv[2];
+	NAPI_OK(napi_get_cb_info(env, info, &argc, argv, NULL, NULL));
+	mtz_handle *h = get_handle(env, argv[0]);
+	const int32_t efd = mtz_event_fd(h);
+	if (efd < 0) return throw_mtz(env, h, efd);
+	Watcher *w = new Watcher();
+	w->efd = efd;
+	w->stop_fd = eventfd(0, EFD_CLOEXEC);
+	napi_value name;
+	NAPI_OK(napi_create_string_utf8(env, "manatee-gpu-wakeup", NAPI_AUTO_LENGTH, &name));
+	if (w->stop_fd < 0 ||
+	    napi_create_threadsafe_function(env, argv[1], NULL, name, 0, 1, NULL, NULL, NULL, NULL,
+	    &w->tsfn) != napi_ok) {
+		if (w->stop_fd >= 0) close(w->stop_fd);
+		delete w;
+		napi_throw_error(env, NULL, "cannot create the wake-up function");
+		return NULL;
+	}
+	// the stage keeps the loop alive through its stream state, not through this function
+	napi_unref_threadsafe_function(env, w->tsfn);
+	w->th = std::thread(watcher_main, w);
+	napi_value ext;
+	NAPI_OK(napi_create_external(env, w, NULL, NULL, &ext));
+	return ext;
+}
+
+static napi_value Unwatch(napi_env env, napi_callback_info info)
+{
+	size_t argc = 1; napi_value argv[1];
+	NAPI_OK(napi_get_cb_info(env, info, &argc, argv, NULL, NULL));
+	void *p = NULL;
+	if (napi_get_value_external(env, argv[0], &p) != napi_ok || p == NULL) return NULL;
+	Watcher *w = (Watcher *)p;
+	if (w->stop_fd >= 0) {
+		const uint64_t one = 1;
+		if (write(w->stop_fd, &one, sizeof one) < 0) { /* thread exits on POLLNVAL at close */ }
+		if (w->th.joinable()) w->th.join();
+		close(w->stop_fd);
+		w->stop_fd = -1;
+	}
+	return NULL;
+}
+
 static napi_value Stats(napi_env env, napi_callback_info info)
 {
 	size_t argc = 1; napi_value argv[1];
@@ -219,6 +302,7 @@ static napi_value Init(napi_env env, napi_value exports)
 		{"consume", 0, Consume, 0, 0, 0, napi_default, 0}, {"eventFd", 0, EventFd, 0, 0, 0, napi_default, 0},
 		{"stats", 0, Stats, 0, 0, 0, napi_default, 0}, {"close", 0, Close, 0, 0, 0, napi_default, 0},
 		{"endChecksum", 0, EndChecksum, 0, 0, 0, napi_default, 0},
+		{"watch", 0, Watch, 0, 0, 0, napi_default, 0}, {"unwatch", 0, Unwatch, 0, 0, 0, napi_default, 0},
 	};
 	napi_define_properties(env, exports, sizeof d / sizeof d[0], d);
 	return exports;

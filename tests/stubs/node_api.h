@@ -71,9 +71,31 @@ napi_status napi_create_bigint_uint64(napi_env env, uint64_t value, napi_value *
 napi_status napi_define_properties(napi_env env, napi_value object, size_t property_count,
     const napi_property_descriptor *properties);
 
+#define NAPI_AUTO_LENGTH SIZE_MAX
+
+typedef struct napi_threadsafe_function__ *napi_threadsafe_function;
+typedef enum { napi_tsfn_release, napi_tsfn_abort } napi_threadsafe_function_release_mode;
+typedef enum { napi_tsfn_nonblocking, napi_tsfn_blocking } napi_threadsafe_function_call_mode;
+typedef void (*napi_threadsafe_function_call_js)(napi_env env, napi_value js_callback, void *context,
+    void *data);
+napi_status napi_create_threadsafe_function(napi_env env, napi_value func, napi_value async_resource,
+    napi_value async_resource_name, size_t max_queue_size, size_t initial_thread_count,
+    void *thread_finalize_data, napi_finalize thread_finalize_cb, void *context,
+    napi_threadsafe_function_call_js call_js_cb, napi_threadsafe_function *result);
+napi_status napi_call_threadsafe_function(napi_threadsafe_function func, void *data,
+    napi_threadsafe_function_call_mode is_blocking);
+napi_status napi_release_threadsafe_function(napi_threadsafe_function func,
+    napi_threadsafe_function_release_mode mode);
+napi_status napi_unref_threadsafe_function(napi_env env, napi_threadsafe_function func);
+
 typedef napi_value (*napi_addon_register_func)(napi_env env, napi_value exports);
+#ifdef __cplusplus
+#define NAPI_MODULE(modname, regfunc) \
+	extern "C" napi_value napi_register_module_v1(napi_env env, napi_value exports) { return regfunc(env, exports); }
+#else
 #define NAPI_MODULE(modname, regfunc) \
 	napi_value napi_register_module_v1(napi_env env, napi_value exports) { return regfunc(env, exports); }
+#endif
 
 #ifdef __cplusplus
 }
