@@ -37,6 +37,7 @@ function GpuSnapshotStage(options) {
     });
     this._pending = null;      // {chunk, off, cb} waiting for ring space
     this._flushCb = null;
+    this._wantMore = true;     // cleared when push() returns false, set again by _read()
     this._closed = false;
     var self = this;
     // wake-up source: the addon poll(2)s the library's eventfd on a native thread and calls
@@ -84,7 +85,12 @@ GpuSnapshotStage.prototype._transform = function (chunk, enc, cb) {
 GpuSnapshotStage.prototype._drain = function () {
     if (this._closed) { return; }
     try {
-        for (;;) {
+        // readable-side backpressure: stop pulling from the pinned output ring as soon as
+        // push() says the consumer (socket / zfs recv stdin) is behind.  The ring then fills,
+        // the engine stalls, the input ring fills, write() returns 0 and _transform's callback
+        // is withheld -- the whole chain slows to the slowest consumer instead of buffering a
+        // multi-GiB stream in the Node heap.  _read() re-arms it.
+        while (this._wantMore) {
             var ab = this._addon.peek(this._h);
             if (ab === null) { break; }
             if (ab === 'eof') {
@@ -98,10 +104,16 @@ GpuSnapshotStage.prototype._drain = function () {
             // copy out of the pinned ring before releasing the slice
             var buf = Buffer.from(Buffer.from(ab));
             this._addon.consume(this._h, buf.length);
-            this.push(buf);
+            if (!this.push(buf)) { this._wantMore = false; }
         }
     } catch (e) { return (this._fail(e)); }
     this._feed();
+};
+
+GpuSnapshotStage.prototype._read = function (n) {
+    this._wantMore = true;
+    this._drain();
+    stream.Transform.prototype._read.call(this, n);
 };
 
 GpuSnapshotStage.prototype._flush = function (cb) {
