@@ -115,6 +115,24 @@ class ClockSampler(object):
 SIMD_NAME = {0: "scalar", 4: "avx2 (4 lanes, as zfs_fletcher_avx2)", 8: "avx512f (8 lanes, as zfs_fletcher_avx512)"}
 
 
+def cpu_verify_baseline(O, stream, nthreads):
+    """cpu_baseline object of the VERIFY workload: the oracle port over `stream` on `nthreads`
+    threads (second of two passes is timed by the caller's convention: buffers warm), plus the
+    one-thread figure -- the shape a real `zfs send` / `zfs recv` stream checksum has."""
+    rc, secs, cst = O.mt_verify(stream, nthreads)
+    assert rc == 0, rc
+    rc, secs1, _ = O.mt_verify(stream, 1)
+    assert rc == 0, rc
+    lanes = O.simd_lanes()
+    flavour = SIMD_NAME.get(lanes, "scalar")
+    return {"value": round(stream.size / GIB / secs, 3), "unit": "GiB/s", "cores": nthreads,
+            "cgroup_cpu_quota": cpu_quota(), "kind": "port", "fletcher4": flavour,
+            "single_thread_value": round(stream.size / GIB / secs1, 3),
+            "sample": "the whole %.2f GiB stream once: record-parallel %s fletcher_4 (oracle/mt.c), "
+                      "%d threads; single_thread_value = one thread, the shape of a real "
+                      "`zfs send`/`zfs recv` stream checksum" % (stream.size / GIB, flavour, nthreads)}
+
+
 def cpu_quota():
     """cgroup CPU quota in cores (None = unlimited): shared GPU boxes often cap it"""
     try:
@@ -274,8 +292,7 @@ def run_reference(args):
     # whole job on the CPU = the same arithmetic over N shards on the same cores
     ms = 1e3 * sum(t) / len(t)
     val = s.size / GIB / (ms / 1e3)
-    lanes = O.simd_lanes()
-    rc, secs1, _ = O.mt_verify(s, 1)           # the shape `zfs send` really has: ONE checksum thread
+    base = cpu_verify_baseline(O, s, nthreads)  # flavour + the one-thread figure
     line = {
         "impl": "reference", "metric": "snapshot_stream_gibs", "value": round(val, 3),
         "unit": "GiB/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -286,13 +303,12 @@ def run_reference(args):
                    "records": int(st.records), "recordsize": RECSIZE},
         "cpu_baseline": {"value": round(val, 3), "unit": "GiB/s", "cores": nthreads,
                          "cgroup_cpu_quota": cpu_quota(), "kind": "port",
-                         "fletcher4": SIMD_NAME.get(lanes, "scalar"),
-                         "single_thread_value": round(s.size / GIB / secs1, 3),
+                         "fletcher4": base["fletcher4"],
+                         "single_thread_value": base["single_thread_value"],
                          "sample": "whole %.2f GiB stream per step, record-parallel %s "
                                    "fletcher_4 + sequential combine (oracle/mt.c); single_thread_value = "
                                    "the same on one thread, which is all a real `zfs send`/`zfs recv` "
-                                   "uses for the stream checksum"
-                                   % (s.size / GIB, SIMD_NAME.get(lanes, "scalar"))},
+                                   "uses for the stream checksum" % (s.size / GIB, base["fletcher4"])},
         "e2e": {"value": round(val, 3), "unit": "GiB/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -549,17 +565,7 @@ def run_ours(args):
         rc, secs, cst = O.mt_verify(shard, nthreads)
         assert rc == 0
         assert cst.end_cksum.tuple() == end_ck, "GPU END checksum differs from the oracle's"
-        rc, secs, cst = O.mt_verify(shard, nthreads)
-        rc, secs1, _ = O.mt_verify(shard, 1)
-        lanes = O.simd_lanes()
-        cpu = {"value": round(shard.size / GIB / secs, 3), "unit": "GiB/s", "cores": nthreads,
-               "cgroup_cpu_quota": cpu_quota(), "kind": "port",
-               "fletcher4": SIMD_NAME.get(lanes, "scalar"),
-               "single_thread_value": round(shard.size / GIB / secs1, 3),
-               "sample": "the whole %.2f GiB stream once: record-parallel %s fletcher_4 "
-                         "(oracle/mt.c), %d threads; single_thread_value = one thread, the shape of "
-                         "a real `zfs send`/`zfs recv` stream checksum"
-                         % (shard.size / GIB, SIMD_NAME.get(lanes, "scalar"), nthreads)}
+        cpu = cpu_verify_baseline(O, shard, nthreads)
 
     if rank == 0:
         peaks = {}
