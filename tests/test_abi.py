@@ -130,3 +130,45 @@ def test_record_alignment_is_part_of_the_format(native, oracle):
             index_host(bad)
         assert ei.value.code == N.EFORMAT
         assert oracle.stream_index(bad)[0] == oracle.EFORMAT
+
+
+def test_host_parser_agrees_with_the_oracle_on_mutated_headers(native, oracle):
+    """mtz_index_host is product code that runs on the CPU (the streaming path parses DRR
+    headers as bytes arrive): fuzz it against the oracle's walker.  Random header-field
+    mutations of a stream that uses every record type must be judged the same way: same
+    record table when the stream still parses, and a format error or a short parse (a length
+    that now runs past the end is 'incomplete' for a streaming parser) when it does not."""
+    import numpy as np
+    from manatee_b200 import index_host
+    from manatee_b200 import _native as N
+    from test_gpu_codec import _all_types_stream
+    s = _all_types_stream(oracle, seed=21)
+    cnt, offs = oracle.stream_index(s)
+    rng = np.random.default_rng(77)
+    fields = [(0, 4), (4, 4), (8, 8), (16, 8), (28, 4), (32, 8), (50, 1), (52, 4), (96, 8)]
+    agree_ok = agree_bad = 0
+    for _ in range(400):
+        m = s.copy()
+        r = int(rng.integers(0, cnt))
+        off, width = fields[int(rng.integers(0, len(fields)))]
+        kind = int(rng.integers(0, 3))
+        if kind == 0:
+            m[int(offs[r]) + off + int(rng.integers(0, width))] ^= 1 << int(rng.integers(0, 8))
+        elif kind == 1:
+            m[int(offs[r]) + off:int(offs[r]) + off + width] = rng.integers(0, 256, width, dtype=np.uint8)
+        else:
+            m[int(offs[r]) + off:int(offs[r]) + off + width] = 0
+        ocnt, ooffs = oracle.stream_index(m)
+        try:
+            recs, used = index_host(m)
+            host_ok = used == m.size
+        except N.MtzError as e:
+            assert e.code == N.EFORMAT
+            host_ok, recs = False, None
+        if ocnt >= 0:
+            assert host_ok and len(recs) == ocnt and np.array_equal(recs["off"], ooffs), (r, off, kind)
+            agree_ok += 1
+        else:
+            assert ocnt == oracle.EFORMAT and not host_ok, (r, off, kind)
+            agree_bad += 1
+    assert agree_ok > 50 and agree_bad > 50, (agree_ok, agree_bad)      # both outcomes were exercised
