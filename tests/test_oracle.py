@@ -246,3 +246,73 @@ def test_golden_fixtures(oracle):
     ps, frame = oracle.zfs_lz4_compress(p)
     assert ps == b["psize"] and hashlib.sha256(frame.tobytes()).hexdigest() == b["frame_sha256"]
     assert ["%016x" % x for x in oracle.fletcher4(p)] == b["fletcher4"]
+
+
+def _parse_block(blk, isize):
+    """LZ4 block -> list of (literal_len, match_out_pos, match_len, offset); checks structure"""
+    b = bytes(blk)
+    ip, op, seqs = 0, 0, []
+    while True:
+        tok = b[ip]; ip += 1
+        ll = tok >> 4
+        if ll == 15:
+            while True:
+                x = b[ip]; ip += 1; ll += x
+                if x != 255:
+                    break
+        ip += ll; op += ll
+        if ip == len(b):
+            seqs.append((ll, None, 0, 0))
+            break
+        off = b[ip] | (b[ip + 1] << 8); ip += 2
+        ml = tok & 15
+        if ml == 15:
+            while True:
+                x = b[ip]; ip += 1; ml += x
+                if x != 255:
+                    break
+        ml += 4
+        assert 1 <= off <= op, "offset reaches before the block"
+        seqs.append((ll, op, ml, off))
+        op += ml
+    assert op == isize
+    return seqs
+
+
+def test_encoder_obeys_the_end_of_block_rules_zfs_decoder_relies_on(oracle):
+    """ZFS's decoder copies in 8-byte strides and is only safe on blocks whose last 5 bytes are
+    literals and whose last match starts at least 12 bytes before the end (LASTLITERALS /
+    MFLIMIT).  The declared encoder must never emit anything else -- checked on inputs built to
+    tempt it: matchable data right up to the end, sizes around MINLENGTH and the 64 KiB switch."""
+    rng = np.random.default_rng(9)
+    sizes = list(range(13, 40)) + [63, 64, 65, 255, 256, 257, 4096, 65535, 65536, 65545, 65546, 65547,
+                                   65548, 131072, 131071, 200000]
+    n_matches = 0
+    for isize in sizes:
+        for kind in range(5):
+            if kind == 0:
+                p = np.zeros(isize, dtype=np.uint8)
+            elif kind == 1:
+                p = np.tile(np.arange(7, dtype=np.uint8), isize // 7 + 1)[:isize].copy()
+            elif kind == 2:
+                p = np.tile(rng.integers(0, 256, 19, dtype=np.uint8), isize // 19 + 1)[:isize].copy()
+            elif kind == 3:
+                p = rng.integers(0, 4, isize, dtype=np.uint8)
+            else:
+                p = rng.integers(0, 256, isize, dtype=np.uint8)
+                if isize > 64:
+                    p[-32:] = p[:32]                       # a long match candidate ending at the end
+            blk = oracle.lz4_compress_block(p, osize=isize + isize // 100 + 64)
+            assert blk.size > 0, (isize, kind)
+            seqs = _parse_block(blk, isize)
+            assert seqs[-1][1] is None
+            matches = [q for q in seqs if q[1] is not None]
+            n_matches += len(matches)
+            if matches:
+                ll, pos, ml, off = matches[-1]
+                assert pos <= isize - 12, (isize, kind, pos)            # MFLIMIT
+                assert pos + ml <= isize - 5, (isize, kind, pos, ml)    # LASTLITERALS
+                assert seqs[-1][0] >= 5
+            n, back = oracle.lz4_decompress_block(blk, isize)
+            assert n == isize and np.array_equal(back, p)
+    assert n_matches > 1000
