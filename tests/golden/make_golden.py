@@ -17,6 +17,56 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 import oracle as O  # noqa: E402
 
 
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def digest_cases():
+    """(name, builder) of seeded inputs too large to commit as files: only digests are stored.
+    Shared with tests/test_zz_golden_digests.py, which rebuilds them and compares."""
+    sys.path.insert(0, os.path.dirname(HERE))
+    from test_gpu_codec import _all_types_stream, _mixed_stream
+    return [
+        ("all_types_seed7", lambda: _all_types_stream(O, seed=7)),
+        ("all_types_seed31", lambda: _all_types_stream(O, seed=31)),
+        ("mixed_24x128k", lambda: _mixed_stream(O, n=24, recsize=131072)),
+        ("mixed_40x16k", lambda: _mixed_stream(O, n=40, recsize=16384)),
+        ("pcg_12x64k", lambda: O.synth_stream(12, recsize=65536, kind=O.PAYLOAD_PCG)),
+    ]
+
+
+BLOCK_CASES = [(kind, idx, n) for kind in ("PAYLOAD_PGPAGE", "PAYLOAD_ZERO") for idx, n in
+               [(1, 1024), (2, 8192), (3, 65546), (4, 65547), (5, 131072), (6, 1 << 20)]]
+
+
+def digests():
+    """Everything the oracle says about each case, as hashes: raw stream, END checksum,
+    COMPRESS output (+ its END checksum and LZ4 record count), RECOMPRESS of that; and the
+    ZFS-LZ4 frame of single blocks on both sides of every table-flavour boundary."""
+    d = {"streams": {}, "blocks": {}}
+    for name, build in digest_cases():
+        s = build()
+        rc, st = O.stream_verify(s)
+        assert rc == 0
+        rc, c, cst = O.stream_compress(s)
+        assert rc == 0
+        rc, r, rst = O.stream_recompress(c)
+        assert rc == 0
+        d["streams"][name] = {
+            "bytes": int(s.size), "records": int(st.records), "sha256": sha(s),
+            "end_cksum": ["%016x" % x for x in st.end_cksum.tuple()],
+            "compress_sha256": sha(c), "compress_bytes": int(c.size), "compress_lz4": int(cst.lz4_out),
+            "compress_end_cksum": ["%016x" % x for x in cst.end_cksum.tuple()],
+            "recompress_sha256": sha(r)}
+    for kind, idx, n in BLOCK_CASES:
+        p = O.gen_payload(getattr(O, kind), idx, n)
+        ps, frame = O.zfs_lz4_compress(p)
+        d["blocks"]["%s_%d_%d" % (kind, idx, n)] = {
+            "payload_sha256": sha(p), "psize": int(ps), "frame_sha256": sha(frame[:ps] if ps < n else p),
+            "fletcher4": ["%016x" % x for x in O.fletcher4(p)]}
+    return d
+
+
 def main():
     meta = {}
     s = O.synth_stream(8, recsize=4096, kind=O.PAYLOAD_PGPAGE)
@@ -42,6 +92,7 @@ def main():
     meta["block_pgpage_42"] = {"psize": int(ps), "payload_sha256": hashlib.sha256(p.tobytes()).hexdigest(),
                                "frame_sha256": hashlib.sha256(frame.tobytes()).hexdigest(),
                                "fletcher4": ["%016x" % x for x in O.fletcher4(p)]}
+    meta["digests"] = digests()
     json.dump(meta, open(os.path.join(HERE, "golden.json"), "w"), indent=1, sort_keys=True)
     print(json.dumps(meta, indent=1))
 
