@@ -1,0 +1,173 @@
+"""The DEVICE code itself, on the CPU: manatee_b200/csrc/kernels_lz4.cuh (and fletcher.cuh) are
+compiled by g++ against tests/emul/cuda_runtime.h -- a stub that maps the warp intrinsics onto
+32 fibers switched at every *_sync -- and the very functions the GPU kernels call
+(warp_lz4_encode3 in all three table flavours, warp_zfs_lz4_compress, warp_lz4_decode,
+warp_fletcher / group_fletcher) are fuzzed against the oracle, inside guard-page buffers so an
+out-of-bounds access is a crash.  Far more inputs than the GPU suite can afford, no GPU needed;
+it is also how a kernel change can be checked for bit-exactness before it ever sees a B200.
+Test infrastructure only: the product has no CPU path."""
+import ctypes as C
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EMUL = os.path.join(ROOT, "tests", "emul")
+ECODEC = -6
+
+
+@pytest.fixture(scope="module")
+def emu(tmp_path_factory):
+    if shutil.which("g++") is None:
+        pytest.skip("no g++")
+    so = os.path.join(str(tmp_path_factory.mktemp("emul")), "libemul.so")
+    r = subprocess.run(["g++", "-std=c++17", "-O2", "-Wall", "-Wextra", "-Wno-unused-variable",
+                        "-Wno-unused-function", "-I" + EMUL, "-shared", "-fPIC", "-o", so,
+                        os.path.join(EMUL, "warp_emul.cc"), os.path.join(EMUL, "emul_kernels.cc")],
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 0, r.stderr
+    L = C.CDLL(so)
+    vp, u32, i32, sz = C.c_void_p, C.c_uint32, C.c_int, C.c_size_t
+    L.emu_zfs_lz4_compress.argtypes = [vp, u32, vp, i32]
+    L.emu_zfs_lz4_compress.restype = u32
+    L.emu_lz4_encode_block.argtypes = [vp, u32, vp, u32, i32]
+    L.emu_lz4_encode_block.restype = u32
+    L.emu_zfs_lz4_decode.argtypes = [vp, u32, vp, u32]
+    L.emu_zfs_lz4_decode.restype = C.c_int32
+    L.emu_guard_alloc.argtypes = [sz, sz, sz]
+    L.emu_guard_alloc.restype = vp
+    L.emu_guard_free.argtypes = [vp, sz, sz, sz]
+    return L
+
+
+class Guarded(object):
+    """numpy view of `size` bytes whose end sits `slack` bytes before an inaccessible page"""
+
+    def __init__(self, L, size, slack=0, front=16, data=None):
+        self.L, self.size, self.slack, self.front = L, size, slack, front
+        self.ptr = L.emu_guard_alloc(size, slack, front)
+        assert self.ptr
+        self.a = np.ctypeslib.as_array((C.c_uint8 * max(size, 1)).from_address(self.ptr))[:size]
+        if data is not None:
+            self.a[:] = data
+
+    def free(self):
+        self.L.emu_guard_free(self.ptr, self.size, self.slack, self.front)
+
+
+def _inputs(oracle, rng, n):
+    kind = int(rng.integers(0, 7))
+    if kind == 0:
+        return oracle.gen_payload(oracle.PAYLOAD_PGPAGE, int(rng.integers(0, 1 << 20)), n)
+    if kind == 1:
+        return rng.integers(0, 256, n, dtype=np.uint8)                         # incompressible
+    if kind == 2:
+        return np.zeros(n, dtype=np.uint8)
+    if kind == 3:
+        period = int(rng.integers(1, 70))
+        return np.tile(rng.integers(0, 256, period, dtype=np.uint8), n // period + 1)[:n].copy()
+    if kind == 4:
+        return rng.integers(0, int(rng.integers(2, 6)), n, dtype=np.uint8)     # tiny alphabet: hash clashes
+    if kind == 5:                                                               # far matches: >64 KiB apart
+        a = rng.integers(0, 256, n, dtype=np.uint8)
+        if n > 70000:
+            a[-3000:] = a[:3000]
+            a[66000:67000] = a[100:1100]
+        return a
+    a = oracle.gen_payload(oracle.PAYLOAD_PGPAGE, int(rng.integers(0, 1 << 20)), n).copy()
+    cut = int(rng.integers(0, n))
+    a[cut:] = rng.integers(0, 256, n - cut, dtype=np.uint8)
+    return a
+
+
+def test_k3_encoder_source_is_bit_exact_on_the_cpu(emu, oracle):
+    """warp_lz4_encode3<TabU16|TabU32|Tab17> vs the oracle's serial greedy encoder: every block
+    flavour, sizes on both sides of every switch, output limits that do and do not fit."""
+    rng = np.random.default_rng(2024)
+    sizes = [13, 14, 20, 64, 100, 1000, 1024, 4096, 8192, 20000, 65535, 65546, 65547, 65548, 100000, 131072]
+    checked = 0
+    for rnd in range(3):
+        for n in sizes:
+            p = _inputs(oracle, rng, n)
+            src = Guarded(emu, n, slack=8, data=p)
+            for osize in sorted({n + n // 100 + 32, n - (n >> 3) - 4 if n >= 64 else n + 32}):
+                if osize <= 0:
+                    continue
+                want = oracle.lz4_compress_block(p, osize=osize)
+                flavours = [0] if n < 65547 else [1, 2]
+                for fl in flavours:
+                    dst = Guarded(emu, osize, slack=0)
+                    got = emu.emu_lz4_encode_block(src.ptr, n, dst.ptr, osize, fl)
+                    assert got != 0xffffffff, "result not warp-uniform"
+                    assert got == want.size, (n, osize, fl, got, want.size)
+                    assert np.array_equal(dst.a[:got], want), (n, osize, fl)
+                    dst.free()
+                    checked += 1
+            src.free()
+    assert checked >= 100
+
+
+def test_k3_zfs_frame_rules_on_the_cpu(emu, oracle):
+    rng = np.random.default_rng(7)
+    for n in [512, 1023, 1024, 1536, 4096, 65536, 131072]:
+        for _ in range(3):
+            p = _inputs(oracle, rng, n)
+            ps, frame = oracle.zfs_lz4_compress(p)
+            src = Guarded(emu, n, slack=8, data=p)
+            for compact in ((0, 1) if n >= 65547 else (0,)):
+                dst = Guarded(emu, n, slack=0)
+                got = emu.emu_zfs_lz4_compress(src.ptr, n, dst.ptr, compact)
+                assert got == ps, (n, compact, got, ps)
+                if ps < n:
+                    assert np.array_equal(dst.a[:ps], frame[:ps])
+                dst.free()
+            src.free()
+
+
+def test_k2_decoder_source_on_the_cpu_valid_and_malformed(emu, oracle):
+    """warp_lz4_decode on valid frames (== input) and on thousands of corrupted ones: it must
+    agree with the oracle's safe decoder on accept / reject, produce the same bytes when it
+    accepts, and never touch a byte outside [src, src+psize) or [dst, dst+lsize)."""
+    rng = np.random.default_rng(99)
+    n_ok = n_bad = 0
+    for n in [1024, 4096, 8192, 65536, 131072]:
+        for _ in range(4):
+            p = _inputs(oracle, rng, n)
+            ps, frame = oracle.zfs_lz4_compress(p)
+            if ps >= n:
+                continue
+            frame = frame[:ps].copy()
+            src = Guarded(emu, ps, slack=0, data=frame)
+            dst = Guarded(emu, n, slack=0)
+            assert emu.emu_zfs_lz4_decode(src.ptr, ps, dst.ptr, n) == 0 and np.array_equal(dst.a, p)
+            clen = int.from_bytes(frame[:4].tobytes(), "big")
+            for _ in range(60 if n <= 8192 else 12):
+                bad = frame.copy()
+                k = int(rng.integers(0, 4))
+                if k == 0:
+                    bad[int(rng.integers(0, clen + 4))] ^= 1 << int(rng.integers(0, 8))
+                elif k == 1:
+                    i = int(rng.integers(4, clen + 4))
+                    bad[i:i + 4] = 255
+                elif k == 2:
+                    bad[:4] = np.frombuffer(int(rng.integers(0, 2 * ps)).to_bytes(4, "big"), dtype=np.uint8)
+                else:
+                    i = int(rng.integers(4, clen + 4))
+                    bad[i:i + 2] = 0
+                src.a[:] = bad
+                dst.a[:] = 0xEE
+                rc = emu.emu_zfs_lz4_decode(src.ptr, ps, dst.ptr, n)
+                orc, oout = oracle.zfs_lz4_decompress(bad, n)
+                assert rc in (0, ECODEC), rc
+                assert (rc == 0) == (orc == 0), (n, k, rc, orc)
+                if rc == 0:
+                    assert np.array_equal(dst.a, oout)
+                    n_ok += 1
+                else:
+                    n_bad += 1
+            src.free()
+            dst.free()
+    assert n_ok > 5 and n_bad > 100, (n_ok, n_bad)
