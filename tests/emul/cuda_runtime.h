@@ -1,8 +1,12 @@
 // cuda_runtime.h -- TEST STUB (tests/emul): lets the DEVICE code of this repository
 // (manatee_b200/csrc/*.cuh, untouched) be compiled by g++ and executed on the CPU under a
-// warp emulator, so that the very source the GPU runs can be fuzzed against the oracle on a
-// machine without a GPU.  32 lanes are 32 fibers (ucontext) switched at every *_sync
-// intrinsic; shared memory is ordinary memory; global memory is ordinary memory.
+// SIMT emulator, so that the very source the GPU runs -- device functions AND __global__
+// kernels -- can be fuzzed against the oracle on a machine without a GPU.
+//   * every CUDA thread is a fiber (ucontext); fibers are switched at every *_sync intrinsic,
+//     __syncthreads() and grid sync, never in between, so one legal interleaving is executed;
+//   * warp intrinsics exchange through a per-warp buffer, __shared__ is one per-process
+//     instance (CTAs of a launch run one after the other; a cooperative launch is emulated
+//     with a single CTA), global memory is ordinary memory.
 // This is test infrastructure only: nothing under tests/ is part of the product, which has no
 // CPU path (mtz_open fails with MTZ_ENOGPU without an sm_100 device).
 #pragma once
@@ -10,7 +14,6 @@
 #include <stddef.h>
 #include <stdio.h>
 #include <string.h>
-#include <ucontext.h>
 #include <functional>
 
 #define MTZ_HOST_EMUL 1
@@ -18,7 +21,7 @@
 #define __device__
 #define __host__
 #define __global__
-#define __shared__
+#define __shared__ thread_local      /* static storage shared by all fibers of the thread */
 #define __forceinline__ inline
 #define __launch_bounds__(...)
 
@@ -26,47 +29,50 @@ struct uint2 { uint32_t x, y; };
 struct uint4 { uint32_t x, y, z, w; };
 static inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { uint4 r = { x, y, z, w }; return r; }
 static inline uint2 make_uint2(uint32_t x, uint32_t y) { uint2 r = { x, y }; return r; }
-struct dim3 { unsigned x = 1, y = 1, z = 1; };
 
 namespace emu {
-struct Warp {
-	ucontext_t main_ctx, ctx[32];
-	char *stack[32];
-	bool done[32];
-	int cur = 0, live = 0;
-	unsigned gen = 0, arrived = 0;
-	uint64_t x[32];
-	std::function<void(int)> body;
-	unsigned long long n_sync = 0;
-};
-extern Warp *W;
-void run_warp(const std::function<void(int)> &body);    // runs lanes 0..31 to completion
-void barrier();
-static inline int lane() { return W->cur; }
+// launch `grid` CTAs of `block` threads (block % 32 == 0) one CTA after the other; the body
+// is the kernel call.  cooperative = all CTAs alive at once is NOT supported: use grid = 1.
+void launch(unsigned grid, unsigned block, const std::function<void()> &kernel);
+void run_warp(const std::function<void(int)> &body);     // 1 CTA of 1 warp, body(lane)
+void barrier_warp();
+void barrier_cta();
+unsigned tid();          // threadIdx.x of the running fiber
+unsigned cta();          // blockIdx.x
+unsigned ncta();         // gridDim.x
+unsigned nthr();         // blockDim.x
+uint64_t *xchg();        // the running fiber's warp exchange buffer (32 slots)
+static inline int lane() { return (int)(tid() & 31u); }
+unsigned long long syncs();
 }
 
-// per-lane built-ins: a kernel launched through the emulator is one CTA of one warp
-struct emu_tid { operator unsigned() const { return (unsigned)emu::lane(); } };
-struct emu_idx3 { emu_tid x; unsigned y = 0, z = 0; };
-static emu_idx3 threadIdx;
-static dim3 blockIdx_zero_dummy;
-struct emu_zero3 { unsigned x = 0, y = 0, z = 0; };
-static emu_zero3 blockIdx;
-static dim3 gridDim, blockDim;
+struct emu_tid_t { operator unsigned() const { return emu::tid(); } };
+struct emu_cta_t { operator unsigned() const { return emu::cta(); } };
+struct emu_nct_t { operator unsigned() const { return emu::ncta(); } };
+struct emu_nth_t { operator unsigned() const { return emu::nthr(); } };
+struct emu_threadIdx_t { emu_tid_t x; unsigned y = 0, z = 0; };
+struct emu_blockIdx_t { emu_cta_t x; unsigned y = 0, z = 0; };
+struct emu_gridDim_t { emu_nct_t x; unsigned y = 1, z = 1; };
+struct emu_blockDim_t { emu_nth_t x; unsigned y = 1, z = 1; };
+static emu_threadIdx_t threadIdx;
+static emu_blockIdx_t blockIdx;
+static emu_gridDim_t gridDim;
+static emu_blockDim_t blockDim;
 
 template <class T> static inline T min(T a, T b) { return a < b ? a : b; }
 template <class T> static inline T max(T a, T b) { return a > b ? a : b; }
 
-static inline void __syncwarp(unsigned = 0xffffffffu) { emu::barrier(); }
+static inline void __syncwarp(unsigned = 0xffffffffu) { emu::barrier_warp(); }
+static inline void __syncthreads() { emu::barrier_cta(); }
 
 template <class T> static inline T emu_xchg(T v, int src)
 {
 	uint64_t raw = 0;
 	memcpy(&raw, &v, sizeof(T));
-	emu::W->x[emu::lane()] = raw;
-	emu::barrier();
-	raw = emu::W->x[src & 31];
-	emu::barrier();
+	emu::xchg()[emu::lane()] = raw;
+	emu::barrier_warp();
+	raw = emu::xchg()[src & 31];
+	emu::barrier_warp();
 	T r;
 	memcpy(&r, &raw, sizeof(T));
 	return r;
@@ -85,11 +91,11 @@ template <class T> static inline T __shfl_down_sync(unsigned, T v, unsigned d, i
 }
 static inline unsigned __ballot_sync(unsigned, int pred)
 {
-	emu::W->x[emu::lane()] = pred ? 1u : 0u;
-	emu::barrier();
+	emu::xchg()[emu::lane()] = pred ? 1u : 0u;
+	emu::barrier_warp();
 	unsigned r = 0;
-	for (int i = 0; i < 32; i++) r |= (unsigned)(emu::W->x[i] & 1u) << i;
-	emu::barrier();
+	for (int i = 0; i < 32; i++) r |= (unsigned)(emu::xchg()[i] & 1u) << i;
+	emu::barrier_warp();
 	return r;
 }
 static inline int __any_sync(unsigned m, int pred) { return __ballot_sync(m, pred) != 0u; }
@@ -98,11 +104,11 @@ template <class T> static inline unsigned __match_any_sync(unsigned, T v)
 {
 	uint64_t raw = 0;
 	memcpy(&raw, &v, sizeof(T));
-	emu::W->x[emu::lane()] = raw;
-	emu::barrier();
+	emu::xchg()[emu::lane()] = raw;
+	emu::barrier_warp();
 	unsigned r = 0;
-	for (int i = 0; i < 32; i++) if (emu::W->x[i] == raw) r |= 1u << i;
-	emu::barrier();
+	for (int i = 0; i < 32; i++) if (emu::xchg()[i] == raw) r |= 1u << i;
+	emu::barrier_warp();
 	return r;
 }
 static inline unsigned __activemask() { return 0xffffffffu; }
@@ -119,8 +125,9 @@ static inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }
 static inline long long clock64() { return 0; }
 
 // fibers never run concurrently: plain read-modify-write is atomic enough
-template <class T> static inline T atomicXor(T *p, T v) { T o = *p; *p = o ^ v; return o; }
-template <class T> static inline T atomicOr(T *p, T v) { T o = *p; *p = o | v; return o; }
-template <class T> static inline T atomicAnd(T *p, T v) { T o = *p; *p = o & v; return o; }
-template <class T> static inline T atomicAdd(T *p, T v) { T o = *p; *p = o + v; return o; }
-template <class T> static inline T atomicMin(T *p, T v) { T o = *p; if (v < o) *p = v; return o; }
+template <class T, class V> static inline T atomicXor(T *p, V v) { T o = *p; *p = o ^ (T)v; return o; }
+template <class T, class V> static inline T atomicOr(T *p, V v) { T o = *p; *p = o | (T)v; return o; }
+template <class T, class V> static inline T atomicAnd(T *p, V v) { T o = *p; *p = o & (T)v; return o; }
+template <class T, class V> static inline T atomicAdd(T *p, V v) { T o = *p; *p = o + (T)v; return o; }
+template <class T, class V> static inline T atomicMin(T *p, V v) { T o = *p; if ((T)v < o) *p = (T)v; return o; }
+template <class T, class V> static inline T atomicMax(T *p, V v) { T o = *p; if ((T)v > o) *p = (T)v; return o; }

@@ -2,9 +2,10 @@
 // functions (compiled for the host through tests/emul/cuda_runtime.h) on one emulated warp.
 #include "cuda_runtime.h"
 #include "../../manatee_b200/csrc/kernels_lz4.cuh"
+#include "../../manatee_b200/csrc/kernels_fletcher.cuh"
 #include <vector>
 
-uint4 s_dyn[1];      // the kernels' `extern __shared__` symbol (kernels are not launched here)
+thread_local uint4 s_dyn[(4 * LZ4_TAB_BIG_WORDS) / 4 + 16];   // the kernels' dynamic shared memory
 
 extern "C" {
 
@@ -79,6 +80,48 @@ void emu_guard_free(void *p, size_t size, size_t slack, size_t front)
 	const size_t npages = (body + page - 1) / page + 2;
 	uint8_t *end = (uint8_t *)p + size + slack;
 	munmap(end - (npages - 1) * page, npages * page);
+}
+
+} // extern "C"
+
+// ---- K1 + scan: the VERIFY pipeline's kernels, launched like launch_k1_kernel / launch_scan
+// in mtz_lib.cu do (same grids' shape, same order), on the emulator.
+extern "C" {
+
+// lanes: 32 = k1_record_sums (warp per record), 16 / 8 / 4 = k1_record_sums_g<G>
+int32_t emu_k1(const uint8_t *base, const mtz_rec *recs, uint32_t nrec, void *sums_out,
+    uint32_t body_from, int lanes, uint32_t grid)
+{
+	mtz::RecSums *sums = (mtz::RecSums *)sums_out;
+	if (lanes == 32) emu::launch(grid, K1_THREADS, [&] { mtz::k1_record_sums(base, recs, nrec, sums, body_from); });
+	else if (lanes == 16) emu::launch(grid, K1_THREADS, [&] { mtz::k1_record_sums_g<16>(base, recs, nrec, sums, body_from); });
+	else if (lanes == 8) emu::launch(grid, K1_THREADS, [&] { mtz::k1_record_sums_g<8>(base, recs, nrec, sums, body_from); });
+	else if (lanes == 4) emu::launch(grid, K1_THREADS, [&] { mtz::k1_record_sums_g<4>(base, recs, nrec, sums, body_from); });
+	else return -1;
+	return 0;
+}
+
+uint32_t emu_recsums_size(void) { return (uint32_t)sizeof(mtz::RecSums); }
+
+// out[0] = bad (0xffffffff none), out[1] = end_seen, out[2..5] = end_ck, out[6..9] = carry,
+// out[10..14] = aggregate (n, A, B, C, D)
+int32_t emu_scan_verify(const void *sums_in, uint32_t nrec, const uint64_t carry_in[4], uint64_t out[15])
+{
+	const mtz::RecSums *sums = (const mtz::RecSums *)sums_in;
+	mtz::ScanResult res;
+	memset(&res, 0, sizeof res);
+	mtz::Ck4 cin = { carry_in[0], carry_in[1], carry_in[2], carry_in[3] };
+	if (nrec == 0) return -1;
+	const uint32_t ntiles = (nrec + SCAN_TILE - 1) / SCAN_TILE;
+	std::vector<mtz::Part> tiles(ntiles + 2);
+	emu::launch(ntiles, SCAN_THREADS, [&] { mtz::k_scan_tiles(sums, nrec, tiles.data()); });
+	emu::launch(1, SCAN_THREADS, [&] { mtz::k_scan_spine(tiles.data(), ntiles, &res); });
+	emu::launch(ntiles, SCAN_THREADS, [&] { mtz::k_scan_verify(sums, nrec, tiles.data(), &cin, &res); });
+	out[0] = res.bad; out[1] = res.end_seen;
+	out[2] = res.end_ck.a; out[3] = res.end_ck.b; out[4] = res.end_ck.c; out[5] = res.end_ck.d;
+	out[6] = res.carry.a; out[7] = res.carry.b; out[8] = res.carry.c; out[9] = res.carry.d;
+	out[10] = res.agg.n; out[11] = res.agg.a; out[12] = res.agg.b; out[13] = res.agg.c; out[14] = res.agg.d;
+	return 0;
 }
 
 } // extern "C"
