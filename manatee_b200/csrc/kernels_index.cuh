@@ -36,6 +36,7 @@ __device__ __forceinline__ int64_t dev_drr_payload(const uint8_t *h, uint32_t *l
 	switch (type) {
 	case 0:
 		if (ld_u64_4(h + 8) != 0x2F5bacbacULL) return -1;
+		if (ld_u32(h + 4) & 7u) return -1;         // records stay 8-byte aligned (as drr_payload())
 		return (int64_t)ld_u32(h + 4);
 	case 1:
 		return (int64_t)(((uint64_t)ld_u32(h + 28) + 7ull) & ~7ull);
@@ -43,13 +44,13 @@ __device__ __forceinline__ int64_t dev_drr_payload(const uint8_t *h, uint32_t *l
 		const uint64_t ls = ld_u64_4(h + 32);
 		const uint32_t c = h[50];
 		const uint64_t l = c ? ld_u64_4(h + 96) : ls;
-		if (l > (1ull << 30) || (l & 3ull) || ls > (1ull << 30)) return -1;
+		if (l > (1ull << 30) || (l & 7ull) || ls > (1ull << 30)) return -1;
 		*lsize = (uint32_t)ls; *comp = c;
 		return (int64_t)l;
 	}
 	case 7: {
 		const uint64_t l = ld_u64_4(h + 16);
-		if (l > (1ull << 30) || (l & 3ull)) return -1;
+		if (l > (1ull << 30) || (l & 7ull)) return -1;
 		return (int64_t)l;
 	}
 	case 8:

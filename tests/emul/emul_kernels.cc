@@ -3,9 +3,13 @@
 #include "cuda_runtime.h"
 #include "../../manatee_b200/csrc/kernels_lz4.cuh"
 #include "../../manatee_b200/csrc/kernels_fletcher.cuh"
+#include "../../manatee_b200/csrc/kernels_codec.cuh"
+#include "../../manatee_b200/csrc/kernels_index.cuh"
 #include <vector>
 
+namespace mtz {
 thread_local uint4 s_dyn[(4 * LZ4_TAB_BIG_WORDS) / 4 + 16];   // the kernels' dynamic shared memory
+}
 
 extern "C" {
 
@@ -121,6 +125,88 @@ int32_t emu_scan_verify(const void *sums_in, uint32_t nrec, const uint64_t carry
 	out[2] = res.end_ck.a; out[3] = res.end_ck.b; out[4] = res.end_ck.c; out[5] = res.end_ck.d;
 	out[6] = res.carry.a; out[7] = res.carry.b; out[8] = res.carry.c; out[9] = res.carry.d;
 	out[10] = res.agg.n; out[11] = res.agg.a; out[12] = res.agg.b; out[13] = res.agg.c; out[14] = res.agg.d;
+	return 0;
+}
+
+} // extern "C"
+
+// ---- the re-encoding pipeline of one batch, launched in the order codec_reset /
+// codec_launch_dec / codec_launch_enc / codec_launch_post (mtz_lib.cu) launch it.
+extern "C" {
+
+// res[0] = out_bytes, res[1] = bad (0xffffffff none), res[2] = n_dec, res[3] = n_enc,
+// res[4..7] = end_ck of the OUTPUT stream, res[8..11] = carry_out after the batch, res[12] = end_seen
+int32_t emu_codec(uint32_t mode, const uint8_t *d_in, const mtz_rec *recs, uint32_t n, uint8_t *d_out,
+    const uint64_t carry_out_in[4], int k1_lanes, uint64_t res[13])
+{
+	using namespace mtz;
+	if (n == 0) return -1;
+	std::vector<CodecRec> cr(n);
+	std::vector<uint64_t> vals(n), offs(n), out_offs(n);
+	std::vector<mtz_job> dec(n), enc(n);
+	std::vector<mtz_rec> orecs(n);
+	std::vector<RecSums> osums(n);
+	uint64_t scratch = 0;
+	bool compact = true;
+	for (uint32_t i = 0; i < n; i++) {
+		if (recs[i].type == 3) {
+			scratch += ((recs[i].lsize + 15u) & ~15u) + 16u;
+			if (recs[i].lsize < (uint32_t)LZ4_64KLIMIT || recs[i].lsize > 131072u) compact = false;
+		}
+	}
+	std::vector<uint8_t> d_logical(scratch + 64, 0xC3), d_enc(scratch + 64, 0x3C);
+	uint64_t outpos = 0;
+	CodecResult cres; memset(&cres, 0, sizeof cres); cres.bad = 0xffffffffu;
+	ScanResult ores; memset(&ores, 0, sizeof ores);
+	Ck4 carry = { carry_out_in[0], carry_out_in[1], carry_out_in[2], carry_out_in[3] };
+	const unsigned tb = 256, gb = (n + tb - 1) / tb;
+
+	emu::launch(gb, tb, [&] { k_plan_need(recs, n, mode, cr.data(), vals.data()); });
+	emu::launch(1, XSCAN_THREADS, [&] { k_xscan_u64(vals.data(), offs.data(), n, nullptr, nullptr); });
+	emu::launch(gb, tb, [&] { k_plan_jobs(d_in, recs, n, cr.data(), offs.data(), d_logical.data(), d_enc.data(), dec.data(), enc.data()); });
+	const unsigned glz = (n + LZ4_WARPS - 1) / LZ4_WARPS > 3 ? 3 : (n + LZ4_WARPS - 1) / LZ4_WARPS;   // grid-stride
+	if (mode != MTZ_MODE_COMPRESS)
+		emu::launch(glz, LZ4_THREADS, [&] { k2_lz4_decode(nullptr, nullptr, dec.data(), n); });
+	if (mode != MTZ_MODE_DECOMPRESS) {
+		if (compact) emu::launch(glz, LZ4_THREADS, [&] { k3_lz4_encode<true>(nullptr, nullptr, enc.data(), n); });
+		else emu::launch(glz, LZ4_THREADS, [&] { k3_lz4_encode<false>(nullptr, nullptr, enc.data(), n); });
+	}
+	emu::launch(gb, tb, [&] { k_layout(recs, n, cr.data(), dec.data(), enc.data(), vals.data(), &cres, 0u); });
+	emu::launch(1, XSCAN_THREADS, [&] { k_xscan_u64(vals.data(), out_offs.data(), n, &outpos, &outpos); });
+	const unsigned ga = (n + 7) / 8 > 4 ? 4 : (n + 7) / 8;
+	emu::launch(ga, ASM_THREADS, [&] { k_assemble(d_in, recs, n, mode, cr.data(), out_offs.data(), enc.data(),
+	    d_logical.data(), d_enc.data(), d_out, orecs.data()); });
+	if (emu_k1(d_out, orecs.data(), n, osums.data(), 312u, k1_lanes, 2) != 0) return -2;
+	emu::launch(1, 32, [&] { k_stamp_chain(d_out, orecs.data(), osums.data(), n, &carry, &ores); });
+	res[0] = outpos; res[1] = cres.bad; res[2] = cres.n_dec; res[3] = cres.n_enc;
+	res[4] = ores.end_ck.a; res[5] = ores.end_ck.b; res[6] = ores.end_ck.c; res[7] = ores.end_ck.d;
+	res[8] = carry.a; res[9] = carry.b; res[10] = carry.c; res[11] = carry.d;
+	res[12] = ores.end_seen;
+	return 0;
+}
+
+} // extern "C"
+
+// ---- the GPU-side DRR parse (k_index; cooperative launch emulated with one CTA) and the
+// shard carry fold
+extern "C" {
+
+// res[0] = nrec, res[1] = consumed, res[2] = status
+int32_t emu_index(const uint8_t *base, uint64_t n, mtz_rec *recs, uint64_t cap, int64_t res[3])
+{
+	mtz::IndexResult r; memset(&r, 0, sizeof r);
+	mtz::IndexShared sh; memset(&sh, 0xff, sizeof sh);
+	emu::launch(1, INDEX_THREADS, [&] { mtz::k_index(base, n, recs, cap, &r, &sh); });
+	res[0] = (int64_t)r.nrec; res[1] = (int64_t)r.consumed; res[2] = (int64_t)r.status;
+	return 0;
+}
+
+// aggs = world x (n, A, B, C, D); carry of shard `rank` = fold of the earlier aggregates
+int32_t emu_fold_carry(const uint64_t *aggs, uint32_t rank, uint64_t carry[4])
+{
+	mtz::Ck4 c = { 0, 0, 0, 0 };
+	emu::launch(1, 1, [&] { mtz::k_fold_carry((const mtz::Part *)aggs, rank, &c); });
+	carry[0] = c.a; carry[1] = c.b; carry[2] = c.c; carry[3] = c.d;
 	return 0;
 }
 

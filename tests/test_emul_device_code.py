@@ -25,7 +25,9 @@ def emu(tmp_path_factory):
         pytest.skip("no g++")
     so = os.path.join(str(tmp_path_factory.mktemp("emul")), "libemul.so")
     r = subprocess.run(["g++", "-std=c++17", "-O2", "-Wall", "-Wextra", "-Wno-unused-variable",
-                        "-Wno-unused-function", "-Wno-unknown-pragmas", "-I" + EMUL, "-shared", "-fPIC", "-o", so,
+                        "-Wno-unused-function", "-Wno-unknown-pragmas",
+                        "-fno-extern-tls-init",      # `extern __shared__` maps to `extern thread_local`
+                        "-I" + EMUL, "-shared", "-fPIC", "-o", so,
                         os.path.join(EMUL, "warp_emul.cc"), os.path.join(EMUL, "emul_kernels.cc")],
                        stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
     assert r.returncode == 0, r.stderr
@@ -42,6 +44,12 @@ def emu(tmp_path_factory):
     L.emu_recsums_size.restype = u32
     L.emu_scan_verify.argtypes = [vp, u32, vp, vp]
     L.emu_scan_verify.restype = C.c_int32
+    L.emu_codec.argtypes = [u32, vp, vp, u32, vp, vp, i32, vp]
+    L.emu_codec.restype = C.c_int32
+    L.emu_index.argtypes = [vp, C.c_uint64, vp, C.c_uint64, vp]
+    L.emu_index.restype = C.c_int32
+    L.emu_fold_carry.argtypes = [vp, u32, vp]
+    L.emu_fold_carry.restype = C.c_int32
     L.emu_guard_alloc.argtypes = [sz, sz, sz]
     L.emu_guard_alloc.restype = vp
     L.emu_guard_free.argtypes = [vp, sz, sz, sz]
@@ -248,3 +256,136 @@ def test_k1_and_scan_kernels_on_the_cpu(emu, oracle):
     tail = np.ascontiguousarray(s[cut:])
     r = _verify_on_emulator(emu, tail, 32, carry_in=first)
     assert r["bad"] == NONE and r["end_ck"] == oracle.stream_verify(s)[1].end_cksum.tuple()
+
+
+def _codec_on_emulator(emu, mode, stream, lanes=32, carry=(0, 0, 0, 0)):
+    from manatee_b200 import index_host
+    recs, used = index_host(stream)
+    assert used == stream.size
+    buf = Guarded(emu, stream.size, slack=(-stream.size) % 16, data=stream)
+    worst = int(sum(312 + max(int(r["payload"]), int(r["lsize"]) if r["type"] == 3 else 0) for r in recs))
+    out = Guarded(emu, worst, slack=(-worst) % 16)
+    out.a[:] = 0x77
+    res = np.zeros(13, dtype=np.uint64)
+    cin = np.array(carry, dtype=np.uint64)
+    rc = emu.emu_codec(mode, buf.ptr, recs.ctypes.data, len(recs), out.ptr, cin.ctypes.data, lanes, res.ctypes.data)
+    assert rc == 0
+    got = out.a[:int(res[0])].copy()
+    buf.free()
+    out.free()
+    return got, {"bad": int(res[1]), "n_dec": int(res[2]), "n_enc": int(res[3]),
+                 "end_ck": tuple(int(x) for x in res[4:8]), "carry": tuple(int(x) for x in res[8:12]),
+                 "end_seen": int(res[12])}
+
+
+def test_codec_kernels_on_the_cpu(emu, oracle):
+    """plan / K2 / K3 / layout / assemble / K1(out) / stamp chain, in the order mtz_lib.cu launches
+    them, on the emulator: COMPRESS, DECOMPRESS and RECOMPRESS outputs must be the oracle's byte
+    for byte (headers, frames, every re-stamped checksum) -- every record type, mixed payload
+    kinds, both table flavours, a few hundred tiny records in one batch."""
+    from test_gpu_codec import _all_types_stream, _mixed_stream
+    NONE = 0xffffffff
+    cases = [(_all_types_stream(oracle, seed=3), 32),
+             (_mixed_stream(oracle, n=12, recsize=131072), 32),            # compact (17-bit) tables
+             (_mixed_stream(oracle, n=30, recsize=16384), 16),
+             (_mixed_stream(oracle, n=300, recsize=4096), 4),              # > 1 plan CTA, lane groups of 4
+             (oracle.synth_stream(40, recsize=1024, kind=oracle.PAYLOAD_PGPAGE), 4),
+             (oracle.synth_stream(0), 32)]
+    for s, lanes in cases:
+        rc, want_c, cst = oracle.stream_compress(s)
+        assert rc == 0
+        got_c, r = _codec_on_emulator(emu, 1, s, lanes)
+        assert np.array_equal(got_c, want_c), ("compress", s.size)
+        assert r["bad"] == NONE and r["n_enc"] == cst.lz4_out and r["end_seen"] == 1
+        assert r["end_ck"] == cst.end_cksum.tuple()
+        got_d, r = _codec_on_emulator(emu, 2, want_c, lanes)
+        assert np.array_equal(got_d, s), ("decompress", s.size)
+        assert r["bad"] == NONE and r["n_dec"] == cst.lz4_out
+        rc, want_r, rst = oracle.stream_recompress(want_c)
+        got_r, r = _codec_on_emulator(emu, 3, want_c, lanes)
+        assert np.array_equal(got_r, want_r), ("recompress", s.size)
+        assert r["end_ck"] == rst.end_cksum.tuple()
+    # a frame that does not decode is reported with its record index, nothing is written past it
+    s = _mixed_stream(oracle, n=12, recsize=131072)
+    rc, c, _ = oracle.stream_compress(s)
+    cnt, offs = oracle.stream_index(c)
+    k = 5
+    bad = c.copy()
+    bad[int(offs[k]) + 312:int(offs[k]) + 316] = 255                         # absurd BE32 length
+    _, r = _codec_on_emulator(emu, 2, bad, 32)
+    assert r["bad"] == k
+
+
+def _index_on_emulator(emu, stream, cap=None):
+    from manatee_b200.stage import REC_DTYPE
+    buf = Guarded(emu, stream.size, slack=0, data=stream)           # the parse must not read past n
+    cap = cap if cap is not None else stream.size // 312 + 8
+    recs = np.zeros(cap, dtype=REC_DTYPE)
+    res = np.zeros(3, dtype=np.int64)
+    assert emu.emu_index(buf.ptr, stream.size, recs.ctypes.data, cap, res.ctypes.data) == 0
+    buf.free()
+    return recs[:int(res[0])], int(res[1]), int(res[2])
+
+
+def test_gpu_side_parser_and_carry_fold_on_the_cpu(emu, oracle):
+    """k_index (speculative strided header walk; the cooperative grid emulated with one CTA)
+    must build the record table the host parser builds -- on valid streams, truncated ones and
+    a few hundred header mutations -- and k_fold_carry must equal the oracle's fold."""
+    from manatee_b200 import index_host
+    from manatee_b200 import _native as N
+    from test_gpu_codec import _all_types_stream
+    EFORMAT, ENOSPC = -4, -7
+    base = _all_types_stream(oracle, seed=17)
+    streams = [base, oracle.synth_stream(0), oracle.synth_stream(700, recsize=512, kind=oracle.PAYLOAD_PCG),
+               oracle.synth_stream(9, recsize=131072, kind=oracle.PAYLOAD_PGPAGE),
+               np.concatenate([base, oracle.synth_stream(5, recsize=4096), base])]
+    rc, comp, _ = oracle.stream_compress(streams[3])
+    streams.append(comp)                                              # ragged record lengths
+    for s in streams:
+        for cut in (0, 100, 312 + 77):
+            t = s[:s.size - cut] if cut else s
+            hrecs, hused = index_host(t)
+            drecs, dused, dst = _index_on_emulator(emu, t)
+            assert dst == 0 and dused == hused and len(drecs) == len(hrecs), (s.size, cut)
+            for f in ("off", "payload", "type", "lsize", "comp"):
+                assert np.array_equal(drecs[f], hrecs[f]), (f, s.size, cut)
+    # too small a table is reported, not overrun
+    _, _, st = _index_on_emulator(emu, streams[2], cap=10)
+    assert st == ENOSPC
+    # header mutations: same verdict as the host parser
+    cnt, offs = oracle.stream_index(base)
+    rng = np.random.default_rng(123)
+    fields = [(0, 4), (4, 4), (8, 8), (28, 4), (32, 8), (50, 1), (52, 4), (96, 8), (16, 8)]
+    n_bad = 0
+    for _ in range(150):
+        m = base.copy()
+        r = int(rng.integers(0, cnt))
+        off, width = fields[int(rng.integers(0, len(fields)))]
+        if rng.integers(0, 2):
+            m[int(offs[r]) + off + int(rng.integers(0, width))] ^= 1 << int(rng.integers(0, 8))
+        else:
+            m[int(offs[r]) + off:int(offs[r]) + off + width] = rng.integers(0, 256, width, dtype=np.uint8)
+        try:
+            hrecs, hused = index_host(m)
+            hst = 0
+        except N.MtzError as e:
+            hst = e.code
+        drecs, dused, dst = _index_on_emulator(emu, m)
+        assert dst == hst, (r, off, dst, hst)
+        if hst == 0:
+            assert dused == hused and len(drecs) == len(hrecs) and np.array_equal(drecs["off"], hrecs["off"])
+        else:
+            assert dst == EFORMAT
+            n_bad += 1
+    assert n_bad > 10
+    # carry fold == applying the earlier shards' aggregates in order
+    parts = [oracle.fletcher4_partial(rng.integers(0, 256, 4 * int(rng.integers(1, 5000)), dtype=np.uint8))
+             for _ in range(6)]
+    aggs = np.array([list(p) for p in parts], dtype=np.uint64)
+    for rank in range(7):
+        want = (0, 0, 0, 0)
+        for p in parts[:rank]:
+            want = oracle.fletcher4_apply(want, p)
+        got = np.zeros(4, dtype=np.uint64)
+        emu.emu_fold_carry(aggs.ctypes.data, rank, got.ctypes.data)
+        assert tuple(int(x) for x in got) == want
