@@ -191,10 +191,11 @@ def run_recompress(args, local, peak_gbs):
         return n.value, secs.value, st
 
     n, _, _ = cpu_recompress(raw, cbuf)               # raw -> oracle-encoded LZ4 stream (the input)
+    del raw
+    L.orc_mt_release()                                # the oracle's scratch is as large as `raw` was
     pin_in = PinnedBuffer(n)
     pin_in.array[:] = cbuf[:n]
     src = pin_in.array
-    del raw
     recs, used = index_host(src)
     assert used == src.size
     d_in = torch.empty(src.size + 512, dtype=torch.uint8, device="cuda")
@@ -262,6 +263,7 @@ def run_recompress(args, local, peak_gbs):
     if not args.no_cpu:
         n2, secs, cst = cpu_recompress(src, cbuf)
         n2, secs, cst = cpu_recompress(src, cbuf)
+        L.orc_mt_release()
         res["cpu_baseline"] = {"value": round(src.size / GIB / secs, 3), "unit": "GiB/s (input stream bytes)",
                                "logical_gibs": round(logical / GIB / secs, 3), "cores": nthreads,
                                "cgroup_cpu_quota": cpu_quota(), "kind": "port",

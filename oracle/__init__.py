@@ -273,6 +273,11 @@ def simd_lanes(force=-1):
     return lib().orc_fletcher4_simd_lanes(force)
 
 
+def mt_release():
+    """free mt_recompress's cached scratch (as large as the logical stream)"""
+    lib().orc_mt_release()
+
+
 def mt_set_lanes(lanes):
     """Fletcher-4 flavour of mt_verify / mt_recompress; returns the lanes in use"""
     return lib().orc_mt_set_lanes(lanes)

@@ -212,6 +212,19 @@ cp_worker(void *v)
 	return (NULL);
 }
 
+/* scratch of orc_mt_recompress (one slot per record, as large as the logical stream) */
+static uint8_t *g_cache = NULL;
+static size_t g_cache_cap = 0;
+
+/* give the cached scratch back (a 64 GiB workload keeps 64 GiB here otherwise) */
+void
+orc_mt_release(void)
+{
+	free(g_cache);
+	g_cache = NULL;
+	g_cache_cap = 0;
+}
+
 int
 orc_mt_recompress(const uint8_t *in, size_t n, uint8_t *out, size_t cap,
     size_t *outn, int nthreads, double *secs, orc_stream_stats_t *st)
@@ -248,15 +261,13 @@ orc_mt_recompress(const uint8_t *in, size_t n, uint8_t *out, size_t cap,
 	/* grow-only cached scratch: steady-state calls pay no page faults (the
 	 * baseline is timed over several steps, like the GPU arm) */
 	{
-		static uint8_t *cache = NULL;
-		static size_t cache_cap = 0;
-		if (cache_cap < (size_t)tot + 64) {
-			free(cache);
-			cache_cap = (size_t)tot + 64;
-			cache = (uint8_t *)malloc(cache_cap);
-			if (cache == NULL) cache_cap = 0;
+		if (g_cache_cap < (size_t)tot + 64) {
+			free(g_cache);
+			g_cache_cap = (size_t)tot + 64;
+			g_cache = (uint8_t *)malloc(g_cache_cap);
+			if (g_cache == NULL) g_cache_cap = 0;
 		}
-		scratch = cache;
+		scratch = g_cache;
 	}
 	if (scratch == NULL) { rc = ORC_ENOSPC; goto done; }
 

@@ -140,6 +140,7 @@ int orc_synth_shard_stamp(uint8_t *out, uint64_t nwrites, uint32_t recsize,
 /* ---- multi-threaded CPU baseline drivers (bench.py --impl reference) ---- */
 /* record-parallel Fletcher-4 verify: per-record partials on nthreads, then
  * the O(records) combine; returns ORC_OK/ORC_ECKSUM, seconds in *secs */
+void orc_mt_release(void);                 /* free orc_mt_recompress's cached scratch */
 int orc_mt_set_lanes(int lanes);          /* -1 best, 0 scalar, 4 avx2, 8 avx512f; returns lanes in use */
 int orc_mt_verify(const uint8_t *in, size_t n, int nthreads, double *secs,
     orc_stream_stats_t *st);
