@@ -211,3 +211,7 @@ int32_t emu_fold_carry(const uint64_t *aggs, uint32_t rank, uint64_t carry[4])
 }
 
 } // extern "C"
+
+// number of barrier waits executed so far (every *_sync intrinsic is 1-2 of them per lane):
+// a rough count of warp-synchronous steps, used to compare formulations offline
+extern "C" unsigned long long emu_syncs(void) { return emu::syncs(); }
