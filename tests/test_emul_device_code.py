@@ -290,7 +290,10 @@ def test_codec_kernels_on_the_cpu(emu, oracle):
              (_mixed_stream(oracle, n=30, recsize=16384), 16),
              (_mixed_stream(oracle, n=300, recsize=4096), 4),              # > 1 plan CTA, lane groups of 4
              (oracle.synth_stream(40, recsize=1024, kind=oracle.PAYLOAD_PGPAGE), 4),
-             (oracle.synth_stream(0), 32)]
+             (oracle.synth_stream(0), 32),
+             # two sub-streams in one batch: the stamp chain restarts at the second BEGIN
+             (np.concatenate([oracle.synth_stream(5, recsize=8192, kind=oracle.PAYLOAD_PGPAGE),
+                              _all_types_stream(oracle, seed=4)]), 8)]
     for s, lanes in cases:
         rc, want_c, cst = oracle.stream_compress(s)
         assert rc == 0
