@@ -199,6 +199,10 @@ int32_t mtz_set_carry(mtz_handle *h, const uint64_t carry_in[4],
 /* ---- kernel-level entry points: the LZ4 kernels on device-resident jobs.  The
  * stage pipeline launches exactly these; they are exported so the parity tests
  * and ncu can drive K2/K3 in isolation.  d_jobs is a device array. ---- */
+/* Access contract (checked on the CPU emulator with guard pages, tests/test_emul_device_code.py):
+ * decode reads exactly [src, src+src_len) and writes exactly [dst, dst+lsize); encode reads its
+ * block through aligned 32-bit words, i.e. up to the 4-byte boundary at or after src+lsize and
+ * down to the one at or before src, and writes only inside the lsize-byte frame slot. */
 int32_t mtz_k_lz4_decode(mtz_handle *h, const void *d_src, void *d_dst,
     mtz_job *d_jobs, uint32_t njobs, void *cuda_stream);
 int32_t mtz_k_lz4_encode(mtz_handle *h, const void *d_src, void *d_dst,
