@@ -131,3 +131,5 @@ template <class T, class V> static inline T atomicAnd(T *p, V v) { T o = *p; *p 
 template <class T, class V> static inline T atomicAdd(T *p, V v) { T o = *p; *p = o + (T)v; return o; }
 template <class T, class V> static inline T atomicMin(T *p, V v) { T o = *p; if ((T)v < o) *p = (T)v; return o; }
 template <class T, class V> static inline T atomicMax(T *p, V v) { T o = *p; if ((T)v > o) *p = (T)v; return o; }
+
+#include "fake_runtime.h"

@@ -20,7 +20,7 @@ struct Cta {
 	const std::function<void()> *kernel = nullptr;
 };
 
-static Cta *C = nullptr;
+static thread_local Cta *C = nullptr;     // one emulated device per OS thread
 static unsigned long long g_syncs = 0;
 static const size_t STACK = 512u << 10;
 

@@ -1,0 +1,206 @@
+"""The WHOLE library on the CPU: tests/emul/make_emul_lib.py compiles manatee_b200/csrc/mtz_lib.cu
+(launch sites rewritten mechanically, nothing else) and every kernel header with g++ against the
+SIMT emulator and a synchronous fake CUDA runtime whose "device" allocations sit in front of guard
+pages.  The product's own Python wrapper is pointed at that build (a monkeypatch of this test
+module only) and
+
+  * the gpu-marked parity tests that need no torch.cuda run unchanged against it: process_host in
+    every mode, the streaming ring engine with its threads, deferred shards, corrupted streams;
+  * the device API (`mtz_dev_*`) is driven with numpy buffers as "device" memory: GPU-side parse,
+    two-phase shards, the sub-batched three-stream RECOMPRESS pipeline (sub-batch size shrunk in
+    this build, so a few thousand tiny records cross it several times) and codec shards with the
+    deferred stamp chain.
+
+It checks the HOST logic of the library (engine, batching, sub-batching, error paths) and its
+memory discipline without a GPU.  Test infrastructure only: the product never loads this build
+and has no CPU path."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EMUL = os.path.join(ROOT, "tests", "emul")
+
+
+@pytest.fixture(scope="module")
+def emul_library(tmp_path_factory):
+    import shutil
+    if shutil.which("g++") is None:
+        pytest.skip("no g++")
+    so = os.path.join(str(tmp_path_factory.mktemp("emul_lib")), "libmanatee_gpu_emul.so")
+    r = subprocess.run([sys.executable, os.path.join(EMUL, "make_emul_lib.py"), so],
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 0, r.stderr
+    from manatee_b200 import _native as N
+    saved = (N.SO_PATH, N._lib)
+    N.SO_PATH, N._lib = so, None
+    try:
+        yield N.lib()
+    finally:
+        N.SO_PATH, N._lib = saved
+
+
+def _gpu_tests():
+    import test_gpu_codec as K
+    import test_gpu_stream as S
+    import test_gpu_verify as V
+    cases = []
+    for p in [(0, 131072), (1, 131072), (5, 512), (33, 4096), (3, 1 << 20)]:
+        cases.append(("verify_end_checksum-%d-%d" % p, V.test_verify_end_checksum_matches_oracle, p))
+    cases.append(("verify_batching-1MiB", V.test_verify_batching_invariance, (1 << 20,)))
+    for w in ("payload", "header", "embedded", "end"):
+        cases.append(("verify_corruption-" + w, V.test_corruption_reports_same_record_as_oracle, (w,)))
+    cases += [("verify_all_ones", V.test_all_ones_wraparound, ()),
+              ("verify_legacy_zero", V.test_legacy_zero_checksums_are_skipped, ()),
+              ("verify_two_streams_one_handle", V.test_two_streams_back_to_back_on_one_handle, ()),
+              ("verify_deferred_shards_host_path", V.test_deferred_shard_verify_via_host_path, ())]
+    for c in (4093, 1 << 20):
+        cases.append(("stream_identity-%d" % c, S.test_verify_stream_identity, (c,)))
+    cases += [("stream_one_byte_chunks", S.test_stream_one_byte_chunks_small, ()),
+              ("stream_corruption", S.test_stream_corruption_fails_the_stage, ()),
+              ("stream_truncated", S.test_stream_truncated_is_eformat, ()),
+              ("stream_passthrough", S.test_passthrough_rings, ()),
+              ("stream_zero_copy", S.test_zero_copy_acquire_commit, ()),
+              ("codec_empty_and_tiny", K.test_empty_and_tiny_streams, ()),
+              ("codec_preconditions", K.test_mode_preconditions_like_the_oracle, ()),
+              ("codec_golden_fixtures", K.test_golden_fixtures_on_gpu, ()),
+              ("codec_corrupt_frame", K.test_corrupt_frame_is_ecodec_at_the_oracles_record, ()),
+              ("codec_incompressible", K.test_incompressible_stream_passes_through, ()),
+              ("codec_transport_identity-4096", K.test_transport_identity_compress_then_decompress, (4096,)),
+              ("codec_randomized-1", K.test_randomized_streams_all_modes, (1,)),
+              ("codec_randomized-3", K.test_randomized_streams_all_modes, (3,))]
+    return cases
+
+
+@pytest.mark.parametrize("name", [c[0] for c in _gpu_tests()])
+def test_gpu_parity_test_against_the_emulated_library(emul_library, oracle, name):
+    fn, args = {c[0]: (c[1], c[2]) for c in _gpu_tests()}[name]
+    fn(oracle, *args)
+
+
+def _dev(a):
+    """a numpy array is 'device memory' for the emulated library"""
+    return a.ctypes.data
+
+
+def test_device_api_two_phase_and_gpu_side_parse(emul_library, oracle):
+    from manatee_b200 import GpuSnapshotStage, index_host
+    from manatee_b200.stage import REC_DTYPE
+    s = np.ascontiguousarray(oracle.synth_stream(60, recsize=16384, kind=oracle.PAYLOAD_PCG))
+    rc, st = oracle.stream_verify(s)
+    want, used = index_host(s)
+    with GpuSnapshotStage("verify") as g:
+        d_recs = np.zeros(len(want) + 8, dtype=REC_DTYPE)
+        nrec, consumed = g.dev_index(_dev(s), s.size, _dev(d_recs), len(d_recs))
+        assert nrec == len(want) and consumed == s.size and np.array_equal(d_recs[:nrec]["off"], want["off"])
+        # two shards of one stream: aggregates first, verdict with the carry of the first
+        cut = 25
+        off = int(want["off"][cut])
+        r0, r1 = want[:cut].copy(), want[cut:].copy()
+        r1["off"] -= off
+        g.dev_submit(_dev(s), off, _dev(r0), len(r0))
+        a0 = g.dev_aggregate()
+        _, carry0, _ = g.dev_finish(carry_in=(0, 0, 0, 0))
+        assert carry0 == oracle.fletcher4(s[:off]) and a0[1:] == oracle.fletcher4_partial(s[:off])[1:]
+        g.dev_submit(_dev(s) + off, s.size - off, _dev(r1), len(r1))
+        _, carry1, _ = g.dev_finish(carry_in=carry0)
+        assert g.end_checksum() == st.end_cksum.tuple() and carry1 == oracle.fletcher4(s)
+    # a too small record table is reported, not overrun (the table sits in front of a guard page)
+    with GpuSnapshotStage("verify") as g:
+        from manatee_b200 import _native as N
+        small = np.zeros(10, dtype=REC_DTYPE)
+        with pytest.raises(N.MtzError) as ei:
+            g.dev_index(_dev(s), s.size, _dev(small), len(small))
+        assert ei.value.code == N.ENOSPC
+
+
+def test_many_tiny_records_through_the_subbatched_codec(emul_library, oracle):
+    """More records than one codec sub-batch holds (65 536 in the product, 700 in the emulated
+    build): plan / K2 / K3 / assemble / K1 / stamp chain run per sub-batch on three streams with
+    the running output offset and checksum chained on the device.  COMPRESS and RECOMPRESS outputs
+    must be the oracle's, also on a second pass over the same handle (bench.py's steps)."""
+    from manatee_b200 import GpuSnapshotStage, index_host
+    small = oracle.synth_stream(2500, recsize=512, kind=oracle.PAYLOAD_PGPAGE)     # stored raw
+    big = oracle.synth_stream(9, recsize=8192, kind=oracle.PAYLOAD_PGPAGE)         # real K2/K3 work
+    cnt, offs = oracle.stream_index(small)
+    cntb, offb = oracle.stream_index(big)
+    writes = big[int(offb[2]):int(offb[cntb - 1])]
+    w = (int(offb[3]) - int(offb[2]))
+    pieces, at = [], 0
+    for k, where in enumerate((5, 699, 700, 1401, 2100)):            # around sub-batch boundaries
+        pieces += [small[at:int(offs[where])], writes[k * w:(k + 1) * w]]
+        at = int(offs[where])
+    pieces.append(small[at:])
+    s = np.ascontiguousarray(np.concatenate(pieces))
+    assert oracle.stream_restamp(s)[0] == 0
+    recs, used = index_host(s)
+    assert used == s.size and len(recs) > 3 * 700
+    rc, want_c, cst = oracle.stream_compress(s)
+    assert rc == 0 and cst.lz4_out == 5
+    out = np.zeros(s.size + (1 << 20), dtype=np.uint8)
+    with GpuSnapshotStage("compress") as g:
+        g.dev_submit(_dev(s), s.size, _dev(recs), len(recs), _dev(out), out.size)
+        ob, carry, carry_out = g.dev_finish()
+        assert ob == want_c.size and np.array_equal(out[:ob], want_c)
+        assert g.end_checksum() == cst.end_cksum.tuple() and carry_out == oracle.fletcher4(want_c)
+        assert g.stats()["lz4_encoded"] == cst.lz4_out
+    c = np.ascontiguousarray(want_c)
+    crecs, _ = index_host(c)
+    rc, want_r, rst = oracle.stream_recompress(c)
+    with GpuSnapshotStage("recompress") as g:
+        for _ in range(2):
+            out[:] = 0
+            g.dev_reset()
+            g.dev_submit(_dev(c), c.size, _dev(crecs), len(crecs), _dev(out), out.size)
+            ob, _, carry_out = g.dev_finish()
+            assert ob == want_r.size and np.array_equal(out[:ob], want_r)
+            assert g.end_checksum() == rst.end_cksum.tuple()
+    # a corrupted frame in a LATER sub-batch is reported with its global record index
+    bad = c.copy()
+    k = int(np.flatnonzero(crecs["comp"] == 15)[-1])
+    bad[int(crecs["off"][k]) + 312:int(crecs["off"][k]) + 316] = 255
+    from manatee_b200 import _native as N
+    with GpuSnapshotStage("decompress") as g:
+        g.dev_submit(_dev(bad), bad.size, _dev(crecs), len(crecs), _dev(out), out.size)
+        with pytest.raises(N.MtzError) as ei:
+            g.dev_finish()
+        assert ei.value.code in (N.ECODEC, N.ECKSUM) and g.stats()["bad_record"] == k
+
+
+def test_codec_shards_with_deferred_chain_on_the_emulated_library(emul_library, oracle):
+    from manatee_b200 import GpuSnapshotStage, index_host
+    from manatee_b200 import shard as SH
+    from manatee_b200._native import FLAG_DEFER_VERIFY
+    from test_gpu_codec import _mixed_stream
+    s = _mixed_stream(oracle, n=20, recsize=16384)
+    rc, c, _ = oracle.stream_compress(s)
+    c = np.ascontiguousarray(c)
+    rc, want, st = oracle.stream_recompress(c)
+    recs, used = index_host(c)
+    cut = 9
+    cut_off = int(recs["off"][cut])
+    shards = [(0, cut_off, recs[:cut].copy()), (cut_off, c.size - cut_off, recs[cut:].copy())]
+    shards[1][2]["off"] -= cut_off
+    stages, outs, aggs = [], [], []
+    for (o, n, r) in reversed(shards):                      # submit order is irrelevant
+        g = GpuSnapshotStage("recompress", flags=FLAG_DEFER_VERIFY)
+        d_o = np.zeros(int(r["lsize"].sum()) + 312 * len(r) + (1 << 20), dtype=np.uint8)
+        g.dev_submit(_dev(c) + o, n, _dev(r), len(r), _dev(d_o), d_o.size)
+        stages.insert(0, g)
+        outs.insert(0, (d_o, r))
+        aggs.insert(0, g.dev_aggregate())
+    try:
+        carry_out = (0, 0, 0, 0)
+        pieces = []
+        for k, g in enumerate(stages):
+            ob, _, carry_out = g.dev_finish(carry_in=SH.carry_before(k, aggs), carry_out_in=carry_out)
+            pieces.append(outs[k][0][:ob].copy())
+        got = np.concatenate(pieces)
+        assert np.array_equal(got, want)
+        assert carry_out == oracle.fletcher4(want) and stages[1].end_checksum() == st.end_cksum.tuple()
+    finally:
+        for g in stages:
+            g.close()
