@@ -204,3 +204,31 @@ def test_codec_shards_with_deferred_chain_on_the_emulated_library(emul_library, 
     finally:
         for g in stages:
             g.close()
+
+
+# ---- the host pipeline with REAL stages (emulated library) in both pipes -------------------------
+from test_host_pipeline import fakezfs  # noqa: E402,F401  (fixture)
+
+
+@pytest.mark.parametrize("name", ["test_gpu_verify_stage_in_both_pipes",
+                                  "test_gpu_compress_on_the_wire_identity_at_zfs_recv",
+                                  "test_gpu_corrupt_stream_fails_the_job",
+                                  "test_gpu_sender_compress_falls_back_for_plain_receiver",
+                                  "test_gpu_decompress_receiver_with_reference_sender"])
+def test_host_pipeline_gpu_tests_against_the_emulated_library(emul_library, fakezfs, tmp_path, name):  # noqa: F811
+    """sender and receiver threads, sockets, fake zfs children and a real stage on each side:
+    the gpu-marked restore tests of tests/test_host_pipeline.py, unchanged"""
+    import inspect
+    import test_host_pipeline as H
+    fn = getattr(H, name)
+    kwargs = {}
+    for p in inspect.signature(fn).parameters:
+        kwargs[p] = {"fakezfs": fakezfs, "tmp_path": tmp_path}[p]
+    fn(**kwargs)
+
+
+@pytest.mark.parametrize("name", ["mixed_40x16k", "pcg_12x64k"])
+def test_committed_digests_against_the_emulated_library(emul_library, oracle, name):
+    """two of the committed digest cases (tests/golden) through every mode of the emulated library"""
+    from test_zz_golden_digests import check_case_through_the_stage
+    check_case_through_the_stage(name)

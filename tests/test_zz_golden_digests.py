@@ -34,24 +34,37 @@ def test_oracle_reproduces_committed_digests(oracle):
         assert got["blocks"][k] == want["blocks"][k], k
 
 
-@pytest.mark.gpu
-def test_gpu_reproduces_committed_digests(oracle):
+CASE_NAMES = ["all_types_seed7", "all_types_seed31", "mixed_24x128k", "mixed_40x16k", "pcg_12x64k"]
+
+
+def check_case_through_the_stage(name):
+    """one digest case through VERIFY / COMPRESS / RECOMPRESS / DECOMPRESS of whatever library the
+    stage is bound to (the GPU one here; tests/test_emul_library.py points it at the emulated one)"""
     import make_golden
     from test_gpu_codec import _gpu
     from manatee_b200 import GpuSnapshotStage
-    want = json.load(open(os.path.join(GOLD, "golden.json")))["digests"]["streams"]
-    for name, build in make_golden.digest_cases():
-        w = want[name]
-        s = build()
-        assert _sha(s) == w["sha256"], name                     # same input as when the digest was made
-        with GpuSnapshotStage("verify", batch_bytes=1 << 20) as g:
-            g.process_host(s)
-            assert ["%016x" % x for x in g.end_checksum()] == w["end_cksum"], name
-            assert g.stats()["records"] == w["records"]
-        c, gs, end = _gpu("compress", s, batch_bytes=1 << 20)
-        assert _sha(c) == w["compress_sha256"] and c.size == w["compress_bytes"], name
-        assert gs["lz4_encoded"] == w["compress_lz4"] and ["%016x" % x for x in end] == w["compress_end_cksum"]
-        r, _, _ = _gpu("recompress", c)
-        assert _sha(r) == w["recompress_sha256"], name
-        d, _, _ = _gpu("decompress", c, cap=s.size + (1 << 20))
-        assert _sha(d) == w["sha256"], name
+    w = json.load(open(os.path.join(GOLD, "golden.json")))["digests"]["streams"][name]
+    s = dict(make_golden.digest_cases())[name]()
+    assert _sha(s) == w["sha256"], name                         # same input as when the digest was made
+    with GpuSnapshotStage("verify", batch_bytes=1 << 20) as g:
+        g.process_host(s)
+        assert ["%016x" % x for x in g.end_checksum()] == w["end_cksum"], name
+        assert g.stats()["records"] == w["records"]
+    c, gs, end = _gpu("compress", s, batch_bytes=1 << 20)
+    assert _sha(c) == w["compress_sha256"] and c.size == w["compress_bytes"], name
+    assert gs["lz4_encoded"] == w["compress_lz4"] and ["%016x" % x for x in end] == w["compress_end_cksum"]
+    r, _, _ = _gpu("recompress", c)
+    assert _sha(r) == w["recompress_sha256"], name
+    d, _, _ = _gpu("decompress", c, cap=s.size + (1 << 20))
+    assert _sha(d) == w["sha256"], name
+
+
+def test_digest_case_list_matches_the_generator():
+    import make_golden
+    assert [n for n, _ in make_golden.digest_cases()] == CASE_NAMES
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", CASE_NAMES)
+def test_gpu_reproduces_committed_digests(oracle, name):
+    check_case_through_the_stage(name)

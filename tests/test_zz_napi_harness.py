@@ -95,20 +95,43 @@ def test_binding_links_the_real_library_and_fails_loudly_without_a_gpu(real_exe,
     assert rc == 3 and js["threw"] == "open" and js["code"] == "-10", js     # MTZ_ENOGPU: no CPU fallback
 
 
-@pytest.mark.gpu
-def test_binding_moves_a_stream_through_the_gpu(real_exe, tmp_path, oracle):
-    s = oracle.synth_stream(40, recsize=131072, kind=oracle.PAYLOAD_PGPAGE)
+def _check_binding_end_to_end(exe, tmp_path, oracle, nrec):
+    s = oracle.synth_stream(nrec, recsize=131072, kind=oracle.PAYLOAD_PGPAGE)
     rc_o, st = oracle.stream_verify(s)
     want_ck = ["%016x" % x for x in st.end_cksum.tuple()]
-    rc, js, out = _run(real_exe, 0, s, tmp_path, chunk=300_000, name="verify")
+    rc, js, out = _run(exe, 0, s, tmp_path, chunk=300_000, name="verify")
     assert rc == 0 and js["ok"], js
     assert np.array_equal(out, s) and js["records"] == st.records and js["endChecksum"] == want_ck
     rc_c, want, cst = oracle.stream_compress(s)
-    rc, js, out = _run(real_exe, 1, s, tmp_path, chunk=1 << 20, name="compress")
+    rc, js, out = _run(exe, 1, s, tmp_path, chunk=1 << 20, name="compress")
     assert rc == 0 and js["ok"], js
     assert np.array_equal(out, want) and js["lz4Encoded"] == cst.lz4_out
     assert js["endChecksum"] == ["%016x" % x for x in cst.end_cksum.tuple()]
     bad = s.copy()
-    bad[7 * 131384 + 5000] ^= 1
-    rc, js, _ = _run(real_exe, 0, bad, tmp_path, name="bad")
+    bad[(nrec // 2) * 131384 + 5000] ^= 1
+    rc, js, _ = _run(exe, 0, bad, tmp_path, name="bad")
     assert rc == 3 and js["code"] == "-5", js              # MTZ_ECKSUM surfaces as a thrown error
+
+
+@pytest.mark.gpu
+def test_binding_moves_a_stream_through_the_gpu(real_exe, tmp_path, oracle):
+    _check_binding_end_to_end(real_exe, tmp_path, oracle, 40)
+
+
+def test_binding_moves_a_stream_through_the_emulated_library(tmp_path_factory, tmp_path, oracle):
+    """the same end-to-end check with the binding linked against the WHOLE library built for the
+    SIMT emulator (tests/emul/make_emul_lib.py): binding.cc -> C ABI -> engine thread -> kernels,
+    all on the CPU"""
+    import sys
+    d = tmp_path_factory.mktemp("napi_emul")
+    so = os.path.join(str(d), "libmanatee_gpu_emul.so")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "emul", "make_emul_lib.py"), so],
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 0, r.stderr
+    exe = os.path.join(str(d), "napi_harness_emul")
+    cmd = ["g++", "-std=c++17", "-O1", "-I" + STUBS, "-pthread", "-o", exe, BINDING,
+           os.path.join(STUBS, "napi_mock.cc"), os.path.join(STUBS, "napi_harness.cc"),
+           "-L" + str(d), "-lmanatee_gpu_emul", "-Wl,-rpath," + str(d)]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 0, r.stderr
+    _check_binding_end_to_end(exe, tmp_path, oracle, 8)
