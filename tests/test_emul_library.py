@@ -232,3 +232,45 @@ def test_committed_digests_against_the_emulated_library(emul_library, oracle, na
     """two of the committed digest cases (tests/golden) through every mode of the emulated library"""
     from test_zz_golden_digests import check_case_through_the_stage
     check_case_through_the_stage(name)
+
+
+def test_stream_ordered_shard_exchange_on_the_emulated_library(emul_library, oracle):
+    """mtz_dev_aggregate_async + mtz_dev_finish_gathered (k_fold_carry on the 'device'): three
+    shards of one stream, carries folded from the gathered 40-byte aggregates"""
+    from manatee_b200 import GpuSnapshotStage, index_host
+    from manatee_b200._native import FLAG_DEFER_VERIFY, MtzError
+    s = np.ascontiguousarray(oracle.synth_stream(60, recsize=16384, kind=oracle.PAYLOAD_PCG))
+    rc, st = oracle.stream_verify(s)
+    recs, used = index_host(s)
+    cuts = [0, 17, 41, len(recs)]
+    aggs = np.zeros(3 * 5, dtype=np.uint64)
+    stages, keep = [], []
+    for k in range(3):
+        r = recs[cuts[k]:cuts[k + 1]].copy()
+        o = int(r["off"][0])
+        n = (int(recs["off"][cuts[k + 1]]) if cuts[k + 1] < len(recs) else s.size) - o
+        r["off"] -= o
+        g = GpuSnapshotStage("verify", flags=FLAG_DEFER_VERIFY)
+        g.dev_submit(_dev(s) + o, n, _dev(r), len(r))
+        g.dev_aggregate_async(_dev(aggs) + 40 * k)
+        stages.append(g)
+        keep.append(r)
+    try:
+        carries = [g.dev_finish_gathered(_dev(aggs), k)[1] for k, g in enumerate(stages)]
+        assert carries[-1] == oracle.fletcher4(s)
+        assert carries[0] == oracle.fletcher4(s[:int(recs["off"][17])])
+        assert stages[2].end_checksum() == st.end_cksum.tuple()
+        bad = s.copy()
+        bad[int(recs["off"][20]) + 312 + 5] ^= 8
+        g = GpuSnapshotStage("verify", flags=FLAG_DEFER_VERIFY)
+        r = recs[17:41].copy()
+        o = int(r["off"][0])
+        r["off"] -= o
+        g.dev_submit(_dev(bad) + o, int(recs["off"][41]) - o, _dev(r), len(r))
+        with pytest.raises(MtzError):
+            g.dev_finish_gathered(_dev(aggs), 1)
+        assert g.stats()["bad_record"] == 4
+        g.close()
+    finally:
+        for g in stages:
+            g.close()
