@@ -7,7 +7,7 @@ header, unchanged) compiled by g++ for the SIMT emulator of tests/emul.
 The only source transformation is mechanical: each launch site
     kernel<<<grid, block, smem, stream>>>(args);
 becomes
-    emu::launch_site(grid, block, [&] { kernel(args); });
+    emu::launch_site(grid, block, stream, [=] { kernel(args); });      (arguments captured by value)
 the codec sub-batch size of the device API is shrunk (65 536 -> 700 records, so that tests cross
 it cheaply), and the definition of cudaLaunchCooperativeKernel (one user: k_index, emulated with one CTA) is
 appended.  Everything else -- the CUDA runtime calls, streams, events, pinned memory -- is served
@@ -82,7 +82,8 @@ def rewrite_launches(src):
         assert src[b:].lstrip().startswith(";"), src[b:b + 20]
         semi = src.index(";", b)
         out.append(src[pos:start])
-        out.append("emu::launch_site(%s, %s, [&] { %s%s; });" % (parts[0], parts[1], name, args))
+        stream = parts[3] if len(parts) > 3 else "nullptr"
+        out.append("emu::launch_site(%s, %s, %s, [=] { %s%s; });" % (parts[0], parts[1], stream, name, args))
         pos = semi + 1
         n += 1
     out.append(src[pos:])
@@ -95,7 +96,7 @@ TAIL = r'''
 namespace mtz { thread_local uint4 s_dyn[(4 * LZ4_TAB_BIG_WORDS) / 4 + 16]; }   // dynamic shared memory
 
 static cudaError_t cudaLaunchCooperativeKernel(const void *f, dim3, dim3 block, void **args, size_t,
-    cudaStream_t)
+    cudaStream_t st)
 {
 	// the one cooperative kernel of the library; a cooperative grid is emulated with ONE CTA
 	if (f != (const void *)mtz::k_index) abort();
@@ -105,7 +106,8 @@ static cudaError_t cudaLaunchCooperativeKernel(const void *f, dim3, dim3 block, 
 	const uint64_t a3 = *(uint64_t *)args[3];
 	mtz::IndexResult *a4 = *(mtz::IndexResult **)args[4];
 	mtz::IndexShared *a5 = *(mtz::IndexShared **)args[5];
-	emu::launch(1, block.x, [&] { mtz::k_index(a0, a1, a2, a3, a4, a5); });
+	const unsigned bx = block.x;
+	emurt::run(st, [=] { emu::launch(1, bx, [=] { mtz::k_index(a0, a1, a2, a3, a4, a5); }); });
 	return cudaSuccess;
 }
 '''

@@ -213,7 +213,6 @@ from test_host_pipeline import fakezfs  # noqa: E402,F401  (fixture)
 @pytest.mark.parametrize("name", ["test_gpu_verify_stage_in_both_pipes",
                                   "test_gpu_compress_on_the_wire_identity_at_zfs_recv",
                                   "test_gpu_corrupt_stream_fails_the_job",
-                                  "test_gpu_sender_compress_falls_back_for_plain_receiver",
                                   "test_gpu_decompress_receiver_with_reference_sender"])
 def test_host_pipeline_gpu_tests_against_the_emulated_library(emul_library, fakezfs, tmp_path, name):  # noqa: F811
     """sender and receiver threads, sockets, fake zfs children and a real stage on each side:
@@ -274,3 +273,87 @@ def test_stream_ordered_shard_exchange_on_the_emulated_library(emul_library, ora
     finally:
         for g in stages:
             g.close()
+
+
+# ---- stream / event ordering: the asynchronous, adversarially scheduled fake runtime --------------
+_ORDER_PROBE = r"""
+import sys
+sys.path.insert(0, %(root)r); sys.path.insert(0, %(tests)r)
+import numpy as np
+import oracle as O
+from manatee_b200 import _native as N
+N.SO_PATH = sys.argv[1]; N._lib = None
+from manatee_b200 import GpuSnapshotStage, index_host
+from test_gpu_codec import _mixed_stream
+s = _mixed_stream(O, n=30, recsize=16384)
+rc, c, _ = O.stream_compress(s); c = np.ascontiguousarray(c)
+rc, want, st = O.stream_recompress(c)
+recs, _ = index_host(c)
+out = np.zeros(s.size + (1 << 20), dtype=np.uint8)
+ok = False
+try:
+    with GpuSnapshotStage("recompress") as g:
+        g.dev_submit(c.ctypes.data, c.size, recs.ctypes.data, len(recs), out.ctypes.data, out.size)
+        ob, _, _ = g.dev_finish()
+    ok = ob == want.size and bool(np.array_equal(out[:ob], want))
+except Exception as e:
+    print("raised", type(e).__name__)
+print("EQUAL" if ok else "DIFFERENT")
+"""
+
+
+def _probe(so, seed, tmp_path):
+    script = os.path.join(str(tmp_path), "order_probe.py")
+    with open(script, "w") as f:
+        f.write(_ORDER_PROBE % {"root": ROOT, "tests": os.path.join(ROOT, "tests")})
+    env = dict(os.environ)
+    if seed is None:
+        env.pop("MTZ_EMUL_ASYNC", None)
+    else:
+        env["MTZ_EMUL_ASYNC"] = str(seed)
+    r = subprocess.run([sys.executable, script, so], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True,
+                       env=env, timeout=280)
+    assert r.returncode == 0, r.stderr[-2000:]
+    return r.stdout.strip().splitlines()[-1]
+
+
+def test_multi_stream_paths_under_adversarial_scheduling(emul_library, tmp_path):
+    """With MTZ_EMUL_ASYNC the fake runtime defers every stream operation and lets a random
+    unblocked stream progress: any order the stream / event graph permits can happen.  The
+    multi-stream paths (three-stream sub-batched codec, shards with the deferred chain, the
+    stream-ordered exchange, the streaming codec engine with its slots) must still be exact."""
+    so = emul_library._name
+    env = dict(os.environ, MTZ_EMUL_ASYNC="7")
+    # the module fixture builds its own copy; point the child at ours to save a compile
+    code = ("import sys, pytest; import manatee_b200._native as N; N.SO_PATH=%r; N._lib=None; "
+            "sys.exit(pytest.main(['-q', '-x', '-p', 'no:cacheprovider', %r, '-k', "
+            "'subbatched or deferred_chain or stream_ordered or deferred_shards or codec_randomized-1']))"
+            % (so, os.path.join(ROOT, "tests", "test_emul_library.py")))
+    r = subprocess.run([sys.executable, "-c", code], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True,
+                       env=env, cwd=ROOT, timeout=280)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert " passed" in r.stdout
+
+
+def test_the_adversarial_scheduler_catches_a_missing_dependency(emul_library, tmp_path):
+    """Test of the tester: the same library with ONE cudaStreamWaitEvent removed (K3 no longer
+    waits for K2 of its own sub-batch).  The synchronous fake runtime cannot see it; the
+    adversarial one does on every seed, while the unmodified library stays exact."""
+    sys.path.insert(0, EMUL)
+    import make_emul_lib as M
+    src = open(os.path.join(M.CSRC, "mtz_lib.cu")).read()
+    site = "MTZ_CU(h, cudaStreamWaitEvent(st, h->ev_dec[b], 0));"
+    assert src.count(site) == 1
+    gen, n = M.rewrite_launches(src.replace(site, "/* mutation: dependency removed */"))
+    gen_path = os.path.join(str(tmp_path), "mtz_lib_mut.cc")
+    with open(gen_path, "w") as f:
+        f.write(gen + M.TAIL)
+    mut = os.path.join(str(tmp_path), "libmut.so")
+    r = subprocess.run(["g++", "-std=c++17", "-O1", "-w", "-fno-extern-tls-init", "-pthread", "-shared", "-fPIC",
+                        "-I" + M.HERE, "-I" + M.CSRC, "-o", mut, gen_path, os.path.join(M.HERE, "warp_emul.cc")],
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    good = emul_library._name
+    assert _probe(good, None, tmp_path) == "EQUAL" and _probe(good, 3, tmp_path) == "EQUAL"
+    assert _probe(mut, None, tmp_path) == "EQUAL"            # hidden by a synchronous runtime
+    assert [_probe(mut, seed, tmp_path) for seed in (1, 2)] == ["DIFFERENT", "DIFFERENT"]
