@@ -97,6 +97,7 @@ struct mtz_handle {
 	cudaStream_t st_dec = nullptr;     // plan + K2 of sub-batch k+1 under K3 of k
 	cudaEvent_t ev_dec[2] = {nullptr, nullptr};
 	cudaEvent_t ev_pre[2] = {nullptr, nullptr}, ev_post[2] = {nullptr, nullptr};
+	cudaEvent_t ev_reset = nullptr;        // codec_reset of this submit is done (gates st_dec / st_post)
 	std::vector<mtz_rec> dv_hrecs;     // host copy of the device record table
 	mtz_rec *dv_all_orecs = nullptr;   // shard mode: output table / sums of the whole submit
 	mtz::RecSums *dv_all_osums = nullptr;

@@ -300,6 +300,7 @@ int32_t mtz_close(mtz_handle *h)
 	for (int i = 0; i < 2; i++) {
 		if (h->ev_dec[i]) cudaEventDestroy(h->ev_dec[i]);
 		if (h->ev_pre[i]) cudaEventDestroy(h->ev_pre[i]);
+		if (i == 0 && h->ev_reset) cudaEventDestroy(h->ev_reset);
 		if (h->ev_post[i]) cudaEventDestroy(h->ev_post[i]);
 	}
 	if (h->dv_all_orecs) cudaFree(h->dv_all_orecs);
@@ -644,6 +645,7 @@ int32_t mtz_dev_submit(mtz_handle *h, const void *d_in, size_t in_bytes,
 		for (int i = 0; i < 2; i++) {
 			MTZ_CU(h, cudaEventCreateWithFlags(&h->ev_dec[i], cudaEventDisableTiming));
 			MTZ_CU(h, cudaEventCreateWithFlags(&h->ev_pre[i], cudaEventDisableTiming));
+			if (i == 0) MTZ_CU(h, cudaEventCreateWithFlags(&h->ev_reset, cudaEventDisableTiming));
 			MTZ_CU(h, cudaEventCreateWithFlags(&h->ev_post[i], cudaEventDisableTiming));
 		}
 	}
@@ -669,8 +671,12 @@ int32_t mtz_dev_submit(mtz_handle *h, const void *d_in, size_t in_bytes,
 	}
 	h->dv_out = (uint8_t *)d_out;
 	MTZ_CU(h, cudaEventRecord(h->dv_c0, st));
-	MTZ_CU(h, cudaEventRecord(h->ev_pre[0], st));              // orders codec_reset before any post
-	MTZ_CU(h, cudaStreamWaitEvent(h->st_post, h->ev_pre[0], 0));
+	// codec_reset (and whatever this stream did before) is ordered before anything the decode
+	// and post streams do for this submit.  A dedicated event: ev_pre[0] is re-recorded after
+	// K3 of sub-batch 0, so waiting on it here would make K2 of sub-batch 1 wait for that K3
+	// instead of running under it.
+	MTZ_CU(h, cudaEventRecord(h->ev_reset, st));
+	MTZ_CU(h, cudaStreamWaitEvent(h->st_post, h->ev_reset, 0));
 	bool used[2] = { false, false };
 	size_t k = 0;
 	for (size_t i0 = 0; i0 < nrec; k++) {
@@ -687,7 +693,7 @@ int32_t mtz_dev_submit(mtz_handle *h, const void *d_in, size_t in_bytes,
 		// decode stream: plan + K2 of sub-batch k run under K3 of sub-batch k-1 (K2 needs no
 		// shared memory and K3 leaves 40 warp slots per SM empty)
 		if (used[b]) MTZ_CU(h, cudaStreamWaitEvent(h->st_dec, h->ev_post[b], 0));   // scratch set free again
-		else MTZ_CU(h, cudaStreamWaitEvent(h->st_dec, h->ev_pre[0], 0));           // after codec_reset
+		else MTZ_CU(h, cudaStreamWaitEvent(h->st_dec, h->ev_reset, 0));            // after codec_reset
 		rc = codec_launch_dec(h, h->st_dec, cb, (const uint8_t *)d_in, d_recs + i0, i1 - i0);
 		if (rc != MTZ_OK) return rc;
 		MTZ_CU(h, cudaEventRecord(h->ev_dec[b], h->st_dec));
