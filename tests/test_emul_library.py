@@ -357,3 +357,14 @@ def test_the_adversarial_scheduler_catches_a_missing_dependency(emul_library, tm
     assert _probe(good, None, tmp_path) == "EQUAL" and _probe(good, 3, tmp_path) == "EQUAL"
     assert _probe(mut, None, tmp_path) == "EQUAL"            # hidden by a synchronous runtime
     assert [_probe(mut, seed, tmp_path) for seed in (1, 2)] == ["DIFFERENT", "DIFFERENT"]
+
+
+def test_hostile_streams_never_crash_the_library_and_are_never_accepted(emul_library):
+    """tools/emul_hostile_fuzz.py in a child process (a guard-page hit would kill it): mutated
+    streams through every mode of the emulated library end in a clean error, never in success"""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "emul_hostile_fuzz.py"), emul_library._name,
+                        "11", "120"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=280)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "hostile fuzz seed 11: 120 iterations" in r.stdout and "MISS" not in r.stdout
+    for code in ("err-4", "err-5"):                       # both format and checksum errors were exercised
+        assert code in r.stdout, r.stdout
