@@ -129,7 +129,9 @@ const char *mtz_strerror(int32_t code);
 int32_t mtz_ring_acquire(mtz_handle *h, size_t want, void **ptr, size_t *got);
 int32_t mtz_ring_commit(mtz_handle *h, size_t n);
 int32_t mtz_write(mtz_handle *h, const void *buf, size_t n, int32_t block);
-/* end of input == Transform._flush(): like stdout 'end' on the zfs send child */
+/* end of input == Transform._flush(): like stdout 'end' on the zfs send child.  A stream that
+ * stops inside a record, or after whole records but before the DRR_END of an open sub-stream
+ * (what a dying `zfs send` leaves), fails the handle with MTZ_EFORMAT. */
 int32_t mtz_flush(mtz_handle *h);
 /* consumer side == Transform.push(): processed stream bytes, in stream order */
 int32_t mtz_out_peek(mtz_handle *h, const void **ptr, size_t *n);

@@ -1136,6 +1136,7 @@ struct Engine {
 	uint64_t out_head = 0;         // published to the consumer
 	uint64_t out_pos = 0;          // consumed
 	bool flushed = false, eof = false, stop = false;
+	bool open_substream = false;   // a DRR_BEGIN has been parsed and its DRR_END has not
 	std::mutex mu;
 	std::condition_variable cv_eng, cv_prod, cv_cons;
 	std::thread thr;
@@ -1211,7 +1212,8 @@ static int32_t engine_parse(Engine *e, bool *cut)
 		if (a == 0) { *cut = true; break; }
 		e->cur.push_back(r);
 		e->parse_pos += rl;
-		if (r.type == 5) { *cut = true; break; }                  // END: ship now
+		if (r.type == 0) e->open_substream = true;
+		if (r.type == 5) { e->open_substream = false; *cut = true; break; }   // END: ship now
 		if (e->bc.budget >= h->cfg.batch_bytes) { *cut = true; break; }
 	}
 	return MTZ_OK;
@@ -1317,6 +1319,11 @@ static void engine_main(Engine *e)
 			if (e->parse_pos != e->in_head) {
 				rc = fail(h, MTZ_EFORMAT, "stream ends inside a record (%llu trailing bytes)",
 				    (unsigned long long)(e->in_head - e->parse_pos));
+			} else if (e->open_substream) {
+				// every record so far verified, but the source closed before DRR_END: what a
+				// dying `zfs send` leaves behind.  `zfs recv` would reject it; say so here.
+				rc = fail(h, MTZ_EFORMAT, "stream ends before DRR_END (cut after %llu bytes)",
+				    (unsigned long long)e->in_head);
 			} else {
 				e->eof = true;
 				e->cv_cons.notify_all();

@@ -368,3 +368,34 @@ def test_hostile_streams_never_crash_the_library_and_are_never_accepted(emul_lib
     assert "hostile fuzz seed 11: 120 iterations" in r.stdout and "MISS" not in r.stdout
     for code in ("err-4", "err-5"):                       # both format and checksum errors were exercised
         assert code in r.stdout, r.stdout
+
+
+def test_streaming_api_rejects_a_stream_that_stops_before_end(emul_library, oracle):
+    """every record verified but the source closed before DRR_END (a dying `zfs send`): the ring
+    API, which knows where the stream ends, reports it; whole-record slices through
+    process_host (shards) stay legal"""
+    from manatee_b200 import GpuSnapshotStage
+    from manatee_b200._native import MtzError, EFORMAT
+    s = oracle.synth_stream(6, recsize=8192, kind=oracle.PAYLOAD_PCG)
+    cnt, offs = oracle.stream_index(s)
+    cut = s[:int(offs[5])]                                   # ends exactly at a record boundary
+    with GpuSnapshotStage("verify", ring_bytes=1 << 20, batch_bytes=1 << 16) as g:
+        with pytest.raises(MtzError) as ei:
+            g.write(cut)
+            g.flush()
+            while g.read(1 << 20) is not None:
+                pass
+        assert ei.value.code == EFORMAT and "before DRR_END" in str(ei.value)
+    with GpuSnapshotStage("verify") as g:                    # a slice of whole records: fine
+        assert g.process_host(cut) == cut.size
+    for whole in (s, np.concatenate([s, s]), np.zeros(0, dtype=np.uint8)):
+        with GpuSnapshotStage("verify", ring_bytes=1 << 20, batch_bytes=1 << 16) as g:
+            g.write(whole)
+            g.flush()
+            n = 0
+            while True:
+                b = g.read(1 << 20)
+                if b is None:
+                    break
+                n += len(b)
+            assert n == whole.size

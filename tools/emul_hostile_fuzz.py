@@ -50,9 +50,34 @@ for it in range(iters):
                 p = int(rng.integers(o + 312, end - 32)); m[p:p + 32] = rng.integers(0, 256, 32, dtype=np.uint8)
     mode = ["verify", "compress", "decompress", "recompress"][int(rng.integers(0, 4))]
     out = np.zeros(max(1, s.size * 3) + (1 << 20), dtype=np.uint8)
+    streaming = rng.random() < 0.35
     try:
-        with GpuSnapshotStage(mode, batch_bytes=int(rng.choice([0, 1 << 19, 1 << 20]))) as g:
-            g.process_host(m, out)
+        if not streaming:
+            with GpuSnapshotStage(mode, batch_bytes=int(rng.choice([0, 1 << 19, 1 << 20]))) as g:
+                g.process_host(m, out)
+        else:
+            # the ring API the Node Transform binds: producer thread + consumer, sticky errors
+            import threading
+            chunk = int(rng.choice([4093, 65536, 1 << 20]))
+            with GpuSnapshotStage(mode, ring_bytes=8 << 20, out_ring_bytes=8 << 20, batch_bytes=1 << 20) as g:
+                perr = []
+
+                def prod():
+                    try:
+                        for i in range(0, m.size, chunk):
+                            g.write(m[i:i + chunk])
+                        g.flush()
+                    except N.MtzError as e:
+                        perr.append(e)
+                th = threading.Thread(target=prod)
+                th.start()
+                try:
+                    while g.read(1 << 20) is not None:
+                        pass
+                finally:
+                    th.join()
+                if perr:
+                    raise perr[0]
         res = "ok"
     except N.MtzError as e:
         res = "err%d" % e.code
@@ -61,8 +86,14 @@ for it in range(iters):
         # accepted: then nothing was really changed, or the stream was cut at a record boundary
         # (a slice of whole records is a legal input of process_host); anything else is a miss
         same = m.size == s.size and bool(np.array_equal(m, s))
-        cut = m.size < s.size and m.size in set(int(x) for x in offs) and bool(np.array_equal(m, s[:m.size]))
+        # (the streaming API knows the stream ended: a cut is an error there, see below)
+        cut = m.size < s.size and bool(np.array_equal(m, s[:m.size])) and \
+            ((not streaming and m.size in set(int(x) for x in offs)) or m.size == 0)
         if not (same or cut):
-            print("MISS: a modified stream was accepted (mode %s, kind %s, seed %d, iteration %d)" % (mode, kind, seed, it))
+            at_boundary = m.size in set(int(x) for x in offs)
+            print("MISS: a modified stream was accepted (mode %s, kind %s, seed %d, iteration %d, streaming %s, "
+                  "size %d of %d, cut at a record boundary %s, bytes changed %d)" % (
+                      mode, kind, seed, it, streaming, m.size, s.size, at_boundary,
+                      int((m != s[:m.size]).sum())))
             sys.exit(1)
 print("hostile fuzz seed %d: %d iterations in %.0fs -> %s" % (seed, iters, time.time() - t0, dict(sorted(counts.items()))))
