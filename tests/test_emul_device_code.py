@@ -19,18 +19,19 @@ EMUL = os.path.join(ROOT, "tests", "emul")
 ECODEC = -6
 
 
-@pytest.fixture(scope="module")
-def emu(tmp_path_factory):
-    if shutil.which("g++") is None:
-        pytest.skip("no g++")
-    so = os.path.join(str(tmp_path_factory.mktemp("emul")), "libemul.so")
-    r = subprocess.run(["g++", "-std=c++17", "-O2", "-Wall", "-Wextra", "-Wno-unused-variable",
-                        "-Wno-unused-function", "-Wno-unknown-pragmas",
-                        "-fno-extern-tls-init",      # `extern __shared__` maps to `extern thread_local`
-                        "-I" + EMUL, "-shared", "-fPIC", "-o", so,
-                        os.path.join(EMUL, "warp_emul.cc"), os.path.join(EMUL, "emul_kernels.cc")],
+FLAGS = ["-std=c++17", "-Wall", "-Wextra", "-Wno-unused-variable", "-Wno-unused-function", "-Wno-unknown-pragmas",
+         "-fno-extern-tls-init",      # `extern __shared__` maps to `extern thread_local`
+         "-I" + EMUL, "-shared", "-fPIC"]
+
+
+def build(so, extra):
+    r = subprocess.run(["g++"] + extra + FLAGS + ["-o", so, os.path.join(EMUL, "warp_emul.cc"),
+                                                  os.path.join(EMUL, "emul_kernels.cc")],
                        stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
     assert r.returncode == 0, r.stderr
+
+
+def bind(so):
     L = C.CDLL(so)
     vp, u32, i32, sz = C.c_void_p, C.c_uint32, C.c_int, C.c_size_t
     L.emu_zfs_lz4_compress.argtypes = [vp, u32, vp, i32]
@@ -54,6 +55,15 @@ def emu(tmp_path_factory):
     L.emu_guard_alloc.restype = vp
     L.emu_guard_free.argtypes = [vp, sz, sz, sz]
     return L
+
+
+@pytest.fixture(scope="module")
+def emu(tmp_path_factory):
+    if shutil.which("g++") is None:
+        pytest.skip("no g++")
+    so = os.path.join(str(tmp_path_factory.mktemp("emul")), "libemul.so")
+    build(so, ["-O2"])
+    return bind(so)
 
 
 class Guarded(object):
@@ -321,7 +331,9 @@ def test_codec_kernels_on_the_cpu(emu, oracle):
 
 def _index_on_emulator(emu, stream, cap=None):
     from manatee_b200.stage import REC_DTYPE
-    buf = Guarded(emu, stream.size, slack=0, data=stream)           # the parse must not read past n
+    # 4-byte aligned like mtz_dev_index demands; at most 3 spare bytes: the parse must not read past n
+    buf = Guarded(emu, stream.size, slack=(-stream.size) % 4, data=stream)
+    assert buf.ptr % 4 == 0
     cap = cap if cap is not None else stream.size // 312 + 8
     recs = np.zeros(cap, dtype=REC_DTYPE)
     res = np.zeros(3, dtype=np.int64)
@@ -392,3 +404,21 @@ def test_gpu_side_parser_and_carry_fold_on_the_cpu(emu, oracle):
         got = np.zeros(4, dtype=np.uint64)
         emu.emu_fold_carry(aggs.ctypes.data, rank, got.ctypes.data)
         assert tuple(int(x) for x in got) == want
+
+
+def test_no_misaligned_access_in_device_code(tmp_path):
+    """x86 tolerates misaligned loads and stores, a GPU faults on them.  The kernel-level tests
+    again, in a child process, against a harness built with -fsanitize=alignment
+    -fno-sanitize-recover: one misaligned access anywhere in the device code aborts the child."""
+    import sys
+    if shutil.which("g++") is None:
+        pytest.skip("no g++")
+    so = os.path.join(str(tmp_path), "libemul_ubsan.so")
+    probe = subprocess.run(["g++", "-fsanitize=alignment", "-x", "c++", "-", "-o", os.path.join(str(tmp_path), "p")],
+                           input="int main(){return 0;}", stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    if probe.returncode != 0:
+        pytest.skip("no UBSan runtime")
+    build(so, ["-O1", "-g", "-fsanitize=alignment", "-fno-sanitize-recover=alignment"])
+    r = subprocess.run([sys.executable, os.path.join(EMUL, "ubsan_driver.py"), so], stdout=subprocess.PIPE,
+                       stderr=subprocess.PIPE, text=True, timeout=280)
+    assert r.returncode == 0 and "UBSAN-CLEAN" in r.stdout, r.stdout[-1500:] + r.stderr[-3000:]
