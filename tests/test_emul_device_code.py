@@ -418,7 +418,8 @@ def test_no_misaligned_access_in_device_code(tmp_path):
                            input="int main(){return 0;}", stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
     if probe.returncode != 0:
         pytest.skip("no UBSan runtime")
-    build(so, ["-O1", "-g", "-fsanitize=alignment", "-fno-sanitize-recover=alignment"])
+    # alignment is the one a GPU punishes; signed overflow / shifts / array bounds come for free
+    build(so, ["-O1", "-g", "-fsanitize=alignment,signed-integer-overflow,shift,bounds", "-fno-sanitize-recover=all"])
     r = subprocess.run([sys.executable, os.path.join(EMUL, "ubsan_driver.py"), so], stdout=subprocess.PIPE,
                        stderr=subprocess.PIPE, text=True, timeout=280)
     assert r.returncode == 0 and "UBSAN-CLEAN" in r.stdout, r.stdout[-1500:] + r.stderr[-3000:]
