@@ -248,65 +248,204 @@ k_assemble(const uint8_t *__restrict__ d_in, const mtz_rec *__restrict__ recs, u
 }
 
 // ---- stamp: dump_record() chain over the output ---------------------------
-// The transform of the running checksum by a stamped record is NOT affine (the
-// 8 checksum words folded in are the halves of the running value itself), so
-// this chain is sequential: O(1) per record on one lane, records staged 32 at a
-// time through shared memory by the whole warp.
-__global__ void __launch_bounds__(32)
-k_stamp_chain(uint8_t *__restrict__ d_out, const mtz_rec *__restrict__ out_recs,
-    const RecSums *__restrict__ osums, uint32_t n, Ck4 *__restrict__ carry_out,
-    ScanResult *__restrict__ res)
+// The transform of the running checksum by a stamped record is NOT affine: the 8
+// words folded in after the header are the 32-bit halves of the running value
+// itself.  It is still "affine plus a linear form of the halves".  With
+//   x_r   = value stamped into record r (running checksum after its 280 header bytes)
+//   w_0..7 = the 32-bit halves of x_r
+//   Q_r   = zero-state sums of [payload of r | header words of r+1], n2 words
+// the next stamp is (word w_k sits n2 + 8 - k words from the end of the segment)
+//   x_{r+1} = apply(x_r, N = n2 + 8) + sum_k T_j(n2 + 8 - k) w_k + Q_r
+// so everything except 3 + 8 multiply-adds per component is computed for all records
+// in parallel (k_stamp_prep) and the serial walk is one step of independent
+// multiply-adds per record, split over four lanes (one per component a, b, c, d) that
+// exchange the new value by shuffle.  BEGIN records (checksum field is data, running
+// value restarts), END records (the running value is also written into the payload-less
+// END header, which changes that header's sums) and the batch edges take the generic
+// path.  Round 1's one-lane recurrence cost 358 ns per record (5.9 ms per 16 384
+// records); see profiles/r2_stamp_chain.md for this one.
+struct alignas(16) StampStep {          // transition x_r -> x_{r+1}; 400 B
+	uint64_t c[4][12];        // lane j: weights of x.a x.b x.c | of w_0..w_7 | constant
+	uint64_t woff;            // byte offset in d_out of record r+1's checksum field
+	uint32_t fast, pad;
+};
+
+__global__ void k_stamp_prep(const mtz_rec *__restrict__ out_recs, const RecSums *__restrict__ osums,
+    uint32_t n, StampStep *__restrict__ steps)
 {
-	__shared__ RecSums s_sums[32];
-	__shared__ uint64_t s_off[32];
-	const int lane = threadIdx.x;
-	Ck4 s = *carry_out;
-	for (uint32_t base = 0; base < n; base += 32u) {
-		const uint32_t cnt = min(32u, n - base);
-		__syncwarp();
-		if ((uint32_t)lane < cnt) {
-			s_sums[lane] = osums[base + lane];
-			s_off[lane] = out_recs[base + lane].off;
-		}
-		__syncwarp();
-		if (lane == 0) {
-			for (uint32_t k = 0; k < cnt; k++) {
-				const RecSums &rs = s_sums[k];
-				uint8_t *hdr = d_out + s_off[k];
-				uint64_t *ck = reinterpret_cast<uint64_t *>(hdr + DRR_CKOFF);
-				Ck4 head = rs.head;
-				if (rs.type == DRR_BEGIN_T) s.a = s.b = s.c = s.d = 0;
-				if (rs.type == DRR_END_T) {
-					uint64_t *e = reinterpret_cast<uint64_t *>(hdr + 8);
-					e[0] = s.a; e[1] = s.b; e[2] = s.c; e[3] = s.d;
-					res->end_ck = s; res->end_seen = 1;
-					// the END header changed under the sums K1 took: redo its 70 words
-					Ck4 t = { 0, 0, 0, 0 };
-					const uint32_t *w = reinterpret_cast<const uint32_t *>(hdr);
-					for (uint32_t i = 0; i < DRR_CKOFF / 4u; i++) {
-						uint32_t v = w[i];
-						if (i >= 2u && i < 10u) {        // bytes 8..39 just written
-							const uint64_t q = (i < 4u) ? s.a : (i < 6u) ? s.b : (i < 8u) ? s.c : s.d;
-							v = (i & 1u) ? (uint32_t)(q >> 32) : (uint32_t)q;
-						}
-						t.a += v; t.b += t.a; t.c += t.b; t.d += t.c;
-					}
-					head = t;
-				}
-				Part h = { DRR_CKOFF / 4u, head.a, head.b, head.c, head.d };
-				Ck4 mid = apply(s, h);
-				if (rs.type != DRR_BEGIN_T) {
-					ck[0] = mid.a; ck[1] = mid.b; ck[2] = mid.c; ck[3] = mid.d;
-					s = fold_cksum_words(mid, mid);
-				} else {
-					s = fold_cksum_words(mid, rs.emb);   // BEGIN: bytes 280..311 are data
-				}
-				Part b = { rs.nbody, rs.body.a, rs.body.b, rs.body.c, rs.body.d };
-				s = apply(s, b);
+	const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+	if (r >= n) return;
+	bool fast = false;
+	if (r + 1u < n) {
+		const uint32_t t1 = osums[r + 1u].type;
+		fast = (t1 != DRR_BEGIN_T && t1 != DRR_END_T);
+	}
+	StampStep *o = &steps[r];
+	if (!fast) { o->fast = 0; o->pad = 0; o->woff = 0; return; }
+	const RecSums rs = osums[r];
+	const Ck4 nh = osums[r + 1u].head;
+	const uint64_t n2 = rs.nbody + DRR_CKOFF / 4u, N = n2 + 8u;
+	const Part b = { rs.nbody, rs.body.a, rs.body.b, rs.body.c, rs.body.d };
+	const Part hd = { DRR_CKOFF / 4u, nh.a, nh.b, nh.c, nh.d };
+	const Part q = concat(b, hd);
+	uint64_t g[4] = { q.a, q.b, q.c, q.d };
+	uint64_t W[4][8];
+#pragma unroll
+	for (int k = 0; k < 8; k++) {
+		const uint64_t x = n2 + 8u - (uint64_t)k;
+		W[0][k] = 1; W[1][k] = x; W[2][k] = tri2(x); W[3][k] = tri3(x);
+	}
+	if (rs.type == DRR_BEGIN_T) {
+		// bytes 280..311 of a BEGIN header are data: their contribution is a constant
+		const uint64_t e[4] = { rs.emb.a, rs.emb.b, rs.emb.c, rs.emb.d };
+#pragma unroll
+		for (int j = 0; j < 4; j++) {
+#pragma unroll
+			for (int k = 0; k < 8; k++) {
+				const uint64_t w = (k & 1) ? (e[k >> 1] >> 32) : (uint64_t)(uint32_t)e[k >> 1];
+				g[j] += W[j][k] * w;
+				W[j][k] = 0;
 			}
 		}
 	}
-	if (lane == 0) { *carry_out = s; res->carry = s; }
+	const uint64_t t2 = tri2(N), t3 = tri3(N);
+	const uint64_t M[4][3] = { { 0, 0, 0 }, { N, 0, 0 }, { t2, N, 0 }, { t3, t2, N } };
+#pragma unroll
+	for (int j = 0; j < 4; j++) {
+		o->c[j][0] = M[j][0]; o->c[j][1] = M[j][1]; o->c[j][2] = M[j][2];
+#pragma unroll
+		for (int k = 0; k < 8; k++) o->c[j][3 + k] = W[j][k];
+		o->c[j][11] = g[j];
+	}
+	o->woff = out_recs[r + 1u].off + DRR_CKOFF;
+	o->fast = 1; o->pad = 0;
+}
+
+// value stamped into record r given the running checksum s that precedes it (generic path)
+__device__ __forceinline__ Ck4 stamp_enter(Ck4 s, uint8_t *__restrict__ d_out,
+    const mtz_rec *__restrict__ out_recs, const RecSums *__restrict__ osums, uint32_t r,
+    ScanResult *__restrict__ res, int lane)
+{
+	const RecSums rs = osums[r];
+	uint8_t *hdr = d_out + out_recs[r].off;
+	Ck4 head = rs.head;
+	if (rs.type == DRR_BEGIN_T) s.a = s.b = s.c = s.d = 0;
+	if (rs.type == DRR_END_T) {
+		if (lane == 0) {
+			uint64_t *e = reinterpret_cast<uint64_t *>(hdr + 8);
+			e[0] = s.a; e[1] = s.b; e[2] = s.c; e[3] = s.d;
+			res->end_ck = s; res->end_seen = 1;
+		}
+		// the END header changed under the sums K1 took: redo its 70 words
+		Ck4 t = { 0, 0, 0, 0 };
+		const uint32_t *w = reinterpret_cast<const uint32_t *>(hdr);
+		for (uint32_t i = 0; i < DRR_CKOFF / 4u; i++) {
+			uint32_t v;
+			if (i >= 2u && i < 10u) {            // bytes 8..39 just written
+				const uint64_t q = (i < 4u) ? s.a : (i < 6u) ? s.b : (i < 8u) ? s.c : s.d;
+				v = (i & 1u) ? (uint32_t)(q >> 32) : (uint32_t)q;
+			} else {
+				v = w[i];
+			}
+			t.a += v; t.b += t.a; t.c += t.b; t.d += t.c;
+		}
+		head = t;
+	}
+	const Part h = { DRR_CKOFF / 4u, head.a, head.b, head.c, head.d };
+	const Ck4 x = apply(s, h);
+	if (rs.type != DRR_BEGIN_T && lane == 0) {
+		uint64_t *ck = reinterpret_cast<uint64_t *>(hdr + DRR_CKOFF);
+		ck[0] = x.a; ck[1] = x.b; ck[2] = x.c; ck[3] = x.d;
+	}
+	return x;
+}
+
+// running checksum after record r given the value x stamped into it (generic path)
+__device__ __forceinline__ Ck4 stamp_leave(const Ck4 &x, const RecSums *__restrict__ osums, uint32_t r)
+{
+	const RecSums rs = osums[r];
+	Ck4 s = fold_cksum_words(x, rs.type == DRR_BEGIN_T ? rs.emb : x);
+	const Part b = { rs.nbody, rs.body.a, rs.body.b, rs.body.c, rs.body.d };
+	return apply(s, b);
+}
+
+#define STAMP_GROUP   32
+#define STAMP_THREADS 64
+// warp 0 walks the chain, warp 1 stages the next STAMP_GROUP transitions into shared memory
+__global__ void __launch_bounds__(STAMP_THREADS)
+k_stamp_chain(uint8_t *__restrict__ d_out, const mtz_rec *__restrict__ out_recs,
+    const RecSums *__restrict__ osums, const StampStep *__restrict__ steps, uint32_t n,
+    Ck4 *__restrict__ carry_out, ScanResult *__restrict__ res)
+{
+	__shared__ StampStep s_steps[2][STAMP_GROUP];
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const int j = lane & 3;
+	if (n == 0u) return;
+	const uint32_t T = n - 1u;                                    // transitions
+	const uint32_t ngroups = (T + STAMP_GROUP - 1u) / STAMP_GROUP;
+	constexpr uint32_t V4 = (uint32_t)(sizeof(StampStep) / sizeof(uint4));
+	auto stage = [&](uint32_t g) {
+		const uint32_t r0 = g * STAMP_GROUP, cnt = min((uint32_t)STAMP_GROUP, T - r0);
+		const uint4 *src = reinterpret_cast<const uint4 *>(steps + r0);
+		uint4 *dst = reinterpret_cast<uint4 *>(&s_steps[g & 1u][0]);
+		for (uint32_t i = (uint32_t)lane; i < cnt * V4; i += 32u) dst[i] = src[i];
+	};
+	if (warp == 1 && ngroups > 0u) stage(0);
+	__syncthreads();
+
+	Ck4 x = { 0, 0, 0, 0 };
+	uint64_t own = 0;
+	if (warp == 0) {
+		x = stamp_enter(*carry_out, d_out, out_recs, osums, 0u, res, lane);
+		own = (j == 0) ? x.a : (j == 1) ? x.b : (j == 2) ? x.c : x.d;
+	}
+	for (uint32_t g = 0; g < ngroups; g++) {
+		if (warp == 1) {
+			if (g + 1u < ngroups) stage(g + 1u);
+		} else {
+			const uint32_t r0 = g * STAMP_GROUP, cnt = min((uint32_t)STAMP_GROUP, T - r0);
+			for (uint32_t i = 0; i < cnt; i++) {
+				const StampStep &st = s_steps[g & 1u][i];
+				// the weights do not depend on the running value: their loads are issued
+				// before the exchange below
+				const uint64_t *c = st.c[j];
+				const uint64_t c0 = c[0], c1 = c[1], c2 = c[2], c3 = c[3], c4 = c[4], c5 = c[5],
+				    c6 = c[6], c7 = c[7], c8 = c[8], c9 = c[9], c10 = c[10], c11 = c[11];
+				const bool fast = st.fast != 0u;
+				const uint64_t woff = st.woff;
+				const uint32_t lo = (uint32_t)own, hi = (uint32_t)(own >> 32);
+				const uint32_t w0 = __shfl_sync(0xffffffffu, lo, 0), w1 = __shfl_sync(0xffffffffu, hi, 0);
+				const uint32_t w2 = __shfl_sync(0xffffffffu, lo, 1), w3 = __shfl_sync(0xffffffffu, hi, 1);
+				const uint32_t w4 = __shfl_sync(0xffffffffu, lo, 2), w5 = __shfl_sync(0xffffffffu, hi, 2);
+				const uint32_t w6 = __shfl_sync(0xffffffffu, lo, 3), w7 = __shfl_sync(0xffffffffu, hi, 3);
+				const uint64_t xa = ((uint64_t)w1 << 32) | w0, xb = ((uint64_t)w3 << 32) | w2;
+				const uint64_t xc = ((uint64_t)w5 << 32) | w4;
+				if (fast) {
+					const uint64_t p0 = own + c0 * xa + c11;
+					const uint64_t p1 = c1 * xb + c2 * xc;
+					const uint64_t p2 = c3 * (uint64_t)w0 + c4 * (uint64_t)w1 + c5 * (uint64_t)w2 + c6 * (uint64_t)w3;
+					const uint64_t p3 = c7 * (uint64_t)w4 + c8 * (uint64_t)w5 + c9 * (uint64_t)w6 + c10 * (uint64_t)w7;
+					own = (p0 + p1) + (p2 + p3);
+					if (lane < 4) *reinterpret_cast<uint64_t *>(d_out + woff + 8u * (uint32_t)lane) = own;
+				} else {
+					x.a = xa; x.b = xb; x.c = xc; x.d = ((uint64_t)w7 << 32) | w6;
+					const Ck4 s = stamp_leave(x, osums, r0 + i);
+					x = stamp_enter(s, d_out, out_recs, osums, r0 + i + 1u, res, lane);
+					own = (j == 0) ? x.a : (j == 1) ? x.b : (j == 2) ? x.c : x.d;
+				}
+			}
+		}
+		__syncthreads();
+	}
+	if (warp == 0) {
+		const uint32_t lo = (uint32_t)own, hi = (uint32_t)(own >> 32);
+		x.a = ((uint64_t)__shfl_sync(0xffffffffu, hi, 0) << 32) | __shfl_sync(0xffffffffu, lo, 0);
+		x.b = ((uint64_t)__shfl_sync(0xffffffffu, hi, 1) << 32) | __shfl_sync(0xffffffffu, lo, 1);
+		x.c = ((uint64_t)__shfl_sync(0xffffffffu, hi, 2) << 32) | __shfl_sync(0xffffffffu, lo, 2);
+		x.d = ((uint64_t)__shfl_sync(0xffffffffu, hi, 3) << 32) | __shfl_sync(0xffffffffu, lo, 3);
+		const Ck4 s = stamp_leave(x, osums, n - 1u);
+		if (lane == 0) { *carry_out = s; res->carry = s; }
+	}
 }
 
 } // namespace mtz

@@ -44,7 +44,7 @@ __device__ __forceinline__ int64_t dev_drr_payload(const uint8_t *h, uint32_t *l
 		const uint64_t ls = ld_u64_4(h + 32);
 		const uint32_t c = h[50];
 		const uint64_t l = c ? ld_u64_4(h + 96) : ls;
-		if (l > (1ull << 30) || (l & 7ull) || ls > (1ull << 30)) return -1;
+		if (l > (1ull << 30) || (l & 7ull) || ls > (1ull << 30) || (ls & 7ull)) return -1;
 		*lsize = (uint32_t)ls; *comp = c;
 		return (int64_t)l;
 	}

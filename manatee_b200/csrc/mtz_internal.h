@@ -24,6 +24,7 @@ struct CodecBufs {
 	mtz_job *dec = nullptr, *enc = nullptr;
 	mtz_rec *out_recs = nullptr;
 	RecSums *osums = nullptr;
+	StampStep *steps = nullptr;                         // per-record transitions of the stamp chain
 	uint8_t *d_logical = nullptr, *d_enc = nullptr;
 	CodecResult *d_cres = nullptr, *h_cres = nullptr;   // h_: pinned
 	ScanResult *d_ores = nullptr, *h_ores = nullptr;    // output-chain result
@@ -101,6 +102,7 @@ struct mtz_handle {
 	std::vector<mtz_rec> dv_hrecs;     // host copy of the device record table
 	mtz_rec *dv_all_orecs = nullptr;   // shard mode: output table / sums of the whole submit
 	mtz::RecSums *dv_all_osums = nullptr;
+	mtz::StampStep *dv_all_steps = nullptr;
 	size_t dv_all_cap = 0;
 	uint8_t *dv_out = nullptr;
 

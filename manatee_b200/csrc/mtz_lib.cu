@@ -27,12 +27,15 @@ int32_t fail(mtz_handle *h, int32_t code, const char *fmt, ...)
 	vsnprintf(buf, sizeof buf, fmt, ap);
 	va_end(ap);
 	if (h) {
-		int32_t expect = 0;
 		{
+			// message and code are set together, once, under the lock: a second failure on
+			// another thread never overwrites the string mtz_last_error() handed out
 			std::lock_guard<std::mutex> g(h->err_mu);
-			if (h->failed.load() == 0) h->err = buf;
+			if (h->failed.load() == 0) {
+				h->err = buf;
+				h->failed.store(code);
+			}
 		}
-		h->failed.compare_exchange_strong(expect, code);
 		engine_wake_all(h);
 	} else {
 		g_open_err = buf;
@@ -80,6 +83,7 @@ const char *mtz_strerror(int32_t code)
 const char *mtz_last_error(mtz_handle *h)
 {
 	if (h == nullptr) return g_open_err.c_str();
+	// h->err is written exactly once (fail()), so the pointer stays valid until mtz_close
 	std::lock_guard<std::mutex> g(h->err_mu);
 	return h->err.c_str();
 }
@@ -120,7 +124,9 @@ static int64_t drr_payload(const uint8_t *h, uint32_t *lsize, uint32_t *comp)
 	case 3: { /* WRITE */
 		const uint64_t ls = rd64(h + 32);
 		const uint64_t l = h[50] ? rd64(h + 96) : ls;
-		if (l > (1ull << 30) || (l & 7) || ls > (1ull << 30)) return -1;
+		// the logical size becomes a payload length in DECOMPRESS / RECOMPRESS output, so it
+		// has to keep records 8-byte aligned too (ZFS block sizes are multiples of 512)
+		if (l > (1ull << 30) || (l & 7) || ls > (1ull << 30) || (ls & 7)) return -1;
 		*lsize = (uint32_t)ls; *comp = h[50];
 		return (int64_t)l;
 	}
@@ -211,6 +217,8 @@ static void free_slot(Slot &s)
 
 #define MAX_RECORD_BYTES ((size_t)(16u << 20) + 4096)
 
+static int32_t k3_set_attributes(mtz_handle *h);
+
 int32_t mtz_open(const mtz_config *cfg, mtz_handle **out)
 {
 	if (cfg == nullptr || out == nullptr) return fail(nullptr, MTZ_EINVAL, "null argument");
@@ -266,7 +274,7 @@ int32_t mtz_open(const mtz_config *cfg, mtz_handle **out)
 		MTZ_CU(h, cudaHostAlloc(&h->dv_hres, sizeof(ScanResult), cudaHostAllocDefault));
 		MTZ_CU(h, cudaEventCreate(&h->dv_k1a));
 		MTZ_CU(h, cudaEventCreate(&h->dv_k1b));
-		return MTZ_OK;
+		return k3_set_attributes(h);
 	};
 	rc = init();
 	if (rc != MTZ_OK) {
@@ -305,6 +313,7 @@ int32_t mtz_close(mtz_handle *h)
 	}
 	if (h->dv_all_orecs) cudaFree(h->dv_all_orecs);
 	if (h->dv_all_osums) cudaFree(h->dv_all_osums);
+	if (h->dv_all_steps) cudaFree(h->dv_all_steps);
 	if (h->d_ires) cudaFree(h->d_ires);
 	if (h->d_ishared) cudaFree(h->d_ishared);
 	if (h->h_ires) cudaFreeHost(h->h_ires);
@@ -456,6 +465,7 @@ static int32_t codec_alloc(mtz_handle *h, CodecBufs &cb, size_t rec_cap, size_t 
 	MTZ_CU(h, cudaMalloc(&cb.enc, rec_cap * sizeof(mtz_job)));
 	MTZ_CU(h, cudaMalloc(&cb.out_recs, rec_cap * sizeof(mtz_rec)));
 	MTZ_CU(h, cudaMalloc(&cb.osums, rec_cap * sizeof(RecSums)));
+	MTZ_CU(h, cudaMalloc(&cb.steps, rec_cap * sizeof(StampStep)));
 	if (h->cfg.mode != MTZ_MODE_COMPRESS) MTZ_CU(h, cudaMalloc(&cb.d_logical, scratch_cap + 512));
 	if (h->cfg.mode != MTZ_MODE_DECOMPRESS) MTZ_CU(h, cudaMalloc(&cb.d_enc, scratch_cap + 512));
 	MTZ_CU(h, cudaMalloc(&cb.d_cres, sizeof(CodecResult)));
@@ -470,7 +480,7 @@ static int32_t codec_alloc(mtz_handle *h, CodecBufs &cb, size_t rec_cap, size_t 
 static void codec_free(CodecBufs &cb)
 {
 	cudaFree(cb.cr); cudaFree(cb.vals); cudaFree(cb.offs); cudaFree(cb.out_offs);
-	cudaFree(cb.dec); cudaFree(cb.enc); cudaFree(cb.out_recs); cudaFree(cb.osums);
+	cudaFree(cb.dec); cudaFree(cb.enc); cudaFree(cb.out_recs); cudaFree(cb.osums); cudaFree(cb.steps);
 	cudaFree(cb.d_logical); cudaFree(cb.d_enc); cudaFree(cb.d_cres); cudaFree(cb.d_ores);
 	cudaFree(cb.d_outpos);
 	if (cb.h_cres) cudaFreeHost(cb.h_cres);
@@ -568,11 +578,15 @@ static int32_t codec_launch_post(mtz_handle *h, cudaStream_t st, CodecBufs &cb, 
 	MTZ_CU(h, cudaGetLastError());
 	// output records of a codec batch are smaller than the logical size: decide by the input's
 	launch_k1_kernel(h, st, d_out, orecs, n, osums, 312u, cb.avg_out_rec);
-	if (all_osums == nullptr)
-		k_stamp_chain<<<1, 32, 0, st>>>(d_out, orecs, osums, n, h->d_carry_out, cb.d_ores);
+	if (all_osums == nullptr) {
+		const unsigned gp = (n + 127u) / 128u;
+		k_stamp_prep<<<gp, 128, 0, st>>>(orecs, osums, n, cb.steps);
+		k_stamp_chain<<<1, STAMP_THREADS, 0, st>>>(d_out, orecs, osums, cb.steps, n, h->d_carry_out, cb.d_ores);
+		count_launch(h, 2);
+	}
 	MTZ_CU(h, cudaGetLastError());
 	MTZ_CU(h, cudaMemcpyAsync(&cb.d_cres->out_bytes, cb.d_outpos, sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
-	count_launch(h, 5);
+	count_launch(h, 4);
 	return MTZ_OK;
 }
 
@@ -664,10 +678,12 @@ int32_t mtz_dev_submit(mtz_handle *h, const void *d_in, size_t in_bytes,
 	if (defer && nrec > h->dv_all_cap) {
 		if (h->dv_all_orecs) MTZ_CU(h, cudaFree(h->dv_all_orecs));
 		if (h->dv_all_osums) MTZ_CU(h, cudaFree(h->dv_all_osums));
-		h->dv_all_orecs = nullptr; h->dv_all_osums = nullptr;
+		if (h->dv_all_steps) MTZ_CU(h, cudaFree(h->dv_all_steps));
+		h->dv_all_orecs = nullptr; h->dv_all_osums = nullptr; h->dv_all_steps = nullptr;
 		h->dv_all_cap = nrec + nrec / 8 + 64;
 		MTZ_CU(h, cudaMalloc(&h->dv_all_orecs, h->dv_all_cap * sizeof(mtz_rec)));
 		MTZ_CU(h, cudaMalloc(&h->dv_all_osums, h->dv_all_cap * sizeof(RecSums)));
+		MTZ_CU(h, cudaMalloc(&h->dv_all_steps, h->dv_all_cap * sizeof(StampStep)));
 	}
 	h->dv_out = (uint8_t *)d_out;
 	MTZ_CU(h, cudaEventRecord(h->dv_c0, st));
@@ -814,10 +830,13 @@ static int32_t dev_finish_impl(mtz_handle *h, const uint64_t carry_in[4], const 
 	if (codec && (h->cfg.flags & MTZ_FLAG_DEFER_VERIFY) && h->dv_nrec > 0) {
 		// shard mode: the stamp chain of the whole shard, from the checksum the previous
 		// shard's output ended with (carry_out_in, uploaded above)
-		k_stamp_chain<<<1, 32, 0, st>>>(h->dv_out, h->dv_all_orecs, h->dv_all_osums,
-		    (uint32_t)h->dv_nrec, h->d_carry_out, h->dv_cb.d_ores);
+		const unsigned gp = ((unsigned)h->dv_nrec + 127u) / 128u;
+		k_stamp_prep<<<gp, 128, 0, st>>>(h->dv_all_orecs, h->dv_all_osums,
+		    (uint32_t)h->dv_nrec, h->dv_all_steps);
+		k_stamp_chain<<<1, STAMP_THREADS, 0, st>>>(h->dv_out, h->dv_all_orecs, h->dv_all_osums,
+		    h->dv_all_steps, (uint32_t)h->dv_nrec, h->d_carry_out, h->dv_cb.d_ores);
 		MTZ_CU(h, cudaGetLastError());
-		count_launch(h, 1);
+		count_launch(h, 2);
 	}
 	if (codec) {
 		MTZ_CU(h, cudaMemcpyAsync(h->dv_cb.h_cres, h->dv_cb.d_cres, sizeof(CodecResult), cudaMemcpyDeviceToHost, st));
@@ -1532,29 +1551,32 @@ int32_t mtz_k_lz4_decode(mtz_handle *h, const void *d_src, void *d_dst, mtz_job 
 	return MTZ_OK;
 }
 
+// Function attributes are per DEVICE (and per context): set them for the current device of
+// every handle at open time, not once per process -- a second GPU opened in the same process
+// would otherwise launch k3_lz4_encode<false> with 64 KiB of dynamic shared memory it never
+// opted into.  Idempotent, so concurrent handles on one device do not need a lock.
+static int32_t k3_set_attributes(mtz_handle *h)
+{
+	MTZ_CU(h, cudaFuncSetAttribute(k3_lz4_encode<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+	    (int)((size_t)LZ4_WARPS * LZ4_TAB_COMPACT_WORDS * 4)));
+	MTZ_CU(h, cudaFuncSetAttribute(k3_lz4_encode<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+	    (int)((size_t)LZ4_WARPS * LZ4_TAB_BIG_WORDS * 4)));
+	// all of the unified L1/shared array as shared memory: K3 is bound by records in
+	// flight (24 tables of 8.5 KiB per SM), measured 62 vs 46 GiB/s at a 75 % carve-out
+	// (profiles/r1_k3_encode.md).  MTZ_K3_CARVEOUT overrides for experiments.
+	const char *e = getenv("MTZ_K3_CARVEOUT");
+	const int pct = e ? atoi(e) : 100;
+	MTZ_CU(h, cudaFuncSetAttribute(k3_lz4_encode<true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+	MTZ_CU(h, cudaFuncSetAttribute(k3_lz4_encode<false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+	return MTZ_OK;
+}
+
 // compact = every block is 64 KiB+11 .. 128 KiB: 8.5 KiB tables, more warps per SM
 static int32_t launch_k3(mtz_handle *h, cudaStream_t st, const void *d_src, void *d_dst,
     mtz_job *d_jobs, uint32_t njobs, bool compact)
 {
 	const size_t tabw = compact ? LZ4_TAB_COMPACT_WORDS : LZ4_TAB_BIG_WORDS;
 	const size_t smem = (size_t)LZ4_WARPS * tabw * sizeof(uint32_t);
-	static bool attr_set = false;
-	if (!attr_set) {
-		MTZ_CU(h, cudaFuncSetAttribute(k3_lz4_encode<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-		    (int)((size_t)LZ4_WARPS * LZ4_TAB_COMPACT_WORDS * 4)));
-		MTZ_CU(h, cudaFuncSetAttribute(k3_lz4_encode<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-		    (int)((size_t)LZ4_WARPS * LZ4_TAB_BIG_WORDS * 4)));
-		// all of the unified L1/shared array as shared memory: K3 is bound by records in
-		// flight (24 tables of 8.5 KiB per SM), measured 62 vs 46 GiB/s at a 75 % carve-out
-		// (profiles/r1_k3_encode.md).  MTZ_K3_CARVEOUT overrides for experiments.
-		{
-			const char *e = getenv("MTZ_K3_CARVEOUT");
-			const int pct = e ? atoi(e) : 100;
-			MTZ_CU(h, cudaFuncSetAttribute(k3_lz4_encode<true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
-			MTZ_CU(h, cudaFuncSetAttribute(k3_lz4_encode<false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
-		}
-		attr_set = true;
-	}
 	const int blocks_per_sm = (int)((227u * 1024u) / (smem + 1024));
 	const int grid = lz4_grid(h, njobs, blocks_per_sm * LZ4_WARPS);
 	if (compact)

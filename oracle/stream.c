@@ -65,9 +65,11 @@ orc_drr_payload_len(const uint8_t *h)
 	case ORC_DRR_OBJECT:
 		return ((int64_t)RUP8((uint64_t)g32(h + OFF_OBJ_BONUSLEN)));
 	case ORC_DRR_WRITE: {
-		uint64_t l = h[OFF_WR_COMP] ? g64(h + OFF_WR_CSIZE) :
-		    g64(h + OFF_WR_LSIZE);
+		uint64_t ls = g64(h + OFF_WR_LSIZE);
+		uint64_t l = h[OFF_WR_COMP] ? g64(h + OFF_WR_CSIZE) : ls;
 		if (l > ((uint64_t)1 << 30) || (l & 7)) return (-1);
+		/* lsize is a payload length on the decoded side: same alignment rule */
+		if (ls > ((uint64_t)1 << 30) || (ls & 7)) return (-1);
 		return ((int64_t)l);
 	}
 	case ORC_DRR_SPILL: {

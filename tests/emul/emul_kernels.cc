@@ -177,7 +177,9 @@ int32_t emu_codec(uint32_t mode, const uint8_t *d_in, const mtz_rec *recs, uint3
 	emu::launch(ga, ASM_THREADS, [&] { k_assemble(d_in, recs, n, mode, cr.data(), out_offs.data(), enc.data(),
 	    d_logical.data(), d_enc.data(), d_out, orecs.data()); });
 	if (emu_k1(d_out, orecs.data(), n, osums.data(), 312u, k1_lanes, 2) != 0) return -2;
-	emu::launch(1, 32, [&] { k_stamp_chain(d_out, orecs.data(), osums.data(), n, &carry, &ores); });
+	std::vector<StampStep> steps(n);
+	emu::launch((n + 127u) / 128u, 128, [&] { k_stamp_prep(orecs.data(), osums.data(), n, steps.data()); });
+	emu::launch(1, STAMP_THREADS, [&] { k_stamp_chain(d_out, orecs.data(), osums.data(), steps.data(), n, &carry, &ores); });
 	res[0] = outpos; res[1] = cres.bad; res[2] = cres.n_dec; res[3] = cres.n_enc;
 	res[4] = ores.end_ck.a; res[5] = ores.end_ck.b; res[6] = ores.end_ck.c; res[7] = ores.end_ck.d;
 	res[8] = carry.a; res[9] = carry.b; res[10] = carry.c; res[11] = carry.d;
