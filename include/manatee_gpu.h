@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define MTZ_ABI_VERSION 1
+#define MTZ_ABI_VERSION 2
 
 /* ---- return codes ---- */
 #define MTZ_OK        0
@@ -43,6 +43,7 @@ extern "C" {
 #define MTZ_ENOMEM   -8
 #define MTZ_EOF      -9   /* consumer: stream finished and fully drained */
 #define MTZ_ENOGPU  -10   /* no usable sm_100 device: there is NO CPU fallback */
+#define MTZ_ECANCELED -11 /* mtz_cancel(): the pipe was torn down from outside */
 
 /* ---- stage modes ---- */
 #define MTZ_MODE_VERIFY      0  /* identity bytes; every stream checksum verified */
@@ -58,16 +59,27 @@ extern "C" {
 
 typedef struct mtz_handle mtz_handle;
 
+#define MTZ_MAX_DEVICES 16
+#define MTZ_MAX_PEERS   16
+
 typedef struct mtz_config {
-	uint32_t struct_size;   /* sizeof(mtz_config), for ABI growth */
-	int32_t  device;        /* CUDA ordinal */
+	uint32_t struct_size;   /* sizeof(mtz_config), for ABI growth (v1 callers stop after n_slots) */
+	int32_t  device;        /* CUDA ordinal (ignored when n_devices > 0) */
 	uint32_t mode;          /* MTZ_MODE_* */
 	uint32_t flags;         /* MTZ_FLAG_* */
 	uint64_t ring_bytes;    /* pinned input ring (0 = max(256 MiB, 2 x batch_bytes)) */
 	uint64_t out_ring_bytes;/* pinned output ring, codec modes (0 = ring_bytes) */
 	uint64_t batch_bytes;   /* target bytes per GPU batch (0 = 32 MiB; 256 MiB in codec modes) */
 	uint32_t record_bytes;  /* expected recordsize hint (0 = 131072) */
-	uint32_t n_slots;       /* batches in flight (0 = 4) */
+	uint32_t n_slots;       /* batches in flight PER DEVICE (0 = 4) */
+	/* ---- ABI v2: the GPUs of one box as ONE stage.  The stream is cut into whole-record
+	 * batches and batch b runs on devices[b % n_devices] (record-index partition); the only
+	 * thing that crosses between GPUs on the single-consumer path is the 64 bytes of running
+	 * checksums that hop with the batches.  The reference serves N peers with N independent
+	 * `zfs send`s (one _send per 'push', lib/backupSender.js:72-73); here one pass over the
+	 * stream feeds every attached peer (mtz_fanout_attach). ---- */
+	uint32_t n_devices;     /* 0 = just `device` */
+	int32_t  devices[MTZ_MAX_DEVICES];
 } mtz_config;
 
 typedef struct mtz_stats {
@@ -85,7 +97,8 @@ typedef struct mtz_stats {
 	double   k1_ms;         /* device time of the Fletcher-4 sums kernel (CUDA events) */
 	double   codec_ms;      /* device time of the LZ4 kernels */
 	uint64_t k1_launches;
-	uint64_t reserved[2];
+	double   k3_ms;         /* device time of the LZ4 encode kernel alone (CUDA events) */
+	uint64_t k3_launches;
 } mtz_stats;
 
 /* One DRR record as seen by the kernels (32 B, little endian). */
@@ -141,6 +154,23 @@ int32_t mtz_read(mtz_handle *h, void *buf, size_t cap, size_t *got, int32_t bloc
  * addon's uv_poll_t / napi_threadsafe_function wake-up source */
 int32_t mtz_event_fd(mtz_handle *h);
 
+/* ---- fan-out: several peers bootstrapping from the same snapshot share ONE pass.  Attach
+ * every peer before the first input byte.  Each peer owns a pinned output ring fed from its
+ * egress GPU devices[peer % n_devices] (one PCIe link / NIC queue per peer); in the re-encoding
+ * modes the processed batch reaches the egress GPUs by an NCCL broadcast over NVLink from the
+ * GPU that produced it (library-owned communicator), in VERIFY the verified input ring is shared
+ * in place.  mtz_out_peek/consume are the peer-0 forms.  Replaces: one socket per _send,
+ * lib/backupSender.js:166-179. ---- */
+int32_t mtz_fanout_attach(mtz_handle *h, int32_t peer_id);
+int32_t mtz_out_peek_peer(mtz_handle *h, int32_t peer_id, const void **ptr, size_t *n);
+int32_t mtz_out_consume_peer(mtz_handle *h, int32_t peer_id, size_t n);
+/* blocking read for one peer (mtz_read is the peer-0 form) */
+int32_t mtz_read_peer(mtz_handle *h, int32_t peer_id, void *buf, size_t cap, size_t *got, int32_t block);
+/* tear the pipe down from outside (socket error, stage.destroy()): fails the handle with
+ * MTZ_ECANCELED and wakes every blocked mtz_write / mtz_read, like the reference's
+ * zfsSend.kill() on a socket 'error' (lib/backupSender.js:230-233) */
+int32_t mtz_cancel(mtz_handle *h);
+
 /* counters for the job object the sender publishes through GET /backup/:uuid
  * (lib/backupServer.js:100-131 serialises the same object the sender mutates,
  * lib/backupSender.js:197-212): additive `job.gpu`, never read by the reference */
@@ -194,6 +224,16 @@ int32_t mtz_dev_finish_gathered(mtz_handle *h, const void *d_all_aggs, uint32_t 
     const uint64_t carry_out_in[4], size_t *out_bytes, uint64_t carry[4],
     uint64_t carry_out[4]);
 int32_t mtz_dev_reset(mtz_handle *h);
+/* ---- the same exchange with a library-owned NCCL communicator, one process per GPU (how
+ * bench.py runs under torchrun): rank 0 makes the id, the host application carries its 128
+ * bytes to the other ranks (any channel), every rank calls mtz_comm_init on its handle.
+ * mtz_dev_finish_exchange then does, stream-ordered and without a host round trip: all-gather
+ * of the 40-byte aggregates, carry fold, verify; in the re-encoding modes the 32-byte output
+ * checksum hops rank to rank (ncclRecv from rank-1, stamp chain, ncclSend to rank+1). ---- */
+int32_t mtz_comm_unique_id(uint8_t id[128]);
+int32_t mtz_comm_init(mtz_handle *h, const uint8_t id[128], int32_t rank, int32_t world);
+int32_t mtz_dev_finish_exchange(mtz_handle *h, size_t *out_bytes, uint64_t carry[4],
+    uint64_t carry_out[4]);
 /* set the running checksums a slice continues from (NULL = leave) */
 int32_t mtz_set_carry(mtz_handle *h, const uint64_t carry_in[4],
     const uint64_t carry_out[4]);

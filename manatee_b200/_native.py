@@ -10,8 +10,9 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.path.join(_HERE, "libmanatee_gpu.so")
 
-OK, EINVAL, EAGAIN, ECUDA, EFORMAT, ECKSUM, ECODEC, ENOSPC, ENOMEM, EOF, ENOGPU = \
-    0, -1, -2, -3, -4, -5, -6, -7, -8, -9, -10
+OK, EINVAL, EAGAIN, ECUDA, EFORMAT, ECKSUM, ECODEC, ENOSPC, ENOMEM, EOF, ENOGPU, ECANCELED = \
+    0, -1, -2, -3, -4, -5, -6, -7, -8, -9, -10, -11
+MAX_DEVICES, MAX_PEERS = 16, 16
 MODE_VERIFY, MODE_COMPRESS, MODE_DECOMPRESS, MODE_RECOMPRESS, MODE_PASSTHROUGH = 0, 1, 2, 3, 4
 FLAG_DEFER_VERIFY = 1
 MODE_NAMES = {"verify": 0, "compress": 1, "decompress": 2, "recompress": 3, "passthrough": 4}
@@ -26,7 +27,8 @@ class MtzError(RuntimeError):
 class Config(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("device", C.c_int32), ("mode", C.c_uint32),
                 ("flags", C.c_uint32), ("ring_bytes", C.c_uint64), ("out_ring_bytes", C.c_uint64),
-                ("batch_bytes", C.c_uint64), ("record_bytes", C.c_uint32), ("n_slots", C.c_uint32)]
+                ("batch_bytes", C.c_uint64), ("record_bytes", C.c_uint32), ("n_slots", C.c_uint32),
+                ("n_devices", C.c_uint32), ("devices", C.c_int32 * 16)]
 
 
 class Stats(C.Structure):
@@ -35,10 +37,10 @@ class Stats(C.Structure):
                 ("lz4_encoded", C.c_uint64), ("batches", C.c_uint64), ("bad_record", C.c_uint64),
                 ("kernel_launches", C.c_uint64), ("gpu_ms", C.c_double), ("end_seen", C.c_uint64),
                 ("k1_ms", C.c_double), ("codec_ms", C.c_double), ("k1_launches", C.c_uint64),
-                ("reserved", C.c_uint64 * 2)]
+                ("k3_ms", C.c_double), ("k3_launches", C.c_uint64)]
 
     def as_dict(self):
-        return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
+        return {k: getattr(self, k) for k, _ in self._fields_}
 
 
 class Rec(C.Structure):
@@ -55,6 +57,8 @@ SYMBOLS = [
     "mtz_index_host", "mtz_dev_index", "mtz_dev_submit", "mtz_dev_aggregate",
     "mtz_dev_finish", "mtz_dev_reset", "mtz_dev_aggregate_async", "mtz_dev_finish_gathered", "mtz_set_carry",
     "mtz_k_lz4_decode", "mtz_k_lz4_encode",
+    "mtz_fanout_attach", "mtz_out_peek_peer", "mtz_out_consume_peer", "mtz_read_peer", "mtz_cancel",
+    "mtz_comm_unique_id", "mtz_comm_init", "mtz_dev_finish_exchange",
 ]
 
 _lib = None
@@ -101,6 +105,14 @@ def lib():
     L.mtz_dev_finish_gathered.argtypes = [H, vp, C.c_uint32, vp, C.POINTER(sz), C.POINTER(u64 * 4),
                                           C.POINTER(u64 * 4)]
     L.mtz_set_carry.argtypes = [H, vp, vp]
+    L.mtz_fanout_attach.argtypes = [H, i32]
+    L.mtz_out_peek_peer.argtypes = [H, i32, C.POINTER(vp), C.POINTER(sz)]
+    L.mtz_out_consume_peer.argtypes = [H, i32, sz]
+    L.mtz_read_peer.argtypes = [H, i32, vp, sz, C.POINTER(sz), i32]
+    L.mtz_cancel.argtypes = [H]
+    L.mtz_comm_unique_id.argtypes = [vp]
+    L.mtz_comm_init.argtypes = [H, vp, i32, i32]
+    L.mtz_dev_finish_exchange.argtypes = [H, C.POINTER(sz), C.POINTER(u64 * 4), C.POINTER(u64 * 4)]
     L.mtz_k_lz4_decode.argtypes = [H, vp, vp, vp, C.c_uint32, vp]
     L.mtz_k_lz4_encode.argtypes = [H, vp, vp, vp, C.c_uint32, vp]
     for s in SYMBOLS:

@@ -8,6 +8,7 @@
 #include <thread>
 #include <vector>
 #include <cuda_runtime.h>
+#include <nccl.h>
 #include "../../include/manatee_gpu.h"
 #include "kernels_fletcher.cuh"
 #include "kernels_lz4.cuh"
@@ -32,7 +33,25 @@ struct CodecBufs {
 	size_t avg_out_rec = 128u << 10;                    // K1 lane-group choice for the output records
 };
 
+// One GPU of the handle's device group.  Batch b of the stream runs on devs[b % G] (record-index
+// partition); the running checksums hop from device to device with the batches.
+struct DevCtx {
+	int device = 0, sm_count = 0;
+	Ck4 *d_carry_in = nullptr;     // running checksum of the INPUT stream (valid on the device of the last batch)
+	Ck4 *d_carry_out = nullptr;    // ... of the OUTPUT stream (codec modes)
+	// fan-out (library-owned NCCL communicator over the group, one rank per device)
+	ncclComm_t comm = nullptr;
+	cudaStream_t fan_st = nullptr;                   // collectives + egress D2H of this device
+	uint8_t *fan_buf[2] = { nullptr, nullptr };      // receive side of the broadcast (double buffered)
+	size_t fan_cap = 0;
+	std::vector<cudaEvent_t> ev_pool;                // egress piece events (device bound)
+};
+
 struct Slot {
+	int di = 0;                   // index into mtz_handle::devs
+	uint64_t seq = 0;             // stream-wide batch number of the batch in the slot
+	int egress_left = 0;          // consumers that have not finished reading the slot's output
+	cudaEvent_t ev_scan = nullptr;   // running checksums updated (the next batch's chain waits on it)
 	uint8_t *d_in = nullptr;      // batch bytes (input stream slice)
 	uint8_t *d_out = nullptr;     // codec modes: output slice
 	size_t cap = 0, out_cap = 0;
@@ -47,6 +66,9 @@ struct Slot {
 	cudaEvent_t ev_start = nullptr, ev_done = nullptr;
 	cudaEvent_t ev_k1a = nullptr, ev_k1b = nullptr;
 	cudaEvent_t ev_c0 = nullptr, ev_c1 = nullptr;     // around K2+K3
+	cudaEvent_t ev_k3a = nullptr, ev_k3b = nullptr;   // around K3 alone
+	bool k3_timed = false;
+	bool d2h_pending = false;     // bulk API: the slot's output copy has been issued, not awaited
 	bool busy = false;
 	size_t nrec = 0, bytes = 0, out_bytes = 0;
 	uint64_t first_rec = 0;       // stream-wide index of the batch's first record
@@ -75,10 +97,15 @@ struct mtz_handle {
 	mtz::Ck4 *h_carry = nullptr;       // pinned scratch (4 entries)
 	uint64_t end_ck[4] = {0, 0, 0, 0};
 
-	std::vector<mtz::Slot> slots;
-	cudaStream_t st = nullptr;         // device-API stream
-	cudaEvent_t ev_prev_scan = nullptr;
-	bool have_prev_scan = false;
+	std::vector<mtz::DevCtx> devs;     // devs[0].device == device
+	std::vector<mtz::Slot> slots;      // slot k lives on devs[k % devs.size()]
+	cudaStream_t st = nullptr;         // device-API stream (devs[0])
+	int prev_scan_slot = -1;           // slot whose ev_scan the next batch's chain waits on
+	bool nccl_ready = false;
+	// multi-process shard exchange (mtz_comm_init): one rank per process on devs[0]
+	ncclComm_t xcomm = nullptr;
+	int xrank = 0, xworld = 1;
+	mtz::Part *d_xagg = nullptr, *d_xall = nullptr;
 	uint64_t records_done = 0;
 
 	// device-API / deferred-verify state: one growing table of per-record sums
@@ -91,6 +118,8 @@ struct mtz_handle {
 	cudaStream_t dv_st = nullptr;
 	cudaEvent_t dv_k1a = nullptr, dv_k1b = nullptr;
 	cudaEvent_t dv_c0 = nullptr, dv_c1 = nullptr;
+	std::vector<cudaEvent_t> dv_k3ev;  // pairs around the K3 launch of every sub-batch
+	size_t dv_k3n = 0;
 	bool dv_timed = false;
 
 	mtz::CodecBufs dv_cb, dv_cb2;      // device-API codec scratch (sub-batched, double-buffered)
@@ -118,6 +147,14 @@ int32_t fail(mtz_handle *h, int32_t code, const char *fmt, ...);
 int32_t fail_cuda(mtz_handle *h, cudaError_t e, const char *what);
 void engine_wake_all(mtz_handle *h);
 }
+
+#define MTZ_NCCL(h, call)                                                      \
+	do {                                                                       \
+		ncclResult_t r__ = (call);                                             \
+		if (r__ != ncclSuccess)                                                \
+			return mtz::fail((h), MTZ_ECUDA, "NCCL error %d (%s) at %s", (int)r__, \
+			    ncclGetErrorString(r__), #call);                               \
+	} while (0)
 
 #define MTZ_CU(h, call)                                                        \
 	do {                                                                       \

@@ -172,17 +172,21 @@ int32_t mtz_index_host(const void *buf, size_t n, mtz_rec *recs, size_t cap,
 }
 
 // ------------------------------------------------------------- lifecycle --
-static int32_t alloc_slot(mtz_handle *h, Slot &s, size_t cap, size_t rec_cap)
+static int32_t alloc_slot(mtz_handle *h, Slot &s, int di, size_t cap, size_t rec_cap)
 {
-	s.cap = cap; s.rec_cap = rec_cap;
+	s.cap = cap; s.rec_cap = rec_cap; s.di = di;
+	MTZ_CU(h, cudaSetDevice(h->devs[di].device));
 	MTZ_CU(h, cudaMalloc(&s.d_in, cap + 512));
 	MTZ_CU(h, cudaMalloc(&s.d_recs, rec_cap * sizeof(mtz_rec)));
-	MTZ_CU(h, cudaHostAlloc(&s.h_recs, rec_cap * sizeof(mtz_rec), cudaHostAllocDefault));
+	MTZ_CU(h, cudaHostAlloc(&s.h_recs, rec_cap * sizeof(mtz_rec), cudaHostAllocPortable));
 	MTZ_CU(h, cudaMalloc(&s.d_sums, rec_cap * sizeof(RecSums)));
 	MTZ_CU(h, cudaMalloc(&s.d_tiles, (rec_cap / SCAN_TILE + 2) * sizeof(Part)));
 	MTZ_CU(h, cudaMalloc(&s.d_res, sizeof(ScanResult)));
-	MTZ_CU(h, cudaHostAlloc(&s.h_res, sizeof(ScanResult), cudaHostAllocDefault));
+	MTZ_CU(h, cudaHostAlloc(&s.h_res, sizeof(ScanResult), cudaHostAllocPortable));
 	MTZ_CU(h, cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking));
+	MTZ_CU(h, cudaEventCreateWithFlags(&s.ev_scan, cudaEventDisableTiming));
+	MTZ_CU(h, cudaEventCreate(&s.ev_k3a));
+	MTZ_CU(h, cudaEventCreate(&s.ev_k3b));
 	MTZ_CU(h, cudaEventCreate(&s.ev_start));
 	MTZ_CU(h, cudaEventCreate(&s.ev_done));
 	MTZ_CU(h, cudaEventCreate(&s.ev_k1a));
@@ -211,6 +215,9 @@ static void free_slot(Slot &s)
 	if (s.ev_k1b) cudaEventDestroy(s.ev_k1b);
 	if (s.ev_c0) cudaEventDestroy(s.ev_c0);
 	if (s.ev_c1) cudaEventDestroy(s.ev_c1);
+	if (s.ev_scan) cudaEventDestroy(s.ev_scan);
+	if (s.ev_k3a) cudaEventDestroy(s.ev_k3a);
+	if (s.ev_k3b) cudaEventDestroy(s.ev_k3b);
 	codec_free(s.cb);
 	s = Slot();
 }
@@ -234,17 +241,34 @@ int32_t mtz_open(const mtz_config *cfg, mtz_handle **out)
 		return fail(nullptr, MTZ_ENOGPU, "no CUDA device: %s (there is no CPU fallback)",
 		    cudaGetErrorString(e));
 	}
-	if (cfg->device < 0 || cfg->device >= ndev)
-		return fail(nullptr, MTZ_EINVAL, "device %d out of range (%d visible)", cfg->device, ndev);
-	cudaDeviceProp prop;
-	if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess || prop.major != 10)
-		return fail(nullptr, MTZ_ENOGPU, "device %d is sm_%d%d; this library is built for sm_100a only",
-		    cfg->device, prop.major, prop.minor);
+	// the device group: v1 callers (struct_size ends before n_devices) and n_devices == 0 get
+	// the single `device`
+	mtz_config full;
+	memset(&full, 0, sizeof full);
+	memcpy(&full, cfg, std::min((size_t)cfg->struct_size, sizeof full));
+	if (full.n_devices > MTZ_MAX_DEVICES)
+		return fail(nullptr, MTZ_EINVAL, "n_devices %u exceeds %d", full.n_devices, MTZ_MAX_DEVICES);
+	if (full.n_devices == 0) { full.n_devices = 1; full.devices[0] = full.device; }
+	full.device = full.devices[0];
+	std::vector<cudaDeviceProp> props(full.n_devices);
+	for (uint32_t i = 0; i < full.n_devices; i++) {
+		const int d = full.devices[i];
+		if (d < 0 || d >= ndev)
+			return fail(nullptr, MTZ_EINVAL, "device %d out of range (%d visible)", d, ndev);
+		for (uint32_t k = 0; k < i; k++)
+			if (full.devices[k] == d) return fail(nullptr, MTZ_EINVAL, "device %d listed twice", d);
+		if (cudaGetDeviceProperties(&props[i], d) != cudaSuccess || props[i].major != 10)
+			return fail(nullptr, MTZ_ENOGPU, "device %d is sm_%d%d; this library is built for sm_100a only",
+			    d, props[i].major, props[i].minor);
+	}
+	if (full.n_devices > 1 && (full.flags & MTZ_FLAG_DEFER_VERIFY))
+		return fail(nullptr, MTZ_EINVAL, "a device group verifies in stream order; DEFER_VERIFY is the "
+		    "one-GPU-per-process shard form");
+	const cudaDeviceProp &prop = props[0];
 
 	mtz_handle *h = new (std::nothrow) mtz_handle();
 	if (h == nullptr) return fail(nullptr, MTZ_ENOMEM, "handle allocation");
-	memset(&h->cfg, 0, sizeof h->cfg);
-	memcpy(&h->cfg, cfg, std::min((size_t)cfg->struct_size, sizeof h->cfg));
+	h->cfg = full;
 	const bool codec_mode = cfg->mode == MTZ_MODE_COMPRESS || cfg->mode == MTZ_MODE_DECOMPRESS ||
 	    cfg->mode == MTZ_MODE_RECOMPRESS;
 	// the LZ4 kernels want thousands of records in flight (one warp per record, ~5 ms per
@@ -256,25 +280,45 @@ int32_t mtz_open(const mtz_config *cfg, mtz_handle **out)
 	if (h->cfg.record_bytes == 0) h->cfg.record_bytes = 131072;
 	if (h->cfg.n_slots == 0) h->cfg.n_slots = 4;
 	if (h->cfg.n_slots > 16) h->cfg.n_slots = 16;
-	h->device = cfg->device;
+	h->device = full.device;
 	h->sm_count = prop.multiProcessorCount;
 	h->stats.bad_record = ~0ull;
+	h->devs.resize(full.n_devices);
 
 	int32_t rc = MTZ_OK;
 	auto init = [&]() -> int32_t {
-		MTZ_CU(h, cudaSetDevice(h->device));
+		// every GPU of the group: its copy of the running checksums, the K3 attributes (they
+		// are per device) and peer access for the 64-byte checksum hop
+		for (size_t i = h->devs.size(); i-- > 0;) {
+			DevCtx &dc = h->devs[i];
+			dc.device = full.devices[i];
+			dc.sm_count = props[i].multiProcessorCount;
+			MTZ_CU(h, cudaSetDevice(dc.device));
+			MTZ_CU(h, cudaMalloc(&dc.d_carry_in, sizeof(Ck4)));
+			MTZ_CU(h, cudaMalloc(&dc.d_carry_out, sizeof(Ck4)));
+			MTZ_CU(h, cudaMemset(dc.d_carry_in, 0, sizeof(Ck4)));
+			MTZ_CU(h, cudaMemset(dc.d_carry_out, 0, sizeof(Ck4)));
+			int32_t r = k3_set_attributes(h);
+			if (r != MTZ_OK) return r;
+			for (size_t k = 0; k < h->devs.size(); k++) {
+				if (k == i) continue;
+				int can = 0;
+				if (cudaDeviceCanAccessPeer(&can, dc.device, full.devices[k]) == cudaSuccess && can) {
+					cudaError_t pe = cudaDeviceEnablePeerAccess(full.devices[k], 0);
+					if (pe != cudaSuccess) (void)cudaGetLastError();     // already enabled: fine
+				}
+			}
+		}
+		// the loop ends on devs[0]: the device-resident API lives there
+		h->d_carry_in = h->devs[0].d_carry_in;
+		h->d_carry_out = h->devs[0].d_carry_out;
 		MTZ_CU(h, cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
-		MTZ_CU(h, cudaEventCreateWithFlags(&h->ev_prev_scan, cudaEventDisableTiming));
-		MTZ_CU(h, cudaMalloc(&h->d_carry_in, sizeof(Ck4)));
-		MTZ_CU(h, cudaMalloc(&h->d_carry_out, sizeof(Ck4)));
-		MTZ_CU(h, cudaHostAlloc(&h->h_carry, 4 * sizeof(Ck4), cudaHostAllocDefault));
-		MTZ_CU(h, cudaMemset(h->d_carry_in, 0, sizeof(Ck4)));
-		MTZ_CU(h, cudaMemset(h->d_carry_out, 0, sizeof(Ck4)));
+		MTZ_CU(h, cudaHostAlloc(&h->h_carry, 4 * sizeof(Ck4), cudaHostAllocPortable));
 		MTZ_CU(h, cudaMalloc(&h->dv_res, sizeof(ScanResult)));
-		MTZ_CU(h, cudaHostAlloc(&h->dv_hres, sizeof(ScanResult), cudaHostAllocDefault));
+		MTZ_CU(h, cudaHostAlloc(&h->dv_hres, sizeof(ScanResult), cudaHostAllocPortable));
 		MTZ_CU(h, cudaEventCreate(&h->dv_k1a));
 		MTZ_CU(h, cudaEventCreate(&h->dv_k1b));
-		return k3_set_attributes(h);
+		return MTZ_OK;
 	};
 	rc = init();
 	if (rc != MTZ_OK) {
@@ -287,13 +331,20 @@ int32_t mtz_open(const mtz_config *cfg, mtz_handle **out)
 }
 
 static void engine_destroy(mtz_handle *h);
+static void fanout_destroy(mtz_handle *h);
 
 int32_t mtz_close(mtz_handle *h)
 {
 	if (h == nullptr) return MTZ_EINVAL;
 	cudaSetDevice(h->device);
 	engine_destroy(h);
-	cudaDeviceSynchronize();
+	for (auto &dc : h->devs) { cudaSetDevice(dc.device); cudaDeviceSynchronize(); }
+	fanout_destroy(h);
+	if (h->xcomm) ncclCommDestroy(h->xcomm);
+	cudaSetDevice(h->device);
+	if (h->d_xagg) cudaFree(h->d_xagg);
+	if (h->d_xall) cudaFree(h->d_xall);
+	for (cudaEvent_t e : h->dv_k3ev) cudaEventDestroy(e);
 	if (h->dv_c0) cudaEventDestroy(h->dv_c0);
 	if (h->dv_c1) cudaEventDestroy(h->dv_c1);
 	if (h->dv_cb2.cr != nullptr) {
@@ -319,16 +370,19 @@ int32_t mtz_close(mtz_handle *h)
 	if (h->h_ires) cudaFreeHost(h->h_ires);
 	if (h->dv_k1a) cudaEventDestroy(h->dv_k1a);
 	if (h->dv_k1b) cudaEventDestroy(h->dv_k1b);
-	for (auto &s : h->slots) free_slot(s);
+	for (auto &s : h->slots) { cudaSetDevice(h->devs[s.di].device); free_slot(s); }
+	cudaSetDevice(h->device);
 	if (h->dv_sums) cudaFree(h->dv_sums);
 	if (h->dv_tiles) cudaFree(h->dv_tiles);
 	if (h->dv_res) cudaFree(h->dv_res);
 	if (h->dv_hres) cudaFreeHost(h->dv_hres);
-	if (h->d_carry_in) cudaFree(h->d_carry_in);
-	if (h->d_carry_out) cudaFree(h->d_carry_out);
 	if (h->h_carry) cudaFreeHost(h->h_carry);
-	if (h->ev_prev_scan) cudaEventDestroy(h->ev_prev_scan);
 	if (h->st) cudaStreamDestroy(h->st);
+	for (auto &dc : h->devs) {
+		cudaSetDevice(dc.device);
+		if (dc.d_carry_in) cudaFree(dc.d_carry_in);
+		if (dc.d_carry_out) cudaFree(dc.d_carry_out);
+	}
 	delete h;
 	return MTZ_OK;
 }
@@ -408,12 +462,13 @@ static int32_t launch_k1(mtz_handle *h, cudaStream_t st, const uint8_t *d_in,
 // Segmented scan of a batch's per-record sums.  phase 0: aggregate only;
 // phase 1: also verify against the running checksum in h->d_carry_in.
 static int32_t launch_scan(mtz_handle *h, cudaStream_t st, const RecSums *d_sums, size_t nrec,
-    Part *d_tiles, ScanResult *d_res, int phase)
+    Part *d_tiles, ScanResult *d_res, int phase, const Ck4 *d_carry_in = nullptr)
 {
+	if (d_carry_in == nullptr) d_carry_in = h->d_carry_in;
 	MTZ_CU(h, cudaMemsetAsync(d_res, 0, sizeof(ScanResult), st));
 	if (nrec == 0) {
 		MTZ_CU(h, cudaMemsetAsync(&d_res->bad, 0xff, sizeof(uint32_t), st));
-		MTZ_CU(h, cudaMemcpyAsync(&d_res->carry, h->d_carry_in, sizeof(Ck4), cudaMemcpyDeviceToDevice, st));
+		MTZ_CU(h, cudaMemcpyAsync(&d_res->carry, d_carry_in, sizeof(Ck4), cudaMemcpyDeviceToDevice, st));
 		return MTZ_OK;
 	}
 	const unsigned ntiles = (unsigned)((nrec + SCAN_TILE - 1) / SCAN_TILE);
@@ -421,7 +476,7 @@ static int32_t launch_scan(mtz_handle *h, cudaStream_t st, const RecSums *d_sums
 	k_scan_spine<<<1, SCAN_THREADS, 0, st>>>(d_tiles, ntiles, d_res);
 	if (phase == 1)
 		k_scan_verify<<<ntiles, SCAN_THREADS, 0, st>>>(d_sums, (uint32_t)nrec, d_tiles,
-		    h->d_carry_in, d_res);
+		    d_carry_in, d_res);
 	MTZ_CU(h, cudaGetLastError());
 	count_launch(h, phase == 1 ? 3 : 2);
 	return MTZ_OK;
@@ -514,16 +569,18 @@ static bool all_compact_blocks(const mtz_rec *recs, size_t n)
 
 static int32_t codec_launch_dec(mtz_handle *h, cudaStream_t st, CodecBufs &cb, const uint8_t *d_in,
     const mtz_rec *d_recs, size_t nrec);
-static int32_t codec_launch_enc(mtz_handle *h, cudaStream_t st, CodecBufs &cb, size_t nrec, bool compact);
+static int32_t codec_launch_enc(mtz_handle *h, cudaStream_t st, CodecBufs &cb, size_t nrec, bool compact,
+    cudaEvent_t ka = nullptr, cudaEvent_t kb = nullptr);
 
 static int32_t codec_launch_pre(mtz_handle *h, cudaStream_t st, CodecBufs &cb, const uint8_t *d_in,
-    const mtz_rec *d_recs, size_t nrec, cudaEvent_t ea, cudaEvent_t eb, bool compact)
+    const mtz_rec *d_recs, size_t nrec, cudaEvent_t ea, cudaEvent_t eb, bool compact,
+    cudaEvent_t ka = nullptr, cudaEvent_t kb = nullptr)
 {
 	if (nrec == 0) return MTZ_OK;
 	if (ea) MTZ_CU(h, cudaEventRecord(ea, st));
 	int32_t rc = codec_launch_dec(h, st, cb, d_in, d_recs, nrec);
 	if (rc != MTZ_OK) return rc;
-	rc = codec_launch_enc(h, st, cb, nrec, compact);
+	rc = codec_launch_enc(h, st, cb, nrec, compact, ka, kb);
 	if (rc != MTZ_OK) return rc;
 	if (eb) MTZ_CU(h, cudaEventRecord(eb, st));
 	return MTZ_OK;
@@ -550,10 +607,14 @@ static int32_t codec_launch_dec(mtz_handle *h, cudaStream_t st, CodecBufs &cb, c
 }
 
 // K3 (encode) of one (sub-)batch
-static int32_t codec_launch_enc(mtz_handle *h, cudaStream_t st, CodecBufs &cb, size_t nrec, bool compact)
+static int32_t codec_launch_enc(mtz_handle *h, cudaStream_t st, CodecBufs &cb, size_t nrec, bool compact,
+    cudaEvent_t ka, cudaEvent_t kb)
 {
 	if (nrec == 0 || h->cfg.mode == MTZ_MODE_DECOMPRESS) return MTZ_OK;
-	return launch_k3(h, st, nullptr, nullptr, cb.enc, (uint32_t)nrec, compact);
+	if (ka) MTZ_CU(h, cudaEventRecord(ka, st));
+	int32_t rc = launch_k3(h, st, nullptr, nullptr, cb.enc, (uint32_t)nrec, compact);
+	if (rc == MTZ_OK && kb) MTZ_CU(h, cudaEventRecord(kb, st));
+	return rc;
 }
 
 // Part 2: layout, assemble into d_out + *cb.d_outpos (the running output offset
@@ -561,9 +622,10 @@ static int32_t codec_launch_enc(mtz_handle *h, cudaStream_t st, CodecBufs &cb, s
 // the output records, and the sequential stamp chain from h->d_carry_out.
 static int32_t codec_launch_post(mtz_handle *h, cudaStream_t st, CodecBufs &cb, const uint8_t *d_in,
     const mtz_rec *d_recs, size_t nrec, uint8_t *d_out, uint32_t rec_base,
-    mtz_rec *all_orecs = nullptr, RecSums *all_osums = nullptr)
+    mtz_rec *all_orecs = nullptr, RecSums *all_osums = nullptr, Ck4 *d_carry_out = nullptr)
 {
 	if (nrec == 0) return MTZ_OK;
+	if (d_carry_out == nullptr) d_carry_out = h->d_carry_out;
 	// shard mode: output record table / sums are kept for the whole submit and the
 	// stamp chain runs later (mtz_dev_finish) from the previous shard's checksum
 	mtz_rec *orecs = all_orecs ? all_orecs + rec_base : cb.out_recs;
@@ -581,7 +643,7 @@ static int32_t codec_launch_post(mtz_handle *h, cudaStream_t st, CodecBufs &cb, 
 	if (all_osums == nullptr) {
 		const unsigned gp = (n + 127u) / 128u;
 		k_stamp_prep<<<gp, 128, 0, st>>>(orecs, osums, n, cb.steps);
-		k_stamp_chain<<<1, STAMP_THREADS, 0, st>>>(d_out, orecs, osums, cb.steps, n, h->d_carry_out, cb.d_ores);
+		k_stamp_chain<<<1, STAMP_THREADS, 0, st>>>(d_out, orecs, osums, cb.steps, n, d_carry_out, cb.d_ores);
 		count_launch(h, 2);
 	}
 	MTZ_CU(h, cudaGetLastError());
@@ -714,7 +776,14 @@ int32_t mtz_dev_submit(mtz_handle *h, const void *d_in, size_t in_bytes,
 		if (rc != MTZ_OK) return rc;
 		MTZ_CU(h, cudaEventRecord(h->ev_dec[b], h->st_dec));
 		MTZ_CU(h, cudaStreamWaitEvent(st, h->ev_dec[b], 0));
-		rc = codec_launch_enc(h, st, cb, i1 - i0, all_compact_blocks(h->dv_hrecs.data() + i0, i1 - i0));
+		while (h->dv_k3ev.size() < 2 * (k + 1)) {
+			cudaEvent_t ev = nullptr;
+			MTZ_CU(h, cudaEventCreate(&ev));
+			h->dv_k3ev.push_back(ev);
+		}
+		rc = codec_launch_enc(h, st, cb, i1 - i0, all_compact_blocks(h->dv_hrecs.data() + i0, i1 - i0),
+		    h->cfg.mode == MTZ_MODE_DECOMPRESS ? nullptr : h->dv_k3ev[2 * k],
+		    h->cfg.mode == MTZ_MODE_DECOMPRESS ? nullptr : h->dv_k3ev[2 * k + 1]);
 		if (rc != MTZ_OK) return rc;
 		MTZ_CU(h, cudaEventRecord(h->ev_pre[b], st));
 		MTZ_CU(h, cudaStreamWaitEvent(h->st_post, h->ev_pre[b], 0));
@@ -729,6 +798,7 @@ int32_t mtz_dev_submit(mtz_handle *h, const void *d_in, size_t in_bytes,
 	for (int b = 0; b < 2; b++)
 		if (used[b]) MTZ_CU(h, cudaStreamWaitEvent(st, h->ev_post[b], 0));
 	MTZ_CU(h, cudaEventRecord(h->dv_c1, st));
+	h->dv_k3n = (h->cfg.mode == MTZ_MODE_DECOMPRESS) ? 0 : k;
 	return MTZ_OK;
 }
 
@@ -787,7 +857,7 @@ int32_t mtz_dev_aggregate_async(mtz_handle *h, void *d_agg)
 
 static int32_t dev_finish_impl(mtz_handle *h, const uint64_t carry_in[4], const void *d_all_aggs,
     uint32_t rank, const uint64_t carry_out_in[4], size_t *out_bytes, uint64_t carry[4],
-    uint64_t carry_out[4]);
+    uint64_t carry_out[4], bool xchg = false);
 
 int32_t mtz_dev_finish(mtz_handle *h, const uint64_t carry_in[4], const uint64_t carry_out_in[4],
     size_t *out_bytes, uint64_t carry[4], uint64_t carry_out[4])
@@ -802,9 +872,49 @@ int32_t mtz_dev_finish_gathered(mtz_handle *h, const void *d_all_aggs, uint32_t 
 	return dev_finish_impl(h, nullptr, d_all_aggs, rank, carry_out_in, out_bytes, carry, carry_out);
 }
 
+// ---- library-owned NCCL for the one-process-per-GPU shard form -----------------------------
+int32_t mtz_comm_unique_id(uint8_t id[128])
+{
+	if (id == nullptr) return MTZ_EINVAL;
+	static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+	ncclUniqueId u;
+	if (ncclGetUniqueId(&u) != ncclSuccess) return MTZ_ECUDA;
+	memcpy(id, &u, 128);
+	return MTZ_OK;
+}
+
+int32_t mtz_comm_init(mtz_handle *h, const uint8_t id[128], int32_t rank, int32_t world)
+{
+	CHECK_H(h);
+	if (id == nullptr || world < 1 || rank < 0 || rank >= world) return fail(h, MTZ_EINVAL, "bad rank/world");
+	if (h->xcomm != nullptr) return fail(h, MTZ_EINVAL, "communicator already initialised");
+	MTZ_CU(h, cudaSetDevice(h->device));
+	ncclUniqueId u;
+	memcpy(&u, id, 128);
+	MTZ_NCCL(h, ncclCommInitRank(&h->xcomm, world, u, rank));
+	h->xrank = rank; h->xworld = world;
+	MTZ_CU(h, cudaMalloc(&h->d_xagg, sizeof(Part)));
+	MTZ_CU(h, cudaMalloc(&h->d_xall, (size_t)world * sizeof(Part)));
+	return MTZ_OK;
+}
+
+int32_t mtz_dev_finish_exchange(mtz_handle *h, size_t *out_bytes, uint64_t carry[4], uint64_t carry_out[4])
+{
+	CHECK_H(h);
+	if (h->xcomm == nullptr) return fail(h, MTZ_EINVAL, "mtz_comm_init first");
+	MTZ_CU(h, cudaSetDevice(h->device));
+	cudaStream_t st = h->dv_st ? h->dv_st : h->st;
+	// the 40-byte aggregate of this shard -> all ranks (the path's one collective)
+	int32_t rc = launch_scan(h, st, h->dv_sums, h->dv_nrec, h->dv_tiles, h->dv_res, 0);
+	if (rc != MTZ_OK) return rc;
+	MTZ_CU(h, cudaMemcpyAsync(h->d_xagg, &h->dv_res->agg, sizeof(Part), cudaMemcpyDeviceToDevice, st));
+	MTZ_NCCL(h, ncclAllGather(h->d_xagg, h->d_xall, sizeof(Part) / 8, ncclUint64, h->xcomm, st));
+	return dev_finish_impl(h, nullptr, h->d_xall, (uint32_t)h->xrank, nullptr, out_bytes, carry, carry_out, true);
+}
+
 static int32_t dev_finish_impl(mtz_handle *h, const uint64_t carry_in[4], const void *d_all_aggs,
     uint32_t rank, const uint64_t carry_out_in[4], size_t *out_bytes, uint64_t carry[4],
-    uint64_t carry_out[4])
+    uint64_t carry_out[4], bool xchg)
 {
 	CHECK_H(h);
 	MTZ_CU(h, cudaSetDevice(h->device));
@@ -827,6 +937,10 @@ static int32_t dev_finish_impl(mtz_handle *h, const uint64_t carry_in[4], const 
 	MTZ_CU(h, cudaMemcpyAsync(h->dv_hres, h->dv_res, sizeof(ScanResult), cudaMemcpyDeviceToHost, st));
 	MTZ_CU(h, cudaMemcpyAsync(h->d_carry_in, &h->dv_res->carry, 32, cudaMemcpyDeviceToDevice, st));
 	const bool codec = is_codec_mode(h->cfg.mode) && h->dv_cb.cr != nullptr;
+	const bool hop = xchg && is_codec_mode(h->cfg.mode) && (h->cfg.flags & MTZ_FLAG_DEFER_VERIFY);
+	// the output checksum hops rank to rank: 32 bytes in from the shard before, stamp, 32 out
+	if (hop && h->xrank > 0)
+		MTZ_NCCL(h, ncclRecv(h->d_carry_out, 4, ncclUint64, h->xrank - 1, h->xcomm, st));
 	if (codec && (h->cfg.flags & MTZ_FLAG_DEFER_VERIFY) && h->dv_nrec > 0) {
 		// shard mode: the stamp chain of the whole shard, from the checksum the previous
 		// shard's output ended with (carry_out_in, uploaded above)
@@ -838,6 +952,8 @@ static int32_t dev_finish_impl(mtz_handle *h, const uint64_t carry_in[4], const 
 		MTZ_CU(h, cudaGetLastError());
 		count_launch(h, 2);
 	}
+	if (hop && h->xrank + 1 < h->xworld)
+		MTZ_NCCL(h, ncclSend(h->d_carry_out, 4, ncclUint64, h->xrank + 1, h->xcomm, st));
 	if (codec) {
 		MTZ_CU(h, cudaMemcpyAsync(h->dv_cb.h_cres, h->dv_cb.d_cres, sizeof(CodecResult), cudaMemcpyDeviceToHost, st));
 		MTZ_CU(h, cudaMemcpyAsync(h->dv_cb.h_ores, h->dv_cb.d_ores, sizeof(ScanResult), cudaMemcpyDeviceToHost, st));
@@ -849,6 +965,14 @@ static int32_t dev_finish_impl(mtz_handle *h, const uint64_t carry_in[4], const 
 			std::lock_guard<std::mutex> g(h->stats_mu);
 			h->stats.codec_ms += cm;
 		}
+		for (size_t i = 0; i < h->dv_k3n; i++) {
+			float km = 0;
+			if (cudaEventElapsedTime(&km, h->dv_k3ev[2 * i], h->dv_k3ev[2 * i + 1]) == cudaSuccess) {
+				std::lock_guard<std::mutex> g(h->stats_mu);
+				h->stats.k3_ms += km; h->stats.k3_launches += 1;
+			}
+		}
+		h->dv_k3n = 0;
 	}
 	if (h->dv_timed) {
 		float ms = 0;
@@ -896,9 +1020,12 @@ static int32_t ensure_slots(mtz_handle *h)
 	if (!h->slots.empty()) return MTZ_OK;
 	const size_t cap = (size_t)h->cfg.batch_bytes + MAX_RECORD_BYTES;
 	const size_t rec_cap = std::max<size_t>(4096, cap / 1024);
-	h->slots.resize(h->cfg.n_slots);
-	for (auto &s : h->slots) {
-		int32_t rc = alloc_slot(h, s, cap, rec_cap);
+	// n_slots batches in flight per device; consecutive batches land on consecutive devices
+	const size_t G = h->devs.size();
+	h->slots.resize((size_t)h->cfg.n_slots * G);
+	for (size_t k = 0; k < h->slots.size(); k++) {
+		Slot &s = h->slots[k];
+		int32_t rc = alloc_slot(h, s, (int)(k % G), cap, rec_cap);
 		if (rc != MTZ_OK) return rc;
 		if (is_codec_mode(h->cfg.mode)) {
 			s.out_cap = cap;
@@ -907,6 +1034,7 @@ static int32_t ensure_slots(mtz_handle *h)
 			if (rc != MTZ_OK) return rc;
 		}
 	}
+	MTZ_CU(h, cudaSetDevice(h->device));
 	return MTZ_OK;
 }
 
@@ -952,7 +1080,9 @@ static int32_t harvest(mtz_handle *h, Slot &s)
 	if (!s.busy) return MTZ_OK;
 	MTZ_CU(h, cudaEventSynchronize(s.ev_done));
 	s.busy = false;
-	float ms = 0, k1 = 0, cm = 0;
+	float ms = 0, k1 = 0, cm = 0, k3 = 0;
+	const bool k3ok = s.k3_timed && cudaEventElapsedTime(&k3, s.ev_k3a, s.ev_k3b) == cudaSuccess;
+	s.k3_timed = false;
 	cudaEventElapsedTime(&ms, s.ev_start, s.ev_done);
 	const bool codec = is_codec_mode(h->cfg.mode);
 	const bool k1ok = s.nrec > 0 && cudaEventElapsedTime(&k1, s.ev_k1a, s.ev_k1b) == cudaSuccess;
@@ -963,6 +1093,7 @@ static int32_t harvest(mtz_handle *h, Slot &s)
 		h->stats.write_records += s.writes;
 		if (k1ok) { h->stats.k1_ms += k1; h->stats.k1_launches += 1; }
 		if (cok) h->stats.codec_ms += cm;
+		if (k3ok) { h->stats.k3_ms += k3; h->stats.k3_launches += 1; }
 	}
 	if (h->cfg.mode == MTZ_MODE_PASSTHROUGH || (h->cfg.flags & MTZ_FLAG_DEFER_VERIFY)) {
 		std::lock_guard<std::mutex> g(h->stats_mu);
@@ -1001,9 +1132,11 @@ static int32_t submit_batch(mtz_handle *h, Slot &s, const uint8_t *p0, size_t n0
     const uint8_t *p1, size_t n1, size_t nrec, uint64_t abs_off, uint8_t *host_out)
 {
 	const size_t bytes = n0 + n1;
+	DevCtx &dc = h->devs[s.di];
 	s.nrec = nrec; s.bytes = bytes; s.out_bytes = bytes; s.in_off = abs_off;
 	s.first_rec = h->records_done;
 	h->records_done += nrec;
+	MTZ_CU(h, cudaSetDevice(dc.device));
 	MTZ_CU(h, cudaEventRecord(s.ev_start, s.st));
 	if (nrec > 0)
 		MTZ_CU(h, cudaMemcpyAsync(s.d_recs, s.h_recs, nrec * sizeof(mtz_rec), cudaMemcpyHostToDevice, s.st));
@@ -1028,22 +1161,35 @@ static int32_t submit_batch(mtz_handle *h, Slot &s, const uint8_t *p0, size_t n0
 			rc = codec_reset(h, s.st, s.cb);
 			if (rc != MTZ_OK) return rc;
 			// K2/K3 of this batch overlap the previous batch's checksum chains
+			const bool enc = h->cfg.mode != MTZ_MODE_DECOMPRESS && nrec > 0;
 			rc = codec_launch_pre(h, s.st, s.cb, s.d_in, s.d_recs, nrec, s.ev_c0, s.ev_c1,
-			    all_compact_blocks(s.h_recs, nrec));
+			    all_compact_blocks(s.h_recs, nrec), enc ? s.ev_k3a : nullptr, enc ? s.ev_k3b : nullptr);
 			if (rc != MTZ_OK) return rc;
+			s.k3_timed = enc;
 		}
-		if (h->have_prev_scan) MTZ_CU(h, cudaStreamWaitEvent(s.st, h->ev_prev_scan, 0));
-		rc = launch_scan(h, s.st, s.d_sums, nrec, s.d_tiles, s.d_res, 1);
+		// the running checksums arrive with the previous batch: wait for its chain and, when it
+		// ran on another GPU of the group, fetch the 64 bytes over NVLink / PCIe
+		if (h->prev_scan_slot >= 0) {
+			const Slot &ps = h->slots[(size_t)h->prev_scan_slot];
+			MTZ_CU(h, cudaStreamWaitEvent(s.st, ps.ev_scan, 0));
+			if (ps.di != s.di) {
+				const DevCtx &pd = h->devs[ps.di];
+				MTZ_CU(h, cudaMemcpyPeerAsync(dc.d_carry_in, dc.device, pd.d_carry_in, pd.device, sizeof(Ck4), s.st));
+				MTZ_CU(h, cudaMemcpyPeerAsync(dc.d_carry_out, dc.device, pd.d_carry_out, pd.device, sizeof(Ck4), s.st));
+			}
+		}
+		rc = launch_scan(h, s.st, s.d_sums, nrec, s.d_tiles, s.d_res, 1, dc.d_carry_in);
 		if (rc != MTZ_OK) return rc;
-		MTZ_CU(h, cudaMemcpyAsync(h->d_carry_in, &s.d_res->carry, 32, cudaMemcpyDeviceToDevice, s.st));
+		MTZ_CU(h, cudaMemcpyAsync(dc.d_carry_in, &s.d_res->carry, 32, cudaMemcpyDeviceToDevice, s.st));
 		if (is_codec_mode(h->cfg.mode)) {
-			rc = codec_launch_post(h, s.st, s.cb, s.d_in, s.d_recs, nrec, s.d_out, 0u);
+			rc = codec_launch_post(h, s.st, s.cb, s.d_in, s.d_recs, nrec, s.d_out, 0u, nullptr, nullptr,
+			    dc.d_carry_out);
 			if (rc != MTZ_OK) return rc;
 			MTZ_CU(h, cudaMemcpyAsync(s.cb.h_cres, s.cb.d_cres, sizeof(CodecResult), cudaMemcpyDeviceToHost, s.st));
 			MTZ_CU(h, cudaMemcpyAsync(s.cb.h_ores, s.cb.d_ores, sizeof(ScanResult), cudaMemcpyDeviceToHost, s.st));
 		}
-		MTZ_CU(h, cudaEventRecord(h->ev_prev_scan, s.st));
-		h->have_prev_scan = true;
+		MTZ_CU(h, cudaEventRecord(s.ev_scan, s.st));
+		h->prev_scan_slot = (int)(&s - h->slots.data());
 		MTZ_CU(h, cudaMemcpyAsync(s.h_res, s.d_res, sizeof(ScanResult), cudaMemcpyDeviceToHost, s.st));
 	}
 	if (host_out != nullptr && !is_codec_mode(h->cfg.mode))
@@ -1081,14 +1227,28 @@ int32_t mtz_process_host(mtz_handle *h, const void *in, size_t n, void *out, siz
 		if (r != MTZ_OK || !was_busy || !codec) return r;
 		if (out_pos + s.out_bytes > out_cap)
 			return fail(h, MTZ_ENOSPC, "output buffer too small (%zu needed so far)", out_pos + s.out_bytes);
+		MTZ_CU(h, cudaSetDevice(h->devs[s.di].device));
+		// issued, not awaited: the copy-out of batch b overlaps the parse + submit of the batches
+		// behind it; the slot is only reused (or the call returns) after `drain_d2h`
 		MTZ_CU(h, cudaMemcpyAsync((uint8_t *)out + out_pos, s.d_out, s.out_bytes, cudaMemcpyDeviceToHost, s.st));
-		MTZ_CU(h, cudaStreamSynchronize(s.st));
+		MTZ_CU(h, cudaEventRecord(s.ev_done, s.st));
+		s.d2h_pending = true;
 		out_pos += s.out_bytes;
 		return MTZ_OK;
 	};
+	auto drain_d2h = [&](Slot &s) -> int32_t {
+		if (!s.d2h_pending) return MTZ_OK;
+		s.d2h_pending = false;
+		MTZ_CU(h, cudaEventSynchronize(s.ev_done));
+		return MTZ_OK;
+	};
+	// output order == submission order: retire the OLDEST batch before cutting the next one once
+	// every slot is taken, so a slot's output copy has a whole ring of batches to finish in
+	const size_t NS = h->slots.size();
 	while (off < n && rc == MTZ_OK) {
-		Slot &s = h->slots[b % h->slots.size()];
+		Slot &s = h->slots[b % NS];
 		rc = retire(s);
+		if (rc == MTZ_OK) rc = drain_d2h(s);
 		if (rc != MTZ_OK) break;
 		BatchCut bc;
 		if (!parse) {
@@ -1116,11 +1276,16 @@ int32_t mtz_process_host(mtz_handle *h, const void *in, size_t n, void *out, siz
 		b++;
 	}
 	// drain in submission order
-	for (size_t k = 0; k < h->slots.size(); k++) {
-		Slot &s = h->slots[(b + k) % h->slots.size()];
+	for (size_t k = 0; k < NS; k++) {
+		Slot &s = h->slots[(b + k) % NS];
 		int32_t r2 = retire(s);
 		if (rc == MTZ_OK) rc = r2;
 	}
+	for (size_t k = 0; k < NS; k++) {
+		int32_t r2 = drain_d2h(h->slots[k]);
+		if (rc == MTZ_OK) rc = r2;
+	}
+	cudaSetDevice(h->device);
 	if (out_n) *out_n = (rc != MTZ_OK) ? 0 : (codec ? out_pos : n);
 	return rc;
 }
@@ -1128,406 +1293,8 @@ int32_t mtz_process_host(mtz_handle *h, const void *in, size_t n, void *out, siz
 } // extern "C"
 
 // ======================================================= streaming engine ==
-// Producer thread -> pinned input ring -> engine thread (parse DRR headers,
-// cut whole-record batches, H2D + kernels on n_slots CUDA streams, harvest in
-// order) -> consumer thread.  In VERIFY mode the output IS the input ring
-// (zero-copy: bytes become consumable once their batch verified); codec and
-// passthrough modes publish into a second pinned ring.
-#include <sys/eventfd.h>
-#include <unistd.h>
-#include <chrono>
-
-namespace mtz {
-
-struct InFlight { int slot; uint64_t in_begin, in_end; };
-
-struct Engine {
-	mtz_handle *h = nullptr;
-	uint8_t *in_buf = nullptr; size_t in_cap = 0;
-	uint8_t *out_buf = nullptr; size_t out_cap = 0;
-	bool own_out = false;          // false: VERIFY (output aliases the input ring)
-	// absolute stream positions, all monotonic
-	uint64_t in_acq = 0;           // end of the producer's outstanding acquire
-	uint64_t in_head = 0;          // committed
-	uint64_t in_tail = 0;          // released for reuse
-	uint64_t parse_pos = 0;        // engine: end of the last whole record parsed
-	uint64_t batch_begin = 0;      // engine: start of the batch being assembled
-	uint64_t out_head = 0;         // published to the consumer
-	uint64_t out_pos = 0;          // consumed
-	bool flushed = false, eof = false, stop = false;
-	bool open_substream = false;   // a DRR_BEGIN has been parsed and its DRR_END has not
-	std::mutex mu;
-	std::condition_variable cv_eng, cv_prod, cv_cons;
-	std::thread thr;
-	int efd = -1;
-	std::vector<mtz_rec> cur;      // records of the batch being assembled
-	BatchCut bc;
-	std::deque<InFlight> inflight;
-	uint64_t next_slot = 0;
-	std::chrono::steady_clock::time_point last_input;
-};
-
-static void signal_efd(Engine *e)
-{
-	if (e->efd >= 0) {
-		uint64_t one = 1;
-		ssize_t r = write(e->efd, &one, sizeof one);
-		(void)r;
-	}
-}
-
-void engine_wake_all(mtz_handle *h)
-{
-	Engine *e = h->eng;
-	if (e == nullptr) return;
-	e->cv_eng.notify_all(); e->cv_prod.notify_all(); e->cv_cons.notify_all();
-	signal_efd(e);
-}
-
-static void CUDART_CB engine_host_cb(void *p)
-{
-	Engine *e = (Engine *)p;
-	e->cv_eng.notify_one();
-}
-
-// copy n bytes at absolute position pos out of the ring (wrap aware)
-static void ring_read(const Engine *e, uint64_t pos, void *dst, size_t n)
-{
-	const size_t o = (size_t)(pos % e->in_cap);
-	const size_t a = std::min(n, e->in_cap - o);
-	memcpy(dst, e->in_buf + o, a);
-	if (n > a) memcpy((uint8_t *)dst + a, e->in_buf, n - a);
-}
-
-// engine thread body; e->mu held on entry to each helper
-static int32_t engine_parse(Engine *e, bool *cut)
-{
-	mtz_handle *h = e->h;
-	*cut = false;
-	const Slot &s0 = h->slots[0];
-	if (h->cfg.mode == MTZ_MODE_PASSTHROUGH) {
-		const uint64_t lim = e->batch_begin + std::min<uint64_t>(h->cfg.batch_bytes, s0.cap);
-		e->parse_pos = std::min(e->in_head, lim);
-		e->bc.in_bytes = (size_t)(e->parse_pos - e->batch_begin);
-		*cut = (e->parse_pos == lim);
-		return MTZ_OK;
-	}
-	while (e->in_head - e->parse_pos >= DRR_HDR) {
-		uint8_t hdr[DRR_HDR];
-		ring_read(e, e->parse_pos, hdr, DRR_HDR);
-		uint32_t ls, comp;
-		const int64_t pl = drr_payload(hdr, &ls, &comp);
-		if (pl < 0)
-			return fail(h, MTZ_EFORMAT, "malformed record header at stream offset %llu",
-			    (unsigned long long)e->parse_pos);
-		const uint64_t rl = DRR_HDR + (uint64_t)pl;
-		if (rl > e->in_cap)
-			return fail(h, MTZ_ENOSPC, "record of %llu bytes exceeds the input ring",
-			    (unsigned long long)rl);
-		if (e->in_head - e->parse_pos < rl) break;                 // incomplete
-		mtz_rec r;
-		const int32_t a = batch_accept(h, s0, e->bc, hdr, pl, ls, comp, e->parse_pos, &r);
-		if (a < 0) return a;
-		if (a == 0) { *cut = true; break; }
-		e->cur.push_back(r);
-		e->parse_pos += rl;
-		if (r.type == 0) e->open_substream = true;
-		if (r.type == 5) { e->open_substream = false; *cut = true; break; }   // END: ship now
-		if (e->bc.budget >= h->cfg.batch_bytes) { *cut = true; break; }
-	}
-	return MTZ_OK;
-}
-
-static int32_t engine_submit(Engine *e)
-{
-	mtz_handle *h = e->h;
-	Slot &s = h->slots[e->next_slot % h->slots.size()];
-	const uint64_t b0 = e->batch_begin, b1 = e->parse_pos;
-	const size_t n = (size_t)(b1 - b0);
-	const size_t o = (size_t)(b0 % e->in_cap);
-	const size_t n0 = std::min(n, e->in_cap - o);
-	if (!e->cur.empty()) memcpy(s.h_recs, e->cur.data(), e->cur.size() * sizeof(mtz_rec));
-	s.writes = e->bc.writes;
-	int32_t rc = submit_batch(h, s, e->in_buf + o, n0, e->in_buf, n - n0, e->cur.size(), b0, nullptr);
-	if (rc != MTZ_OK) return rc;
-	MTZ_CU(h, cudaLaunchHostFunc(s.st, engine_host_cb, e));
-	InFlight f; f.slot = (int)(e->next_slot % h->slots.size()); f.in_begin = b0; f.in_end = b1;
-	e->inflight.push_back(f);
-	e->next_slot++;
-	e->batch_begin = b1;
-	e->cur.clear(); e->bc = BatchCut();
-	return MTZ_OK;
-}
-
-// harvest the oldest in-flight batch if it is done (or block when must_wait)
-static int32_t engine_harvest(Engine *e, std::unique_lock<std::mutex> &lk, bool *progress)
-{
-	mtz_handle *h = e->h;
-	while (!e->inflight.empty()) {
-		InFlight f = e->inflight.front();
-		Slot &s = h->slots[f.slot];
-		cudaError_t q = cudaEventQuery(s.ev_done);
-		if (q == cudaErrorNotReady) return MTZ_OK;
-		if (q != cudaSuccess) return fail_cuda(h, q, "cudaEventQuery(batch)");
-		int32_t rc = harvest(h, s);
-		if (rc != MTZ_OK) return rc;
-		const bool codec = is_codec_mode(h->cfg.mode);
-		const size_t n = codec ? s.out_bytes : (size_t)(f.in_end - f.in_begin);
-		const uint8_t *dsrc = codec ? s.d_out : s.d_in;
-		if (e->own_out) {
-			// copy the batch result into the output ring (wait for room)
-			size_t done = 0;
-			while (done < n) {
-				while (e->out_cap - (size_t)(e->out_head - e->out_pos) == 0) {
-					if (e->stop || h->failed.load() != 0) return h->failed.load() ? h->failed.load() : MTZ_EINVAL;
-					e->cv_eng.wait_for(lk, std::chrono::milliseconds(2));
-				}
-				const size_t room = e->out_cap - (size_t)(e->out_head - e->out_pos);
-				const size_t oo = (size_t)(e->out_head % e->out_cap);
-				const size_t c = std::min(std::min(room, n - done), e->out_cap - oo);
-				lk.unlock();
-				cudaError_t ce = cudaMemcpyAsync(e->out_buf + oo, dsrc + done, c, cudaMemcpyDeviceToHost, s.st);
-				if (ce == cudaSuccess) ce = cudaStreamSynchronize(s.st);
-				lk.lock();
-				if (ce != cudaSuccess) return fail_cuda(h, ce, "D2H to output ring");
-				done += c;
-				e->out_head += c;
-				e->cv_cons.notify_all();
-				signal_efd(e);
-			}
-			e->in_tail = f.in_end;               // input bytes no longer needed
-			e->cv_prod.notify_all();
-		} else {
-			e->out_head = f.in_end;              // verified: consumable in place
-			e->cv_cons.notify_all();
-			signal_efd(e);
-		}
-		e->inflight.pop_front();
-		*progress = true;
-	}
-	return MTZ_OK;
-}
-
-static void engine_main(Engine *e)
-{
-	mtz_handle *h = e->h;
-	cudaSetDevice(h->device);
-	std::unique_lock<std::mutex> lk(e->mu);
-	while (!e->stop) {
-		if (h->failed.load() != 0) { e->cv_eng.wait_for(lk, std::chrono::milliseconds(20)); continue; }
-		bool progress = false, cut = false;
-		int32_t rc = engine_harvest(e, lk, &progress);
-		if (rc == MTZ_OK && e->inflight.size() < h->slots.size()) {
-			const uint64_t before = e->parse_pos;
-			rc = engine_parse(e, &cut);
-			if (rc == MTZ_OK) {
-				if (e->parse_pos != before) progress = true;
-				const bool pending = e->parse_pos > e->batch_begin;
-				const auto idle = std::chrono::steady_clock::now() - e->last_input;
-				const bool all_parsed = (e->parse_pos == e->in_head);
-				const bool ring_full = (e->in_acq - e->in_tail) >= e->in_cap - DRR_HDR;
-				if (pending && (cut || (e->flushed && all_parsed) || ring_full ||
-				    (e->inflight.empty() && idle > std::chrono::milliseconds(5)))) {
-					rc = engine_submit(e);
-					progress = true;
-				}
-			}
-		}
-		if (rc == MTZ_OK && e->flushed && !e->eof && e->inflight.empty() &&
-		    e->parse_pos == e->batch_begin) {
-			if (e->parse_pos != e->in_head) {
-				rc = fail(h, MTZ_EFORMAT, "stream ends inside a record (%llu trailing bytes)",
-				    (unsigned long long)(e->in_head - e->parse_pos));
-			} else if (e->open_substream) {
-				// every record so far verified, but the source closed before DRR_END: what a
-				// dying `zfs send` leaves behind.  `zfs recv` would reject it; say so here.
-				rc = fail(h, MTZ_EFORMAT, "stream ends before DRR_END (cut after %llu bytes)",
-				    (unsigned long long)e->in_head);
-			} else {
-				e->eof = true;
-				e->cv_cons.notify_all();
-				signal_efd(e);
-				progress = true;
-			}
-		}
-		if (rc != MTZ_OK) continue;               // fail() already woke everybody
-		if (!progress) e->cv_eng.wait_for(lk, std::chrono::milliseconds(2));
-	}
-}
-
-} // namespace mtz
-
+#include "mtz_engine.inl"
 extern "C" {
-
-static int32_t engine_get(mtz_handle *h, Engine **out)
-{
-	std::lock_guard<std::mutex> g(h->eng_mu);
-	if (h->eng != nullptr) { *out = h->eng; return MTZ_OK; }
-	if (h->cfg.flags & MTZ_FLAG_DEFER_VERIFY)
-		return fail(h, MTZ_EINVAL, "streaming API cannot defer verification");
-	MTZ_CU(h, cudaSetDevice(h->device));
-	int32_t rc = ensure_slots(h);
-	if (rc != MTZ_OK) return rc;
-	Engine *e = new (std::nothrow) Engine();
-	if (e == nullptr) return fail(h, MTZ_ENOMEM, "engine allocation");
-	e->h = h;
-	e->in_cap = (size_t)h->cfg.ring_bytes;
-	if (e->in_cap < 2 * (size_t)h->cfg.batch_bytes) e->in_cap = 2 * (size_t)h->cfg.batch_bytes;
-	cudaError_t ce = cudaHostAlloc(&e->in_buf, e->in_cap, cudaHostAllocDefault);
-	if (ce != cudaSuccess) { delete e; return fail_cuda(h, ce, "cudaHostAlloc(input ring)"); }
-	e->own_out = (h->cfg.mode != MTZ_MODE_VERIFY);
-	if (e->own_out) {
-		e->out_cap = (size_t)h->cfg.out_ring_bytes;
-		ce = cudaHostAlloc(&e->out_buf, e->out_cap, cudaHostAllocDefault);
-		if (ce != cudaSuccess) { cudaFreeHost(e->in_buf); delete e; return fail_cuda(h, ce, "cudaHostAlloc(output ring)"); }
-	}
-	e->efd = eventfd(0, EFD_NONBLOCK | EFD_CLOEXEC);
-	e->last_input = std::chrono::steady_clock::now();
-	h->eng = e;
-	e->thr = std::thread(engine_main, e);
-	*out = e;
-	return MTZ_OK;
-}
-
-static void engine_destroy(mtz_handle *h)
-{
-	Engine *e = h->eng;
-	if (e == nullptr) return;
-	{
-		std::lock_guard<std::mutex> g(e->mu);
-		e->stop = true;
-	}
-	e->cv_eng.notify_all(); e->cv_prod.notify_all(); e->cv_cons.notify_all();
-	if (e->thr.joinable()) e->thr.join();
-	cudaDeviceSynchronize();
-	if (e->in_buf) cudaFreeHost(e->in_buf);
-	if (e->out_buf) cudaFreeHost(e->out_buf);
-	if (e->efd >= 0) close(e->efd);
-	h->eng = nullptr;
-	delete e;
-}
-
-#define GET_ENGINE(h, e)                                                       \
-	CHECK_H(h);                                                                \
-	Engine *e = nullptr;                                                       \
-	{ int32_t rc__ = engine_get((h), &e); if (rc__ != MTZ_OK) return rc__; }
-
-int32_t mtz_ring_acquire(mtz_handle *h, size_t want, void **ptr, size_t *got)
-{
-	GET_ENGINE(h, e);
-	if (ptr == nullptr || got == nullptr) return MTZ_EINVAL;
-	std::lock_guard<std::mutex> g(e->mu);
-	if (e->flushed) return fail(h, MTZ_EINVAL, "write after flush");
-	if (e->in_acq != e->in_head) return fail(h, MTZ_EINVAL, "acquire with an uncommitted slice outstanding");
-	const size_t used = (size_t)(e->in_head - e->in_tail);
-	const size_t o = (size_t)(e->in_head % e->in_cap);
-	size_t n = std::min(e->in_cap - used, e->in_cap - o);
-	if (want != 0) n = std::min(n, want);
-	*ptr = e->in_buf + o; *got = n;
-	if (n == 0) return MTZ_EAGAIN;
-	e->in_acq = e->in_head + n;
-	return MTZ_OK;
-}
-
-int32_t mtz_ring_commit(mtz_handle *h, size_t n)
-{
-	GET_ENGINE(h, e);
-	std::lock_guard<std::mutex> g(e->mu);
-	if (n > (size_t)(e->in_acq - e->in_head)) return fail(h, MTZ_EINVAL, "commit beyond the acquired slice");
-	e->in_head += n;
-	e->in_acq = e->in_head;
-	e->last_input = std::chrono::steady_clock::now();
-	e->cv_eng.notify_one();
-	return MTZ_OK;
-}
-
-int32_t mtz_write(mtz_handle *h, const void *buf, size_t n, int32_t block)
-{
-	GET_ENGINE(h, e);
-	const uint8_t *src = (const uint8_t *)buf;
-	size_t done = 0;
-	while (done < n) {
-		void *p = nullptr; size_t got = 0;
-		int32_t rc = mtz_ring_acquire(h, n - done, &p, &got);
-		if (rc == MTZ_EAGAIN) {
-			if (!block) return done ? (int32_t)MTZ_OK : (int32_t)MTZ_EAGAIN;
-			std::unique_lock<std::mutex> lk(e->mu);
-			if ((size_t)(e->in_head - e->in_tail) >= e->in_cap && h->failed.load() == 0)
-				e->cv_prod.wait_for(lk, std::chrono::milliseconds(50));
-			if (h->failed.load() != 0) return h->failed.load();
-			continue;
-		}
-		if (rc != MTZ_OK) return rc;
-		memcpy(p, src + done, got);
-		rc = mtz_ring_commit(h, got);
-		if (rc != MTZ_OK) return rc;
-		done += got;
-	}
-	return MTZ_OK;
-}
-
-int32_t mtz_flush(mtz_handle *h)
-{
-	GET_ENGINE(h, e);
-	std::lock_guard<std::mutex> g(e->mu);
-	e->flushed = true;
-	e->cv_eng.notify_one();
-	return MTZ_OK;
-}
-
-int32_t mtz_out_peek(mtz_handle *h, const void **ptr, size_t *n)
-{
-	GET_ENGINE(h, e);
-	if (ptr == nullptr || n == nullptr) return MTZ_EINVAL;
-	std::lock_guard<std::mutex> g(e->mu);
-	const uint8_t *buf = e->own_out ? e->out_buf : e->in_buf;
-	const size_t cap = e->own_out ? e->out_cap : e->in_cap;
-	const size_t avail = (size_t)(e->out_head - e->out_pos);
-	const size_t o = (size_t)(e->out_pos % cap);
-	*ptr = buf + o;
-	*n = std::min(avail, cap - o);
-	if (*n == 0) return e->eof ? MTZ_EOF : MTZ_EAGAIN;
-	return MTZ_OK;
-}
-
-int32_t mtz_out_consume(mtz_handle *h, size_t n)
-{
-	GET_ENGINE(h, e);
-	std::lock_guard<std::mutex> g(e->mu);
-	if (n > (size_t)(e->out_head - e->out_pos)) return fail(h, MTZ_EINVAL, "consume beyond published output");
-	e->out_pos += n;
-	if (!e->own_out) { e->in_tail = e->out_pos; e->cv_prod.notify_all(); }
-	e->cv_eng.notify_one();
-	return MTZ_OK;
-}
-
-int32_t mtz_read(mtz_handle *h, void *buf, size_t cap, size_t *got, int32_t block)
-{
-	GET_ENGINE(h, e);
-	if (got == nullptr) return MTZ_EINVAL;
-	*got = 0;
-	for (;;) {
-		const void *p = nullptr; size_t n = 0;
-		int32_t rc = mtz_out_peek(h, &p, &n);
-		if (rc == MTZ_OK) {
-			n = std::min(n, cap);
-			memcpy(buf, p, n);
-			*got = n;
-			return mtz_out_consume(h, n);
-		}
-		if (rc != MTZ_EAGAIN || !block) return rc;
-		std::unique_lock<std::mutex> lk(e->mu);
-		if (e->out_head == e->out_pos && !e->eof && h->failed.load() == 0)
-			e->cv_cons.wait_for(lk, std::chrono::milliseconds(50));
-		if (h->failed.load() != 0) return h->failed.load();
-	}
-}
-
-int32_t mtz_event_fd(mtz_handle *h)
-{
-	GET_ENGINE(h, e);
-	return e->efd;
-}
 
 // ---------------------------------------------------- LZ4 kernel entries ---
 static int32_t lz4_grid(mtz_handle *h, uint32_t njobs, int warps_per_sm)

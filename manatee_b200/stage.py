@@ -20,12 +20,18 @@ class GpuSnapshotStage(object):
     """One stage instance == one mtz_handle == one stream (like one Transform)."""
 
     def __init__(self, mode="verify", device=0, ring_bytes=0, batch_bytes=0, n_slots=0,
-                 out_ring_bytes=0, flags=0):
+                 out_ring_bytes=0, flags=0, devices=None):
+        """``devices`` = CUDA ordinals of a device group: the GPUs of one box run as ONE stage,
+        batch b of the stream on ``devices[b % len(devices)]`` (mtz_config.devices[])."""
         self._L = N.lib()
         self._h = C.c_void_p()
         cfg = N.Config()
         cfg.struct_size = C.sizeof(N.Config)
         cfg.device = device
+        if devices:
+            cfg.n_devices = len(devices)
+            for i, d in enumerate(devices):
+                cfg.devices[i] = int(d)
         cfg.mode = N.MODE_NAMES[mode] if isinstance(mode, str) else int(mode)
         cfg.flags = flags
         cfg.ring_bytes = ring_bytes
@@ -113,6 +119,41 @@ class GpuSnapshotStage(object):
     def event_fd(self):
         return self._L.mtz_event_fd(self._h)
 
+    # -- fan-out: several peers share one pass (mtz_fanout_attach) -----------
+    def fanout_attach(self, peer_id):
+        """Attach peer ``peer_id`` (before the first byte); returns its egress GPU ordinal."""
+        rc = self._L.mtz_fanout_attach(self._h, peer_id)
+        if rc < 0:
+            self._check(rc)
+        return rc
+
+    def read_peer(self, peer_id, cap=1 << 20, block=True):
+        buf = np.empty(cap, dtype=np.uint8)
+        got = C.c_size_t(0)
+        rc = self._check(self._L.mtz_read_peer(self._h, peer_id, buf.ctypes.data, cap, C.byref(got),
+                                               1 if block else 0), allow=(N.EAGAIN, N.EOF))
+        if rc == N.EOF:
+            return None
+        return buf[:got.value].tobytes()
+
+    def peek_peer(self, peer_id):
+        """(address, nbytes) of the next contiguous run in the peer's pinned ring; (0, 0) when
+        nothing is ready, None at EOF."""
+        p, n = C.c_void_p(), C.c_size_t()
+        rc = self._check(self._L.mtz_out_peek_peer(self._h, peer_id, C.byref(p), C.byref(n)),
+                         allow=(N.EAGAIN, N.EOF))
+        if rc == N.EOF:
+            return None
+        return (p.value or 0, n.value) if rc == N.OK else (0, 0)
+
+    def consume_peer(self, peer_id, n):
+        self._check(self._L.mtz_out_consume_peer(self._h, peer_id, n))
+
+    def cancel(self):
+        """Tear the pipe down from outside: every blocked write/read returns ECANCELED."""
+        if self._h is not None and self._h.value:
+            self._L.mtz_cancel(self._h)
+
     # -- device-resident API -----------------------------------------------
     def set_carry(self, carry_in=None, carry_out=None):
         ci = (C.c_uint64 * 4)(*carry_in) if carry_in is not None else None
@@ -152,6 +193,18 @@ class GpuSnapshotStage(object):
                                                     C.byref(c1), C.byref(c2)))
         return ob.value, tuple(int(x) for x in c1), tuple(int(x) for x in c2)
 
+    def comm_init(self, unique_id, rank, world):
+        """Library-owned NCCL communicator for the one-process-per-GPU shard form."""
+        buf = (C.c_uint8 * 128).from_buffer_copy(bytes(unique_id))
+        self._check(self._L.mtz_comm_init(self._h, buf, rank, world))
+
+    def dev_finish_exchange(self):
+        ob = C.c_size_t(0)
+        c1 = (C.c_uint64 * 4)()
+        c2 = (C.c_uint64 * 4)()
+        self._check(self._L.mtz_dev_finish_exchange(self._h, C.byref(ob), C.byref(c1), C.byref(c2)))
+        return ob.value, tuple(int(x) for x in c1), tuple(int(x) for x in c2)
+
     def dev_finish(self, carry_in=None, carry_out_in=None):
         ob = C.c_size_t(0)
         c1 = (C.c_uint64 * 4)()
@@ -160,6 +213,16 @@ class GpuSnapshotStage(object):
         co = (C.c_uint64 * 4)(*carry_out_in) if carry_out_in is not None else None
         self._check(self._L.mtz_dev_finish(self._h, ci, co, C.byref(ob), C.byref(c1), C.byref(c2)))
         return ob.value, tuple(int(x) for x in c1), tuple(int(x) for x in c2)
+
+
+def comm_unique_id():
+    """128 bytes to carry from rank 0 to the other ranks (mtz_comm_unique_id)."""
+    L = N.lib()
+    buf = (C.c_uint8 * 128)()
+    rc = L.mtz_comm_unique_id(buf)
+    if rc != N.OK:
+        raise N.MtzError(rc, "mtz_comm_unique_id")
+    return bytes(buf)
 
 
 def index_host(stream):

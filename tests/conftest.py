@@ -36,3 +36,23 @@ def native():
     """libmanatee_gpu.so must be built and loadable; GPU tests fail loudly otherwise."""
     from manatee_b200 import _native
     return _native.lib()
+
+
+@pytest.fixture(scope="session")
+def emul_so(tmp_path_factory):
+    """libmanatee_gpu_emul.so (tests/emul/make_emul_lib.py): the whole library compiled for the CPU
+    SIMT emulator, built once per session; child pytest processes inherit it through MTZ_EMUL_SO.
+    Test infrastructure only -- the product never loads it."""
+    import shutil
+    import subprocess
+    pre = os.environ.get("MTZ_EMUL_SO")
+    if pre and os.path.exists(pre):
+        return pre
+    if shutil.which("g++") is None:
+        pytest.skip("no g++")
+    so = os.path.join(str(tmp_path_factory.mktemp("emul_lib")), "libmanatee_gpu_emul.so")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "emul", "make_emul_lib.py"), so],
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 0, r.stderr
+    os.environ["MTZ_EMUL_SO"] = so
+    return so

@@ -123,7 +123,16 @@ inline void run(cudaStream_t st, std::function<void()> fn) { emu_op o; o.fn = st
 
 static inline const char *cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no error" : "emulated CUDA error"; }
 static inline cudaError_t cudaGetLastError() { return cudaSuccess; }
-static inline cudaError_t cudaGetDeviceCount(int *n) { *n = getenv("MTZ_EMUL_NO_DEVICE") ? 0 : 1; return cudaSuccess; }
+// MTZ_EMUL_DEVICES=<n>: a box of n identical emulated GPUs (device memory is host memory, so a
+// "peer copy" is a copy; what the multi-device tests exercise is the library's ordering)
+static inline cudaError_t cudaGetDeviceCount(int *n)
+{
+	const char *e = getenv("MTZ_EMUL_DEVICES");
+	*n = getenv("MTZ_EMUL_NO_DEVICE") ? 0 : (e && atoi(e) > 0 ? atoi(e) : 1);
+	return cudaSuccess;
+}
+static inline cudaError_t cudaDeviceCanAccessPeer(int *can, int, int) { *can = 1; return cudaSuccess; }
+static inline cudaError_t cudaDeviceEnablePeerAccess(int, unsigned) { return cudaSuccess; }
 static inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
 static inline cudaError_t cudaDeviceSynchronize() { emurt::drain_all(); return cudaSuccess; }
 static inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp *p, int)
@@ -183,6 +192,11 @@ static inline cudaError_t cudaFreeHost(void *p) { emu_dev_free(p); return cudaSu
 static inline cudaError_t cudaMemcpy(void *d, const void *s, size_t n, cudaMemcpyKind) { emurt::drain_all(); memmove(d, s, n); return cudaSuccess; }
 static inline cudaError_t cudaMemset(void *d, int v, size_t n) { emurt::drain_all(); memset(d, v, n); return cudaSuccess; }
 static inline cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind, cudaStream_t st = nullptr)
+{
+	emurt::run(st, [d, s, n] { memmove(d, s, n); });
+	return cudaSuccess;
+}
+static inline cudaError_t cudaMemcpyPeerAsync(void *d, int, const void *s, int, size_t n, cudaStream_t st = nullptr)
 {
 	emurt::run(st, [d, s, n] { memmove(d, s, n); });
 	return cudaSuccess;

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol(native):
     exported = set(re.findall(r" T (mtz_[a-z0-9_]+)", out))
     missing = [s for s in hdr if s not in exported]
     assert not missing, missing
-    assert native.mtz_abi_version() == 1
+    assert native.mtz_abi_version() == 2
 
 
 def test_error_strings_and_null_handles(native):

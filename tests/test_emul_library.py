@@ -26,14 +26,8 @@ EMUL = os.path.join(ROOT, "tests", "emul")
 
 
 @pytest.fixture(scope="module")
-def emul_library(tmp_path_factory):
-    import shutil
-    if shutil.which("g++") is None:
-        pytest.skip("no g++")
-    so = os.path.join(str(tmp_path_factory.mktemp("emul_lib")), "libmanatee_gpu_emul.so")
-    r = subprocess.run([sys.executable, os.path.join(EMUL, "make_emul_lib.py"), so],
-                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
-    assert r.returncode == 0, r.stderr
+def emul_library(emul_so):
+    so = emul_so
     from manatee_b200 import _native as N
     saved = (N.SO_PATH, N._lib)
     N.SO_PATH, N._lib = so, None

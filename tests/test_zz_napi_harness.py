@@ -118,17 +118,13 @@ def test_binding_moves_a_stream_through_the_gpu(real_exe, tmp_path, oracle):
     _check_binding_end_to_end(real_exe, tmp_path, oracle, 40)
 
 
-def test_binding_moves_a_stream_through_the_emulated_library(tmp_path_factory, tmp_path, oracle):
+def test_binding_moves_a_stream_through_the_emulated_library(tmp_path_factory, tmp_path, oracle, emul_so):
     """the same end-to-end check with the binding linked against the WHOLE library built for the
     SIMT emulator (tests/emul/make_emul_lib.py): binding.cc -> C ABI -> engine thread -> kernels,
     all on the CPU"""
     import sys
-    d = tmp_path_factory.mktemp("napi_emul")
-    so = os.path.join(str(d), "libmanatee_gpu_emul.so")
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "emul", "make_emul_lib.py"), so],
-                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
-    assert r.returncode == 0, r.stderr
-    exe = os.path.join(str(d), "napi_harness_emul")
+    d = os.path.dirname(emul_so)                     # the session's one emulated build (conftest.py)
+    exe = os.path.join(str(tmp_path_factory.mktemp("napi_emul")), "napi_harness_emul")
     cmd = ["g++", "-std=c++17", "-O1", "-I" + STUBS, "-pthread", "-o", exe, BINDING,
            os.path.join(STUBS, "napi_mock.cc"), os.path.join(STUBS, "napi_harness.cc"),
            "-L" + str(d), "-lmanatee_gpu_emul", "-Wl,-rpath," + str(d)]
