@@ -1,23 +1,31 @@
 #!/usr/bin/env python
 """bench.py -- snapshot-stream GiB/s of the peer-bootstrap hot path on B200.
 
-One "step" = one full pass of the stage over the workload's synthetic ZFS-send
-stream.  Default workload = BASELINE.json configs[1]:
-16 GiB uncompressed stream, Fletcher-4 verification (mode VERIFY), per GPU.
+Headline workload = BASELINE.json configs[2], the config its `metric` ("Fletcher-4+LZ4") is quoted
+on: a 64 GiB (logical) ZFS-send stream of LZ4-compressed 128 KiB records, mode RECOMPRESS
+(decode -> verify every stream checksum -> re-encode with the declared ZFS encoder -> re-stamp).
+One "step" = one full pass of the stage over that stream.  The metric counts INPUT STREAM bytes
+(wire-format bytes, headers + compressed payloads, BEGIN...END) per second.
 
-  value     whole-job GiB/s with the stream already resident in HBM
-            (mtz_dev_submit / mtz_dev_finish, CUDA events, max over ranks)
-  e2e       same metric through the host-facing C-ABI call mtz_process_host()
-            with the stream in pinned HOST memory: H2D copies inside the region
-  roofline  K1 (Fletcher-4 sums kernel) achieved HBM GB/s vs MEASURED_PEAKS.json
+  value     whole-job GiB/s with the stream resident in HBM (mtz_dev_submit / mtz_dev_finish[_exchange],
+            CUDA events on the launching stream, max over ranks)
+  e2e       the same through the host-facing C-ABI call a caller makes (mtz_process_host, pinned host
+            buffers in and out, H2D + D2H inside the timed region).  With N GPUs it is ONE process
+            driving the device group mtz_config.devices[0..N) -- what a Node backupserver would do.
+  e2e_stream_api   the ring API the N-API Transform binds (acquire/commit, write, peek/consume)
+  roofline  K3 (LZ4 encode, the dominant kernel) algorithmic HBM bytes / its CUDA-event time
   cpu_baseline / --impl reference
-            the oracle's scalar restatement of what runs today inside
-            `zfs send`/`zfs recv` (lib/backupSender.js:177, lib/zfsClient.js:793),
-            record-parallel over all host cores.  Reported, not the target.
+            the oracle port of the same arithmetic on all host threads (oracle/mt.c), on a bounded
+            sample of the same workload.  Reported, not the target.
 
-N > 1 (torchrun, one rank per GPU): ONE logical stream of N x 16 GiB partitioned
-by record index; each rank verifies its shard, the only exchange is an
-all-gather of the 40-byte shard aggregate (n,A,B,C,D) over NCCL.  Weak scaling.
+N > 1 (torchrun, one rank per GPU): STRONG scaling of the same 64 GiB stream, partitioned by record
+index into N contiguous shards; the only data-path exchange is the library-owned NCCL all-gather of
+the 40-byte shard aggregate plus the 32-byte output checksum hopping rank to rank
+(mtz_dev_finish_exchange).  Rank 0 then measures, in one process over all N GPUs, `e2e` and the
+fan-out of the processed stream to P attached peers (BASELINE configs[3]/[4]).
+
+`--workload verify` keeps round 1's headline (configs[1]: 16 GiB uncompressed, Fletcher-4 only) as a
+selectable workload; the default run reports it as `workloads.verify`.
 """
 import argparse
 import json
@@ -39,17 +47,19 @@ REC_BYTES = 312 + RECSIZE
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="verify", choices=["verify"])
-    ap.add_argument("--gib", type=float, default=16.0, help="stream GiB per GPU")
-    ap.add_argument("--ref-gib", type=float, default=16.0, help="CPU sample GiB")
+    ap.add_argument("--workload", default="recompress", choices=["recompress", "verify"])
+    ap.add_argument("--gib", type=float, default=0.0,
+                    help="workload size: logical GiB of the whole job (recompress, default 64) / "
+                         "stream GiB per GPU (verify, default 16)")
+    ap.add_argument("--ref-gib", type=float, default=8.0,
+                    help="CPU arms: GiB (logical for recompress) of the bounded sample each step processes")
+    ap.add_argument("--verify-gib", type=float, default=16.0, help="side workload (N=1), 0 = skip")
+    ap.add_argument("--e2e-steps", type=int, default=8)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--recompress-gib", type=float, default=64.0,
-                    help="logical GiB of the configs[2] RECOMPRESS side measurement (N=1 only, 0 = skip)")
-    ap.add_argument("--recompress-steps", type=int, default=3)
     ap.add_argument("--recsize", type=int, default=131072, help="DRR_WRITE logical size (dataset recordsize)")
     return ap.parse_args()
 
@@ -69,7 +79,7 @@ class ClockSampler(object):
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                 "--format=csv,noheader,nounits", "-lms", "20"],
+                 "--format=csv,noheader,nounits", "-lms", "50"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -115,24 +125,6 @@ class ClockSampler(object):
 SIMD_NAME = {0: "scalar", 4: "avx2 (4 lanes, as zfs_fletcher_avx2)", 8: "avx512f (8 lanes, as zfs_fletcher_avx512)"}
 
 
-def cpu_verify_baseline(O, stream, nthreads):
-    """cpu_baseline object of the VERIFY workload: the oracle port over `stream` on `nthreads`
-    threads (second of two passes is timed by the caller's convention: buffers warm), plus the
-    one-thread figure -- the shape a real `zfs send` / `zfs recv` stream checksum has."""
-    rc, secs, cst = O.mt_verify(stream, nthreads)
-    assert rc == 0, rc
-    rc, secs1, _ = O.mt_verify(stream, 1)
-    assert rc == 0, rc
-    lanes = O.simd_lanes()
-    flavour = SIMD_NAME.get(lanes, "scalar")
-    return {"value": round(stream.size / GIB / secs, 3), "unit": "GiB/s", "cores": nthreads,
-            "cgroup_cpu_quota": cpu_quota(), "kind": "port", "fletcher4": flavour,
-            "single_thread_value": round(stream.size / GIB / secs1, 3),
-            "sample": "the whole %.2f GiB stream once: record-parallel %s fletcher_4 (oracle/mt.c), "
-                      "%d threads; single_thread_value = one thread, the shape of a real "
-                      "`zfs send`/`zfs recv` stream checksum" % (stream.size / GIB, flavour, nthreads)}
-
-
 def cpu_quota():
     """cgroup CPU quota in cores (None = unlimited): shared GPU boxes often cap it"""
     try:
@@ -149,487 +141,606 @@ def host_threads():
         return os.cpu_count() or 1
 
 
-def make_shard(O, rank, world, nwrites, pinned_array):
-    """Rank's slice of ONE logical stream (record-index partition).  Payloads are
-    generated in parallel on every rank; the checksum chain hops rank to rank."""
-    import torch.distributed as dist
-    import torch
-    flags = (1 if rank == 0 else 0) | (2 if rank == world - 1 else 0)
-    buf, ppay = O.synth_shard_fill(nwrites, RECSIZE, O.PAYLOAD_PCG, rank * nwrites, flags,
-                                   out=pinned_array, nthreads=max(1, host_threads() // world))
-    from manatee_b200 import shard as SH
-    state = (0, 0, 0, 0)
-    carry_in = state
-    for r in range(world):
-        if r == rank:
-            carry_in = state
-            state = O.synth_shard_stamp(buf, nwrites, RECSIZE, flags, ppay, state)
-        state = SH.broadcast_state(state, r)
-    return buf, carry_in
+def load_peaks():
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(peaks["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (a STREAM copy, read+write)"
+    except Exception:
+        return 6650.0, "fallback 6650 GB/s (B200_PROFILING.md)"
 
 
-def run_recompress(args, local, peak_gbs):
-    """BASELINE configs[2]: LZ4-compressed 128 KiB records, decode -> verify -> re-encode ->
-    re-stamp (mode RECOMPRESS) on one GPU.  Reported beside the headline VERIFY line."""
+# ------------------------------------------------------------------ CPU legs (oracle port) --
+def cpu_verify_baseline(O, stream, nthreads):
+    """cpu_baseline object of the VERIFY workload: the oracle port over `stream` on `nthreads`
+    threads, plus the one-thread figure -- the shape a real `zfs send` / `zfs recv` stream checksum
+    has."""
+    rc, secs, cst = O.mt_verify(stream, nthreads)
+    assert rc == 0, rc
+    rc, secs, cst = O.mt_verify(stream, nthreads)          # second pass: buffers warm
+    assert rc == 0, rc
+    rc, secs1, _ = O.mt_verify(stream, 1)
+    assert rc == 0, rc
+    lanes = O.simd_lanes()
+    flavour = SIMD_NAME.get(lanes, "scalar")
+    return {"value": round(stream.size / GIB / secs, 3), "unit": "GiB/s", "cores": nthreads,
+            "cgroup_cpu_quota": cpu_quota(), "kind": "port", "fletcher4": flavour,
+            "single_thread_value": round(stream.size / GIB / secs1, 3),
+            "sample": "the whole %.2f GiB stream, second of two passes: record-parallel %s fletcher_4 "
+                      "(oracle/mt.c), %d threads; single_thread_value = one thread, the shape of a real "
+                      "`zfs send`/`zfs recv` stream checksum" % (stream.size / GIB, flavour, nthreads)}
+
+
+def cpu_recompress(O, src, out, nthreads):
+    """one oracle RECOMPRESS pass (record-parallel LZ4 decode + encode, vector Fletcher-4, sequential
+    stamp) -> (output bytes, seconds)"""
+    import ctypes as C
+    L = O.lib()
+    n = C.c_size_t(0); st = O.StreamStats(); secs = C.c_double(0)
+    rc = L.orc_mt_recompress(src.ctypes.data, src.size, out.ctypes.data, out.size, C.byref(n),
+                             nthreads, C.byref(secs), C.byref(st))
+    assert rc == 0, rc
+    return n.value, secs.value
+
+
+def make_lz4_stream(O, logical_gib, nthreads, pinned=True):
+    """The configs[2] input: `logical_gib` of pg-page 128 KiB records (SURVEY 8d payload model), each
+    stored as the declared encoder's ZFS-LZ4 frame, checksums stamped -- i.e. what `zfs send -c` of
+    an lz4 dataset carries.  Returns (stream array, logical bytes, holder to free)."""
     import numpy as np
-    import torch
-    import oracle as O
-    from manatee_b200 import GpuSnapshotStage, PinnedBuffer, index_host
-    nthreads = host_threads()
-    nwrites = max(1, int(args.recompress_gib * GIB) // REC_BYTES)
+    nwrites = max(1, int(logical_gib * GIB) // REC_BYTES)
     raw = O.synth_stream(nwrites, RECSIZE, O.PAYLOAD_PGPAGE, nthreads=nthreads)
     logical = float(raw.size)
     cbuf = np.empty(raw.size + (1 << 20), dtype=np.uint8)
-    import ctypes as C
-    L = O.lib()
-
-    def cpu_recompress(src, out):
-        n = C.c_size_t(0); st = O.StreamStats(); secs = C.c_double(0)
-        rc = L.orc_mt_recompress(src.ctypes.data, src.size, out.ctypes.data, out.size, C.byref(n),
-                                 nthreads, C.byref(secs), C.byref(st))
-        assert rc == 0, rc
-        return n.value, secs.value, st
-
-    n, _, _ = cpu_recompress(raw, cbuf)               # raw -> oracle-encoded LZ4 stream (the input)
+    n, _ = cpu_recompress(O, raw, cbuf, nthreads)          # raw -> oracle-encoded LZ4 stream
     del raw
-    L.orc_mt_release()                                # the oracle's scratch is as large as `raw` was
-    pin_in = PinnedBuffer(n)
-    pin_in.array[:] = cbuf[:n]
-    src = pin_in.array
-    recs, used = index_host(src)
-    assert used == src.size
-    d_in = torch.empty(src.size + 512, dtype=torch.uint8, device="cuda")
-    d_in[:src.size].copy_(torch.from_numpy(src))
-    d_recs = torch.from_numpy(recs.view(np.uint8).copy()).cuda()
-    worst = int((recs["lsize"].astype(np.int64).clip(min=0) + 312).sum()) + (1 << 20)
-    d_out = torch.empty(worst, dtype=torch.uint8, device="cuda")
+    O.lib().orc_mt_release()                               # its scratch is as large as `raw` was
+    if not pinned:
+        return cbuf[:n].copy(), logical, None
+    from manatee_b200 import PinnedBuffer
+    pin = PinnedBuffer(n)
+    pin.array[:] = cbuf[:n]
+    return pin.array, logical, pin
+
+
+def recompress_config(total_logical_gib, stream_bytes=None, records=None, ratio=None):
+    """`config` of the RECOMPRESS workload -- the SAME object on both arms."""
+    return {"workload": "recompress: %.0f GiB logical ZFS-send stream of LZ4-compressed 128 KiB records, "
+                        "decode + Fletcher-4 verify + re-encode + re-stamp (BASELINE configs[2])" % total_logical_gib,
+            "recordsize": RECSIZE, "payload": "pg-page model, Zipf dictionary seed 0x5047 (LZ4 ratio ~2.5)",
+            "metric_bytes": "input stream bytes (312 B headers + compressed payloads, BEGIN..END)"}
+
+
+def verify_config(gib_per_gpu):
+    return {"workload": "verify: %.0f GiB/GPU uncompressed ZFS-send stream, Fletcher-4 (BASELINE configs[1])" % gib_per_gpu,
+            "recordsize": RECSIZE, "payload": "PCG32 seed 0x4D414E41 (incompressible)",
+            "metric_bytes": "input stream bytes"}
+
+
+# ----------------------------------------------------------------------------- reference arm --
+def run_reference(args):
+    """CPU arm: the oracle port of the path's arithmetic on all host threads, each step a bounded
+    sample of the arm's workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import numpy as np
+    import oracle as O
+    O.build()
+    nthreads = host_threads()
+    note = ("reference = Node identity pipe + in-kernel ZFS arithmetic (`zfs send`/`zfs recv`, "
+            "lib/backupSender.js:177, lib/zfsClient.js:793); node/zfs are not installable here, so the "
+            "oracle port of that arithmetic is timed (kind=port), record-parallel over every host thread "
+            "-- more parallelism than the reference's single `zfs send` thread has")
+    if args.workload == "verify":
+        gib = args.gib or 16.0
+        nwrites = max(1, int(min(args.ref_gib * 2, gib) * GIB) // REC_BYTES)
+        s = O.synth_stream(nwrites, RECSIZE, O.PAYLOAD_PCG, nthreads=nthreads)
+        for _ in range(max(1, min(args.warmup, 2))):
+            assert O.mt_verify(s, nthreads)[0] == 0
+        t = []
+        for _ in range(args.steps):
+            rc, secs, st = O.mt_verify(s, nthreads)
+            assert rc == 0
+            t.append(secs)
+        ms = 1e3 * sum(t) / len(t)
+        val = s.size / GIB / (ms / 1e3)
+        cfg = verify_config(gib)
+        sample = ("%.2f GiB of the stream per step: record-parallel %s fletcher_4 + sequential combine "
+                  "(oracle/mt.c)" % (s.size / GIB, SIMD_NAME.get(O.simd_lanes(), "scalar")))
+        dtype = "u32->u64 (mod 2^64)"
+    else:
+        gib = args.gib or 64.0
+        src, logical, _ = make_lz4_stream(O, min(args.ref_gib, gib), nthreads, pinned=False)
+        out = np.empty(src.size + (1 << 20), dtype=np.uint8)
+        for _ in range(max(1, min(args.warmup, 2))):
+            n, _s = cpu_recompress(O, src, out, nthreads)
+        assert n == src.size and np.array_equal(out[:n], src), "oracle RECOMPRESS is not idempotent"
+        t = []
+        for _ in range(args.steps):
+            n, secs = cpu_recompress(O, src, out, nthreads)
+            t.append(secs)
+        ms = 1e3 * sum(t) / len(t)
+        val = src.size / GIB / (ms / 1e3)
+        cfg = recompress_config(gib)
+        sample = ("%.2f GiB logical (%.2f GiB of input stream) of the workload per step: record-parallel "
+                  "oracle LZ4 decode + encode + vector Fletcher-4, sequential stamp (oracle/mt.c); "
+                  "logical %.2f GiB/s" % (logical / GIB, src.size / GIB, logical / GIB / (ms / 1e3)))
+        dtype = "u8 / u32->u64 (mod 2^64)"
+    line = {
+        "impl": "reference", "metric": "snapshot_stream_gibs", "value": round(val, 3),
+        "unit": "GiB/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(ms, 3), "higher_is_better": True,
+        "scaling": "strong" if args.workload == "recompress" else "weak",
+        "vs_baseline": None, "dtype": dtype, "data": "synthetic", "config": cfg,
+        "cpu_baseline": {"value": round(val, 3), "unit": "GiB/s", "cores": nthreads,
+                         "cgroup_cpu_quota": cpu_quota(), "kind": "port", "sample": sample},
+        "e2e": {"value": round(val, 3), "unit": "GiB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "note": note,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------- ring API helpers --
+def ring_run(g, src, peers=(0,), producer="write", nthreads=4, chunk=32 << 20):
+    """Drive the streaming API: one producer feeding `src` (numpy u8), one zero-copy consumer thread
+    per peer.  producer = "write" (mtz_write, one memcpy thread), "acquire" (mtz_ring_acquire /
+    commit, the slice filled by `nthreads` parallel memcpys) or "pipe" (read(2) from a pipe straight
+    into the acquired slice -- the shape of zfsSend.stdout).  Returns (seconds, ok, detail)."""
+    import ctypes as C
+    import numpy as np
+    from concurrent.futures import ThreadPoolExecutor
+    from manatee_b200 import _native as N
+    L = N.lib()
+    errs, got = [], {}
+
+    def consumer(p):
+        try:
+            ptr, n, tot = C.c_void_p(), C.c_size_t(), 0
+            while True:
+                rc = L.mtz_out_peek_peer(g._h, p, C.byref(ptr), C.byref(n))
+                if rc == N.OK:
+                    tot += n.value
+                    L.mtz_out_consume_peer(g._h, p, n.value)
+                elif rc == N.EOF:
+                    break
+                elif rc == N.EAGAIN:
+                    time.sleep(0.0002)
+                else:
+                    errs.append("peer %d: rc %d" % (p, rc))
+                    break
+            got[p] = tot
+        except Exception as e:              # noqa: BLE001
+            errs.append(repr(e))
+
+    def produce():
+        try:
+            if producer == "write":
+                for o in range(0, src.size, chunk):
+                    g.write(src[o:o + chunk])
+            else:
+                pool = ThreadPoolExecutor(nthreads) if producer == "acquire" else None
+                rfd = wfd = None
+                if producer == "pipe":
+                    import fcntl
+                    rfd, wfd = os.pipe()
+                    try:
+                        fcntl.fcntl(wfd, 1031, 1 << 20)          # F_SETPIPE_SZ
+                    except OSError:
+                        pass
+
+                    def feed():
+                        mv = memoryview(src)
+                        o = 0
+                        while o < len(mv):
+                            o += os.write(wfd, mv[o:o + (1 << 20)])
+                        os.close(wfd)
+                    threading.Thread(target=feed, daemon=True).start()
+                ptr, n, o = C.c_void_p(), C.c_size_t(), 0
+                while o < src.size:
+                    rc = L.mtz_ring_acquire(g._h, min(chunk, src.size - o), C.byref(ptr), C.byref(n))
+                    if rc == N.EAGAIN:
+                        time.sleep(0.0001)
+                        continue
+                    if rc != N.OK:
+                        raise RuntimeError("acquire rc %d" % rc)
+                    dst = np.ctypeslib.as_array((C.c_uint8 * n.value).from_address(ptr.value))
+                    if producer == "pipe":
+                        k = os.readv(rfd, [memoryview(dst)])
+                        if k <= 0:
+                            raise RuntimeError("pipe closed early")
+                    else:
+                        k = n.value
+                        part = (k + nthreads - 1) // nthreads
+                        list(pool.map(lambda i: np.copyto(dst[i * part:min(k, (i + 1) * part)],
+                                                          src[o + i * part:o + min(k, (i + 1) * part)]),
+                                      range(nthreads)))
+                    rc = L.mtz_ring_commit(g._h, k)
+                    if rc != N.OK:
+                        raise RuntimeError("commit rc %d" % rc)
+                    o += k
+                if pool:
+                    pool.shutdown()
+                if rfd is not None:
+                    os.close(rfd)
+            g.flush()
+        except Exception as e:              # noqa: BLE001
+            errs.append(repr(e))
+            g.cancel()
+
+    ts = [threading.Thread(target=consumer, args=(p,)) for p in peers]
+    t0 = time.perf_counter()
+    tp = threading.Thread(target=produce)
+    tp.start()
+    for t in ts:
+        t.start()
+    tp.join()
+    for t in ts:
+        t.join()
+    dt = time.perf_counter() - t0
+    return dt, (not errs), {"errors": errs[:3], "delivered": got}
+
+
+# -------------------------------------------------------------------------------- our arm --
+def run_verify_resident(args, O, local, steps, warm, peak):
+    """configs[1] on one GPU: 16 GiB uncompressed stream resident in HBM; GPU parse + K1 + scan per
+    step (round 1's headline, kept as a workload)."""
+    import numpy as np
+    import torch
+    from manatee_b200 import GpuSnapshotStage, PinnedBuffer, index_host
+    gib = args.verify_gib if args.workload != "verify" else (args.gib or 16.0)
+    nthreads = host_threads()
+    nwrites = max(1, int(gib * GIB) // REC_BYTES)
+    nbytes = O.lib().orc_synth_stream_size(nwrites, RECSIZE)
+    pin = PinnedBuffer(nbytes)
+    s = O.synth_stream(nwrites, RECSIZE, O.PAYLOAD_PCG, nthreads=nthreads, out=pin.array)
+    recs, used = index_host(s)
+    assert used == s.size
+    d_stream = torch.empty(s.size + 512, dtype=torch.uint8, device="cuda")
+    d_stream[:s.size].copy_(torch.from_numpy(s))
+    d_recs = torch.empty((len(recs) + 16) * 32, dtype=torch.uint8, device="cuda")
     st = torch.cuda.Stream()
     res = {}
-    with GpuSnapshotStage("recompress", device=local) as g:
+    with GpuSnapshotStage("verify", device=local) as g:
         def step():
-            g.dev_submit(d_in.data_ptr(), src.size, d_recs.data_ptr(), len(recs), d_out.data_ptr(),
-                         d_out.numel(), cuda_stream=st.cuda_stream)
-            return g.dev_finish()
-        ob, _, _ = step()
-        # size-independent parity property at full size: the input was produced by the declared
-        # encoder, so RECOMPRESS must reproduce it bit for bit (idempotence)
-        same = bool(torch.equal(d_out[:ob], d_in[:src.size])) if ob == src.size else False
+            n_idx, used_idx = g.dev_index(d_stream.data_ptr(), s.size, d_recs.data_ptr(), len(recs) + 16,
+                                          cuda_stream=st.cuda_stream)
+            assert n_idx == len(recs) and used_idx == s.size
+            g.dev_submit(d_stream.data_ptr(), s.size, d_recs.data_ptr(), n_idx, cuda_stream=st.cuda_stream)
+            return g.dev_finish(carry_in=(0, 0, 0, 0))
+        for _ in range(warm):
+            step()
         s0 = g.stats()
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
         e0.record(st)
-        for _ in range(args.recompress_steps):
-            g.dev_reset(); step()
+        for _ in range(steps):
+            step()
         e1.record(st)
         torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / args.recompress_steps
+        ms = e0.elapsed_time(e1) / steps
         s1 = g.stats()
-        # dev_reset() zeroes the counters every step: s1 describes the last step alone
-        codec_ms = s1["codec_ms"]
-        res["launches"] = int(s1["kernel_launches"])
-        res["lz4_decoded"] = int(s1["lz4_decoded"])
-        res["lz4_encoded"] = int(s1["lz4_encoded"])
-    del d_out
-    res.update({
-        "workload": "recompress: %.1f GiB logical / %.2f GiB stream, %d LZ4 128 KiB records "
-                    "(BASELINE configs[2]), pg-page payload model, ratio %.2f" % (
-                        logical / GIB, src.size / GIB, int((recs["type"] == 3).sum()), logical / src.size),
-        "value": round(src.size / GIB / (ms / 1e3), 3), "unit": "GiB/s (input stream bytes)",
-        "logical_gibs": round(logical / GIB / (ms / 1e3), 3), "ms_per_step": round(ms, 3),
-        "steps": args.recompress_steps, "idempotent_at_full_size": same,
-        "roofline": {"bound": "hbm", "kernel": "k2_lz4_decode + k3_lz4_encode",
-                     "achieved": round((2.0 * src.size + 624.0 * len(recs)) / (codec_ms / 1e3) / 1e9, 1),
-                     "peak": peak_gbs, "unit": "GB/s",
-                     "frac": round((2.0 * src.size + 624.0 * len(recs)) / (codec_ms / 1e3) / 1e9 / peak_gbs, 4),
-                     "algorithmic_bytes_per_launch": 2.0 * src.size + 624.0 * len(recs),
-                     "codec_ms": round(codec_ms, 2),
-                     "note": "fused lower bound 624 + C_in + C_out per record (SURVEY 8d); LZ4 is a "
-                             "serial token chain per record: latency-bound, far below HBM"}})
+        k1_ms = (s1["k1_ms"] - s0["k1_ms"]) / max(1, s1["k1_launches"] - s0["k1_launches"])
+        end_ck = g.end_checksum()
+        res.update({"value": round(s.size / GIB / (ms / 1e3), 3), "unit": "GiB/s", "ms_per_step": round(ms, 4),
+                    "steps": steps, "gpu_launches": int((s1["kernel_launches"] - s0["kernel_launches"]) // steps),
+                    "config": verify_config(gib),
+                    "roofline": {"bound": "hbm", "kernel": "k1_record_sums",
+                                 "achieved": round(s.size / (k1_ms / 1e3) / 1e9, 1), "peak": peak, "unit": "GB/s",
+                                 "frac": round(s.size / (k1_ms / 1e3) / 1e9 / peak, 4), "traffic": None,
+                                 "algorithmic_bytes_per_launch": float(s.size), "k1_ms": round(k1_ms, 4),
+                                 "note": "K1 only reads; the peak is a copy (read+write), so ~1.0 is the roof"}})
+    del d_stream, d_recs
+    torch.cuda.empty_cache()
     if not args.no_e2e:
-        pin_out = PinnedBuffer(src.size + (64 << 20))
-        with GpuSnapshotStage("recompress", device=local, n_slots=4) as ge:
-            ge.process_host(src, pin_out.array)
-            torch.cuda.synchronize()
+        with GpuSnapshotStage("verify", device=local, batch_bytes=64 << 20, n_slots=4) as ge:
+            ge.process_host(s)
             t0 = time.perf_counter()
-            for _ in range(args.recompress_steps):
-                n_out = ge.process_host(src, pin_out.array)
-            dt = (time.perf_counter() - t0) / args.recompress_steps
-        res["e2e"] = {"value": round(src.size / GIB / dt, 3), "unit": "GiB/s (input stream bytes)",
-                      "logical_gibs": round(logical / GIB / dt, 3),
-                      "h2d_bytes_per_step": int(src.size + len(recs) * 32),
-                      "d2h_bytes_per_step": int(n_out),
-                      "call": "mtz_process_host, pinned host in -> pinned host out"}
-        pin_out.free()
+            k = max(1, min(steps, args.e2e_steps))
+            for _ in range(k):
+                ge.process_host(s)
+            dt = (time.perf_counter() - t0) / k
+        res["e2e"] = {"value": round(s.size / GIB / dt, 3), "unit": "GiB/s",
+                      "h2d_bytes_per_step": int(s.size + len(recs) * 32),
+                      "d2h_bytes_per_step": int(((s.size + (64 << 20) - 1) // (64 << 20)) * 120),
+                      "call": "mtz_process_host, pinned host stream in, verdict out (output == input)"}
+        # the ring API at link rate: acquire/commit, the slice filled by parallel memcpys
+        with GpuSnapshotStage("verify", device=local, ring_bytes=1 << 30, batch_bytes=64 << 20, n_slots=4) as gr:
+            dt, ok, det = ring_run(gr, s, producer="acquire", nthreads=min(8, max(2, nthreads // 2)))
+            res["ring_acquire_commit"] = {"value": round(s.size / GIB / dt, 3), "unit": "GiB/s", "ok": bool(
+                ok and det["delivered"].get(0) == s.size and gr.end_checksum() == end_ck),
+                "call": "mtz_ring_acquire/commit (slices filled by parallel host memcpys) -> engine -> "
+                        "mtz_out_peek/consume in place (zero copy)"}
     if not args.no_cpu:
-        n2, secs, cst = cpu_recompress(src, cbuf)
-        n2, secs, cst = cpu_recompress(src, cbuf)
-        L.orc_mt_release()
-        res["cpu_baseline"] = {"value": round(src.size / GIB / secs, 3), "unit": "GiB/s (input stream bytes)",
-                               "logical_gibs": round(logical / GIB / secs, 3), "cores": nthreads,
-                               "cgroup_cpu_quota": cpu_quota(), "kind": "port",
-                               "sample": "whole stream once (second call, buffers warm): record-parallel "
-                                         "oracle LZ4 decode + encode + vector Fletcher-4 (oracle/mt.c)"}
-    pin_in.free()
+        rc, secs, cst = O.mt_verify(s, nthreads)
+        assert rc == 0 and cst.end_cksum.tuple() == end_ck, "GPU END checksum differs from the oracle's"
+        res["cpu_baseline"] = cpu_verify_baseline(O, s[:min(s.size, int(4 * GIB))], nthreads)
+    res["end_checksum"] = ["%016x" % x for x in (end_ck or ())]
+    pin.free()
     return res
-
-
-def run_reference(args):
-    """CPU arm: the oracle port of the path's arithmetic on all host threads."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return 0
-    import oracle as O
-    O.build()
-    nthreads = host_threads()
-    nwrites = max(1, int(args.ref_gib * GIB) // REC_BYTES)
-    s = O.synth_stream(nwrites, RECSIZE, O.PAYLOAD_PCG, nthreads=nthreads)
-    for _ in range(max(1, min(args.warmup, 2))):
-        rc, secs, st = O.mt_verify(s, nthreads)
-        assert rc == 0
-    t = []
-    for _ in range(args.steps):
-        rc, secs, st = O.mt_verify(s, nthreads)
-        assert rc == 0
-        t.append(secs)
-    # whole job on the CPU = the same arithmetic over N shards on the same cores
-    ms = 1e3 * sum(t) / len(t)
-    val = s.size / GIB / (ms / 1e3)
-    base = cpu_verify_baseline(O, s, nthreads)  # flavour + the one-thread figure
-    line = {
-        "impl": "reference", "metric": "snapshot_stream_gibs", "value": round(val, 3),
-        "unit": "GiB/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": round(ms, 3), "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "u32->u64 (mod 2^64)", "data": "synthetic",
-        "config": {"workload": "verify: %.2f GiB uncompressed ZFS-send stream, Fletcher-4 "
-                               "(BASELINE configs[1])" % (s.size / GIB),
-                   "records": int(st.records), "recordsize": RECSIZE},
-        "cpu_baseline": {"value": round(val, 3), "unit": "GiB/s", "cores": nthreads,
-                         "cgroup_cpu_quota": cpu_quota(), "kind": "port",
-                         "fletcher4": base["fletcher4"],
-                         "single_thread_value": base["single_thread_value"],
-                         "sample": "whole %.2f GiB stream per step, record-parallel %s "
-                                   "fletcher_4 + sequential combine (oracle/mt.c); single_thread_value = "
-                                   "the same on one thread, which is all a real `zfs send`/`zfs recv` "
-                                   "uses for the stream checksum" % (s.size / GIB, base["fletcher4"])},
-        "e2e": {"value": round(val, 3), "unit": "GiB/s", "h2d_bytes_per_step": 0,
-                "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
-        "note": "reference = Node identity pipe + in-kernel ZFS arithmetic; node/zfs are not "
-                "installable here, so the oracle port of that arithmetic is timed (kind=port): the "
-                "vector Fletcher-4 ZFS itself uses, made record-parallel over every host thread "
-                "(more parallelism than the reference's single `zfs send` thread has)",
-    }
-    print(json.dumps(line), flush=True)
-    return 0
 
 
 def run_ours(args):
     import numpy as np
     import torch
     import torch.distributed as dist
-    import oracle as O                      # generator + cpu_baseline leg only
-    from manatee_b200 import GpuSnapshotStage, PinnedBuffer, index_host
+    import oracle as O                      # generator, parity checks and the cpu_baseline leg only
+    from manatee_b200 import GpuSnapshotStage, PinnedBuffer, comm_unique_id, index_host
     from manatee_b200 import _native as N
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus:
-        if world == 1 and args.gpus > 1:
-            raise SystemExit("--gpus %d needs torchrun with one rank per GPU" % args.gpus)
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        raise SystemExit("--gpus %d needs torchrun with one rank per GPU" % args.gpus)
     torch.cuda.set_device(local)
+    gl = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        gl = dist.new_group(backend="gloo")          # CPU-side waits must not spin a kernel on the GPUs
     O.build()
+    nthreads = host_threads()
+    peak, peak_src = load_peaks()
 
-    nwrites = max(1, int(args.gib * GIB) // REC_BYTES)
-    flags = (1 if rank == 0 else 0) | (2 if rank == world - 1 else 0)
-    nbytes = O.lib().orc_synth_shard_size(nwrites, RECSIZE, flags)
-    pin = PinnedBuffer(nbytes)
-    shard, carry_in = make_shard(O, rank, world, nwrites, pin.array)
-    recs, used = index_host(shard)
-    assert used == shard.size
-    d_stream = torch.empty(shard.size + 512, dtype=torch.uint8, device="cuda")
-    d_stream[:shard.size].copy_(torch.from_numpy(shard))
+    if args.workload == "verify":
+        if world > 1:
+            raise SystemExit("--workload verify is the single-GPU configs[1] measurement; the multi-GPU "
+                             "line is the recompress workload")
+        clocks = ClockSampler(local); clocks.start()
+        t0 = time.time()
+        r = run_verify_resident(args, O, local, args.steps, args.warmup, peak)
+        clk = clocks.stop(t0, time.time())
+        line = {"metric": "snapshot_stream_gibs", "value": r["value"], "unit": "GiB/s", "n_gpus": 1,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "u32->u64 (mod 2^64)", "data": "synthetic", "config": r["config"],
+                "e2e": r.get("e2e"), "gpu_launches": r["gpu_launches"], "roofline": r["roofline"],
+                "cpu_baseline": r.get("cpu_baseline"), "e2e_stream_api": r.get("ring_acquire_commit"),
+                "clocks": clk, "end_checksum": r["end_checksum"]}
+        print(json.dumps(line), flush=True)
+        return 0
+
+    # ------------------------------------------------------------------ the stream (rank 0 makes it)
+    total_gib = args.gib or 64.0
+    shm = "/dev/shm/mtz_bench_%s.bin" % os.environ.get("MASTER_PORT", str(os.getpid()))
+    src = pin_in = None
+    meta = [None]
+    if rank == 0:
+        src, logical, pin_in = make_lz4_stream(O, total_gib, nthreads)
+        if world > 1:
+            with open(shm, "wb") as f:
+                f.write(memoryview(src))
+        meta = [{"bytes": int(src.size), "logical": float(logical)}]
+    if world > 1:
+        dist.broadcast_object_list(meta, src=0, group=gl)
+        whole = src if rank == 0 else np.memmap(shm, dtype=np.uint8, mode="r", shape=(meta[0]["bytes"],))
+    else:
+        whole = src
+    logical = meta[0]["logical"]
+    total_bytes = float(meta[0]["bytes"])
+    recs_all, used = index_host(whole)
+    assert used == whole.size
+    # record-index partition: rank r takes records [r n / N, (r+1) n / N)
+    r0, r1 = (rank * len(recs_all)) // world, ((rank + 1) * len(recs_all)) // world
+    b0 = int(recs_all["off"][r0])
+    b1 = int(recs_all["off"][r1]) if r1 < len(recs_all) else int(whole.size)
+    recs = recs_all[r0:r1].copy()
+    recs["off"] -= b0
+    shard_bytes = b1 - b0
+    d_in = torch.empty(shard_bytes + 512, dtype=torch.uint8, device="cuda")
+    d_in[:shard_bytes].copy_(torch.from_numpy(np.ascontiguousarray(whole[b0:b1])))
     d_recs = torch.from_numpy(recs.view(np.uint8).copy()).cuda()
+    worst = int((np.maximum(recs["lsize"].astype(np.int64), recs["payload"].astype(np.int64)) + 312).sum()) + (1 << 20)
+    d_out = torch.empty(worst, dtype=torch.uint8, device="cuda")
+    nwrites_total = int((recs_all["type"] == 3).sum())
+    if rank != 0:
+        del whole
     torch.cuda.synchronize()
-
     st = torch.cuda.Stream()
 
-    from manatee_b200 import shard as SH
+    # ------------------------------------------------------------------ resident timing: `value`
+    g = GpuSnapshotStage("recompress", device=local, flags=N.FLAG_DEFER_VERIFY if world > 1 else 0)
+    if world > 1:
+        uid = [comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0, group=gl)
+        g.comm_init(uid[0], rank, world)            # the library owns the communicator of the exchange
 
-    def exchange(g):
-        """all-gather of the 40-byte shard aggregate; returns this rank's carry-in."""
-        return SH.carry_before(rank, SH.all_gather_aggregates(g.dev_aggregate()))
-
-    # ---------------- resident (HBM) timing: `value` ----------------
-    g = GpuSnapshotStage("verify", device=local)
-
-    d_recs_gpu = torch.empty((len(recs) + 16) * 32, dtype=torch.uint8, device="cuda")
-
-    agg_t = torch.zeros(5, dtype=torch.int64, device="cuda")
-    all_t = torch.zeros(5 * world, dtype=torch.int64, device="cuda")
-
-    def step_resident():
-        # the DRR record table is rebuilt ON THE GPU every step (K4 parse half): nothing but
-        # the stream bytes is assumed to be resident when the timed region starts
-        n_idx, used_idx = g.dev_index(d_stream.data_ptr(), shard.size, d_recs_gpu.data_ptr(),
-                                      len(recs) + 16, cuda_stream=st.cuda_stream)
-        assert n_idx == len(recs) and used_idx == shard.size
-        g.dev_submit(d_stream.data_ptr(), shard.size, d_recs_gpu.data_ptr(), n_idx,
-                     cuda_stream=st.cuda_stream)
-        if world == 1:
-            _, carry, _ = g.dev_finish(carry_in=(0, 0, 0, 0))
-            return carry
-        # shard exchange without a host round trip: aggregate -> NCCL all-gather -> carry fold
-        # -> verify, all ordered on one CUDA stream; the only sync is the verdict read
-        with torch.cuda.stream(st):
-            g.dev_aggregate_async(agg_t.data_ptr())
-            dist.all_gather_into_tensor(all_t, agg_t)
-            _, carry, _ = g.dev_finish_gathered(all_t.data_ptr(), rank)
-        return carry
+    def step():
+        g.dev_reset()
+        g.dev_submit(d_in.data_ptr(), shard_bytes, d_recs.data_ptr(), len(recs), d_out.data_ptr(),
+                     d_out.numel(), cuda_stream=st.cuda_stream)
+        return g.dev_finish() if world == 1 else g.dev_finish_exchange()
 
     clocks = ClockSampler(local)
     if rank == 0:
-        clocks.start()                  # before warm-up: nvidia-smi needs >100 ms to start
-    warm_done = 0
-    t_w = time.time()
-    # W warm-up steps, plus (untimed) extra ones until the clock sampler is delivering rows, so
-    # that the short timed region is actually covered by samples
-    while True:
-        carry = step_resident()
-        warm_done += 1
-        live = torch.tensor([1 if (rank != 0 or clocks.proc is None or len(clocks.rows) >= 2 or
-                                   time.time() - t_w > 2.0) else 0], device="cuda")
-        if world > 1:
-            dist.all_reduce(live, op=dist.ReduceOp.MIN)
-        if warm_done >= args.warmup and int(live.item()) == 1:
-            break
+        clocks.start()
+    ob = 0
+    for _ in range(max(1, args.warmup)):
+        ob, _, carry_out = step()
+    # size-independent parity at full size: the input was produced by the declared encoder, so
+    # RECOMPRESS must reproduce every shard bit for bit (idempotence), re-stamped checksums included
+    same = torch.tensor([1 if (ob == shard_bytes and bool(torch.equal(d_out[:ob], d_in[:shard_bytes]))) else 0],
+                        device="cuda")
     if world > 1:
-        # the stamped stream is the oracle's: the carry-in we derived on the GPU must
-        # equal the generator's running checksum at the shard boundary
-        assert exchange(g) == carry_in, "GPU shard carry differs from the oracle's"
-    e0 = torch.cuda.Event(enable_timing=True)
-    e1 = torch.cuda.Event(enable_timing=True)
-    s0 = g.stats()
-    if world > 1:
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
         dist.barrier()
+    same = bool(int(same.item()))
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     t_wall0 = time.time()
     e0.record(st)
     for _ in range(args.steps):
-        carry = step_resident()
+        step()
     e1.record(st)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    ms_total = e0.elapsed_time(e1)
-    clk = clocks.stop(t_wall0, time.time()) if rank == 0 else None
-    s1 = g.stats()
-    t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+    s1 = g.stats()                       # dev_reset() zeroes the counters every step: the last step alone
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    ksum = torch.tensor([s1["k3_ms"], s1["codec_ms"], float(s1["k3_launches"]), float(s1["kernel_launches"])],
+                        dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(ksum, op=dist.ReduceOp.SUM)
+    clk = clocks.stop(t_wall0, time.time()) if rank == 0 else None
     ms_step = float(t.item()) / args.steps
-    total_bytes = torch.tensor([float(shard.size)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(total_bytes, op=dist.ReduceOp.SUM)
-    total_bytes = float(total_bytes.item())
     value = total_bytes / GIB / (ms_step / 1e3)
-    # ---------------- fan-out to N concurrent peers (configs[3]/[4]) ----------------
-    fan = None
-    if world > 1:
-        from manatee_b200 import fanout as FO
-        sizes = FO.shard_sizes(shard.size)
-        recv = torch.empty(max(sizes), dtype=torch.uint8, device="cuda")
-        touched = [0]
-
-        def consume(src, t):            # stand-in for the egress writer of this GPU's peer
-            touched[0] += int(t.numel())
-        # warm-up pass doubles as the correctness check: every rank must have streamed the
-        # same bytes (wrap-around int64 sum of the whole stream, compared across ranks)
-        acc = torch.zeros(1, dtype=torch.int64, device="cuda")
-
-        def consume_check(src, t):
-            acc.add_(t[:(t.numel() // 8) * 8].view(torch.int64).sum())
-        FO.broadcast_shards(d_stream[:shard.size], sizes, consume_check, recv)
-        accs = [torch.zeros_like(acc) for _ in range(world)]
-        dist.all_gather(accs, acc)
-        assert all(int(a.item()) == int(accs[0].item()) for a in accs), "fan-out delivered different bytes"
-        f0 = torch.cuda.Event(enable_timing=True); f1 = torch.cuda.Event(enable_timing=True)
-        dist.barrier(); torch.cuda.synchronize()
-        f0.record()
-        for _ in range(3):
-            FO.broadcast_shards(d_stream[:shard.size], sizes, consume, recv)
-        f1.record()
-        torch.cuda.synchronize(); dist.barrier()
-        tf = torch.tensor([f0.elapsed_time(f1) / 3.0], dtype=torch.float64, device="cuda")
-        dist.all_reduce(tf, op=dist.ReduceOp.MAX)
-        fms = float(tf.item())
-        fan = {"peers": world, "ms_per_stream": round(fms, 3),
-               "source_once_gibs": round(sum(sizes) / GIB / (fms / 1e3), 2),
-               "delivered_gibs": round(world * sum(sizes) / GIB / (fms / 1e3), 2),
-               "how": "each rank NCCL-broadcasts its verified shard; every egress GPU streams the "
-                      "whole %d x shard stream (rolling receive buffer)" % world}
-        del recv
-    k1_ms = (s1["k1_ms"] - s0["k1_ms"]) / max(1, s1["k1_launches"] - s0["k1_launches"])
-    launches = (s1["kernel_launches"] - s0["kernel_launches"]) // args.steps
+    k3_ms, codec_ms, k3_launches, launches = [float(x) for x in ksum.tolist()]
     end_ck = g.end_checksum()
     g.close()
+    del d_out, d_in, d_recs
+    torch.cuda.empty_cache()
 
-    # ---------------- host-facing C-ABI timing: `e2e` ----------------
-    e2e = None
-    if not args.no_e2e:
-        flags_cfg = N.FLAG_DEFER_VERIFY if world > 1 else 0
-        ge = GpuSnapshotStage("verify", device=local, batch_bytes=64 << 20, n_slots=4,
-                              flags=flags_cfg)
-
-        def step_e2e():
-            ge.process_host(shard)
-            if world > 1:
-                c = exchange(ge)
-                ge.dev_finish(carry_in=c)
-                ge.dev_reset()
-
-        for _ in range(min(args.warmup, 2)):
-            step_e2e()
-        b0 = ge.stats()["batches"]
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            step_e2e()
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dt = float(tt.item()) / args.steps
-        nb = max(1, (shard.size + (64 << 20) - 1) // (64 << 20))
-        e2e = {"value": round(total_bytes / GIB / dt, 3), "unit": "GiB/s",
-               "h2d_bytes_per_step": int(shard.size + len(recs) * 32),
-               "d2h_bytes_per_step": int(nb * 120),
-               "call": "mtz_process_host (pinned host stream -> cudaMemcpyAsync H2D -> K1+scan "
-                       "-> verdict D2H), host wall clock around the synchronous call, max over ranks",
-               "note": "VERIFY output bytes are the input bytes (identity), so only the "
-                       "verdict crosses back"}
-        ge.close()
-
-    # ---------------- streaming-ring API (what the Node Transform binds), N=1 ----------------
-    ring = None
-    if not args.no_e2e and world == 1:
-        import ctypes as C
-        L = N.lib()
-        gr = GpuSnapshotStage("verify", device=local, ring_bytes=1 << 30, batch_bytes=64 << 20, n_slots=4)
-        sample = shard[:min(shard.size, 4 << 30)]
-        # cut the sample at a record boundary so the stream ends cleanly
-        cutrec = int(np.searchsorted(recs["off"], sample.size, side="right")) - 1
-        sample = shard[:int(recs["off"][cutrec])]
-        perr = []
-
-        def producer():
-            try:
-                step = 8 << 20
-                for o in range(0, sample.size, step):
-                    gr.write(sample[o:o + step])
-                gr.flush()
-            except Exception as e:              # noqa: BLE001
-                perr.append(e)
-        t0 = time.perf_counter()
-        th = threading.Thread(target=producer)
-        th.start()
-        got = 0
-        p, n = C.c_void_p(), C.c_size_t()
-        while True:                             # zero-copy consumer: peek / consume
-            rc = L.mtz_out_peek(gr._h, C.byref(p), C.byref(n))
-            if rc == N.OK:
-                got += n.value
-                L.mtz_out_consume(gr._h, n.value)
-            elif rc == N.EOF:
-                break
-            elif rc == N.EAGAIN:
-                time.sleep(0.0002)
-            else:
-                break
-        th.join()
-        dt = time.perf_counter() - t0
-        ok = (not perr) and got == sample.size
-        ring = {"value": round(sample.size / GIB / dt, 3), "unit": "GiB/s", "ok": bool(ok),
-                "sample_gib": round(sample.size / GIB, 2),
-                "call": "mtz_write (8 MiB chunks, one producer thread memcpy into the pinned ring) -> "
-                        "engine thread -> mtz_out_peek/consume; bound by the single host memcpy thread"}
-        gr.close()
-
-    # ---------------- CPU baseline (rank 0, N=1) ----------------
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
-        nthreads = host_threads()
-        rc, secs, cst = O.mt_verify(shard, nthreads)
-        assert rc == 0
-        assert cst.end_cksum.tuple() == end_ck, "GPU END checksum differs from the oracle's"
-        cpu = cpu_verify_baseline(O, shard, nthreads)
-
+    # everything below is rank 0 alone (ONE process over all N GPUs); the others wait on the CPU
+    e2e = ring = fan = cpu = side = None
+    failed = []
     if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        peak = float(peaks.get("hbm_gbs", 6650.0))
-        alg_bytes = float(shard.size)          # 312+P bytes read per record: 1.000 B / stream B
-        ach = alg_bytes / (k1_ms / 1e3) / 1e9 if k1_ms > 0 else None
+        devices = list(range(world)) if world > 1 else None
+        nrec = len(recs_all)
+        if not args.no_e2e:
+            pin_out = PinnedBuffer(int(total_bytes) + (64 << 20))
+            with GpuSnapshotStage("recompress", device=local, devices=devices, n_slots=4) as ge:
+                n_out = ge.process_host(src, pin_out.array)
+                ok = (n_out == src.size and ge.end_checksum() is not None)
+                for o in (0, (src.size // 2) & ~4095, max(0, src.size - (64 << 20))):
+                    ok = ok and np.array_equal(pin_out.array[o:o + (64 << 20)][:n_out - o], src[o:o + (64 << 20)])
+                if not ok:
+                    failed.append("e2e output differs from the oracle-encoded input")
+                k = max(1, min(args.steps, args.e2e_steps))
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                for _ in range(k):
+                    n_out = ge.process_host(src, pin_out.array)
+                dt = (time.perf_counter() - t0) / k
+            e2e = {"value": round(total_bytes / GIB / dt, 3), "unit": "GiB/s",
+                   "logical_gibs": round(logical / GIB / dt, 3), "steps": k,
+                   "h2d_bytes_per_step": int(total_bytes + nrec * 32), "d2h_bytes_per_step": int(n_out),
+                   "output_equals_input": bool(ok),
+                   "call": "mtz_process_host(pinned host stream in, pinned host stream out) on ONE handle over "
+                           "%s, host wall clock around the synchronous call" % (
+                               "the device group mtz_config.devices[0..%d) of a single process" % world
+                               if world > 1 else "one GPU")}
+            pin_out.free()
+            # ---- the ring API (what js/src/binding.cc binds) on the same workload
+            ring = {}
+            for name, prod in (("write", "write"), ("acquire_commit", "acquire"), ("pipe", "pipe")):
+                with GpuSnapshotStage("recompress", device=local, devices=devices, ring_bytes=1 << 30,
+                                      out_ring_bytes=1 << 30, n_slots=4) as gr:
+                    dt, ok, det = ring_run(gr, src, producer=prod, nthreads=min(8, max(2, nthreads // 2)))
+                    ok = ok and det["delivered"].get(0) == src.size and gr.end_checksum() == end_ck_of(O, end_ck, gr)
+                ring[name] = {"value": round(src.size / GIB / dt, 3), "unit": "GiB/s", "ok": bool(ok),
+                              "logical_gibs": round(logical / GIB / dt, 3)}
+                if not ok:
+                    failed.append("ring API leg %s: %s" % (name, det["errors"]))
+            ring["call"] = ("write = mtz_write (one producer thread memcpy into the pinned ring); acquire_commit = "
+                            "mtz_ring_acquire/commit with the slice filled by parallel memcpys; pipe = read(2) "
+                            "from a pipe into the slice (zfsSend.stdout shape, bound by the pipe); consumer = "
+                            "mtz_out_peek/consume on the pinned output ring")
+            ring["ok"] = all(v.get("ok", True) for v in ring.values() if isinstance(v, dict))
+            ring["value"] = ring.get("acquire_commit", {}).get("value")
+            ring["unit"] = "GiB/s"
+            # ---- fan-out of the PROCESSED stream to P attached peers (configs[3]/[4])
+            if world > 1:
+                P = {2: 2, 4: 3, 8: 8}.get(world, min(world, 8))
+                with GpuSnapshotStage("recompress", device=local, devices=devices, ring_bytes=1 << 30,
+                                      out_ring_bytes=512 << 20, n_slots=4) as gf:
+                    eg = [gf.fanout_attach(p) for p in range(P)]
+                    dt, ok, det = ring_run(gf, src, peers=tuple(range(P)), producer="acquire",
+                                           nthreads=min(8, max(2, nthreads // 2)))
+                    ok = ok and all(det["delivered"].get(p) == src.size for p in range(P))
+                fan = {"peers": P, "egress_gpus": eg, "ok": bool(ok),
+                       "source_once_gibs": round(total_bytes / GIB / dt, 2),
+                       "delivered_gibs": round(P * total_bytes / GIB / dt, 2),
+                       "delivered_logical_gibs": round(P * logical / GIB / dt, 2), "seconds": round(dt, 3),
+                       "how": "one pass over the stream on %d GPUs; every batch's output crosses NVLink by one "
+                              "grouped ncclBroadcast (library-owned communicator) to the egress GPUs and is "
+                              "copied D2H into each peer's own pinned ring (mtz_fanout_attach / "
+                              "mtz_out_peek_peer); consumers drain the rings" % world}
+                if not ok:
+                    failed.append("fan-out: %s" % det["errors"])
+        if not args.no_cpu and world == 1:
+            target = int(src.size * min(1.0, args.ref_gib * GIB / logical))
+            k = int(np.searchsorted(recs_all["off"], target, side="right")) - 1
+            cut = int(recs_all["off"][max(1, k)]) if k + 1 < len(recs_all) else int(src.size)
+            sample = src[:cut]
+            out = np.empty(sample.size + (1 << 20), dtype=np.uint8)
+            n2, secs = cpu_recompress(O, sample, out, nthreads)
+            n2, secs = cpu_recompress(O, sample, out, nthreads)
+            O.lib().orc_mt_release()
+            slog = logical * sample.size / total_bytes
+            cpu = {"value": round(sample.size / GIB / secs, 3), "unit": "GiB/s", "cores": nthreads,
+                   "cgroup_cpu_quota": cpu_quota(), "kind": "port",
+                   "logical_gibs": round(slog / GIB / secs, 3),
+                   "sample": "the first %.2f GiB of the input stream (%.2f GiB logical), second of two passes: "
+                             "record-parallel oracle LZ4 decode + encode + vector Fletcher-4, sequential stamp "
+                             "(oracle/mt.c)" % (sample.size / GIB, slog / GIB)}
+            del out
+        if world == 1 and args.verify_gib > 0:
+            pin_in.free(); pin_in = None; src = None
+            side = {"verify": run_verify_resident(args, O, local, min(args.steps, 20), args.warmup, peak)}
+
+    if world > 1:
+        dist.barrier(group=gl)
+    if rank == 0:
+        alg = 2.0 * total_bytes + 624.0 * len(recs_all)
+        ach = alg / (k3_ms / 1e3) / 1e9 if k3_ms > 0 else None
         traffic = None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "k1_traffic.json"))).get(
-                "dram_bytes_per_stream_byte")
-            if traffic is not None:
-                traffic = traffic * alg_bytes
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r2_k3_traffic.json")))
+            traffic = tj.get("dram_bytes_per_algorithmic_byte") * alg / max(1.0, k3_launches)
         except Exception:
             pass
+        cfg = recompress_config(total_gib)            # identical on both arms (the driver compares them)
+        detail = {"records": int(len(recs_all)), "write_records": nwrites_total,
+                  "stream_gib": round(total_bytes / GIB, 3), "logical_gib": round(logical / GIB, 3),
+                  "ratio": round(logical / total_bytes, 3),
+                  "partition": ("record-index, %d contiguous shards; 40-B aggregate all-gather + 32-B output "
+                                "checksum hop over library-owned NCCL" % world) if world > 1 else "single GPU",
+                  "l2": "inputs_exceed_l2 (%.1f GiB per GPU >> 126 MB)" % (total_bytes / world / GIB)}
         line = {
             "metric": "snapshot_stream_gibs", "value": round(value, 3), "unit": "GiB/s",
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "warmup_done": warm_done,
-            "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "u32->u64 (mod 2^64)", "data": "synthetic",
-            "config": {
-                "workload": "verify: %.2f GiB/GPU uncompressed ZFS-send stream, Fletcher-4 "
-                            "(BASELINE configs[1])" % (shard.size / GIB),
-                "records_per_gpu": int(len(recs)), "recordsize": RECSIZE,
-                "partition": "record-index, contiguous shard per rank; all-gather of 40 B "
-                             "aggregates" if world > 1 else "single GPU",
-                "l2": "inputs_exceed_l2 (%.1f GiB >> 126 MB)" % (shard.size / GIB),
-                "payload": "PCG32 seed 0x4D414E41 (incompressible)"},
-            "e2e": e2e,
-            "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "k1_record_sums",
-                         "achieved": round(ach, 1) if ach else None, "peak": peak,
-                         "unit": "GB/s", "frac": round(ach / peak, 4) if ach else None,
-                         "traffic": traffic,
-                         "peak_source": ("MEASURED_PEAKS.json hbm_gbs" if peaks else
-                                         "fallback 6650 (B200_PROFILING.md)") +
-                                        " -- a STREAM copy (read+write); K1 is read-only, so a "
-                                        "fraction slightly above 1.0 is expected",
-                         "algorithmic_bytes_per_launch": alg_bytes,
-                         "k1_ms": round(k1_ms, 4)},
-            "cpu_baseline": cpu,
-            "e2e_stream_api": ring,
-            "fanout": fan,
-            "clocks": clk,
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": round(ms_step, 3), "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "u8 / u32->u64 (mod 2^64)", "data": "synthetic",
+            "config": cfg, "workload_detail": detail,
+            "logical_gibs": round(logical / GIB / (ms_step / 1e3), 3),
+            "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "k3_lz4_encode", "achieved": round(ach, 1) if ach else None,
+                         "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 5) if ach else None,
+                         "traffic": traffic, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg / max(1.0, k3_launches),
+                         "launches_per_step": int(k3_launches),
+                         "k3_ms_per_step": round(k3_ms / world, 3), "codec_ms_per_step": round(codec_ms / world, 3),
+                         "note": "algorithmic bytes = the fused lower bound 624 + C_in + C_out per record (SURVEY "
+                                 "8d) over all records of the step / summed K3 launch time (CUDA events in the "
+                                 "library, summed over ranks); LZ4 encode is a serial match chain per record, "
+                                 "bound by dependent latency at the shared-memory occupancy limit, not by HBM"},
+            "idempotent_at_full_size": same,
+            "cpu_baseline": cpu, "e2e_stream_api": ring, "fanout": fan, "workloads": side, "clocks": clk,
             "end_checksum": ["%016x" % x for x in (end_ck or ())],
         }
-        if world == 1 and args.recompress_gib > 0:
-            del d_stream
-            pin.free()
-            pin = None
-            torch.cuda.empty_cache()
-            line["workloads"] = {"recompress": run_recompress(args, local, peak)}
+        if not same:
+            failed.append("RECOMPRESS output differs from the oracle-encoded input")
+        if failed:
+            line["failed"] = failed
         print(json.dumps(line), flush=True)
+        if world > 1:
+            try:
+                os.unlink(shm)
+            except OSError:
+                pass
     if world > 1:
-        dist.barrier()
+        dist.barrier(group=gl)
         dist.destroy_process_group()
-    if pin is not None:
-        pin.free()
-    return 0
+    if pin_in is not None:
+        pin_in.free()
+    return 1 if failed else 0
+
+
+def end_ck_of(O, resident_ck, stage):
+    """END checksum the ring run must reproduce: the resident run's when it saw the END record (N=1),
+    else whatever this stage reports (N>1: the resident ranks each saw a shard)."""
+    return resident_ck if resident_ck is not None else stage.end_checksum()
 
 
 def main():
@@ -637,13 +748,6 @@ def main():
     args = parse_args()
     RECSIZE = args.recsize
     REC_BYTES = 312 + RECSIZE
-    if RECSIZE != 131072 and args.recompress_gib:
-        # BASELINE configs[2] is defined on 128 KiB records; the small-recordsize sweeps are
-        # VERIFY-only (a 64 GiB codec workload of millions of tiny records took the GPU box
-        # down in round 1 -- not reproduced yet, so it is not run implicitly)
-        print("note: --recsize %d: recompress workload skipped (pass it alone with --recsize 131072)"
-              % RECSIZE, file=sys.stderr)
-        args.recompress_gib = 0
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)
