@@ -73,6 +73,20 @@ def lib():
         raise ImportError(
             "libmanatee_gpu.so is not built: run `python -c 'import __graft_entry__ as g; "
             "g.build()'` (there is no CPU fallback for the snapshot stage)")
+    # The library binds NCCL at run time (csrc/mtz_nccl.h).  In a Python process that will also
+    # import torch, point it at the libnccl torch bundles: torch cannot import behind an older
+    # libnccl.so.2 that somebody else loaded first under the same SONAME.
+    if "MTZ_NCCL_LIB" not in os.environ:
+        try:
+            import importlib.util
+            spec = importlib.util.find_spec("nvidia.nccl")
+            for d in (spec.submodule_search_locations or []) if spec else []:
+                cand = os.path.join(d, "lib", "libnccl.so.2")
+                if os.path.exists(cand):
+                    os.environ["MTZ_NCCL_LIB"] = cand
+                    break
+        except Exception:
+            pass
     L = C.CDLL(SO_PATH)
     vp, sz, i32, u64 = C.c_void_p, C.c_size_t, C.c_int32, C.c_uint64
     H = vp

@@ -123,6 +123,8 @@ static void CUDART_CB engine_host_cb(void *p)
 static int32_t fanout_init(mtz_handle *h, size_t chunk_cap)
 {
 	if (h->nccl_ready) return MTZ_OK;
+	std::string why;
+	if (!nccl_available(&why)) return fail(h, MTZ_ECUDA, "fan-out over a device group needs NCCL: %s", why.c_str());
 	const int G = (int)h->devs.size();
 	std::vector<ncclComm_t> comms((size_t)G);
 	std::vector<int> ids((size_t)G);

@@ -8,7 +8,7 @@
 #include <thread>
 #include <vector>
 #include <cuda_runtime.h>
-#include <nccl.h>
+#include "mtz_nccl.h"
 #include "../../include/manatee_gpu.h"
 #include "kernels_fletcher.cuh"
 #include "kernels_lz4.cuh"

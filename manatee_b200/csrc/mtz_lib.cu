@@ -878,6 +878,7 @@ int32_t mtz_comm_unique_id(uint8_t id[128])
 	if (id == nullptr) return MTZ_EINVAL;
 	static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
 	ncclUniqueId u;
+	if (!nccl_available(nullptr)) return MTZ_ECUDA;
 	if (ncclGetUniqueId(&u) != ncclSuccess) return MTZ_ECUDA;
 	memcpy(id, &u, 128);
 	return MTZ_OK;
@@ -888,6 +889,8 @@ int32_t mtz_comm_init(mtz_handle *h, const uint8_t id[128], int32_t rank, int32_
 	CHECK_H(h);
 	if (id == nullptr || world < 1 || rank < 0 || rank >= world) return fail(h, MTZ_EINVAL, "bad rank/world");
 	if (h->xcomm != nullptr) return fail(h, MTZ_EINVAL, "communicator already initialised");
+	std::string why;
+	if (!nccl_available(&why)) return fail(h, MTZ_ECUDA, "the shard exchange needs NCCL: %s", why.c_str());
 	MTZ_CU(h, cudaSetDevice(h->device));
 	ncclUniqueId u;
 	memcpy(&u, id, 128);
