@@ -454,7 +454,9 @@ def run_verify_resident(args, O, local, steps, warm, peak):
     if not args.no_cpu:
         rc, secs, cst = O.mt_verify(s, nthreads)
         assert rc == 0 and cst.end_cksum.tuple() == end_ck, "GPU END checksum differs from the oracle's"
-        res["cpu_baseline"] = cpu_verify_baseline(O, s[:min(s.size, int(4 * GIB))], nthreads)
+        k = int(np.searchsorted(recs["off"], min(s.size, int(4 * GIB)), side="right")) - 1
+        cut = s.size if k + 1 >= len(recs) else int(recs["off"][max(1, k)])      # whole records only
+        res["cpu_baseline"] = cpu_verify_baseline(O, s[:cut], nthreads)
     res["end_checksum"] = ["%016x" % x for x in (end_ck or ())]
     pin.free()
     return res
@@ -677,7 +679,11 @@ def run_ours(args):
             del out
         if world == 1 and args.verify_gib > 0:
             pin_in.free(); pin_in = None; src = None
-            side = {"verify": run_verify_resident(args, O, local, min(args.steps, 20), args.warmup, peak)}
+            try:
+                side = {"verify": run_verify_resident(args, O, local, min(args.steps, 20), args.warmup, peak)}
+            except Exception as e:              # noqa: BLE001 -- a side workload never costs the headline line
+                side = {"verify": {"error": repr(e)}}
+                failed.append("side workload verify: %r" % (e,))
 
     if world > 1:
         dist.barrier(group=gl)
