@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libmanatee_gpu.so")
+# MTZ_SO: load another build of the SAME library (kernel A/B experiments, tools/gpu/); default in-tree
+SO_PATH = os.environ.get("MTZ_SO") or os.path.join(_HERE, "libmanatee_gpu.so")
 
 OK, EINVAL, EAGAIN, ECUDA, EFORMAT, ECKSUM, ECODEC, ENOSPC, ENOMEM, EOF, ENOGPU, ECANCELED = \
     0, -1, -2, -3, -4, -5, -6, -7, -8, -9, -10, -11

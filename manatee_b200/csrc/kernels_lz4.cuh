@@ -537,9 +537,18 @@ __device__ __forceinline__ uint32_t warp_zfs_lz4_compress(const uint8_t *__restr
 	return psize;
 }
 
-// per-warp shared memory: the hash table
+// per-warp shared memory: the hash table.  CTA shape: K3_THREADS/32 encoder warps; the launch
+// picks as many CTAs per SM as tables fit (24 tables of 8.5 KiB at 4 warps x 6 CTAs, 26 at
+// 13 warps x 2 CTAs -- the carve-out has room for 26).
+#ifndef K3_THREADS
+#define K3_THREADS 128
+#endif
+#ifndef K3_MIN_BLOCKS
+#define K3_MIN_BLOCKS 6
+#endif
+#define K3_WARPS (K3_THREADS / 32)
 template <bool COMPACT>
-__global__ void __launch_bounds__(LZ4_THREADS)
+__global__ void __launch_bounds__(K3_THREADS, K3_MIN_BLOCKS)
 k3_lz4_encode(const uint8_t *__restrict__ src_base, uint8_t *__restrict__ dst_base,
     mtz_job *__restrict__ jobs, uint32_t njobs)
 {
@@ -548,8 +557,8 @@ k3_lz4_encode(const uint8_t *__restrict__ src_base, uint8_t *__restrict__ dst_ba
 	constexpr uint32_t PERW = TABW;
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	uint32_t *tab = reinterpret_cast<uint32_t *>(s_dyn) + warp * PERW;
-	const uint32_t gw = blockIdx.x * LZ4_WARPS + (uint32_t)warp;
-	const uint32_t nw = gridDim.x * LZ4_WARPS;
+	const uint32_t gw = blockIdx.x * K3_WARPS + (uint32_t)warp;
+	const uint32_t nw = gridDim.x * K3_WARPS;
 	for (uint32_t j = gw; j < njobs; j += nw) {
 		const mtz_job job = jobs[j];
 		if (job.lsize == 0u) continue;

@@ -1328,9 +1328,9 @@ int32_t mtz_k_lz4_decode(mtz_handle *h, const void *d_src, void *d_dst, mtz_job 
 static int32_t k3_set_attributes(mtz_handle *h)
 {
 	MTZ_CU(h, cudaFuncSetAttribute(k3_lz4_encode<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-	    (int)((size_t)LZ4_WARPS * LZ4_TAB_COMPACT_WORDS * 4)));
+	    (int)((size_t)K3_WARPS * LZ4_TAB_COMPACT_WORDS * 4)));
 	MTZ_CU(h, cudaFuncSetAttribute(k3_lz4_encode<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-	    (int)((size_t)LZ4_WARPS * LZ4_TAB_BIG_WORDS * 4)));
+	    (int)((size_t)K3_WARPS * LZ4_TAB_BIG_WORDS * 4)));
 	// all of the unified L1/shared array as shared memory: K3 is bound by records in
 	// flight (24 tables of 8.5 KiB per SM), measured 62 vs 46 GiB/s at a 75 % carve-out
 	// (profiles/r1_k3_encode.md).  MTZ_K3_CARVEOUT overrides for experiments.
@@ -1346,13 +1346,19 @@ static int32_t launch_k3(mtz_handle *h, cudaStream_t st, const void *d_src, void
     mtz_job *d_jobs, uint32_t njobs, bool compact)
 {
 	const size_t tabw = compact ? LZ4_TAB_COMPACT_WORDS : LZ4_TAB_BIG_WORDS;
-	const size_t smem = (size_t)LZ4_WARPS * tabw * sizeof(uint32_t);
-	const int blocks_per_sm = (int)((227u * 1024u) / (smem + 1024));
-	const int grid = lz4_grid(h, njobs, blocks_per_sm * LZ4_WARPS);
+	const size_t smem = (size_t)K3_WARPS * tabw * sizeof(uint32_t);
+	int blocks_per_sm = (int)((227u * 1024u) / (smem + 1024));
+	{
+		// experiments only (tools/k3_bound.py): fewer encoder CTAs per SM than the tables allow
+		const char *e = getenv("MTZ_K3_BLOCKS_PER_SM");
+		if (e && atoi(e) > 0) blocks_per_sm = std::min(blocks_per_sm, atoi(e));
+	}
+	const uint32_t need = (njobs + K3_WARPS - 1) / K3_WARPS;
+	const int grid = (int)std::max(1u, std::min(need, (uint32_t)h->sm_count * (uint32_t)blocks_per_sm));
 	if (compact)
-		k3_lz4_encode<true><<<grid, LZ4_THREADS, smem, st>>>((const uint8_t *)d_src, (uint8_t *)d_dst, d_jobs, njobs);
+		k3_lz4_encode<true><<<grid, K3_THREADS, smem, st>>>((const uint8_t *)d_src, (uint8_t *)d_dst, d_jobs, njobs);
 	else
-		k3_lz4_encode<false><<<grid, LZ4_THREADS, smem, st>>>((const uint8_t *)d_src, (uint8_t *)d_dst, d_jobs, njobs);
+		k3_lz4_encode<false><<<grid, K3_THREADS, smem, st>>>((const uint8_t *)d_src, (uint8_t *)d_dst, d_jobs, njobs);
 	MTZ_CU(h, cudaGetLastError());
 	count_launch(h, 1);
 	return MTZ_OK;
@@ -1365,7 +1371,9 @@ int32_t mtz_k_lz4_encode(mtz_handle *h, const void *d_src, void *d_dst, mtz_job 
 	if (njobs == 0) return MTZ_OK;
 	MTZ_CU(h, cudaSetDevice(h->device));
 	cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : h->st;
-	return launch_k3(h, st, d_src, d_dst, d_jobs, njobs, false);
+	// MTZ_K3_FORCE_COMPACT: the caller vouches that every job is a 128 KiB-class block (experiments)
+	const char *e = getenv("MTZ_K3_FORCE_COMPACT");
+	return launch_k3(h, st, d_src, d_dst, d_jobs, njobs, e != nullptr && atoi(e) != 0);
 }
 
 // ------------------------------------------------------- GPU-side parse ---

@@ -168,8 +168,8 @@ int32_t emu_codec(uint32_t mode, const uint8_t *d_in, const mtz_rec *recs, uint3
 	if (mode != MTZ_MODE_COMPRESS)
 		emu::launch(glz, LZ4_THREADS, [&] { k2_lz4_decode(nullptr, nullptr, dec.data(), n); });
 	if (mode != MTZ_MODE_DECOMPRESS) {
-		if (compact) emu::launch(glz, LZ4_THREADS, [&] { k3_lz4_encode<true>(nullptr, nullptr, enc.data(), n); });
-		else emu::launch(glz, LZ4_THREADS, [&] { k3_lz4_encode<false>(nullptr, nullptr, enc.data(), n); });
+		if (compact) emu::launch(glz, K3_THREADS, [&] { k3_lz4_encode<true>(nullptr, nullptr, enc.data(), n); });
+		else emu::launch(glz, K3_THREADS, [&] { k3_lz4_encode<false>(nullptr, nullptr, enc.data(), n); });
 	}
 	emu::launch(gb, tb, [&] { k_layout(recs, n, cr.data(), dec.data(), enc.data(), vals.data(), &cres, 0u); });
 	emu::launch(1, XSCAN_THREADS, [&] { k_xscan_u64(vals.data(), out_offs.data(), n, &outpos, &outpos); });
