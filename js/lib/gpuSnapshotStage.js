@@ -30,6 +30,7 @@ function GpuSnapshotStage(options) {
     this._h = this._addon.open({
         mode: MODES[options.mode || 'verify'],
         device: options.device || 0,
+        deviceMask: options.deviceMask || 0,    // device group: bit i = CUDA device i
         ringBytes: options.ringBytes || 0,
         outRingBytes: options.outRingBytes || 0,
         batchBytes: options.batchBytes || 0,
@@ -53,6 +54,21 @@ GpuSnapshotStage.prototype._fail = function (err) {
     // (lib/zfsClient.js:867-876)
     this._cleanup();
     this.destroy(err);
+};
+
+/*
+ * destroy() from outside (socket 'error', pipeline teardown): without this the native handle --
+ * pinned rings, GPU slots, the engine and watcher threads -- would leak on every failed restore
+ * of a long-lived daemon.  cancel() first: a chunk parked in _pending is waiting for ring space
+ * that will never come.
+ */
+GpuSnapshotStage.prototype._destroy = function (err, cb) {
+    if (!this._closed) {
+        try { this._addon.cancel(this._h); } catch (e) {}
+    }
+    this._pending = null;
+    this._cleanup();
+    cb(err);
 };
 
 GpuSnapshotStage.prototype._cleanup = function () {

@@ -9,13 +9,17 @@
 // (tests/test_zz_napi_harness.py).
 //
 // JS surface (used by js/lib/gpuSnapshotStage.js):
-//   open({mode, device, ringBytes, outRingBytes, batchBytes, slots}) -> handle (external)
+//   open({mode, device, deviceMask, ringBytes, outRingBytes, batchBytes, slots}) -> handle (external)
+//                                  deviceMask: bit i set = CUDA device i is part of the device group
+//                                  (mtz_config.devices[]); 0 = just `device`
+//   attach(handle, peer)           -> egress GPU of the peer; before the first byte (mtz_fanout_attach)
+//   cancel(handle)                 -> fail the handle with MTZ_ECANCELED, wake everything (stage._destroy)
 //   acquire(handle, want)          -> ArrayBuffer over the PINNED input ring slice (zero copy) | null
 //   commit(handle, n)
 //   write(handle, Buffer)          -> bytes accepted (non-blocking; 0 == ring full)
 //   flush(handle)
-//   peek(handle)                   -> ArrayBuffer over the pinned output slice | null | 'eof'
-//   consume(handle, n)
+//   peek(handle[, peer])           -> ArrayBuffer over the pinned output slice | null | 'eof'
+//   consume(handle, n[, peer])
 //   eventFd(handle)                -> the library's eventfd (readable when output / error / EOF is pending)
 //   watch(handle, fn)              -> watcher (external): a small native thread poll(2)s that fd and
 //                                     calls fn() ON THE EVENT LOOP through a napi_threadsafe_function,
@@ -73,6 +77,9 @@ static napi_value Open(napi_env env, napi_callback_info info)
 	cfg.out_ring_bytes = get_u64_prop(env, argv[0], "outRingBytes");
 	cfg.batch_bytes = get_u64_prop(env, argv[0], "batchBytes");
 	cfg.n_slots = (uint32_t)get_u64_prop(env, argv[0], "slots");
+	const uint64_t mask = get_u64_prop(env, argv[0], "deviceMask");
+	for (int d = 0; d < MTZ_MAX_DEVICES; d++)
+		if (mask & (1ull << d)) cfg.devices[cfg.n_devices++] = d;
 	mtz_handle *h = NULL;
 	int32_t rc = mtz_open(&cfg, &h);
 	if (rc != MTZ_OK) return throw_mtz(env, NULL, rc);
@@ -143,13 +150,35 @@ static napi_value Flush(napi_env env, napi_callback_info info)
 	return NULL;
 }
 
-static napi_value Peek(napi_env env, napi_callback_info info)
+static napi_value Attach(napi_env env, napi_callback_info info)
+{
+	size_t argc = 2; napi_value argv[2];
+	NAPI_OK(napi_get_cb_info(env, info, &argc, argv, NULL, NULL));
+	mtz_handle *h = get_handle(env, argv[0]);
+	uint32_t peer = 0; napi_get_value_uint32(env, argv[1], &peer);
+	int32_t rc = mtz_fanout_attach(h, (int32_t)peer);
+	if (rc < 0) return throw_mtz(env, h, rc);
+	napi_value out; napi_create_int32(env, rc, &out);
+	return out;
+}
+
+static napi_value Cancel(napi_env env, napi_callback_info info)
 {
 	size_t argc = 1; napi_value argv[1];
 	NAPI_OK(napi_get_cb_info(env, info, &argc, argv, NULL, NULL));
+	mtz_cancel(get_handle(env, argv[0]));
+	return NULL;
+}
+
+static napi_value Peek(napi_env env, napi_callback_info info)
+{
+	size_t argc = 2; napi_value argv[2];
+	NAPI_OK(napi_get_cb_info(env, info, &argc, argv, NULL, NULL));
 	mtz_handle *h = get_handle(env, argv[0]);
+	uint32_t peer = 0;
+	if (argc >= 2) napi_get_value_uint32(env, argv[1], &peer);
 	const void *p = NULL; size_t n = 0;
-	int32_t rc = mtz_out_peek(h, &p, &n);
+	int32_t rc = mtz_out_peek_peer(h, (int32_t)peer, &p, &n);
 	napi_value out;
 	if (rc == MTZ_EAGAIN) { napi_get_null(env, &out); return out; }
 	if (rc == MTZ_EOF) { napi_create_string_utf8(env, "eof", 3, &out); return out; }
@@ -160,11 +189,12 @@ static napi_value Peek(napi_env env, napi_callback_info info)
 
 static napi_value Consume(napi_env env, napi_callback_info info)
 {
-	size_t argc = 2; napi_value argv[2];
+	size_t argc = 3; napi_value argv[3];
 	NAPI_OK(napi_get_cb_info(env, info, &argc, argv, NULL, NULL));
 	mtz_handle *h = get_handle(env, argv[0]);
-	uint32_t n = 0; napi_get_value_uint32(env, argv[1], &n);
-	int32_t rc = mtz_out_consume(h, n);
+	uint32_t n = 0, peer = 0; napi_get_value_uint32(env, argv[1], &n);
+	if (argc >= 3) napi_get_value_uint32(env, argv[2], &peer);
+	int32_t rc = mtz_out_consume_peer(h, (int32_t)peer, n);
 	if (rc != MTZ_OK) return throw_mtz(env, h, rc);
 	return NULL;
 }
@@ -206,6 +236,25 @@ static void watcher_main(Watcher *w)
 	napi_release_threadsafe_function(w->tsfn, napi_tsfn_release);
 }
 
+static void watcher_stop(Watcher *w)
+{
+	if (w->stop_fd >= 0) {
+		const uint64_t one = 1;
+		if (write(w->stop_fd, &one, sizeof one) < 0) { /* thread exits on POLLNVAL at close */ }
+		if (w->th.joinable()) w->th.join();
+		close(w->stop_fd);
+		w->stop_fd = -1;
+	}
+}
+
+// the Watcher lives as long as its JS external: unwatch() stops the thread, GC frees the struct
+static void watcher_finalize(napi_env, void *data, void *)
+{
+	Watcher *w = (Watcher *)data;
+	watcher_stop(w);
+	delete w;
+}
+
 static napi_value Watch(napi_env env, napi_callback_info info)
 {
 	size_t argc = 2; napi_value argv[2];
@@ -230,7 +279,7 @@ static napi_value Watch(napi_env env, napi_callback_info info)
 	napi_unref_threadsafe_function(env, w->tsfn);
 	w->th = std::thread(watcher_main, w);
 	napi_value ext;
-	NAPI_OK(napi_create_external(env, w, NULL, NULL, &ext));
+	NAPI_OK(napi_create_external(env, w, watcher_finalize, NULL, &ext));
 	return ext;
 }
 
@@ -240,14 +289,7 @@ static napi_value Unwatch(napi_env env, napi_callback_info info)
 	NAPI_OK(napi_get_cb_info(env, info, &argc, argv, NULL, NULL));
 	void *p = NULL;
 	if (napi_get_value_external(env, argv[0], &p) != napi_ok || p == NULL) return NULL;
-	Watcher *w = (Watcher *)p;
-	if (w->stop_fd >= 0) {
-		const uint64_t one = 1;
-		if (write(w->stop_fd, &one, sizeof one) < 0) { /* thread exits on POLLNVAL at close */ }
-		if (w->th.joinable()) w->th.join();
-		close(w->stop_fd);
-		w->stop_fd = -1;
-	}
+	watcher_stop((Watcher *)p);
 	return NULL;
 }
 
@@ -303,6 +345,7 @@ static napi_value Init(napi_env env, napi_value exports)
 		{"stats", 0, Stats, 0, 0, 0, napi_default, 0}, {"close", 0, Close, 0, 0, 0, napi_default, 0},
 		{"endChecksum", 0, EndChecksum, 0, 0, 0, napi_default, 0},
 		{"watch", 0, Watch, 0, 0, 0, napi_default, 0}, {"unwatch", 0, Unwatch, 0, 0, 0, napi_default, 0},
+		{"attach", 0, Attach, 0, 0, 0, napi_default, 0}, {"cancel", 0, Cancel, 0, 0, 0, napi_default, 0},
 	};
 	napi_define_properties(env, exports, sizeof d / sizeof d[0], d);
 	return exports;

@@ -225,6 +225,8 @@ static void free_slot(Slot &s)
 #define MAX_RECORD_BYTES ((size_t)(16u << 20) + 4096)
 
 static int32_t k3_set_attributes(mtz_handle *h);
+static int32_t launch_k2(mtz_handle *h, cudaStream_t st, const void *d_src, void *d_dst, mtz_job *d_jobs,
+    uint32_t njobs);
 
 int32_t mtz_open(const mtz_config *cfg, mtz_handle **out)
 {
@@ -600,7 +602,7 @@ static int32_t codec_launch_dec(mtz_handle *h, cudaStream_t st, CodecBufs &cb, c
 	MTZ_CU(h, cudaGetLastError());
 	count_launch(h, 3);
 	if (mode != MTZ_MODE_COMPRESS) {
-		int32_t rc = mtz_k_lz4_decode(h, nullptr, nullptr, cb.dec, n, st);
+		int32_t rc = launch_k2(h, st, nullptr, nullptr, cb.dec, n);
 		if (rc != MTZ_OK) return rc;
 	}
 	return MTZ_OK;
@@ -1307,6 +1309,19 @@ static int32_t lz4_grid(mtz_handle *h, uint32_t njobs, int warps_per_sm)
 	return (int32_t)std::max(1u, std::min(blocks_needed, cap));
 }
 
+// K2 on `st`, which belongs to the CURRENT device (the caller selected it: a slot of the device
+// group, or devs[0] for the exported entry)
+static int32_t launch_k2(mtz_handle *h, cudaStream_t st, const void *d_src, void *d_dst, mtz_job *d_jobs,
+    uint32_t njobs)
+{
+	if (njobs == 0) return MTZ_OK;
+	k2_lz4_decode<<<lz4_grid(h, njobs, 64), LZ4_THREADS, 0, st>>>((const uint8_t *)d_src,
+	    (uint8_t *)d_dst, d_jobs, njobs);
+	MTZ_CU(h, cudaGetLastError());
+	count_launch(h, 1);
+	return MTZ_OK;
+}
+
 int32_t mtz_k_lz4_decode(mtz_handle *h, const void *d_src, void *d_dst, mtz_job *d_jobs,
     uint32_t njobs, void *cuda_stream)
 {
@@ -1314,11 +1329,7 @@ int32_t mtz_k_lz4_decode(mtz_handle *h, const void *d_src, void *d_dst, mtz_job 
 	if (njobs == 0) return MTZ_OK;
 	MTZ_CU(h, cudaSetDevice(h->device));
 	cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : h->st;
-	k2_lz4_decode<<<lz4_grid(h, njobs, 64), LZ4_THREADS, 0, st>>>((const uint8_t *)d_src,
-	    (uint8_t *)d_dst, d_jobs, njobs);
-	MTZ_CU(h, cudaGetLastError());
-	count_launch(h, 1);
-	return MTZ_OK;
+	return launch_k2(h, st, d_src, d_dst, d_jobs, njobs);
 }
 
 // Function attributes are per DEVICE (and per context): set them for the current device of

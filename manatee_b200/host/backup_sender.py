@@ -128,7 +128,7 @@ class BackupSender(object):
         g = dict(self._gpu)
         if g["mode"] == "compress" and (backupJob is None or backupJob.get("wire") != "lz4-stage-v1"):
             g["mode"] = "verify"
-        return GpuSnapshotStage(g["mode"], device=g.get("device", 0),
+        return GpuSnapshotStage(g["mode"], device=g.get("device", 0), devices=g.get("devices"),
                                 ring_bytes=g.get("ringBytes", 0), batch_bytes=g.get("batchBytes", 0),
                                 out_ring_bytes=g.get("outRingBytes", 0), n_slots=g.get("slots", 0))
 
@@ -188,14 +188,27 @@ class BackupSender(object):
                 if j.get("done") == "failed" and not err:
                     continue
                 self_cb[id(j)](err)
-        self._send(shared, cb, sock=Tee(socks))
+        if self._gpu and self._gpu.get("mode", "off") != "off":
+            # ONE zfs send, ONE pass of the stage, every requester attached as a fan-out peer of
+            # the library (mtz_fanout_attach): each peer drains its own pinned ring, fed from
+            # its egress GPU -- the NCCL broadcast replaces N independent sends
+            # (lib/backupSender.js:72-73).  A peer whose socket dies keeps being drained (and
+            # discarded) so that it never back-pressures the others.
+            def peer_failed(k, e):
+                j = jobs_by_id[k]
+                j["done"] = "failed"
+                self_cb[k](e)
+            self._send(shared, cb, sock=None, peer_socks=[(k, socks[k]) for k in socks],
+                       peer_failed=peer_failed)
+        else:
+            self._send(shared, cb, sock=Tee(socks))
 
     # -- lib/backupSender.js:154-242
-    def _send(self, backupJob, callback, sock=None):
+    def _send(self, backupJob, callback, sock=None, peer_socks=None, peer_failed=None):
         zfsSend = stage = None
         try:
             snapshot = self._getLatestSnapshot()
-            if sock is None:
+            if sock is None and peer_socks is None:
                 self._decide_wire([backupJob])
                 sock = socket.create_connection((backupJob["host"], int(backupJob["port"])))
             zfsSend = subprocess.Popen([self._zfsPath, "send", "-v", "-P", snapshot],
@@ -224,7 +237,52 @@ class BackupSender(object):
 
             stage = self._make_stage(backupJob)
             pump_err = []
-            if stage is None:
+            if peer_socks is not None:
+                assert stage is not None
+                dead = {}
+                for p, _ in enumerate(peer_socks):
+                    stage.fanout_attach(p)
+
+                def drain_peer(p, key, so):
+                    try:
+                        while True:
+                            b = stage.read_peer(p, CHUNK)
+                            if b is None:
+                                break
+                            if key in dead:
+                                continue              # keep the ring moving for the others
+                            try:
+                                so.sendall(b)
+                            except OSError as e:
+                                dead[key] = e
+                                peer_failed(key, e)
+                        if key not in dead:
+                            so.shutdown(socket.SHUT_WR)
+                    except Exception as e:                    # noqa: BLE001  (stage failure)
+                        pump_err.append(e)
+                        stage.cancel()
+                tds = [threading.Thread(target=drain_peer, args=(p, k, so), daemon=True)
+                       for p, (k, so) in enumerate(peer_socks)]
+                for t_ in tds:
+                    t_.start()
+                try:
+                    while True:                               # stdout.pipe(stage)
+                        buf = zfsSend.stdout.read(CHUNK)
+                        if not buf:
+                            break
+                        stage.write(buf)
+                    stage.flush()
+                except Exception as e:                        # noqa: BLE001
+                    pump_err.append(e)
+                    stage.cancel()
+                if pump_err and zfsSend.poll() is None:
+                    zfsSend.terminate()
+                for t_ in tds:
+                    t_.join()
+                backupJob["gpu"] = stage.stats()
+                if len(dead) == len(peer_socks) and not pump_err:
+                    pump_err.append(OSError("every coalesced receiver went away"))
+            elif stage is None:
                 while True:                                   # stdout.pipe(socket)
                     buf = zfsSend.stdout.read(CHUNK)
                     if not buf:
@@ -240,6 +298,9 @@ class BackupSender(object):
                             sock.sendall(b)
                     except Exception as e:                    # noqa: BLE001
                         pump_err.append(e)
+                        # the receiver went away (or the stage failed): nobody will empty the
+                        # ring any more, so a producer blocked in stage.write() must be woken
+                        stage.cancel()
                 td = threading.Thread(target=drain, daemon=True)
                 td.start()
                 try:
@@ -251,6 +312,12 @@ class BackupSender(object):
                     stage.flush()
                 except Exception as e:                        # noqa: BLE001
                     pump_err.append(e)
+                    stage.cancel()                            # a drain thread waiting for output
+                if pump_err and zfsSend.poll() is None:
+                    # nobody reads zfsSend.stdout any more: the child sits in write(2) on a full
+                    # pipe and would never exit.  Kill it like the reference does on a socket
+                    # error (lib/backupSender.js:230-233) BEFORE waiting for it.
+                    zfsSend.terminate()
                 td.join()
                 backupJob["gpu"] = stage.stats()              # additive field
             code = zfsSend.wait()
@@ -260,7 +327,8 @@ class BackupSender(object):
             if code != 0:
                 backupJob["done"] = "failed"
                 raise RuntimeError("zfs send: %s %d" % (last_msg[0], code))
-            sock.shutdown(socket.SHUT_WR)
+            if sock is not None:
+                sock.shutdown(socket.SHUT_WR)
             backupJob["done"] = True
             callback(None)
         except Exception as e:                                # noqa: BLE001
@@ -273,3 +341,5 @@ class BackupSender(object):
                 stage.close()
             if sock is not None:
                 sock.close()
+            for _k, so in (peer_socks or []):
+                so.close()

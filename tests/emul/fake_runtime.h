@@ -36,13 +36,13 @@ struct cudaDeviceProp { char name[256]; int major, minor, multiProcessorCount; s
 typedef void (*cudaHostFn_t)(void *);
 
 // ------------------------------------------------------------------ streams and events
-struct emu_event_ { unsigned long long recorded = 0, completed = 0; };
+struct emu_event_ { unsigned long long recorded = 0, completed = 0; int dev = 0; };
 struct emu_op {
 	std::function<void()> fn;                 // work (may be empty)
 	emu_event_ *wait_ev = nullptr; unsigned long long wait_seq = 0;
 	emu_event_ *rec_ev = nullptr; unsigned long long rec_seq = 0;
 };
-struct emu_stream_ { std::deque<emu_op> q; bool busy = false; };
+struct emu_stream_ { std::deque<emu_op> q; bool busy = false; int dev = 0; };
 
 namespace emurt {
 struct State {
@@ -121,8 +121,19 @@ inline void enqueue(cudaStream_t st_, emu_op &&o)
 inline void run(cudaStream_t st, std::function<void()> fn) { emu_op o; o.fn = std::move(fn); enqueue(st, std::move(o)); }
 } // namespace emurt
 
-static inline const char *cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no error" : "emulated CUDA error"; }
-static inline cudaError_t cudaGetLastError() { return cudaSuccess; }
+// Device discipline, as the real runtime enforces it: a kernel launch or an event record needs the
+// stream's device to be the CURRENT device of the calling thread (else error 400, "invalid
+// resource handle", reported by the next cudaGetLastError like a failed launch is).
+enum { cudaErrorInvalidResourceHandle = 400 };
+namespace emurt {
+inline int &cur_dev() { static thread_local int d = 0; return d; }
+inline cudaError_t &sticky() { static thread_local cudaError_t e = cudaSuccess; return e; }
+}
+static inline const char *cudaGetErrorString(cudaError_t e)
+{
+	return e == cudaSuccess ? "no error" : e == cudaErrorInvalidResourceHandle ? "invalid resource handle" : "emulated CUDA error";
+}
+static inline cudaError_t cudaGetLastError() { cudaError_t e = emurt::sticky(); emurt::sticky() = cudaSuccess; return e; }
 // MTZ_EMUL_DEVICES=<n>: a box of n identical emulated GPUs (device memory is host memory, so a
 // "peer copy" is a copy; what the multi-device tests exercise is the library's ordering)
 static inline cudaError_t cudaGetDeviceCount(int *n)
@@ -133,7 +144,7 @@ static inline cudaError_t cudaGetDeviceCount(int *n)
 }
 static inline cudaError_t cudaDeviceCanAccessPeer(int *can, int, int) { *can = 1; return cudaSuccess; }
 static inline cudaError_t cudaDeviceEnablePeerAccess(int, unsigned) { return cudaSuccess; }
-static inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
+static inline cudaError_t cudaSetDevice(int d) { emurt::cur_dev() = d; return cudaSuccess; }
 static inline cudaError_t cudaDeviceSynchronize() { emurt::drain_all(); return cudaSuccess; }
 static inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp *p, int)
 {
@@ -210,6 +221,7 @@ static inline cudaError_t cudaMemsetAsync(void *d, int v, size_t n, cudaStream_t
 static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned)
 {
 	*s = new emu_stream_();
+	(*s)->dev = emurt::cur_dev();
 	std::lock_guard<std::recursive_mutex> g(emurt::S().mu);
 	emurt::S().streams.push_back(*s);
 	return cudaSuccess;
@@ -229,10 +241,11 @@ static inline cudaError_t cudaStreamDestroy(cudaStream_t st)
 	delete st;
 	return cudaSuccess;
 }
-static inline cudaError_t cudaEventCreate(cudaEvent_t *e) { *e = new emu_event_(); return cudaSuccess; }
+static inline cudaError_t cudaEventCreate(cudaEvent_t *e) { *e = new emu_event_(); (*e)->dev = emurt::cur_dev(); return cudaSuccess; }
 static inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t *e, unsigned) { return cudaEventCreate(e); }
 static inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t st = nullptr)
 {
+	if (st != nullptr && (st->dev != e->dev || st->dev != emurt::cur_dev())) return cudaErrorInvalidResourceHandle;
 	emu_op o;
 	{
 		std::lock_guard<std::recursive_mutex> g(emurt::S().mu);
@@ -289,6 +302,7 @@ namespace emu {
 template <class G, class B, class F> static inline void launch_site(G g, B b, cudaStream_t st, const F &f)
 {
 	const unsigned grid = (unsigned)g, block = (unsigned)b;
+	if (st != nullptr && st->dev != emurt::cur_dev()) { emurt::sticky() = cudaErrorInvalidResourceHandle; return; }
 	std::function<void()> k(f);
 	emurt::run(st, [grid, block, k] { launch(grid, block, k); });
 }

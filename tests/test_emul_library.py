@@ -393,3 +393,21 @@ def test_streaming_api_rejects_a_stream_that_stops_before_end(emul_library, orac
                     break
                 n += len(b)
             assert n == whole.size
+
+
+from test_host_pipeline import fakezfs  # noqa: E402,F401  (fixture: fake `zfs` + seeded stream)
+
+
+def test_sender_failure_paths_do_not_hang(emul_library, fakezfs, tmp_path, oracle):  # noqa: F811
+    """the two ways `_send` used to hang with the stage in the pipe -- a stage
+    failure while `zfs send` still writes, and a receiver that hangs up mid-transfer -- against the
+    emulated library (the same tests are gpu-marked in tests/test_host_pipeline.py)."""
+    import test_host_pipeline as H
+    H.test_gpu_corruption_in_the_first_batch_does_not_hang_the_sender(fakezfs, tmp_path, oracle)
+    H.test_gpu_receiver_disconnect_mid_transfer_fails_the_job(fakezfs, tmp_path, oracle)
+
+
+def test_coalesced_sender_feeds_the_library_fan_out(emul_library, fakezfs, tmp_path):  # noqa: F811
+    """f1 end to end on the emulated library: one `zfs send`, one stage pass, two attached peers."""
+    import test_host_pipeline as H
+    H.test_gpu_coalesced_restores_fan_out_of_one_stage_pass(fakezfs, tmp_path)

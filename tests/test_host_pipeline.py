@@ -186,23 +186,105 @@ def test_gpu_corrupt_stream_fails_the_job(fakezfs, tmp_path):
     assert events and events[0][0] == "err" and "checksum" in str(events[0][1])
 
 
+def _big_stream(oracle, tmp_path, nwrites=96, corrupt_at=None):
+    """a stream several times larger than the pipe + the rings the failure tests configure"""
+    s = oracle.synth_stream(nwrites, recsize=131072, kind=oracle.PAYLOAD_PCG).copy()
+    if corrupt_at is not None:
+        s[corrupt_at] ^= 0x04
+    p = tmp_path / "big.bin"
+    s.tofile(str(p))
+    return s, str(p)
+
+
+@pytest.mark.gpu
+def test_gpu_corruption_in_the_first_batch_does_not_hang_the_sender(fakezfs, tmp_path, oracle):
+    """ADVICE r1 (high, a): the stage fails on the FIRST batch while `zfs send` still has megabytes
+    to write.  The sender must kill the child instead of wait()ing on it forever: job.done ==
+    'failed', 'err' emitted, and the restore returns within seconds."""
+    s, path = _big_stream(oracle, tmp_path, corrupt_at=400_000)
+    t0 = time.time()
+    res, cli, events = _run_restore(fakezfs, sender_gpu={"mode": "verify", "batchBytes": 1 << 20, "ringBytes": 2 << 20},
+                                    env_extra={"FAKE_ZFS_STREAM": path})
+    assert time.time() - t0 < 30
+    assert res["err"] is not None
+    assert events and events[0][0] == "err" and "checksum" in str(events[0][1])
+    assert cli._restoreObject is None or cli._restoreObject.get("done") in ("failed", 0, False)
+
+
+@pytest.mark.gpu
+def test_gpu_receiver_disconnect_mid_transfer_fails_the_job(fakezfs, tmp_path, oracle):
+    """ADVICE r1 (high, b): the receiver closes its socket mid-transfer.  The drain thread's send
+    error must cancel the stage so that the producer blocked on the full ring wakes up, the child
+    is killed and the job ends 'failed' -- not a writer spinning in mtz_write forever."""
+    from manatee_b200.host import BackupSender, BackupQueue
+    s, path = _big_stream(oracle, tmp_path)
+    env = dict(fakezfs["env"], FAKE_ZFS_STREAM=path)
+    q = BackupQueue({"log": None})
+    sender = BackupSender.start({"log": None, "dataset": "zones/x/data/manatee", "zfsPath": fakezfs["zfs"],
+                                 "queue": q, "env": env,
+                                 "gpu": {"mode": "verify", "batchBytes": 1 << 20, "ringBytes": 2 << 20}})
+    events = []
+    sender.on("err", lambda e: events.append(("err", e)))
+    sender.on("done", lambda j: events.append(("done", j)))
+    lsock = socket.socket()
+    lsock.bind(("127.0.0.1", 0))
+    lsock.listen(1)
+
+    def rude_receiver():
+        c, _ = lsock.accept()
+        got = 0
+        while got < (1 << 20):                       # take the first MiB, then hang up
+            b = c.recv(1 << 16)
+            if not b:
+                break
+            got += len(b)
+        c.setsockopt(socket.SOL_SOCKET, socket.SO_LINGER, b"\x01\x00\x00\x00\x00\x00\x00\x00")
+        c.close()
+    t = threading.Thread(target=rude_receiver, daemon=True)
+    t.start()
+    job = {"uuid": "u-1", "host": "127.0.0.1", "port": lsock.getsockname()[1], "dataset": "x", "done": False}
+    t0 = time.time()
+    q.push(job)
+    sender.join(30)
+    assert time.time() - t0 < 30, "the sender hung"
+    assert job["done"] == "failed" and events and events[0][0] == "err"
+    lsock.close()
+
+
 def test_coalesced_restores_share_one_send(fakezfs, tmp_path):
     """two peers asking within the window get the same bytes from ONE
     `zfs send` (the reference would run two).  Default (coalesceMs absent) stays per-job."""
+    _coalesced(fakezfs, tmp_path, None, None)
+
+
+@pytest.mark.gpu
+def test_gpu_coalesced_restores_fan_out_of_one_stage_pass(fakezfs, tmp_path):
+    """f1 joined to the library's fan-out: the coalesced sender runs ONE zfs send through ONE stage
+    (COMPRESS on the wire) with both requesters attached as fan-out peers (mtz_fanout_attach: one
+    pinned ring per peer); each receiver decompresses and hands `zfs recv` the original bytes."""
+    results = _coalesced(fakezfs, tmp_path, {"mode": "compress", "batchBytes": 1 << 20, "ringBytes": 4 << 20,
+                                             "outRingBytes": 2 << 20}, {"mode": "decompress"})
+    for res, cli in results:
+        job = cli._restoreObject
+        assert job["wire"] == "lz4-stage-v1" and job["gpu"]["lz4_encoded"] > 0
+        assert job["gpuRecv"]["lz4_decoded"] == job["gpu"]["lz4_encoded"]
+
+
+def _coalesced(fakezfs, tmp_path, sender_gpu, recv_gpu):
     from manatee_b200.host import BackupSender, BackupServer, ZfsClient
     env = dict(fakezfs["env"])
     counter = tmp_path / "sends"
     env["FAKE_ZFS_SEND_COUNT"] = str(counter)
     srv = BackupServer.start({"log": None, "port": 0, "host": "127.0.0.1"})
     sender = BackupSender.start({"log": None, "dataset": "zones/x/data/manatee", "zfsPath": fakezfs["zfs"],
-                                 "queue": srv.getQueue(), "env": env, "coalesceMs": 300})
+                                 "queue": srv.getQueue(), "env": env, "coalesceMs": 300, "gpu": sender_gpu})
     outs, results, threads = [], [], []
     for k in range(2):
         e2 = dict(env); e2["FAKE_ZFS_RECV_OUT"] = str(tmp_path / ("recv%d.out" % k))
         outs.append(e2["FAKE_ZFS_RECV_OUT"])
         cli = ZfsClient({"log": None, "dataset": "zones/y%d/data/manatee" % k, "dbUser": "postgres",
                          "mountpoint": "/manatee/pg", "pollInterval": 50, "zfsHost": "127.0.0.1",
-                         "zfsPath": fakezfs["zfs"], "zfsPort": _free_port(), "env": e2,
+                         "zfsPath": fakezfs["zfs"], "zfsPort": _free_port(), "env": e2, "gpu": recv_gpu,
                          "zfsBin": fakezfs["zfs"], "zfsEnv": e2})
         res = {}
         results.append((res, cli))
@@ -221,6 +303,7 @@ def test_coalesced_restores_share_one_send(fakezfs, tmp_path):
         assert digest == want and int(n) == fakezfs["stream"].size
         assert cli._restoreObject["done"] is True
     assert open(str(counter)).read().count("send") == 1, "coalesced requests must share one zfs send"
+    return results
 
 
 class _IdentityStageDouble(object):
