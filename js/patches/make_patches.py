@@ -41,6 +41,48 @@ EDITS = {
 
     /** @type {object} GPU stage config {mode, device, ringBytes, ...}; absent == off */
     this._gpu = options.gpu || { mode: 'off' };
+    /**
+     * @type {number} Requests for the latest snapshot that arrive within this
+     * many ms of each other share ONE zfs send and ONE pass of the GPU stage
+     * (fan-out to one pinned ring per peer).  0 == one send per request, as
+     * before.
+     */
+    this._coalesceMs = this._gpu.coalesceMs || 0;
+    this._waiting = [];
+"""),
+        ("""    self._queue.on('push', function (backupJob) {
+        self._send(backupJob, function (err) {
+""", """    var jobDone = function (backupJob, err) {
+        if (err) {
+            self._log.error({ backupJob: backupJob, err: err },
+                            'unable to send backup');
+            self.emit('err', err);
+            backupJob.err = err;
+        } else {
+            self._log.info({ backupJob: backupJob },
+                           'successfully sent backup');
+            self.emit('done', backupJob);
+        }
+    };
+
+    self._queue.on('push', function (backupJob) {
+        if (self._coalesceMs > 0 && self._gpu.mode &&
+            self._gpu.mode !== 'off') {
+            /*
+             * The first request opens the window; everybody who asks before
+             * it closes rides the same send.
+             */
+            self._waiting.push(backupJob);
+            if (self._waiting.length === 1) {
+                setTimeout(function () {
+                    var jobs = self._waiting;
+                    self._waiting = [];
+                    self._sendGroup(jobs, jobDone);
+                }, self._coalesceMs);
+            }
+            return;
+        }
+        self._send(backupJob, function (err) {
 """),
         ("""            log.info({port: backupJob.port, host: backupJob.host},
                      'BackupSender._send: creating socket for zfs send');
@@ -125,7 +167,109 @@ EDITS = {
                 if (zfsSend) {
                     zfsSend.kill('SIGTERM');
                 }
+                if (stage) {
+                    /* frees the pinned rings, GPU slots and native threads */
+                    stage.destroy();
+                }
                 return _cb(err);
+"""),
+        ("""/**
+ * @callback BackupSender-cb
+""", """/**
+ * One `zfs send`, one pass of the GPU stage, N receivers (SURVEY 8f f1).  Every
+ * job gets its own socket and its own output ring of the stage
+ * (gpuFanoutStage: mtz_fanout_attach / mtz_out_peek_peer); progress fields are
+ * mirrored into every job object, and a receiver that goes away only fails its
+ * own job.
+ *
+ * @param {object[]} jobs The coalesced backup jobs.
+ * @param {function} jobDone Called once per job with (job, err).
+ */
+BackupSender.prototype._sendGroup = function (jobs, jobDone) {
+    var self = this;
+    var log = self._log;
+    var finished = {};
+    var finish = function (job, err) {
+        if (finished[job.uuid]) {
+            return;
+        }
+        finished[job.uuid] = true;
+        job.done = err ? 'failed' : true;
+        jobDone(job, err);
+    };
+    var failAll = function (err) {
+        jobs.forEach(function (job) { finish(job, err); });
+    };
+
+    self._getLatestSnapshot(function (err, snapshot) {
+        if (err) {
+            return failAll(err);
+        }
+        var compress = (self._gpu.mode === 'compress' &&
+            jobs.every(function (j) { return j.accept === 'lz4-stage-v1'; }));
+        jobs.forEach(function (j) {
+            j.wire = compress ? 'lz4-stage-v1' : 'raw';
+            j.size = null;
+            j.done = 0;
+        });
+        var GpuFanoutStage = require('manatee-gpu/lib/gpuFanoutStage');
+        var gpuCfg = JSON.parse(JSON.stringify(self._gpu));
+        if (gpuCfg.mode === 'compress' && !compress) {
+            gpuCfg.mode = 'verify';
+        }
+        gpuCfg.peers = jobs.length;
+        var fan;
+        try {
+            fan = new GpuFanoutStage(gpuCfg);
+        } catch (e) {
+            return failAll(e);
+        }
+        var zfsSend = spawn(self._zfsPath, ['send', '-v', '-P', snapshot]);
+        var left = jobs.length;
+        jobs.forEach(function (job, i) {
+            var socket = net.connect(job.port, job.host);
+            socket.on('error', function (serr) {
+                log.error({err: serr, job: job}, 'coalesced receiver failed');
+                fan.peer(i).destroy();      /* keeps draining, discards */
+                finish(job, serr);
+            });
+            fan.peer(i).on('end', function () {
+                job.gpu = fan.stats;
+                finish(job);
+                if (--left === 0) {
+                    log.info('coalesced backup jobs completed');
+                }
+            });
+            fan.peer(i).pipe(socket);
+        });
+        fan.on('error', function (ferr) {
+            zfsSend.kill('SIGTERM');
+            failAll(ferr);
+        });
+        var msg = '';
+        zfsSend.stderr.on('data', function (data) {
+            var dataStr = data.toString();
+            var m;
+            if ((m = ZFS_PROGRESS_HEADER.exec(dataStr)) !== null) {
+                jobs.forEach(function (j) { j.size = m[1]; });
+            } else if ((m = ZFS_PROGRESS_REGEX.exec(dataStr)) !== null) {
+                jobs.forEach(function (j) { j.completed = m[1]; });
+            }
+            msg = dataStr;
+        });
+        zfsSend.on('exit', function (code) {
+            if (code !== 0) {
+                fan.destroy();
+                failAll(new verror.VError('zfs send: ' + msg + ' ' + code));
+            }
+        });
+        zfsSend.stdout.pipe(fan);
+        return (undefined);
+    });
+};
+
+/**
+ * @callback BackupSender-cb
 """),
     ],
     "lib/zfsClient.js": [

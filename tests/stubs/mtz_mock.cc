@@ -146,6 +146,24 @@ int32_t mtz_out_consume(mtz_handle *h, size_t n)
 
 int32_t mtz_event_fd(mtz_handle *h) { return h ? h->efd : MTZ_EINVAL; }
 
+// single-consumer stand-in: peer 0 only
+int32_t mtz_fanout_attach(mtz_handle *h, int32_t peer) { return (h && peer == 0) ? 0 : MTZ_EINVAL; }
+int32_t mtz_out_peek_peer(mtz_handle *h, int32_t peer, const void **ptr, size_t *n)
+{
+	return peer == 0 ? mtz_out_peek(h, ptr, n) : MTZ_EINVAL;
+}
+int32_t mtz_out_consume_peer(mtz_handle *h, int32_t peer, size_t n)
+{
+	return peer == 0 ? mtz_out_consume(h, n) : MTZ_EINVAL;
+}
+int32_t mtz_cancel(mtz_handle *h)
+{
+	if (h == nullptr) return MTZ_EINVAL;
+	std::lock_guard<std::mutex> g(h->mu);
+	if (!h->err) h->err = MTZ_ECANCELED;
+	return MTZ_OK;
+}
+
 int32_t mtz_get_stats(mtz_handle *h, mtz_stats *st)
 {
 	if (h == nullptr || st == nullptr) return MTZ_EINVAL;
