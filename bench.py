@@ -282,14 +282,35 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------- ring API helpers --
-def ring_run(g, src, peers=(0,), producer="write", nthreads=4, chunk=32 << 20):
+_PUMP = None
+
+
+def ring_pump():
+    """tools/libringpump.so: native producers for the ring API (bench infrastructure, built by
+    __graft_entry__.build(); rebuilt here if it did not travel)."""
+    global _PUMP
+    if _PUMP is None:
+        import ctypes as C
+        so = os.path.join(ROOT, "tools", "libringpump.so")
+        if not os.path.exists(so):
+            subprocess.check_call(["gcc", "-O2", "-shared", "-fPIC", "-pthread", "-o", so,
+                                   os.path.join(ROOT, "tools", "ringpump.c")])
+        P = C.CDLL(so)
+        P.pump_memcpy.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int]
+        P.pump_memcpy.restype = C.c_int32
+        P.pump_pipe.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]
+        P.pump_pipe.restype = C.c_int32
+        _PUMP = P
+    return _PUMP
+
+
+def ring_run(g, src, peers=(0,), producer="write", nthreads=4, chunk=64 << 20):
     """Drive the streaming API: one producer feeding `src` (numpy u8), one zero-copy consumer thread
-    per peer.  producer = "write" (mtz_write, one memcpy thread), "acquire" (mtz_ring_acquire /
-    commit, the slice filled by `nthreads` parallel memcpys) or "pipe" (read(2) from a pipe straight
-    into the acquired slice -- the shape of zfsSend.stdout).  Returns (seconds, ok, detail)."""
+    per peer (mtz_out_peek_peer / mtz_out_consume_peer).  producer = "write" (mtz_write: one thread,
+    one memcpy into the pinned ring), "acquire" (mtz_ring_acquire / commit, the slice filled by
+    `nthreads` parallel memcpys, native: tools/ringpump.c) or "pipe" (a pipe(2) read(2) straight into
+    the acquired slice -- the shape of zfsSend.stdout).  Returns (seconds, ok, detail)."""
     import ctypes as C
-    import numpy as np
-    from concurrent.futures import ThreadPoolExecutor
     from manatee_b200 import _native as N
     L = N.lib()
     errs, got = [], {}
@@ -319,50 +340,15 @@ def ring_run(g, src, peers=(0,), producer="write", nthreads=4, chunk=32 << 20):
                 for o in range(0, src.size, chunk):
                     g.write(src[o:o + chunk])
             else:
-                pool = ThreadPoolExecutor(nthreads) if producer == "acquire" else None
-                rfd = wfd = None
-                if producer == "pipe":
-                    import fcntl
-                    rfd, wfd = os.pipe()
-                    try:
-                        fcntl.fcntl(wfd, 1031, 1 << 20)          # F_SETPIPE_SZ
-                    except OSError:
-                        pass
-
-                    def feed():
-                        mv = memoryview(src)
-                        o = 0
-                        while o < len(mv):
-                            o += os.write(wfd, mv[o:o + (1 << 20)])
-                        os.close(wfd)
-                    threading.Thread(target=feed, daemon=True).start()
-                ptr, n, o = C.c_void_p(), C.c_size_t(), 0
-                while o < src.size:
-                    rc = L.mtz_ring_acquire(g._h, min(chunk, src.size - o), C.byref(ptr), C.byref(n))
-                    if rc == N.EAGAIN:
-                        time.sleep(0.0001)
-                        continue
-                    if rc != N.OK:
-                        raise RuntimeError("acquire rc %d" % rc)
-                    dst = np.ctypeslib.as_array((C.c_uint8 * n.value).from_address(ptr.value))
-                    if producer == "pipe":
-                        k = os.readv(rfd, [memoryview(dst)])
-                        if k <= 0:
-                            raise RuntimeError("pipe closed early")
-                    else:
-                        k = n.value
-                        part = (k + nthreads - 1) // nthreads
-                        list(pool.map(lambda i: np.copyto(dst[i * part:min(k, (i + 1) * part)],
-                                                          src[o + i * part:o + min(k, (i + 1) * part)]),
-                                      range(nthreads)))
-                    rc = L.mtz_ring_commit(g._h, k)
-                    if rc != N.OK:
-                        raise RuntimeError("commit rc %d" % rc)
-                    o += k
-                if pool:
-                    pool.shutdown()
-                if rfd is not None:
-                    os.close(rfd)
+                P = ring_pump()
+                acq = C.cast(L.mtz_ring_acquire, C.c_void_p)
+                com = C.cast(L.mtz_ring_commit, C.c_void_p)
+                if producer == "acquire":
+                    rc = P.pump_memcpy(acq, com, g._h, src.ctypes.data, src.size, chunk, nthreads)
+                else:
+                    rc = P.pump_pipe(acq, com, g._h, src.ctypes.data, src.size, chunk)
+                if rc != 0:
+                    raise RuntimeError("ring pump rc %d: %s" % (rc, (L.mtz_last_error(g._h) or b"").decode()))
             g.flush()
         except Exception as e:              # noqa: BLE001
             errs.append(repr(e))
