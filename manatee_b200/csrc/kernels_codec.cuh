@@ -20,8 +20,14 @@ namespace mtz {
 
 #define FEAT_LZ4        (1ull << 17)
 #define FEAT_COMPRESSED (1ull << 22)
-#define VI_STAGE        (1ull << 63)
-#define VI_ORIG_LZ4     (1ull << 62)
+// wire format "lz4-stage-v1": a 32-byte preamble in front of every DRR_BEGIN of a COMPRESS output
+// (u64 magic "MTZLZ4W1", u32 version, u32 flags, 16 zero bytes), outside the stream checksum.  The
+// host paths write and strip it; the kernels only see its one flag, carried in mtz_rec.resv of
+// the BEGIN record: the original stream had the LZ4 feature flag.
+#define WIRE_MAGIC      0x3157345A4C5A544DULL
+#define WIRE_VERSION    1u
+#define WIRE_PRE_BYTES  32u
+#define WIRE_F_ORIG_LZ4 1u
 #define ZIO_LZ4         15u
 
 struct CodecRec {          // 32 B per record, device only
@@ -224,14 +230,12 @@ k_assemble(const uint8_t *__restrict__ d_in, const mtz_rec *__restrict__ recs, u
 		} else if (rec.type == DRR_BEGIN_T && lane == 0) {
 			uint64_t vi = *reinterpret_cast<const uint64_t *>(hin + 16);
 			const uint64_t feat = (vi >> 2) & ((1ull << 30) - 1ull);
+			(void)feat;
 			if (mode == MTZ_MODE_COMPRESS) {
-				if (feat & FEAT_LZ4) vi |= VI_ORIG_LZ4;
-				vi |= VI_STAGE;
 				vi |= (FEAT_COMPRESSED | FEAT_LZ4) << 2;
 			} else if (mode == MTZ_MODE_DECOMPRESS) {
 				vi &= ~((FEAT_COMPRESSED | FEAT_LZ4) << 2);
-				if (vi & VI_ORIG_LZ4) vi |= FEAT_LZ4 << 2;
-				vi &= ~(VI_STAGE | VI_ORIG_LZ4);
+				if (rec.resv & WIRE_F_ORIG_LZ4) vi |= FEAT_LZ4 << 2;    // from the wire preamble
 			} else if (mode == MTZ_MODE_RECOMPRESS) {
 				vi |= (FEAT_COMPRESSED | FEAT_LZ4) << 2;
 			}

@@ -46,6 +46,7 @@ struct Peer {
 	uint64_t issue = 0;        // ring space reserved by issued copies
 	uint64_t cur_seq = 0;      // batch this peer is copying out
 	size_t cur_off = 0;        // bytes of it already issued
+	bool pre_done = false;     // the wire preamble in front of that batch has been written
 	std::deque<Piece> pend;
 };
 
@@ -75,6 +76,7 @@ struct Engine {
 	uint64_t parse_pos = 0;        // end of the last whole record parsed
 	uint64_t batch_begin = 0;      // start of the batch being assembled
 	bool open_substream = false;   // a DRR_BEGIN has been parsed and its DRR_END has not
+	WireState ws;                  // lz4-stage-v1 framing on the input side (DECOMPRESS)
 	std::vector<mtz_rec> cur;      // records of the batch being assembled
 	BatchCut bc;
 	std::deque<InFlight> inflight;
@@ -189,6 +191,21 @@ static int32_t engine_parse(Engine *e, uint64_t head, bool *cut)
 			hdr = wrapped;
 		}
 		uint32_t ls, comp;
+		if (h->cfg.mode == MTZ_MODE_DECOMPRESS && !e->ws.pre_seen && rd64(hdr) == WIRE_MAGIC) {
+			// the preamble of the lz4-stage-v1 wire is stripped between two batches
+			if (e->parse_pos > e->batch_begin) { *cut = true; break; }
+			if (wire_parse(hdr, &e->ws.pre_flags) < 0)
+				return fail(h, MTZ_EFORMAT, "unsupported wire version / capability in the preamble at "
+				    "stream offset %llu", (unsigned long long)e->parse_pos);
+			e->ws.pre_seen = true;
+			e->parse_pos += WIRE_PRE_BYTES;
+			e->batch_begin = e->parse_pos;
+			{
+				std::lock_guard<std::mutex> g(h->stats_mu);
+				h->stats.bytes_in += WIRE_PRE_BYTES;
+			}
+			continue;
+		}
 		const int64_t pl = drr_payload(hdr, &ls, &comp);
 		if (pl < 0)
 			return fail(h, MTZ_EFORMAT, "malformed record header at stream offset %llu",
@@ -199,7 +216,7 @@ static int32_t engine_parse(Engine *e, uint64_t head, bool *cut)
 			    (unsigned long long)rl);
 		if (head - e->parse_pos < rl) break;                     // incomplete
 		mtz_rec r;
-		const int32_t a = batch_accept(h, s0, e->bc, hdr, pl, ls, comp, e->parse_pos, &r);
+		const int32_t a = batch_accept(h, s0, e->bc, hdr, pl, ls, comp, e->parse_pos, &r, &e->ws);
 		if (a < 0) return a;
 		if (a == 0) { *cut = true; break; }
 		e->cur.push_back(r);
@@ -222,6 +239,7 @@ static int32_t engine_submit(Engine *e)
 	const size_t n0 = std::min(n, e->in_cap - o);
 	if (!e->cur.empty()) memcpy(s.h_recs, e->cur.data(), e->cur.size() * sizeof(mtz_rec));
 	s.writes = e->bc.writes;
+	s.emit_pre = e->bc.emit_pre; s.pre_flags = e->bc.pre_flags;
 	s.seq = e->next_seq;
 	int32_t rc = submit_batch(h, s, e->in_buf + o, n0, e->in_buf, n - n0, e->cur.size(), b0, nullptr);
 	if (rc != MTZ_OK) return rc;
@@ -303,9 +321,27 @@ static int32_t engine_egress(Engine *e, const uint64_t *pos, bool *progress)
 				if (rc != MTZ_OK) return rc;
 				*progress = true;
 			}
+			if (s.emit_pre && !pe.pre_done) {
+				// lz4-stage-v1 wire: the preamble goes into the peer's ring right in front of the
+				// batch that starts with BEGIN (host bytes; published with the batch's first copy)
+				if (pe.cap - (size_t)(pe.issue - pos[p]) < WIRE_PRE_BYTES) break;
+				uint8_t pre[WIRE_PRE_BYTES];
+				wire_preamble(pre, s.pre_flags);
+				const size_t po = (size_t)(pe.issue % pe.cap);
+				const size_t pa = std::min((size_t)WIRE_PRE_BYTES, pe.cap - po);
+				memcpy(pe.buf + po, pre, pa);
+				if (pa < WIRE_PRE_BYTES) memcpy(pe.buf, pre + pa, WIRE_PRE_BYTES - pa);
+				pe.issue += WIRE_PRE_BYTES;
+				pe.pre_done = true;
+				if (p == 0) {
+					std::lock_guard<std::mutex> g(h->stats_mu);
+					h->stats.bytes_out += WIRE_PRE_BYTES;
+				}
+				*progress = true;
+			}
 			if (pe.cur_off == f->n_out) {                 // (an empty batch: nothing to copy)
 				if (--s.egress_left == 0) *progress = true;
-				pe.cur_seq++; pe.cur_off = 0;
+				pe.cur_seq++; pe.cur_off = 0; pe.pre_done = false;
 				continue;
 			}
 			const size_t room = pe.cap - (size_t)(pe.issue - pos[p]);
@@ -326,7 +362,7 @@ static int32_t engine_egress(Engine *e, const uint64_t *pos, bool *progress)
 			pc.last = (pe.cur_off == f->n_out);
 			pe.pend.push_back(pc);
 			*progress = true;
-			if (pc.last) { pe.cur_seq++; pe.cur_off = 0; }
+			if (pc.last) { pe.cur_seq++; pe.cur_off = 0; pe.pre_done = false; }
 		}
 	}
 	return MTZ_OK;

@@ -68,6 +68,8 @@ struct Slot {
 	cudaEvent_t ev_c0 = nullptr, ev_c1 = nullptr;     // around K2+K3
 	cudaEvent_t ev_k3a = nullptr, ev_k3b = nullptr;   // around K3 alone
 	bool k3_timed = false;
+	bool emit_pre = false;        // COMPRESS: the slot's output is preceded by a wire preamble
+	uint32_t pre_flags = 0;
 	bool d2h_pending = false;     // bulk API: the slot's output copy has been issued, not awaited
 	bool busy = false;
 	size_t nrec = 0, bytes = 0, out_bytes = 0;

@@ -1045,11 +1045,38 @@ static int32_t ensure_slots(mtz_handle *h)
 
 // Batch assembly shared by the bulk and the streaming paths: decides whether the
 // record whose header is `hdr` still fits the batch being cut for slot s.
-struct BatchCut { size_t cnt = 0, in_bytes = 0, budget = 0; uint64_t writes = 0; };
+struct BatchCut {
+	size_t cnt = 0, in_bytes = 0, budget = 0; uint64_t writes = 0;
+	bool emit_pre = false;           // COMPRESS: the batch starts with BEGIN, its output gets a preamble
+	uint32_t pre_flags = 0;
+};
+
+// state of the lz4-stage-v1 wire framing on the INPUT side (DECOMPRESS): a preamble was read and
+// the BEGIN it announces has not arrived yet
+struct WireState { bool pre_seen = false; uint32_t pre_flags = 0; };
+
+static void wire_preamble(uint8_t out[WIRE_PRE_BYTES], uint32_t flags)
+{
+	memset(out, 0, WIRE_PRE_BYTES);
+	const uint64_t m = WIRE_MAGIC;
+	const uint32_t v = WIRE_VERSION;
+	memcpy(out, &m, 8); memcpy(out + 8, &v, 4); memcpy(out + 12, &flags, 4);
+}
+
+// 1: a preamble this side speaks (flags out); 0: not a preamble; <0: a preamble of a version or
+// with capability bits this side does not know
+static int wire_parse(const uint8_t *p, uint32_t *flags)
+{
+	if (rd64(p) != WIRE_MAGIC) return 0;
+	if (rd32(p + 8) != WIRE_VERSION || (rd32(p + 12) & ~WIRE_F_ORIG_LZ4) != 0) return -1;
+	for (unsigned k = 16; k < WIRE_PRE_BYTES; k++) if (p[k] != 0) return -1;
+	*flags = rd32(p + 12);
+	return 1;
+}
 
 // returns 1 accepted, 0 batch is full (cut first), <0 error (already reported)
 static int32_t batch_accept(mtz_handle *h, const Slot &s, BatchCut &bc, const uint8_t *hdr,
-    int64_t pl, uint32_t ls, uint32_t comp, uint64_t stream_off, mtz_rec *out)
+    int64_t pl, uint32_t ls, uint32_t comp, uint64_t stream_off, mtz_rec *out, WireState *ws)
 {
 	const size_t rl = DRR_HDR + (size_t)pl;
 	const bool codec = is_codec_mode(h->cfg.mode);
@@ -1060,19 +1087,30 @@ static int32_t batch_accept(mtz_handle *h, const Slot &s, BatchCut &bc, const ui
 		return fail(h, MTZ_ENOSPC, "record of %zu bytes at stream offset %llu exceeds the batch slot",
 		    cost, (unsigned long long)stream_off);
 	if (bc.cnt > 0 && (bc.budget + cost > s.cap || bc.cnt >= s.rec_cap)) return 0;
+	uint64_t resv = 0;
+	if (ws->pre_seen && type != 0)
+		return fail(h, MTZ_EFORMAT, "wire preamble at stream offset %llu is not followed by DRR_BEGIN",
+		    (unsigned long long)stream_off);
 	if (codec && type == 0) {
 		// BEGIN: the modes are only defined on the streams oracle/stream.c accepts
 		const uint64_t vi = rd64(hdr + 16);
 		const uint64_t feat = (vi >> 2) & ((1ull << 30) - 1ull);
-		const bool marked = (vi & VI_STAGE) != 0;
-		if (h->cfg.mode == MTZ_MODE_COMPRESS && ((feat & FEAT_COMPRESSED) || marked))
-			return fail(h, MTZ_EINVAL, "COMPRESS: stream is already compressed");
-		if (h->cfg.mode == MTZ_MODE_DECOMPRESS && !marked)
-			return fail(h, MTZ_EINVAL, "DECOMPRESS: stream was not produced by the COMPRESS stage");
+		if (h->cfg.mode == MTZ_MODE_COMPRESS) {
+			if (feat & FEAT_COMPRESSED) return fail(h, MTZ_EINVAL, "COMPRESS: stream is already compressed");
+			// the lz4-stage-v1 wire puts a preamble in front of every BEGIN: BEGIN opens its batch
+			if (bc.cnt > 0) return 0;
+			bc.emit_pre = true;
+			bc.pre_flags = (feat & FEAT_LZ4) ? WIRE_F_ORIG_LZ4 : 0u;
+		} else if (h->cfg.mode == MTZ_MODE_DECOMPRESS) {
+			if (!ws->pre_seen)
+				return fail(h, MTZ_EINVAL, "DECOMPRESS: stream was not produced by the COMPRESS stage");
+			resv = ws->pre_flags;
+			ws->pre_seen = false;
+		}
 	}
 	mtz_rec r;
 	r.off = bc.in_bytes; r.payload = (uint32_t)pl; r.type = type;
-	r.lsize = ls; r.comp = comp; r.resv = 0;
+	r.lsize = ls; r.comp = comp; r.resv = resv;
 	*out = r;
 	bc.cnt++; bc.in_bytes += rl; bc.budget += cost;
 	if (type == 3) bc.writes++;
@@ -1230,8 +1268,15 @@ int32_t mtz_process_host(mtz_handle *h, const void *in, size_t n, void *out, siz
 		const bool was_busy = s.busy;
 		int32_t r = harvest(h, s);
 		if (r != MTZ_OK || !was_busy || !codec) return r;
-		if (out_pos + s.out_bytes > out_cap)
-			return fail(h, MTZ_ENOSPC, "output buffer too small (%zu needed so far)", out_pos + s.out_bytes);
+		const size_t pre = s.emit_pre ? WIRE_PRE_BYTES : 0;
+		if (out_pos + pre + s.out_bytes > out_cap)
+			return fail(h, MTZ_ENOSPC, "output buffer too small (%zu needed so far)", out_pos + pre + s.out_bytes);
+		if (pre) {
+			wire_preamble((uint8_t *)out + out_pos, s.pre_flags);
+			out_pos += pre;
+			std::lock_guard<std::mutex> g(h->stats_mu);
+			h->stats.bytes_out += pre;
+		}
 		MTZ_CU(h, cudaSetDevice(h->devs[s.di].device));
 		// issued, not awaited: the copy-out of batch b overlaps the parse + submit of the batches
 		// behind it; the slot is only reused (or the call returns) after `drain_d2h`
@@ -1250,6 +1295,7 @@ int32_t mtz_process_host(mtz_handle *h, const void *in, size_t n, void *out, siz
 	// output order == submission order: retire the OLDEST batch before cutting the next one once
 	// every slot is taken, so a slot's output copy has a whole ring of batches to finish in
 	const size_t NS = h->slots.size();
+	WireState ws;
 	while (off < n && rc == MTZ_OK) {
 		Slot &s = h->slots[b % NS];
 		rc = retire(s);
@@ -1263,18 +1309,36 @@ int32_t mtz_process_host(mtz_handle *h, const void *in, size_t n, void *out, siz
 				const size_t at = off + bc.in_bytes;
 				const uint8_t *hp = src + at;
 				uint32_t ls, comp;
+				if (h->cfg.mode == MTZ_MODE_DECOMPRESS && !ws.pre_seen && n - at >= WIRE_PRE_BYTES &&
+				    rd64(hp) == WIRE_MAGIC) {
+					// the preamble of the lz4-stage-v1 wire: stripped here, between two batches
+					if (bc.cnt > 0) break;
+					if (wire_parse(hp, &ws.pre_flags) < 0) {
+						rc = fail(h, MTZ_EFORMAT, "unsupported wire version / capability in the preamble at offset %zu", at);
+						break;
+					}
+					ws.pre_seen = true;
+					off += WIRE_PRE_BYTES;
+					{
+						std::lock_guard<std::mutex> g(h->stats_mu);
+						h->stats.bytes_in += WIRE_PRE_BYTES;
+					}
+					continue;
+				}
 				if (n - at < DRR_HDR) { rc = fail(h, MTZ_EFORMAT, "truncated record header at offset %zu", at); break; }
 				const int64_t pl = drr_payload(hp, &ls, &comp);
 				if (pl < 0) { rc = fail(h, MTZ_EFORMAT, "malformed record header at offset %zu", at); break; }
 				if ((uint64_t)pl > n - at - DRR_HDR) { rc = fail(h, MTZ_EFORMAT, "truncated payload at offset %zu", at); break; }
-				const int32_t a = batch_accept(h, s, bc, hp, pl, ls, comp, at, &s.h_recs[bc.cnt]);
+				const int32_t a = batch_accept(h, s, bc, hp, pl, ls, comp, at, &s.h_recs[bc.cnt], &ws);
 				if (a < 0) { rc = a; break; }
 				if (a == 0) break;
 				if (bc.budget >= (size_t)h->cfg.batch_bytes) break;
 			}
 		}
 		if (rc != MTZ_OK) break;
+		if (bc.cnt == 0 && bc.in_bytes == 0 && parse) continue;      // (only a preamble was consumed)
 		s.writes = bc.writes;
+		s.emit_pre = bc.emit_pre; s.pre_flags = bc.pre_flags;
 		uint8_t *ho = (!codec && out != nullptr && out != in) ? (uint8_t *)out + off : nullptr;
 		rc = submit_batch(h, s, src + off, bc.in_bytes, nullptr, 0, bc.cnt, off, ho);
 		off += bc.in_bytes;

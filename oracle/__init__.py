@@ -212,6 +212,43 @@ def stream_compress(stream, cap=None):
     return _xform("compress", stream, cap)
 
 
+WIRE_MAGIC = bytes.fromhex("4d545a4c5a345731")          # "MTZLZ4W1", mtz_oracle.h ORC_WIRE_MAGIC
+WIRE_PRE_BYTES = 32
+
+
+def wire_strip(stream):
+    """The COMPRESS output without the lz4-stage-v1 preambles (32 bytes in front of every BEGIN):
+    the plain compressed send stream underneath, i.e. what `zfs send -c` would carry."""
+    a = _u8(stream)
+    L = lib()
+    L.orc_drr_payload_len.restype = C.c_int64
+    L.orc_drr_payload_len.argtypes = [C.c_void_p]
+    parts, pos, start = [], 0, 0
+    n = a.size
+    while pos < n:
+        if n - pos >= WIRE_PRE_BYTES and a[pos:pos + 8].tobytes() == WIRE_MAGIC:
+            if pos > start:
+                parts.append(a[start:pos])
+            pos += WIRE_PRE_BYTES
+            start = pos
+            continue
+        if n - pos < 312:
+            break
+        pl = L.orc_drr_payload_len(a[pos:].ctypes.data)
+        if pl < 0:
+            break
+        pos += 312 + pl
+    parts.append(a[start:])
+    return np.ascontiguousarray(np.concatenate(parts)) if len(parts) > 1 else np.ascontiguousarray(parts[0])
+
+
+def stream_compress_plain(stream, cap=None):
+    """COMPRESS without the wire framing: the compressed send stream itself (what the device-level
+    pipeline produces and what RECOMPRESS / VERIFY take) -- stream_compress() minus its preambles."""
+    rc, c, st = stream_compress(stream, cap)
+    return rc, (wire_strip(c) if rc == 0 else c), st
+
+
 def stream_decompress(stream, cap=None):
     return _xform("decompress", stream, cap)
 

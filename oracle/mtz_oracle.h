@@ -73,8 +73,15 @@ uint64_t orc_tri3(uint64_t n);   /* n(n+1)(n+2)/6 mod 2^64, exact */
 #define ORC_FEAT_LZ4         (1ULL << 17)
 #define ORC_FEAT_COMPRESSED  (1ULL << 22)
 /* versioninfo bits above the 30-bit feature field: private to the two stages */
-#define ORC_VI_STAGE_COMPRESSED (1ULL << 63)
-#define ORC_VI_ORIG_LZ4         (1ULL << 62)
+/* wire format "lz4-stage-v1" (the TCP leg between a compressing sender stage and a decompressing
+ * receiver stage; the raw wire is a plain send stream): every DRR_BEGIN is preceded by a 32-byte
+ * preamble, outside the stream checksum (which restarts at BEGIN):
+ *   u64 magic "MTZLZ4W1" | u32 version = 1 | u32 flags | 16 reserved zero bytes
+ * flags bit 0: the original stream's BEGIN carried the LZ4 feature flag (restored by DECOMPRESS) */
+#define ORC_WIRE_MAGIC      0x3157345A4C5A544DULL
+#define ORC_WIRE_VERSION    1u
+#define ORC_WIRE_PRE_BYTES  32u
+#define ORC_WIRE_F_ORIG_LZ4 1u
 #define ORC_ZIO_COMPRESS_LZ4 15
 
 int64_t orc_drr_payload_len(const uint8_t *hdr);  /* <0: malformed */

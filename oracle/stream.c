@@ -133,7 +133,8 @@ walk(const uint8_t *in, size_t n, uint8_t *out, size_t cap, size_t *outn,
 	uint8_t hdr[ORC_DRR_HDR];
 	uint8_t *tmp = NULL, *tmp2 = NULL;
 	size_t tmpcap = 0;
-	int rc = ORC_OK, seen_begin = 0, stage_marked = 0;
+	int rc = ORC_OK, seen_begin = 0, pre_seen = 0;
+	uint32_t pre_flags = 0;
 	static const uint8_t zero32[32] = { 0 };
 
 	stats_init(st);
@@ -144,6 +145,21 @@ walk(const uint8_t *in, size_t n, uint8_t *out, size_t cap, size_t *outn,
 		uint64_t opl;
 		uint32_t type;
 
+		/* the lz4-stage-v1 wire: a preamble in front of every BEGIN (DECOMPRESS input only) */
+		if (mode == 2 && !pre_seen && n - off >= ORC_WIRE_PRE_BYTES &&
+		    g64(h) == ORC_WIRE_MAGIC) {
+			uint32_t k;
+			if (g32(h + 8) != ORC_WIRE_VERSION ||
+			    (g32(h + 12) & ~ORC_WIRE_F_ORIG_LZ4) != 0) {
+				rc = ORC_EFORMAT; goto bad;      /* a wire version this side does not speak */
+			}
+			for (k = 16; k < ORC_WIRE_PRE_BYTES; k++)
+				if (h[k] != 0) { rc = ORC_EFORMAT; goto bad; }
+			pre_seen = 1;
+			pre_flags = g32(h + 12);
+			off += ORC_WIRE_PRE_BYTES;
+			continue;
+		}
 		if (n - off < ORC_DRR_HDR) { rc = ORC_EFORMAT; goto bad; }
 		pl = orc_drr_payload_len(h);
 		if (pl < 0 || (uint64_t)pl > n - off - ORC_DRR_HDR) {
@@ -151,6 +167,7 @@ walk(const uint8_t *in, size_t n, uint8_t *out, size_t cap, size_t *outn,
 		}
 		type = g32(h);
 		pay = h + ORC_DRR_HDR;
+		if (pre_seen && type != ORC_DRR_BEGIN) { rc = ORC_EFORMAT; goto bad; }
 		if (!seen_begin && type != ORC_DRR_BEGIN) {
 			rc = ORC_EFORMAT; goto bad;
 		}
@@ -183,20 +200,26 @@ walk(const uint8_t *in, size_t n, uint8_t *out, size_t cap, size_t *outn,
 			uint64_t vi = g64(h + OFF_BEGIN_VI);
 			uint64_t feat = (vi >> 2) & (((uint64_t)1 << 30) - 1);
 			seen_begin = 1;
-			stage_marked = (vi & ORC_VI_STAGE_COMPRESSED) != 0;
 			if (mode == 1) {
-				if ((feat & ORC_FEAT_COMPRESSED) || stage_marked) {
-					rc = ORC_EINVAL; goto bad;
+				uint8_t pre[ORC_WIRE_PRE_BYTES];
+				if (feat & ORC_FEAT_COMPRESSED) { rc = ORC_EINVAL; goto bad; }
+				memset(pre, 0, sizeof (pre));
+				p64(pre, ORC_WIRE_MAGIC);
+				pre[8] = ORC_WIRE_VERSION;
+				pre[12] = (feat & ORC_FEAT_LZ4) ? ORC_WIRE_F_ORIG_LZ4 : 0;
+				if (out != NULL) {
+					if (cap - oo < sizeof (pre)) { rc = ORC_ENOSPC; goto bad; }
+					memcpy(out + oo, pre, sizeof (pre));
 				}
-				if (feat & ORC_FEAT_LZ4) vi |= ORC_VI_ORIG_LZ4;
-				vi |= ORC_VI_STAGE_COMPRESSED;
+				oo += sizeof (pre);
 				vi |= (ORC_FEAT_COMPRESSED | ORC_FEAT_LZ4) << 2;
 				p64(hdr + OFF_BEGIN_VI, vi);
 			} else if (mode == 2) {
-				if (!stage_marked) { rc = ORC_EINVAL; goto bad; }
+				/* only what the COMPRESS stage produced is inverted exactly */
+				if (!pre_seen) { rc = ORC_EINVAL; goto bad; }
 				vi &= ~((ORC_FEAT_COMPRESSED | ORC_FEAT_LZ4) << 2);
-				if (vi & ORC_VI_ORIG_LZ4) vi |= ORC_FEAT_LZ4 << 2;
-				vi &= ~(ORC_VI_STAGE_COMPRESSED | ORC_VI_ORIG_LZ4);
+				if (pre_flags & ORC_WIRE_F_ORIG_LZ4) vi |= ORC_FEAT_LZ4 << 2;
+				pre_seen = 0;
 				p64(hdr + OFF_BEGIN_VI, vi);
 			} else if (mode == 3) {
 				vi |= (ORC_FEAT_COMPRESSED | ORC_FEAT_LZ4) << 2;

@@ -26,7 +26,7 @@ for name in ("test_k3_zfs_frame_rules_on_the_cpu", "test_k1_and_scan_kernels_on_
     print("ok", name, flush=True)
 # the codec pipeline in every mode over one stream with every record type and odd sizes
 s = _all_types_stream(O, seed=9)
-rc, c, _ = O.stream_compress(s)
+rc, c, _ = O.stream_compress_plain(s)
 for mode, inp, want in ((1, s, c), (2, c, s), (3, c, O.stream_recompress(c)[1])):
     got, r = T._codec_on_emulator(L, mode, inp, 8)
     assert np.array_equal(got, want), mode

@@ -50,7 +50,7 @@ def digests():
         assert rc == 0
         rc, c, cst = O.stream_compress(s)
         assert rc == 0
-        rc, r, rst = O.stream_recompress(c)
+        rc, r, rst = O.stream_recompress(O.wire_strip(c))     # of the send stream under the wire framing
         assert rc == 0
         d["streams"][name] = {
             "bytes": int(s.size), "records": int(st.records), "sha256": sha(s),

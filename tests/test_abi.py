@@ -63,7 +63,7 @@ def test_host_index_matches_oracle(native, oracle):
     assert set(recs["payload"][2:-1]) == {4096}
     # a compressed stream exposes lsize/comp
     sp = oracle.synth_stream(6, recsize=131072, kind=oracle.PAYLOAD_PGPAGE)
-    rc, c, st = oracle.stream_compress(sp)
+    rc, c, st = oracle.stream_compress_plain(sp)
     recs, used = index_host(c)
     assert used == c.size
     w = recs[recs["type"] == 3]

@@ -305,7 +305,7 @@ def test_codec_kernels_on_the_cpu(emu, oracle):
              (np.concatenate([oracle.synth_stream(5, recsize=8192, kind=oracle.PAYLOAD_PGPAGE),
                               _all_types_stream(oracle, seed=4)]), 8)]
     for s, lanes in cases:
-        rc, want_c, cst = oracle.stream_compress(s)
+        rc, want_c, cst = oracle.stream_compress_plain(s)
         assert rc == 0
         got_c, r = _codec_on_emulator(emu, 1, s, lanes)
         assert np.array_equal(got_c, want_c), ("compress", s.size)
@@ -320,7 +320,7 @@ def test_codec_kernels_on_the_cpu(emu, oracle):
         assert r["end_ck"] == rst.end_cksum.tuple()
     # a frame that does not decode is reported with its record index, nothing is written past it
     s = _mixed_stream(oracle, n=12, recsize=131072)
-    rc, c, _ = oracle.stream_compress(s)
+    rc, c, _ = oracle.stream_compress_plain(s)
     cnt, offs = oracle.stream_index(c)
     k = 5
     bad = c.copy()
@@ -354,7 +354,7 @@ def test_gpu_side_parser_and_carry_fold_on_the_cpu(emu, oracle):
     streams = [base, oracle.synth_stream(0), oracle.synth_stream(700, recsize=512, kind=oracle.PAYLOAD_PCG),
                oracle.synth_stream(9, recsize=131072, kind=oracle.PAYLOAD_PGPAGE),
                np.concatenate([base, oracle.synth_stream(5, recsize=4096), base])]
-    rc, comp, _ = oracle.stream_compress(streams[3])
+    rc, comp, _ = oracle.stream_compress_plain(streams[3])
     streams.append(comp)                                              # ragged record lengths
     for s in streams:
         for cut in (0, 100, 312 + 77):

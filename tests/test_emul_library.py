@@ -64,6 +64,7 @@ def _gpu_tests():
               ("codec_corrupt_frame", K.test_corrupt_frame_is_ecodec_at_the_oracles_record, ()),
               ("codec_incompressible", K.test_incompressible_stream_passes_through, ()),
               ("codec_transport_identity-4096", K.test_transport_identity_compress_then_decompress, (4096,)),
+              ("codec_wire_preamble", K.test_wire_preamble_versioning, ()),
               ("codec_randomized-1", K.test_randomized_streams_all_modes, (1,)),
               ("codec_randomized-3", K.test_randomized_streams_all_modes, (3,))]
     return cases
@@ -132,7 +133,7 @@ def test_many_tiny_records_through_the_subbatched_codec(emul_library, oracle):
     assert oracle.stream_restamp(s)[0] == 0
     recs, used = index_host(s)
     assert used == s.size and len(recs) > 3 * 700
-    rc, want_c, cst = oracle.stream_compress(s)
+    rc, want_c, cst = oracle.stream_compress_plain(s)
     assert rc == 0 and cst.lz4_out == 5
     out = np.zeros(s.size + (1 << 20), dtype=np.uint8)
     with GpuSnapshotStage("compress") as g:
@@ -170,7 +171,7 @@ def test_codec_shards_with_deferred_chain_on_the_emulated_library(emul_library, 
     from manatee_b200._native import FLAG_DEFER_VERIFY
     from test_gpu_codec import _mixed_stream
     s = _mixed_stream(oracle, n=20, recsize=16384)
-    rc, c, _ = oracle.stream_compress(s)
+    rc, c, _ = oracle.stream_compress_plain(s)
     c = np.ascontiguousarray(c)
     rc, want, st = oracle.stream_recompress(c)
     recs, used = index_host(c)
@@ -280,7 +281,7 @@ N.SO_PATH = sys.argv[1]; N._lib = None
 from manatee_b200 import GpuSnapshotStage, index_host
 from test_gpu_codec import _mixed_stream
 s = _mixed_stream(O, n=30, recsize=16384)
-rc, c, _ = O.stream_compress(s); c = np.ascontiguousarray(c)
+rc, c, _ = O.stream_compress_plain(s); c = np.ascontiguousarray(c)
 rc, want, st = O.stream_recompress(c)
 recs, _ = index_host(c)
 out = np.zeros(s.size + (1 << 20), dtype=np.uint8)

@@ -61,7 +61,7 @@ def test_transport_identity_compress_then_decompress(oracle, recsize):
 
 def test_recompress_matches_oracle_and_is_idempotent(oracle):
     s = _mixed_stream(oracle, n=30)
-    rc, c, _ = oracle.stream_compress(s)
+    rc, c, _ = oracle.stream_compress_plain(s)
     # a stream compressed by a DIFFERENT encoder: rebuild frames with liblz4
     import ctypes as C
     lz = C.CDLL("liblz4.so.1")
@@ -106,7 +106,8 @@ def test_incompressible_stream_passes_through(oracle):
     s = oracle.synth_stream(12, kind=oracle.PAYLOAD_PCG)
     rc, want, st = oracle.stream_compress(s)
     got, gs, _ = _gpu("compress", s)
-    assert np.array_equal(got, want) and gs["lz4_encoded"] == 0 and got.size == s.size
+    assert np.array_equal(got, want) and gs["lz4_encoded"] == 0
+    assert got.size == s.size + oracle.WIRE_PRE_BYTES     # stored raw; only the wire preamble is added
 
 
 def test_streaming_compress_and_decompress(oracle):
@@ -141,7 +142,7 @@ def test_device_api_recompress_subbatched(oracle):
     import torch
     from manatee_b200 import GpuSnapshotStage, index_host
     s = _mixed_stream(oracle, n=64)
-    rc, c, _ = oracle.stream_compress(s)
+    rc, c, _ = oracle.stream_compress_plain(s)
     rc, want, st = oracle.stream_recompress(c)
     recs, used = index_host(c)
     d_in = torch.from_numpy(c).cuda()
@@ -161,10 +162,11 @@ def test_corrupt_frame_is_ecodec_at_the_oracles_record(oracle):
     s = _mixed_stream(oracle, n=20)
     rc, c, _ = oracle.stream_compress(s)
     c = c.copy()
-    cnt, offs = oracle.stream_index(c)
-    o = int(offs[9])
+    W = oracle.WIRE_PRE_BYTES                              # the lz4-stage-v1 preamble in front of BEGIN
+    cnt, offs = oracle.stream_index(c[W:])
+    o = W + int(offs[9])
     c[o + 312 + 6] = 0xff; c[o + 312 + 7] = 0xff          # first match offset -> beyond block start
-    assert oracle.stream_restamp(c)[0] == 0                # checksums valid, frame is not
+    assert oracle.stream_restamp(c[W:])[0] == 0            # checksums valid, frame is not
     rc, _, st = oracle.stream_decompress(c)
     assert rc == oracle.ECODEC
     with pytest.raises(MtzError) as ei:
@@ -175,7 +177,7 @@ def test_corrupt_frame_is_ecodec_at_the_oracles_record(oracle):
 def test_mode_preconditions_like_the_oracle(oracle):
     from manatee_b200._native import MtzError, EINVAL
     s = _mixed_stream(oracle, n=4)
-    rc, c, _ = oracle.stream_compress(s)
+    rc, c, _ = oracle.stream_compress_plain(s)             # an already compressed send stream
     assert oracle.stream_compress(c)[0] == oracle.EINVAL
     assert oracle.stream_decompress(s)[0] == oracle.EINVAL
     with pytest.raises(MtzError) as ei:
@@ -261,8 +263,9 @@ def test_every_record_type_all_modes(oracle):
     assert np.array_equal(got, want) and end == st.end_cksum.tuple()
     back, _, _ = _gpu("decompress", got)
     assert np.array_equal(back, s)
-    rc, want_r, _ = oracle.stream_recompress(got)
-    got_r, _, _ = _gpu("recompress", got)
+    plain = oracle.wire_strip(got)                  # RECOMPRESS takes the send stream, not the stage wire
+    rc, want_r, _ = oracle.stream_recompress(plain)
+    got_r, _, _ = _gpu("recompress", plain)
     assert np.array_equal(got_r, want_r)
 
 
@@ -342,8 +345,9 @@ def test_randomized_streams_all_modes(oracle, seed):
     assert np.array_equal(got_c, want_c) and end == cst.end_cksum.tuple()
     got_d, _, _ = _gpu("decompress", got_c, cap=s.size + (1 << 20), batch_bytes=batch)
     assert np.array_equal(got_d, s)
-    rc, want_r, _ = oracle.stream_recompress(got_c)
-    got_r, _, _ = _gpu("recompress", got_c, cap=s.size + (1 << 20), batch_bytes=batch)
+    plain = oracle.wire_strip(got_c)
+    rc, want_r, _ = oracle.stream_recompress(plain)
+    got_r, _, _ = _gpu("recompress", plain, cap=s.size + (1 << 20), batch_bytes=batch)
     assert np.array_equal(got_r, want_r)
 
 
@@ -356,7 +360,7 @@ def test_codec_shards_with_deferred_chain(oracle):
     from manatee_b200 import shard as SH
     from manatee_b200._native import FLAG_DEFER_VERIFY
     s = _mixed_stream(oracle, n=48)
-    rc, c, _ = oracle.stream_compress(s)
+    rc, c, _ = oracle.stream_compress_plain(s)
     rc, want, st = oracle.stream_recompress(c)
     recs, used = index_host(c)
     cut = 23
@@ -432,3 +436,51 @@ def test_size_independent_properties_at_2gib(oracle):
         with pytest.raises(MtzError) as ei:
             g.dev_finish()
         assert ei.value.code == ECKSUM and g.stats()["bad_record"] == kbad + 1
+
+
+def test_wire_preamble_versioning(oracle):
+    """the lz4-stage-v1 wire is framed -- a 32-byte preamble (magic, version, capability
+    word) in front of every DRR_BEGIN of a COMPRESS output, outside the stream checksum.  DECOMPRESS
+    speaks exactly the versions / capabilities it knows and inverts only what the stage produced;
+    the other modes never see a preamble (the raw wire stays the reference's byte stream)."""
+    from manatee_b200 import GpuSnapshotStage
+    from manatee_b200._native import MtzError, EFORMAT, EINVAL
+    two = np.concatenate([_mixed_stream(oracle, n=6, recsize=16384), _mixed_stream(oracle, n=3, recsize=8192)])
+    rc, want, st = oracle.stream_compress(two)
+    assert rc == 0
+    W = oracle.WIRE_PRE_BYTES
+    got, _, _ = _gpu("compress", two, batch_bytes=1 << 20)
+    assert np.array_equal(got, want)
+    # one preamble per sub-stream, each directly in front of a BEGIN (magic 0x2F5bacbac at +8 of it)
+    at = [i for i in range(0, got.size - 8, 8) if got[i:i + 8].tobytes() == oracle.WIRE_MAGIC]
+    assert len(at) == 2 and at[0] == 0
+    for a in at:
+        assert int.from_bytes(got[a + 8:a + 12].tobytes(), "little") == 1          # version
+        assert int.from_bytes(got[a + W + 8:a + W + 16].tobytes(), "little") == 0x2F5bacbac
+    back, _, _ = _gpu("decompress", got, cap=two.size + (1 << 20), batch_bytes=1 << 20)
+    assert np.array_equal(back, two)
+    cases = []
+    v2 = got.copy(); v2[8] = 2
+    cases.append((v2, EFORMAT))                                   # a newer wire version
+    cap = got.copy(); cap[at[1] + 13] = 0x80
+    cases.append((cap, EFORMAT))                                  # a capability bit this side does not know
+    cases.append((oracle.wire_strip(got), EINVAL))                # not produced by the COMPRESS stage
+    lone = np.concatenate([got[:W], got[W + 312:]])               # preamble not followed by BEGIN
+    cases.append((lone, EFORMAT))
+    for bad, code in cases:
+        assert oracle.stream_decompress(bad)[0] == code
+        with pytest.raises(MtzError) as ei:
+            _gpu("decompress", bad, cap=two.size + (1 << 20))
+        assert ei.value.code == code
+        with GpuSnapshotStage("decompress", ring_bytes=4 << 20, out_ring_bytes=4 << 20, batch_bytes=1 << 20) as g:
+            with pytest.raises(MtzError) as ei:
+                g.write(bad)
+                g.flush()
+                while g.read(1 << 20) is not None:
+                    pass
+            assert ei.value.code == code
+    # the wire framing is for the decompressing peer only
+    for mode in ("verify", "recompress", "compress"):
+        with pytest.raises(MtzError) as ei:
+            _gpu(mode, got)
+        assert ei.value.code == EFORMAT

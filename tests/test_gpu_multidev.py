@@ -37,6 +37,14 @@ def _mixed_stream(oracle, n=48, recsize=65536):
     return s
 
 
+def _source(oracle, mode, raw):
+    """input of `mode`: DECOMPRESS takes the stage wire (preamble + stream), RECOMPRESS a plain
+    compressed send stream"""
+    if mode in ("verify", "compress"):
+        return raw
+    return oracle.stream_compress(raw)[1] if mode == "decompress" else oracle.stream_compress_plain(raw)[1]
+
+
 def _want(oracle, mode, s):
     if mode == "verify":
         rc, st = oracle.stream_verify(s)
@@ -55,7 +63,7 @@ def test_group_bulk_call_equals_the_oracle(oracle, mode):
     from manatee_b200 import GpuSnapshotStage
     devs = _devices()
     raw = _mixed_stream(oracle)
-    src = raw if mode in ("verify", "compress") else oracle.stream_compress(raw)[1]
+    src = _source(oracle, mode, raw)
     want, st = _want(oracle, mode, src)
     out = np.zeros(raw.size * 2 + (1 << 20), dtype=np.uint8)
     with GpuSnapshotStage(mode, devices=devs, batch_bytes=300 << 10, n_slots=2) as g:
@@ -125,7 +133,7 @@ def test_fanout_every_peer_gets_the_oracles_stream(oracle, mode):
     from manatee_b200 import GpuSnapshotStage
     devs = _devices(4)
     raw = _mixed_stream(oracle)
-    src = raw if mode in ("verify", "compress") else oracle.stream_compress(raw)[1]
+    src = _source(oracle, mode, raw)
     want, st = _want(oracle, mode, src)
     wd = hashlib.sha256(want.tobytes()).hexdigest()
     peers = [0, 1, 2]

@@ -191,7 +191,7 @@ def test_gpu_side_parse_matches_host_parser(oracle):
     from manatee_b200 import GpuSnapshotStage, index_host
     from manatee_b200.stage import REC_DTYPE
     raw = oracle.synth_stream(300, recsize=16384, kind=oracle.PAYLOAD_PGPAGE)
-    rc, comp, _ = oracle.stream_compress(raw)              # variable-length records
+    rc, comp, _ = oracle.stream_compress_plain(raw)              # variable-length records
     two = np.concatenate([oracle.synth_stream(5, recsize=512), raw])
     for s in (raw, comp, two, raw[:-1000], oracle.synth_stream(0)):
         want, used = index_host(s)

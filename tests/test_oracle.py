@@ -215,14 +215,23 @@ def test_stream_transforms_round_trip(oracle):
     s = oracle.synth_stream(12, recsize=16384, kind=oracle.PAYLOAD_PGPAGE)
     rc, c, st = oracle.stream_compress(s)
     assert rc == 0 and st.lz4_out == 12 and c.size < s.size
-    assert oracle.stream_verify(c)[0] == 0
+    assert c[:8].tobytes() == oracle.WIRE_MAGIC and oracle.stream_verify(c)[0] == oracle.EFORMAT
+    z = oracle.wire_strip(c)                                      # the send stream under the wire framing
+    assert z.size == c.size - oracle.WIRE_PRE_BYTES and oracle.stream_verify(z)[0] == 0
     rc, d, _ = oracle.stream_decompress(c)
     assert rc == 0 and np.array_equal(d, s)                       # transport identity
-    rc, r, _ = oracle.stream_recompress(c)
-    assert rc == 0 and np.array_equal(r, c)                       # idempotence
-    rc, secs, g, _ = oracle.mt_recompress(c, 4)
-    assert rc == 0 and np.array_equal(g, c)                       # MT driver == single thread
-    assert oracle.mt_verify(c, 4)[0] == 0
+    rc, r, _ = oracle.stream_recompress(z)
+    assert rc == 0 and np.array_equal(r, z)                       # idempotence
+    rc, secs, g, _ = oracle.mt_recompress(z, 4)
+    assert rc == 0 and np.array_equal(g, z)                       # MT driver == single thread
+    assert oracle.mt_verify(z, 4)[0] == 0
+    # versioned framing: a preamble of another version, or with capability bits this
+    # side does not know, is refused; a stream without one was not produced by the stage
+    v2 = c.copy(); v2[8] = 2
+    assert oracle.stream_decompress(v2)[0] == oracle.EFORMAT
+    cap = c.copy(); cap[13] = 1
+    assert oracle.stream_decompress(cap)[0] == oracle.EFORMAT
+    assert oracle.stream_decompress(z)[0] == oracle.EINVAL
 
 
 def test_golden_fixtures(oracle):

@@ -22,17 +22,23 @@ base_raw = [_all_types_stream(O, seed=5), _mixed_stream(O, n=10, recsize=16384)]
 base = []
 for s in base_raw:
     base.append(("raw", s))
-    base.append(("lz4", O.stream_compress(s)[1]))
+    base.append(("lz4", O.stream_compress(s)[1]))            # the stage wire (preamble + stream)
+    base.append(("lz4-plain", O.stream_compress_plain(s)[1]))
 counts = {}
 t0 = time.time()
 for it in range(iters):
     kind, s = base[int(rng.integers(0, len(base)))]
     m = s.copy()
-    cnt, offs = O.stream_index(s)
+    W = O.WIRE_PRE_BYTES if kind == "lz4" else 0          # the stage wire starts with a preamble
+    cnt, offs = O.stream_index(s[W:])
+    offs = offs + W
     nmut = int(rng.integers(1, 4))
     for _ in range(nmut):
         r = int(rng.integers(0, cnt))
-        how = int(rng.integers(0, 5))
+        how = int(rng.integers(0, 6 if W else 5))
+        if how == 5:      # the wire preamble itself: magic, version, capability word, reserved bytes
+            m[int(rng.integers(0, W))] ^= 1 << int(rng.integers(0, 8))
+            continue
         o = int(offs[r])
         end = int(offs[r + 1]) if r + 1 < cnt else s.size
         if how == 0:      # header field
