@@ -300,8 +300,24 @@ def ring_pump():
         P.pump_memcpy.restype = C.c_int32
         P.pump_pipe.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]
         P.pump_pipe.restype = C.c_int32
+        P.pump_selfcopy.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int]
+        P.pump_selfcopy.restype = C.c_int32
         _PUMP = P
     return _PUMP
+
+
+def host_memcpy_ceiling(src, nthreads, chunk=64 << 20):
+    """GiB/s of the producer alone: the pump's parallel memcpys from `src` into one pinned 64 MiB
+    slice, no library behind it -- what an acquire/commit leg cannot exceed on this host."""
+    from manatee_b200 import PinnedBuffer
+    pin = PinnedBuffer(chunk)
+    n = min(src.size, 8 << 30)
+    P = ring_pump()
+    t0 = time.perf_counter()
+    P.pump_selfcopy(pin.array.ctypes.data, src.ctypes.data, n, chunk, nthreads)
+    dt = time.perf_counter() - t0
+    pin.free()
+    return round(n / GIB / dt, 3)
 
 
 def ring_run(g, src, peers=(0,), producer="write", nthreads=4, chunk=64 << 20):
@@ -432,9 +448,11 @@ def run_verify_resident(args, O, local, steps, warm, peak):
                       "call": "mtz_process_host, pinned host stream in, verdict out (output == input)"}
         # the ring API at link rate: acquire/commit, the slice filled by parallel memcpys
         with GpuSnapshotStage("verify", device=local, ring_bytes=1 << 30, batch_bytes=64 << 20, n_slots=4) as gr:
-            dt, ok, det = ring_run(gr, s, producer="acquire", nthreads=min(8, max(2, nthreads // 2)))
+            nt = min(16, max(2, nthreads // 2))
+            dt, ok, det = ring_run(gr, s, producer="acquire", nthreads=nt)
             res["ring_acquire_commit"] = {"value": round(s.size / GIB / dt, 3), "unit": "GiB/s", "ok": bool(
                 ok and det["delivered"].get(0) == s.size and gr.end_checksum() == end_ck),
+                "producer_threads": nt, "host_memcpy_ceiling_gibs": host_memcpy_ceiling(s, nt),
                 "call": "mtz_ring_acquire/commit (slices filled by parallel host memcpys) -> engine -> "
                         "mtz_out_peek/consume in place (zero copy)"}
     if not args.no_cpu:
@@ -614,7 +632,7 @@ def run_ours(args):
             for name, prod in (("write", "write"), ("acquire_commit", "acquire"), ("pipe", "pipe")):
                 with GpuSnapshotStage("recompress", device=local, devices=devices, ring_bytes=1 << 30,
                                       out_ring_bytes=1 << 30, n_slots=4) as gr:
-                    dt, ok, det = ring_run(gr, src, producer=prod, nthreads=min(8, max(2, nthreads // 2)))
+                    dt, ok, det = ring_run(gr, src, producer=prod, nthreads=min(16, max(2, nthreads // 2)))
                     ok = ok and det["delivered"].get(0) == src.size and gr.end_checksum() == end_ck_of(O, end_ck, gr)
                 ring[name] = {"value": round(src.size / GIB / dt, 3), "unit": "GiB/s", "ok": bool(ok),
                               "logical_gibs": round(logical / GIB / dt, 3)}
@@ -634,7 +652,7 @@ def run_ours(args):
                                       out_ring_bytes=512 << 20, n_slots=4) as gf:
                     eg = [gf.fanout_attach(p) for p in range(P)]
                     dt, ok, det = ring_run(gf, src, peers=tuple(range(P)), producer="acquire",
-                                           nthreads=min(8, max(2, nthreads // 2)))
+                                           nthreads=min(16, max(2, nthreads // 2)))
                     ok = ok and all(det["delivered"].get(p) == src.size for p in range(P))
                 fan = {"peers": P, "egress_gpus": eg, "ok": bool(ok),
                        "source_once_gibs": round(total_bytes / GIB / dt, 2),

@@ -53,6 +53,7 @@ struct Peer {
 struct InFlight {
 	int slot; uint64_t seq; uint64_t in_begin, in_end;
 	bool harvested = false;
+	bool in_released = false;  // own-output modes: its input bytes have left the ring (H2D done)
 	size_t n_out = 0;
 	bool bcast = false;        // fan-out broadcast of this batch has been launched
 };
@@ -146,6 +147,8 @@ static int32_t fanout_init(mtz_handle *h, size_t chunk_cap)
 }
 
 } // namespace mtz
+
+static void CUDART_CB engine_kick(void *engine) { mtz::engine_host_cb(engine); }
 
 static void fanout_destroy(mtz_handle *h)
 {
@@ -409,6 +412,19 @@ static void engine_main(Engine *e)
 			if (!e->own_out) { new_out_head = f.in_end; have_out_head = true; }   // verified: consumable in place
 			progress = true;
 		}
+		// 1b. modes with their own output ring: a batch's input bytes are free as soon as they are
+		// in HBM (in stream order), long before the batch has been processed and copied out
+		if (rc == MTZ_OK && e->own_out) {
+			for (auto &f : e->inflight) {
+				if (f.in_released) continue;
+				cudaError_t q = cudaEventQuery(h->slots[(size_t)f.slot].ev_h2d);
+				if (q == cudaErrorNotReady) break;
+				if (q != cudaSuccess) { rc = fail_cuda(h, q, "cudaEventQuery(H2D)"); break; }
+				f.in_released = true;
+				new_tail = f.in_end; have_tail = true;
+				progress = true;
+			}
+		}
 		// 2. output copies (and the NVLink broadcast in front of them)
 		if (rc == MTZ_OK && e->own_out) rc = engine_egress(e, pos, &progress);
 		// 3. finished copies become visible to their consumer
@@ -433,7 +449,7 @@ static void engine_main(Engine *e)
 			InFlight &f = e->inflight.front();
 			if (!f.harvested) break;
 			if (e->own_out && h->slots[(size_t)f.slot].egress_left > 0) break;
-			if (e->own_out) { new_tail = f.in_end; have_tail = true; }
+			if (e->own_out && !f.in_released) { new_tail = f.in_end; have_tail = true; }
 			e->retired_seq = f.seq + 1;
 			e->inflight.pop_front();
 			progress = true;

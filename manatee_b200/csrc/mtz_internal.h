@@ -52,6 +52,7 @@ struct Slot {
 	uint64_t seq = 0;             // stream-wide batch number of the batch in the slot
 	int egress_left = 0;          // consumers that have not finished reading the slot's output
 	cudaEvent_t ev_scan = nullptr;   // running checksums updated (the next batch's chain waits on it)
+	cudaEvent_t ev_h2d = nullptr;    // the batch's input bytes have left the host ring
 	uint8_t *d_in = nullptr;      // batch bytes (input stream slice)
 	uint8_t *d_out = nullptr;     // codec modes: output slice
 	size_t cap = 0, out_cap = 0;

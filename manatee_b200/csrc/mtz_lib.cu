@@ -185,6 +185,7 @@ static int32_t alloc_slot(mtz_handle *h, Slot &s, int di, size_t cap, size_t rec
 	MTZ_CU(h, cudaHostAlloc(&s.h_res, sizeof(ScanResult), cudaHostAllocPortable));
 	MTZ_CU(h, cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking));
 	MTZ_CU(h, cudaEventCreateWithFlags(&s.ev_scan, cudaEventDisableTiming));
+	MTZ_CU(h, cudaEventCreateWithFlags(&s.ev_h2d, cudaEventDisableTiming));
 	MTZ_CU(h, cudaEventCreate(&s.ev_k3a));
 	MTZ_CU(h, cudaEventCreate(&s.ev_k3b));
 	MTZ_CU(h, cudaEventCreate(&s.ev_start));
@@ -216,6 +217,7 @@ static void free_slot(Slot &s)
 	if (s.ev_c0) cudaEventDestroy(s.ev_c0);
 	if (s.ev_c1) cudaEventDestroy(s.ev_c1);
 	if (s.ev_scan) cudaEventDestroy(s.ev_scan);
+	if (s.ev_h2d) cudaEventDestroy(s.ev_h2d);
 	if (s.ev_k3a) cudaEventDestroy(s.ev_k3a);
 	if (s.ev_k3b) cudaEventDestroy(s.ev_k3b);
 	codec_free(s.cb);
@@ -277,7 +279,8 @@ int32_t mtz_open(const mtz_config *cfg, mtz_handle **out)
 	// record): measured e2e RECOMPRESS 26 / 41 / 48 / 49 GiB/s logical at 64 / 128 / 256 /
 	// 512 MiB batches; Fletcher alone is happy with 32 MiB batches
 	if (h->cfg.batch_bytes == 0) h->cfg.batch_bytes = codec_mode ? (256ull << 20) : (32ull << 20);
-	if (h->cfg.ring_bytes == 0) h->cfg.ring_bytes = std::max<uint64_t>(256ull << 20, 2 * h->cfg.batch_bytes);
+	// the input ring holds the batch being filled plus the ones whose H2D copy is still pending
+	if (h->cfg.ring_bytes == 0) h->cfg.ring_bytes = std::max<uint64_t>(256ull << 20, (codec_mode ? 3 : 2) * h->cfg.batch_bytes);
 	if (h->cfg.out_ring_bytes == 0) h->cfg.out_ring_bytes = h->cfg.ring_bytes;
 	if (h->cfg.record_bytes == 0) h->cfg.record_bytes = 131072;
 	if (h->cfg.n_slots == 0) h->cfg.n_slots = 4;
@@ -1169,6 +1172,8 @@ static int32_t harvest(mtz_handle *h, Slot &s)
 	return rc;
 }
 
+static void CUDART_CB engine_kick(void *engine);      // mtz_engine.inl
+
 // Enqueue one batch: the bytes come from up to two host pieces (ring wrap),
 // s.h_recs[0..nrec) is already filled with batch-relative offsets.
 static int32_t submit_batch(mtz_handle *h, Slot &s, const uint8_t *p0, size_t n0,
@@ -1185,6 +1190,9 @@ static int32_t submit_batch(mtz_handle *h, Slot &s, const uint8_t *p0, size_t n0
 		MTZ_CU(h, cudaMemcpyAsync(s.d_recs, s.h_recs, nrec * sizeof(mtz_rec), cudaMemcpyHostToDevice, s.st));
 	if (n0) MTZ_CU(h, cudaMemcpyAsync(s.d_in, p0, n0, cudaMemcpyHostToDevice, s.st));
 	if (n1) MTZ_CU(h, cudaMemcpyAsync(s.d_in + n0, p1, n1, cudaMemcpyHostToDevice, s.st));
+	MTZ_CU(h, cudaEventRecord(s.ev_h2d, s.st));
+	// streaming: wake the engine so that it hands the batch's ring space back to the producer
+	if (h->eng != nullptr && h->cfg.mode != MTZ_MODE_VERIFY) MTZ_CU(h, cudaLaunchHostFunc(s.st, engine_kick, h->eng));
 	int32_t rc = MTZ_OK;
 	if (h->cfg.mode == MTZ_MODE_VERIFY && (h->cfg.flags & MTZ_FLAG_DEFER_VERIFY)) {
 		// shard mode: sums accumulate in the handle-wide table; verdict later
