@@ -45,3 +45,13 @@ def test_reference_arm_prints_the_contract_line():
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert "workload" in d["config"] and d["gpu_launches"] == 0
+
+
+def test_restated_plumbing_pump_pair_moves_the_stream_unchanged():
+    """BASELINE.md row B0': tools/pump_pair.c (the reference's two pipes restated in C) between the
+    fake zfs children -- SHA-256 at `zfs recv` == SHA-256 at `zfs send`."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "bench_plumbing.py"), "0.03", "cpump"],
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=120, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads(r.stdout.strip().splitlines()[-1])["plumbing"]["cpump"]
+    assert d["identity"] is True and d["exit_codes"] == [0, 0, 0, 0] and d["stream_gibs"] > 0

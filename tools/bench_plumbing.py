@@ -4,7 +4,11 @@ loopback TCP with a fake `zfs` -- POST /backup, `zfs send` child -> [stage] -> s
 [stage] -> `zfs recv` child, job polling -- through the Python mirror of the reference's
 modules (Node is not installed, so the reference's own JS cannot be timed here).
 
-  python tools/bench_plumbing.py [GiB] [off|verify|compress]
+  python tools/bench_plumbing.py [GiB] [off|verify|compress|cpump]
+
+`cpump` is row B0' proper: tools/pump_pair.c, the two pipes of the reference restated in C (read <= 64 KiB
+-> write, one thread per side, loopback TCP) between the same fake `zfs send` / `zfs recv` children
+-- the ceiling of the reference's plumbing on a box without Node.js, labelled "restated".
 """
 import hashlib, json, os, socket, stat, sys, tempfile, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -16,6 +20,28 @@ from manatee_b200.host import BackupSender, BackupServer, ZfsClient
 
 def free_port():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def cpump(zfs, env, s, want):
+    """`zfs send` | pump_pair send  ==TCP==>  pump_pair recv | `zfs recv`"""
+    import subprocess
+    exe = os.path.join(ROOT, "tools", "pump_pair")
+    if not os.path.exists(exe):
+        subprocess.check_call(["gcc", "-O2", "-o", exe, os.path.join(ROOT, "tools", "pump_pair.c")])
+    port = free_port()
+    t0 = time.perf_counter()
+    recv = subprocess.Popen([exe, "recv", str(port)], stdout=subprocess.PIPE, env=env)
+    zrecv = subprocess.Popen([zfs, "recv", "-v", "-u", "zones/y/data/manatee"], stdin=recv.stdout, env=env,
+                             stderr=subprocess.DEVNULL)
+    zsend = subprocess.Popen([zfs, "send", "-v", "-P", "zones/x/data/manatee@1"], stdout=subprocess.PIPE, env=env,
+                             stderr=subprocess.DEVNULL)
+    send = subprocess.Popen([exe, "send", "127.0.0.1", str(port)], stdin=zsend.stdout, env=env)
+    rcs = [p.wait() for p in (zsend, send, recv, zrecv)]
+    dt = time.perf_counter() - t0
+    digest, n = open(env["FAKE_ZFS_RECV_OUT"]).read().split()
+    return {"gib": round(s.size / 2**30, 3), "seconds": round(dt, 3), "stream_gibs": round(s.size / 2**30 / dt, 3),
+            "identity": digest == want and int(n) == s.size, "exit_codes": rcs,
+            "what": "restated plumbing (tools/pump_pair.c), NOT the reference's Node.js; includes child start-up"}
 
 
 def main():
@@ -33,6 +59,9 @@ def main():
                FAKE_ZFS_RECV_OUT=os.path.join(d, "recv.out"))
     out = {}
     for mode in modes:
+        if mode == "cpump":
+            out[mode] = cpump(zfs, env, s, want)
+            continue
         sg = rg = None
         if mode == "verify":
             sg = rg = {"mode": "verify"}
