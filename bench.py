@@ -306,6 +306,14 @@ def ring_pump():
     return _PUMP
 
 
+def pump_threads():
+    """memcpy threads of the native producer: half of what the process may use (the cgroup quota
+    counts), so that the library's engine thread and the CUDA callback thread are not starved"""
+    q = cpu_quota()
+    n = min(host_threads(), int(q)) if q else host_threads()
+    return max(2, min(12, n // 2))
+
+
 def host_memcpy_ceiling(src, nthreads, chunk=64 << 20):
     """GiB/s of the producer alone: the pump's parallel memcpys from `src` into one pinned 64 MiB
     slice, no library behind it -- what an acquire/commit leg cannot exceed on this host."""
@@ -448,7 +456,7 @@ def run_verify_resident(args, O, local, steps, warm, peak):
                       "call": "mtz_process_host, pinned host stream in, verdict out (output == input)"}
         # the ring API at link rate: acquire/commit, the slice filled by parallel memcpys
         with GpuSnapshotStage("verify", device=local, ring_bytes=1 << 30, batch_bytes=64 << 20, n_slots=4) as gr:
-            nt = min(16, max(2, nthreads // 2))
+            nt = pump_threads()
             dt, ok, det = ring_run(gr, s, producer="acquire", nthreads=nt)
             res["ring_acquire_commit"] = {"value": round(s.size / GIB / dt, 3), "unit": "GiB/s", "ok": bool(
                 ok and det["delivered"].get(0) == s.size and gr.end_checksum() == end_ck),
@@ -632,7 +640,7 @@ def run_ours(args):
             for name, prod in (("write", "write"), ("acquire_commit", "acquire"), ("pipe", "pipe")):
                 with GpuSnapshotStage("recompress", device=local, devices=devices, ring_bytes=1 << 30,
                                       out_ring_bytes=1 << 30, n_slots=4) as gr:
-                    dt, ok, det = ring_run(gr, src, producer=prod, nthreads=min(16, max(2, nthreads // 2)))
+                    dt, ok, det = ring_run(gr, src, producer=prod, nthreads=pump_threads())
                     ok = ok and det["delivered"].get(0) == src.size and gr.end_checksum() == end_ck_of(O, end_ck, gr)
                 ring[name] = {"value": round(src.size / GIB / dt, 3), "unit": "GiB/s", "ok": bool(ok),
                               "logical_gibs": round(logical / GIB / dt, 3)}
@@ -652,7 +660,7 @@ def run_ours(args):
                                       out_ring_bytes=512 << 20, n_slots=4) as gf:
                     eg = [gf.fanout_attach(p) for p in range(P)]
                     dt, ok, det = ring_run(gf, src, peers=tuple(range(P)), producer="acquire",
-                                           nthreads=min(16, max(2, nthreads // 2)))
+                                           nthreads=pump_threads())
                     ok = ok and all(det["delivered"].get(p) == src.size for p in range(P))
                 fan = {"peers": P, "egress_gpus": eg, "ok": bool(ok),
                        "source_once_gibs": round(total_bytes / GIB / dt, 2),

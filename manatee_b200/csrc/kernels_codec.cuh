@@ -374,8 +374,12 @@ __device__ __forceinline__ Ck4 stamp_leave(const Ck4 &x, const RecSums *__restri
 }
 
 #define STAMP_GROUP   32
-#define STAMP_THREADS 64
-// warp 0 walks the chain, warp 1 stages the next STAMP_GROUP transitions into shared memory
+#define STAMP_THREADS 128
+#define STAMP_LOADERS (STAMP_THREADS / 32 - 1)
+// warp 0 walks the chain; warps 1..3 stage the next STAMP_GROUP transitions (12.8 KB) into shared
+// memory.  One loader warp with one load in flight per lane took ~12 000 cycles per group, four
+// times what the chain needs for it (profiles/r2_stamp_chain.md): three warps, four loads in
+// flight per lane
 __global__ void __launch_bounds__(STAMP_THREADS)
 k_stamp_chain(uint8_t *__restrict__ d_out, const mtz_rec *__restrict__ out_recs,
     const RecSums *__restrict__ osums, const StampStep *__restrict__ steps, uint32_t n,
@@ -392,9 +396,21 @@ k_stamp_chain(uint8_t *__restrict__ d_out, const mtz_rec *__restrict__ out_recs,
 		const uint32_t r0 = g * STAMP_GROUP, cnt = min((uint32_t)STAMP_GROUP, T - r0);
 		const uint4 *src = reinterpret_cast<const uint4 *>(steps + r0);
 		uint4 *dst = reinterpret_cast<uint4 *>(&s_steps[g & 1u][0]);
-		for (uint32_t i = (uint32_t)lane; i < cnt * V4; i += 32u) dst[i] = src[i];
+		const uint32_t nv = cnt * V4, stride = 32u * STAMP_LOADERS;
+		for (uint32_t i = (uint32_t)(warp - 1) * 32u + (uint32_t)lane; i < nv; i += 4u * stride) {
+			uint4 t0, t1, t2, t3;                      // four independent loads in flight
+			const uint32_t i1 = i + stride, i2 = i + 2u * stride, i3 = i + 3u * stride;
+			t0 = src[i];
+			if (i1 < nv) t1 = src[i1];
+			if (i2 < nv) t2 = src[i2];
+			if (i3 < nv) t3 = src[i3];
+			dst[i] = t0;
+			if (i1 < nv) dst[i1] = t1;
+			if (i2 < nv) dst[i2] = t2;
+			if (i3 < nv) dst[i3] = t3;
+		}
 	};
-	if (warp == 1 && ngroups > 0u) stage(0);
+	if (warp >= 1 && ngroups > 0u) stage(0);
 	__syncthreads();
 
 	Ck4 x = { 0, 0, 0, 0 };
@@ -404,7 +420,7 @@ k_stamp_chain(uint8_t *__restrict__ d_out, const mtz_rec *__restrict__ out_recs,
 		own = (j == 0) ? x.a : (j == 1) ? x.b : (j == 2) ? x.c : x.d;
 	}
 	for (uint32_t g = 0; g < ngroups; g++) {
-		if (warp == 1) {
+		if (warp >= 1) {
 			if (g + 1u < ngroups) stage(g + 1u);
 		} else {
 			const uint32_t r0 = g * STAMP_GROUP, cnt = min((uint32_t)STAMP_GROUP, T - r0);

@@ -148,8 +148,6 @@ static int32_t fanout_init(mtz_handle *h, size_t chunk_cap)
 
 } // namespace mtz
 
-static void CUDART_CB engine_kick(void *engine) { mtz::engine_host_cb(engine); }
-
 static void fanout_destroy(mtz_handle *h)
 {
 	for (auto &dc : h->devs) {
@@ -504,7 +502,13 @@ static void engine_main(Engine *e)
 			// polls it, so the engine has to keep polling while batches are in flight
 			e->cv_eng.wait_for(lk, std::chrono::microseconds(e->inflight.empty() ? 5000 : 50));
 #else
-			e->cv_eng.wait_for(lk, std::chrono::milliseconds(partial ? 5 : 200));
+			// Idle: woken by commits, consumes, flush and the stream host-function at the end of
+			// every batch.  With batches in flight the engine also looks every 200 us on its own
+			// (H2D-complete and copy-out events have no callback; a host-function can be late by
+			// milliseconds when the producer's threads have eaten the process's CPU quota, and
+			// everything queued behind it in its stream would wait with it).
+			if (!e->inflight.empty()) e->cv_eng.wait_for(lk, std::chrono::microseconds(200));
+			else e->cv_eng.wait_for(lk, std::chrono::milliseconds(partial ? 5 : 200));
 #endif
 		}
 	}

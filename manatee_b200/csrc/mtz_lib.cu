@@ -1172,8 +1172,6 @@ static int32_t harvest(mtz_handle *h, Slot &s)
 	return rc;
 }
 
-static void CUDART_CB engine_kick(void *engine);      // mtz_engine.inl
-
 // Enqueue one batch: the bytes come from up to two host pieces (ring wrap),
 // s.h_recs[0..nrec) is already filled with batch-relative offsets.
 static int32_t submit_batch(mtz_handle *h, Slot &s, const uint8_t *p0, size_t n0,
@@ -1191,8 +1189,6 @@ static int32_t submit_batch(mtz_handle *h, Slot &s, const uint8_t *p0, size_t n0
 	if (n0) MTZ_CU(h, cudaMemcpyAsync(s.d_in, p0, n0, cudaMemcpyHostToDevice, s.st));
 	if (n1) MTZ_CU(h, cudaMemcpyAsync(s.d_in + n0, p1, n1, cudaMemcpyHostToDevice, s.st));
 	MTZ_CU(h, cudaEventRecord(s.ev_h2d, s.st));
-	// streaming: wake the engine so that it hands the batch's ring space back to the producer
-	if (h->eng != nullptr && h->cfg.mode != MTZ_MODE_VERIFY) MTZ_CU(h, cudaLaunchHostFunc(s.st, engine_kick, h->eng));
 	int32_t rc = MTZ_OK;
 	if (h->cfg.mode == MTZ_MODE_VERIFY && (h->cfg.flags & MTZ_FLAG_DEFER_VERIFY)) {
 		// shard mode: sums accumulate in the handle-wide table; verdict later

@@ -26,7 +26,7 @@ def _devices(want=8):
     return list(range(min(want, n)))
 
 
-def _mixed_stream(oracle, n=48, recsize=65536):
+def _mixed_stream(oracle, n=72, recsize=16384):
     s = oracle.synth_stream(n, recsize=recsize, kind=oracle.PAYLOAD_PGPAGE).copy()
     cnt, offs = oracle.stream_index(s)
     for k in range(2, cnt - 1):
@@ -66,7 +66,7 @@ def test_group_bulk_call_equals_the_oracle(oracle, mode):
     src = _source(oracle, mode, raw)
     want, st = _want(oracle, mode, src)
     out = np.zeros(raw.size * 2 + (1 << 20), dtype=np.uint8)
-    with GpuSnapshotStage(mode, devices=devs, batch_bytes=300 << 10, n_slots=2) as g:
+    with GpuSnapshotStage(mode, devices=devs, batch_bytes=100 << 10, n_slots=2) as g:
         for _ in range(2):                       # a second stream on the same handle
             n = g.process_host(src, out)
             assert n == want.size and np.array_equal(out[:n], want)
@@ -80,17 +80,17 @@ def test_group_reports_the_oracles_bad_record(oracle):
     devs = _devices()
     s = _mixed_stream(oracle).copy()
     cnt, offs = oracle.stream_index(s)
-    s[int(offs[29]) + 312 + 777] ^= 0x40
+    s[int(offs[41]) + 312 + 777] ^= 0x40
     rc, st = oracle.stream_verify(s)
     assert rc == oracle.ECKSUM
-    with GpuSnapshotStage("verify", devices=devs, batch_bytes=300 << 10, n_slots=2) as g:
+    with GpuSnapshotStage("verify", devices=devs, batch_bytes=100 << 10, n_slots=2) as g:
         with pytest.raises(MtzError) as ei:
             g.process_host(s)
         assert ei.value.code == oracle.ECKSUM
         assert g.stats()["bad_record"] == st.bad_record
 
 
-def _run_peers(g, data, peers, chunk=1 << 18, slow_peer=None):
+def _run_peers(g, data, peers, chunk=1 << 16, slow_peer=None):
     """producer thread writes `data`; one consumer thread per peer hashes what it is given."""
     err, digests, totals = [], {}, {}
 
@@ -137,8 +137,8 @@ def test_fanout_every_peer_gets_the_oracles_stream(oracle, mode):
     want, st = _want(oracle, mode, src)
     wd = hashlib.sha256(want.tobytes()).hexdigest()
     peers = [0, 1, 2]
-    with GpuSnapshotStage(mode, devices=devs, ring_bytes=2 << 20, out_ring_bytes=1 << 20,
-                          batch_bytes=300 << 10, n_slots=2) as g:
+    with GpuSnapshotStage(mode, devices=devs, ring_bytes=1 << 20, out_ring_bytes=256 << 10,
+                          batch_bytes=100 << 10, n_slots=2) as g:
         egress = [g.fanout_attach(p) for p in peers]
         assert egress == [devs[p % len(devs)] for p in peers]
         digests, totals, err = _run_peers(g, src.tobytes(), peers, slow_peer=1)
@@ -155,8 +155,8 @@ def test_group_single_consumer_streaming(oracle):
     devs = _devices()
     raw = _mixed_stream(oracle)
     want, st = _want(oracle, "compress", raw)
-    with GpuSnapshotStage("compress", devices=devs, ring_bytes=2 << 20, out_ring_bytes=1 << 20,
-                          batch_bytes=300 << 10, n_slots=2) as g:
+    with GpuSnapshotStage("compress", devices=devs, ring_bytes=1 << 20, out_ring_bytes=256 << 10,
+                          batch_bytes=100 << 10, n_slots=2) as g:
         digests, totals, err = _run_peers(g, raw.tobytes(), [0])
         assert not err, err
         assert totals[0] == want.size

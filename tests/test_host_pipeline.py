@@ -37,7 +37,7 @@ def fakezfs(tmp_path, oracle):
     zfs = z / "zfs"
     zfs.write_text("#!/bin/sh\nexec %s %s \"$@\"\n" % (sys.executable, os.path.join(ROOT, "tools", "fake_zfs.py")))
     zfs.chmod(zfs.stat().st_mode | stat.S_IEXEC)
-    stream = oracle.synth_stream(40, recsize=131072, kind=oracle.PAYLOAD_PGPAGE)
+    stream = oracle.synth_stream(24, recsize=131072, kind=oracle.PAYLOAD_PGPAGE)
     sp = tmp_path / "stream.bin"
     stream.tofile(str(sp))
     env = dict(os.environ)
