@@ -373,6 +373,12 @@ __device__ __forceinline__ Ck4 stamp_leave(const Ck4 &x, const RecSums *__restri
 	return apply(s, b);
 }
 
+// keep a 64-bit value in its register at this point (defeats re-association across it)
+#ifdef MTZ_HOST_EMUL
+#define MTZ_PIN64(x) do { } while (0)
+#else
+#define MTZ_PIN64(x) asm volatile("" : "+l"(x))
+#endif
 #define STAMP_GROUP   32
 #define STAMP_THREADS 128
 #define STAMP_LOADERS (STAMP_THREADS / 32 - 1)
@@ -424,15 +430,26 @@ k_stamp_chain(uint8_t *__restrict__ d_out, const mtz_rec *__restrict__ out_recs,
 			if (g + 1u < ngroups) stage(g + 1u);
 		} else {
 			const uint32_t r0 = g * STAMP_GROUP, cnt = min((uint32_t)STAMP_GROUP, T - r0);
+			// software pipeline: the weights of transition i+1 are loaded (shared memory, 29 cycles)
+			// while transition i is computed; nothing below waits for a load it just issued
+			const StampStep *sg = &s_steps[g & 1u][0];
+			uint64_t cn[12];
+			uint64_t woffn = sg[0].woff;
+			uint32_t fastn = sg[0].fast;
+#pragma unroll
+			for (int q = 0; q < 12; q++) cn[q] = sg[0].c[j][q];
 			for (uint32_t i = 0; i < cnt; i++) {
-				const StampStep &st = s_steps[g & 1u][i];
-				// the weights do not depend on the running value: their loads are issued
-				// before the exchange below
-				const uint64_t *c = st.c[j];
-				const uint64_t c0 = c[0], c1 = c[1], c2 = c[2], c3 = c[3], c4 = c[4], c5 = c[5],
-				    c6 = c[6], c7 = c[7], c8 = c[8], c9 = c[9], c10 = c[10], c11 = c[11];
-				const bool fast = st.fast != 0u;
-				const uint64_t woff = st.woff;
+				uint64_t c[12];
+#pragma unroll
+				for (int q = 0; q < 12; q++) c[q] = cn[q];
+				const bool fast = fastn != 0u;
+				const uint64_t woff = woffn;
+				if (i + 1u < cnt) {
+					const StampStep &nx = sg[i + 1u];
+#pragma unroll
+					for (int q = 0; q < 12; q++) cn[q] = nx.c[j][q];
+					woffn = nx.woff; fastn = nx.fast;
+				}
 				const uint32_t lo = (uint32_t)own, hi = (uint32_t)(own >> 32);
 				const uint32_t w0 = __shfl_sync(0xffffffffu, lo, 0), w1 = __shfl_sync(0xffffffffu, hi, 0);
 				const uint32_t w2 = __shfl_sync(0xffffffffu, lo, 1), w3 = __shfl_sync(0xffffffffu, hi, 1);
@@ -441,10 +458,13 @@ k_stamp_chain(uint8_t *__restrict__ d_out, const mtz_rec *__restrict__ out_recs,
 				const uint64_t xa = ((uint64_t)w1 << 32) | w0, xb = ((uint64_t)w3 << 32) | w2;
 				const uint64_t xc = ((uint64_t)w5 << 32) | w4;
 				if (fast) {
-					const uint64_t p0 = own + c0 * xa + c11;
-					const uint64_t p1 = c1 * xb + c2 * xc;
-					const uint64_t p2 = c3 * (uint64_t)w0 + c4 * (uint64_t)w1 + c5 * (uint64_t)w2 + c6 * (uint64_t)w3;
-					const uint64_t p3 = c7 * (uint64_t)w4 + c8 * (uint64_t)w5 + c9 * (uint64_t)w6 + c10 * (uint64_t)w7;
+					// four independent multiply-add chains of three terms (pinned: left alone the
+					// compiler folds all twelve into ONE dependent chain, ~10 cycles per term)
+					uint64_t p0 = own + c[11] + c[0] * xa + c[1] * xb;
+					uint64_t p1 = c[2] * xc + c[3] * (uint64_t)w0 + c[4] * (uint64_t)w1;
+					uint64_t p2 = c[5] * (uint64_t)w2 + c[6] * (uint64_t)w3 + c[7] * (uint64_t)w4;
+					uint64_t p3 = c[8] * (uint64_t)w5 + c[9] * (uint64_t)w6 + c[10] * (uint64_t)w7;
+					MTZ_PIN64(p0); MTZ_PIN64(p1); MTZ_PIN64(p2); MTZ_PIN64(p3);
 					own = (p0 + p1) + (p2 + p3);
 					if (lane < 4) *reinterpret_cast<uint64_t *>(d_out + woff + 8u * (uint32_t)lane) = own;
 				} else {

@@ -172,3 +172,25 @@ def test_host_parser_agrees_with_the_oracle_on_mutated_headers(native, oracle):
             assert ocnt == oracle.EFORMAT and not host_ok, (r, off, kind)
             agree_bad += 1
     assert agree_ok > 50 and agree_bad > 50, (agree_ok, agree_bad)      # both outcomes were exercised
+
+
+def test_unaligned_logical_size_is_a_format_error_everywhere(native, oracle):
+    """drr_logical_size becomes a PAYLOAD length in DECOMPRESS / RECOMPRESS
+    output, so an LZ4 record with lsize = 1001 would misalign every record behind it (a
+    misaligned-address fault on the GPU).  The host parser, the GPU parser and the oracle all
+    refuse it up front, like a payload length that is not a multiple of 8."""
+    import numpy as np
+    from manatee_b200 import index_host
+    from manatee_b200 import _native as N
+    s = oracle.synth_stream(6, recsize=4096, kind=oracle.PAYLOAD_PGPAGE)
+    rc, c, _ = oracle.stream_compress_plain(s)
+    cnt, offs = oracle.stream_index(c)
+    bad = c.copy()
+    o = int(offs[3])
+    assert int.from_bytes(bad[o:o + 4].tobytes(), "little") == 3 and bad[o + 50] == 15
+    bad[o + 32:o + 40] = np.frombuffer((1001).to_bytes(8, "little"), dtype=np.uint8)
+    assert oracle.stream_verify(bad)[0] == oracle.EFORMAT
+    assert oracle.stream_recompress(bad)[0] == oracle.EFORMAT
+    with pytest.raises(N.MtzError) as ei:
+        index_host(bad)
+    assert ei.value.code == N.EFORMAT

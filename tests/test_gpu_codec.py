@@ -484,3 +484,33 @@ def test_wire_preamble_versioning(oracle):
         with pytest.raises(MtzError) as ei:
             _gpu(mode, got)
         assert ei.value.code == EFORMAT
+
+
+def test_unaligned_logical_size_never_reaches_a_kernel(oracle):
+    """lsize = 1001 on an LZ4 record: MTZ_EFORMAT from the bulk call, the ring API and
+    the GPU-side parser -- never a misaligned store in k_assemble."""
+    import torch
+    from manatee_b200 import GpuSnapshotStage
+    from manatee_b200._native import MtzError, EFORMAT
+    from manatee_b200.stage import REC_DTYPE
+    s = oracle.synth_stream(6, recsize=4096, kind=oracle.PAYLOAD_PGPAGE)
+    rc, c, _ = oracle.stream_compress_plain(s)
+    cnt, offs = oracle.stream_index(c)
+    bad = c.copy()
+    o = int(offs[3])
+    bad[o + 32:o + 40] = np.frombuffer((1001).to_bytes(8, "little"), dtype=np.uint8)
+    with pytest.raises(MtzError) as ei:
+        _gpu("recompress", bad)
+    assert ei.value.code == EFORMAT
+    with GpuSnapshotStage("recompress", ring_bytes=4 << 20, out_ring_bytes=4 << 20, batch_bytes=1 << 20) as g:
+        with pytest.raises(MtzError) as ei:
+            g.write(bad); g.flush()
+            while g.read(1 << 20) is not None:
+                pass
+        assert ei.value.code == EFORMAT
+    d = torch.from_numpy(bad).cuda()
+    d_recs = torch.zeros((cnt + 8) * 32, dtype=torch.uint8, device="cuda")
+    with GpuSnapshotStage("verify") as g:
+        with pytest.raises(MtzError) as ei:
+            g.dev_index(d.data_ptr(), bad.size, d_recs.data_ptr(), cnt + 8)
+        assert ei.value.code == EFORMAT

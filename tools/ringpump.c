@@ -100,6 +100,26 @@ pump_selfcopy(uint8_t *dst, const uint8_t *src, size_t n, size_t chunk, int nthr
 	return (pump_memcpy(selfcopy_acq, selfcopy_com, dst, src, n, chunk, nthreads));
 }
 
+/* acquire + commit without touching the bytes: what the library does with a producer that costs
+ * nothing (only meaningful in PASSTHROUGH mode, which does not parse) */
+int32_t
+pump_nocopy(acquire_fn acq, commit_fn com, void *h, size_t n, size_t chunk)
+{
+	int32_t rc = 0;
+	size_t o = 0;
+	while (o < n) {
+		void *p = NULL; size_t got = 0;
+		size_t want = n - o < chunk ? n - o : chunk;
+		rc = acq(h, want, &p, &got);
+		if (rc == MTZ_EAGAIN) { usleep(50); rc = 0; continue; }
+		if (rc != 0) break;
+		rc = com(h, got);
+		if (rc != 0) break;
+		o += got;
+	}
+	return (rc);
+}
+
 typedef struct { int fd; const uint8_t *src; size_t n; } feeder_t;
 
 static void *
