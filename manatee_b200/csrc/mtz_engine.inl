@@ -25,6 +25,7 @@
 #include <sys/eventfd.h>
 #include <unistd.h>
 #include <chrono>
+#include <cstdio>
 
 namespace mtz {
 
@@ -58,8 +59,30 @@ struct InFlight {
 	bool bcast = false;        // fan-out broadcast of this batch has been launched
 };
 
+// MTZ_TRACE=<file>: the engine appends one line per event (microseconds since the engine started)
+// -- where a stream's wall time goes when the GPU is idle between batches (tools/ring_probe.py)
+struct Trace {
+	FILE *f = nullptr;
+	std::chrono::steady_clock::time_point t0;
+	void open()
+	{
+		const char *p = getenv("MTZ_TRACE");
+		if (p && *p) f = fopen(p, "a");
+		t0 = std::chrono::steady_clock::now();
+	}
+	void ev(const char *what, unsigned long long a = 0, unsigned long long b = 0)
+	{
+		if (f == nullptr) return;
+		const long long us = std::chrono::duration_cast<std::chrono::microseconds>(
+		    std::chrono::steady_clock::now() - t0).count();
+		fprintf(f, "%lld %s %llu %llu\n", us, what, a, b);
+	}
+	void close() { if (f) fclose(f); f = nullptr; }
+};
+
 struct Engine {
 	mtz_handle *h = nullptr;
+	Trace tr;
 	uint8_t *in_buf = nullptr; size_t in_cap = 0;
 	bool own_out = false;          // false: VERIFY (output aliases the input ring)
 	// ---- shared with producer / consumers, guarded by mu ----
@@ -245,6 +268,7 @@ static int32_t engine_submit(Engine *e)
 	int32_t rc = submit_batch(h, s, e->in_buf + o, n0, e->in_buf, n - n0, e->cur.size(), b0, nullptr);
 	if (rc != MTZ_OK) return rc;
 	MTZ_CU(h, cudaLaunchHostFunc(s.st, engine_host_cb, e));
+	e->tr.ev("submit", e->next_seq, n);
 	InFlight f;
 	f.slot = (int)si; f.seq = e->next_seq; f.in_begin = b0; f.in_end = b1;
 	e->inflight.push_back(f);
@@ -358,6 +382,7 @@ static int32_t engine_egress(Engine *e, const uint64_t *pos, bool *progress)
 			MTZ_CU(h, cudaMemcpyAsync(pe.buf + oo, src + pe.cur_off, c, cudaMemcpyDeviceToHost, dc.fan_st));
 			MTZ_CU(h, cudaEventRecord(pc.ev, dc.fan_st));
 			MTZ_CU(h, cudaLaunchHostFunc(dc.fan_st, engine_host_cb, e));
+			e->tr.ev("d2h_issue", f->seq, c);
 			pe.issue += c; pe.cur_off += c;
 			pc.end = pe.issue; pc.di = edi; pc.slot = f->slot;
 			pc.last = (pe.cur_off == f->n_out);
@@ -405,6 +430,7 @@ static void engine_main(Engine *e)
 			rc = harvest(h, s);
 			if (rc != MTZ_OK) break;
 			f.harvested = true;
+			e->tr.ev("harvest", f.seq);
 			f.n_out = is_codec_mode(h->cfg.mode) ? s.out_bytes : (size_t)(f.in_end - f.in_begin);
 			s.egress_left = e->own_out ? e->n_attached : 0;
 			if (!e->own_out) { new_out_head = f.in_end; have_out_head = true; }   // verified: consumable in place
@@ -434,6 +460,7 @@ static void engine_main(Engine *e)
 					cudaError_t q = cudaEventQuery(pc.ev);
 					if (q == cudaErrorNotReady) break;
 					if (q != cudaSuccess) { rc = fail_cuda(h, q, "cudaEventQuery(output copy)"); break; }
+					e->tr.ev("d2h_done", (unsigned long long)p, pc.end);
 					new_heads[p] = pc.end; head_moved[p] = true;
 					if (pc.last) h->slots[(size_t)pc.slot].egress_left--;
 					h->devs[(size_t)pc.di].ev_pool.push_back(pc.ev);
@@ -493,7 +520,9 @@ static void engine_main(Engine *e)
 		if (wake_cons) { e->cv_cons.notify_all(); signal_efd(e); }
 		if (wake_prod) e->cv_prod.notify_all();
 		if (rc != MTZ_OK) continue;               // fail() already woke everybody
+		if (head != e->in_head) e->tr.ev("commit_seen", e->in_head);
 		if (!progress && !e->kick && !e->stop) {
+			e->tr.ev("sleep", e->inflight.size());
 			// woken by commits, consumes, flush and stream host-functions; the timeout only
 			// bounds the wait for the short-batch rule (5 ms of idle input)
 			const bool partial = e->parse_pos > e->batch_begin && e->inflight.empty() && !e->flushed;
@@ -569,6 +598,7 @@ static int32_t engine_get(mtz_handle *h, Engine **out)
 		}
 	}
 	e->efd = eventfd(0, EFD_NONBLOCK | EFD_CLOEXEC);
+	e->tr.open();
 	e->last_input = std::chrono::steady_clock::now();
 	e->thr = std::thread(engine_main, e);
 	*out = e;
@@ -593,6 +623,7 @@ static void engine_destroy(mtz_handle *h)
 		if (pe.buf) cudaFreeHost(pe.buf);
 	}
 	if (e->in_buf) cudaFreeHost(e->in_buf);
+	e->tr.close();
 	if (e->efd >= 0) close(e->efd);
 	h->eng = nullptr;
 	delete e;

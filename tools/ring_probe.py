@@ -38,6 +38,8 @@ with GpuSnapshotStage("passthrough", ring_bytes=1 << 30, out_ring_bytes=1 << 30,
             if rc == N.OK: got[0] += n.value; L.mtz_out_consume(g._h, n.value)
             elif rc == N.EOF: break
             else: time.sleep(0.0002)
+    _p, _n = C.c_void_p(), C.c_size_t()
+    if L.mtz_ring_acquire(g._h, 1, C.byref(_p), C.byref(_n)) == N.OK: L.mtz_ring_commit(g._h, 0)   # engine + rings exist
     t = threading.Thread(target=cons); t0 = time.perf_counter(); t.start()
     rc = P.pump_nocopy(C.cast(L.mtz_ring_acquire, C.c_void_p), C.cast(L.mtz_ring_commit, C.c_void_p), g._h, s.size, 64 << 20)
     g.flush(); t.join(); dt = time.perf_counter() - t0
