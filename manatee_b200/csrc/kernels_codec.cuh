@@ -268,8 +268,12 @@ k_assemble(const uint8_t *__restrict__ d_in, const mtz_rec *__restrict__ recs, u
 // END header, which changes that header's sums) and the batch edges take the generic
 // path.  Round 1's one-lane recurrence cost 358 ns per record (5.9 ms per 16 384
 // records); see profiles/r2_stamp_chain.md for this one.
-struct alignas(16) StampStep {          // transition x_r -> x_{r+1}; 400 B
-	uint64_t c[4][12];        // lane j: weights of x.a x.b x.c | of w_0..w_7 | constant
+// Folded once more: x.a .. x.d ARE the halves (x_i = w_2i + 2^32 w_2i+1), so the apply() part
+// multiplies the same eight words -- component j of x_{r+1} is ONE linear form of w_0..w_7 plus a
+// constant, with 64-bit weights  C_k = T_j(n2+8-k) + E_j,i  (k = 2i)  or  + (E_j,i << 32)  (k = 2i+1),
+// E = [[1],[N,1],[T2N,N,1],[T3N,T2N,N,1]]: eight 64x32-bit multiply-adds per lane and step.
+struct alignas(16) StampStep {          // transition x_r -> x_{r+1}; 304 B
+	uint64_t c[4][9];         // lane j: weights of w_0..w_7 | constant
 	uint64_t woff;            // byte offset in d_out of record r+1's checksum field
 	uint32_t fast, pad;
 };
@@ -313,13 +317,13 @@ __global__ void k_stamp_prep(const mtz_rec *__restrict__ out_recs, const RecSums
 		}
 	}
 	const uint64_t t2 = tri2(N), t3 = tri3(N);
-	const uint64_t M[4][3] = { { 0, 0, 0 }, { N, 0, 0 }, { t2, N, 0 }, { t3, t2, N } };
+	const uint64_t E[4][4] = { { 1, 0, 0, 0 }, { N, 1, 0, 0 }, { t2, N, 1, 0 }, { t3, t2, N, 1 } };
 #pragma unroll
 	for (int j = 0; j < 4; j++) {
-		o->c[j][0] = M[j][0]; o->c[j][1] = M[j][1]; o->c[j][2] = M[j][2];
 #pragma unroll
-		for (int k = 0; k < 8; k++) o->c[j][3 + k] = W[j][k];
-		o->c[j][11] = g[j];
+		for (int k = 0; k < 8; k++)
+			o->c[j][k] = W[j][k] + ((k & 1) ? (E[j][k >> 1] << 32) : E[j][k >> 1]);
+		o->c[j][8] = g[j];
 	}
 	o->woff = out_recs[r + 1u].off + DRR_CKOFF;
 	o->fast = 1; o->pad = 0;
@@ -430,50 +434,52 @@ k_stamp_chain(uint8_t *__restrict__ d_out, const mtz_rec *__restrict__ out_recs,
 			if (g + 1u < ngroups) stage(g + 1u);
 		} else {
 			const uint32_t r0 = g * STAMP_GROUP, cnt = min((uint32_t)STAMP_GROUP, T - r0);
-			// software pipeline: the weights of transition i+1 are loaded (shared memory, 29 cycles)
-			// while transition i is computed; nothing below waits for a load it just issued
+			// The weights of transition i+1 are loaded from shared memory (29 cycles) while transition
+			// i is computed; two register sets alternate so that no value is ever copied.
 			const StampStep *sg = &s_steps[g & 1u][0];
-			uint64_t cn[12];
-			uint64_t woffn = sg[0].woff;
-			uint32_t fastn = sg[0].fast;
+			uint64_t ca[9], cb[9];
+			uint64_t woa = sg[0].woff, wob = 0;
+			uint32_t fa = sg[0].fast, fb = 0;
 #pragma unroll
-			for (int q = 0; q < 12; q++) cn[q] = sg[0].c[j][q];
-			for (uint32_t i = 0; i < cnt; i++) {
-				uint64_t c[12];
-#pragma unroll
-				for (int q = 0; q < 12; q++) c[q] = cn[q];
-				const bool fast = fastn != 0u;
-				const uint64_t woff = woffn;
-				if (i + 1u < cnt) {
-					const StampStep &nx = sg[i + 1u];
-#pragma unroll
-					for (int q = 0; q < 12; q++) cn[q] = nx.c[j][q];
-					woffn = nx.woff; fastn = nx.fast;
-				}
-				const uint32_t lo = (uint32_t)own, hi = (uint32_t)(own >> 32);
-				const uint32_t w0 = __shfl_sync(0xffffffffu, lo, 0), w1 = __shfl_sync(0xffffffffu, hi, 0);
-				const uint32_t w2 = __shfl_sync(0xffffffffu, lo, 1), w3 = __shfl_sync(0xffffffffu, hi, 1);
-				const uint32_t w4 = __shfl_sync(0xffffffffu, lo, 2), w5 = __shfl_sync(0xffffffffu, hi, 2);
-				const uint32_t w6 = __shfl_sync(0xffffffffu, lo, 3), w7 = __shfl_sync(0xffffffffu, hi, 3);
-				const uint64_t xa = ((uint64_t)w1 << 32) | w0, xb = ((uint64_t)w3 << 32) | w2;
-				const uint64_t xc = ((uint64_t)w5 << 32) | w4;
-				if (fast) {
-					// four independent multiply-add chains of three terms (pinned: left alone the
-					// compiler folds all twelve into ONE dependent chain, ~10 cycles per term)
-					uint64_t p0 = own + c[11] + c[0] * xa + c[1] * xb;
-					uint64_t p1 = c[2] * xc + c[3] * (uint64_t)w0 + c[4] * (uint64_t)w1;
-					uint64_t p2 = c[5] * (uint64_t)w2 + c[6] * (uint64_t)w3 + c[7] * (uint64_t)w4;
-					uint64_t p3 = c[8] * (uint64_t)w5 + c[9] * (uint64_t)w6 + c[10] * (uint64_t)w7;
-					MTZ_PIN64(p0); MTZ_PIN64(p1); MTZ_PIN64(p2); MTZ_PIN64(p3);
-					own = (p0 + p1) + (p2 + p3);
-					if (lane < 4) *reinterpret_cast<uint64_t *>(d_out + woff + 8u * (uint32_t)lane) = own;
-				} else {
-					x.a = xa; x.b = xb; x.c = xc; x.d = ((uint64_t)w7 << 32) | w6;
-					const Ck4 s = stamp_leave(x, osums, r0 + i);
-					x = stamp_enter(s, d_out, out_recs, osums, r0 + i + 1u, res, lane);
-					own = (j == 0) ? x.a : (j == 1) ? x.b : (j == 2) ? x.c : x.d;
-				}
+			for (int q = 0; q < 9; q++) { ca[q] = sg[0].c[j][q]; cb[q] = 0; }
+#define STAMP_STEP(C, WOFF, FAST, NC, NWOFF, NFAST, IDX)                                         \
+			{                                                                                    \
+				const uint32_t i_ = (IDX);                                                       \
+				if (i_ + 1u < cnt) {                                                             \
+					const StampStep &nx = sg[i_ + 1u];                                           \
+					_Pragma("unroll") for (int q = 0; q < 9; q++) NC[q] = nx.c[j][q];            \
+					NWOFF = nx.woff; NFAST = nx.fast;                                            \
+				}                                                                                \
+				const uint32_t lo = (uint32_t)own, hi = (uint32_t)(own >> 32);                   \
+				const uint32_t w0 = __shfl_sync(0xffffffffu, lo, 0), w1 = __shfl_sync(0xffffffffu, hi, 0); \
+				const uint32_t w2 = __shfl_sync(0xffffffffu, lo, 1), w3 = __shfl_sync(0xffffffffu, hi, 1); \
+				const uint32_t w4 = __shfl_sync(0xffffffffu, lo, 2), w5 = __shfl_sync(0xffffffffu, hi, 2); \
+				const uint32_t w6 = __shfl_sync(0xffffffffu, lo, 3), w7 = __shfl_sync(0xffffffffu, hi, 3); \
+				if (FAST != 0u) {                                                                \
+					/* four independent multiply-add chains (pinned: left alone the compiler     \
+					 * folds them into ONE dependent chain of ~10 cycles per term) */            \
+					uint64_t p0 = C[8] + C[0] * (uint64_t)w0 + C[1] * (uint64_t)w1;              \
+					uint64_t p1 = C[2] * (uint64_t)w2 + C[3] * (uint64_t)w3;                     \
+					uint64_t p2 = C[4] * (uint64_t)w4 + C[5] * (uint64_t)w5;                     \
+					uint64_t p3 = C[6] * (uint64_t)w6 + C[7] * (uint64_t)w7;                     \
+					MTZ_PIN64(p0); MTZ_PIN64(p1); MTZ_PIN64(p2); MTZ_PIN64(p3);                  \
+					own = (p0 + p1) + (p2 + p3);                                                 \
+					if (lane < 4) *reinterpret_cast<uint64_t *>(d_out + WOFF + 8u * (uint32_t)lane) = own; \
+				} else {                                                                         \
+					x.a = ((uint64_t)w1 << 32) | w0; x.b = ((uint64_t)w3 << 32) | w2;            \
+					x.c = ((uint64_t)w5 << 32) | w4; x.d = ((uint64_t)w7 << 32) | w6;            \
+					const Ck4 s_ = stamp_leave(x, osums, r0 + i_);                               \
+					x = stamp_enter(s_, d_out, out_recs, osums, r0 + i_ + 1u, res, lane);        \
+					own = (j == 0) ? x.a : (j == 1) ? x.b : (j == 2) ? x.c : x.d;                \
+				}                                                                                \
 			}
+			uint32_t i = 0;
+			for (; i + 1u < cnt; i += 2u) {
+				STAMP_STEP(ca, woa, fa, cb, wob, fb, i)
+				STAMP_STEP(cb, wob, fb, ca, woa, fa, i + 1u)
+			}
+			if (i < cnt) STAMP_STEP(ca, woa, fa, cb, wob, fb, i)
+#undef STAMP_STEP
 		}
 		__syncthreads();
 	}
