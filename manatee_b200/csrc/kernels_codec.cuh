@@ -395,7 +395,7 @@ k_stamp_chain(uint8_t *__restrict__ d_out, const mtz_rec *__restrict__ out_recs,
     const RecSums *__restrict__ osums, const StampStep *__restrict__ steps, uint32_t n,
     Ck4 *__restrict__ carry_out, ScanResult *__restrict__ res)
 {
-	__shared__ StampStep s_steps[2][STAMP_GROUP];
+	__shared__ StampStep s_steps[2][STAMP_GROUP + 1];     // +1: the weight prefetch of step i+1 needs no bounds check
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const int j = lane & 3;
 	if (n == 0u) return;
@@ -445,8 +445,8 @@ k_stamp_chain(uint8_t *__restrict__ d_out, const mtz_rec *__restrict__ out_recs,
 #define STAMP_STEP(C, WOFF, FAST, NC, NWOFF, NFAST, IDX)                                         \
 			{                                                                                    \
 				const uint32_t i_ = (IDX);                                                       \
-				if (i_ + 1u < cnt) {                                                             \
-					const StampStep &nx = sg[i_ + 1u];                                           \
+				{                                                                                \
+					const StampStep &nx = sg[i_ + 1u];       /* (slot 32 is padding) */          \
 					_Pragma("unroll") for (int q = 0; q < 9; q++) NC[q] = nx.c[j][q];            \
 					NWOFF = nx.woff; NFAST = nx.fast;                                            \
 				}                                                                                \
@@ -464,7 +464,8 @@ k_stamp_chain(uint8_t *__restrict__ d_out, const mtz_rec *__restrict__ out_recs,
 					uint64_t p3 = C[6] * (uint64_t)w6 + C[7] * (uint64_t)w7;                     \
 					MTZ_PIN64(p0); MTZ_PIN64(p1); MTZ_PIN64(p2); MTZ_PIN64(p3);                  \
 					own = (p0 + p1) + (p2 + p3);                                                 \
-					if (lane < 4) *reinterpret_cast<uint64_t *>(d_out + WOFF + 8u * (uint32_t)lane) = own; \
+					/* every lane stores (lanes 4..31 repeat lanes 0..3): no divergent branch */   \
+					*reinterpret_cast<uint64_t *>(d_out + WOFF + 8u * (uint32_t)j) = own;        \
 				} else {                                                                         \
 					x.a = ((uint64_t)w1 << 32) | w0; x.b = ((uint64_t)w3 << 32) | w2;            \
 					x.c = ((uint64_t)w5 << 32) | w4; x.d = ((uint64_t)w7 << 32) | w6;            \
