@@ -232,8 +232,22 @@ int32_t mtz_dev_reset(mtz_handle *h);
  * checksum hops rank to rank (ncclRecv from rank-1, stamp chain, ncclSend to rank+1). ---- */
 int32_t mtz_comm_unique_id(uint8_t id[128]);
 int32_t mtz_comm_init(mtz_handle *h, const uint8_t id[128], int32_t rank, int32_t world);
-int32_t mtz_dev_finish_exchange(mtz_handle *h, size_t *out_bytes, uint64_t carry[4],
-    uint64_t carry_out[4]);
+/* a second handle of the same process and device rides the first one's communicator (two handles
+ * alternate so that the kernels of chunk k+1 run under the exchange of chunk k) */
+int32_t mtz_comm_share(mtz_handle *h, mtz_handle *owner);
+/* The ranks take the stream's chunks round-robin (chunk j on rank j % world) so that the serial
+ * part -- the stamp chain -- of one rank's chunk runs under the other ranks' LZ4 kernels:
+ *   round_base_in   running INPUT checksum in front of this round's first chunk (NULL = zero)
+ *   flags           MTZ_XCHG_FIRST: this chunk opens the stream (nothing to receive);
+ *                   MTZ_XCHG_LAST: it closes it (nothing to send).  The output checksum travels
+ *                   the ring rank-1 -> rank -> rank+1 (mod world).
+ *   round_base_out  the base of the next round
+ * One contiguous shard per rank is the special case of one round: NULL, FIRST on rank 0, LAST on
+ * the last rank. */
+#define MTZ_XCHG_FIRST 1u
+#define MTZ_XCHG_LAST  2u
+int32_t mtz_dev_finish_exchange(mtz_handle *h, const uint64_t round_base_in[4], uint32_t flags,
+    size_t *out_bytes, uint64_t carry[4], uint64_t carry_out[4], uint64_t round_base_out[4]);
 /* set the running checksums a slice continues from (NULL = leave) */
 int32_t mtz_set_carry(mtz_handle *h, const uint64_t carry_in[4],
     const uint64_t carry_out[4]);

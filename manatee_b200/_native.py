@@ -16,6 +16,7 @@ OK, EINVAL, EAGAIN, ECUDA, EFORMAT, ECKSUM, ECODEC, ENOSPC, ENOMEM, EOF, ENOGPU,
 MAX_DEVICES, MAX_PEERS = 16, 16
 MODE_VERIFY, MODE_COMPRESS, MODE_DECOMPRESS, MODE_RECOMPRESS, MODE_PASSTHROUGH = 0, 1, 2, 3, 4
 FLAG_DEFER_VERIFY = 1
+XCHG_FIRST, XCHG_LAST = 1, 2
 MODE_NAMES = {"verify": 0, "compress": 1, "decompress": 2, "recompress": 3, "passthrough": 4}
 
 
@@ -59,7 +60,7 @@ SYMBOLS = [
     "mtz_dev_finish", "mtz_dev_reset", "mtz_dev_aggregate_async", "mtz_dev_finish_gathered", "mtz_set_carry",
     "mtz_k_lz4_decode", "mtz_k_lz4_encode",
     "mtz_fanout_attach", "mtz_out_peek_peer", "mtz_out_consume_peer", "mtz_read_peer", "mtz_cancel",
-    "mtz_comm_unique_id", "mtz_comm_init", "mtz_dev_finish_exchange",
+    "mtz_comm_unique_id", "mtz_comm_init", "mtz_comm_share", "mtz_dev_finish_exchange",
 ]
 
 _lib = None
@@ -127,7 +128,9 @@ def lib():
     L.mtz_cancel.argtypes = [H]
     L.mtz_comm_unique_id.argtypes = [vp]
     L.mtz_comm_init.argtypes = [H, vp, i32, i32]
-    L.mtz_dev_finish_exchange.argtypes = [H, C.POINTER(sz), C.POINTER(u64 * 4), C.POINTER(u64 * 4)]
+    L.mtz_comm_share.argtypes = [H, H]
+    L.mtz_dev_finish_exchange.argtypes = [H, vp, C.c_uint32, C.POINTER(sz), C.POINTER(u64 * 4),
+                                          C.POINTER(u64 * 4), C.POINTER(u64 * 4)]
     L.mtz_k_lz4_decode.argtypes = [H, vp, vp, vp, C.c_uint32, vp]
     L.mtz_k_lz4_encode.argtypes = [H, vp, vp, vp, C.c_uint32, vp]
     for s in SYMBOLS:

@@ -291,11 +291,20 @@ k_scan_verify(const RecSums *__restrict__ sums, uint32_t nrec,
 
 // carry-in of shard `rank` = fold of the aggregates of all earlier shards (device-side
 // twin of manatee_b200/shard.py::carry_before)
-__global__ void k_fold_carry(const Part *__restrict__ aggs, uint32_t rank, Ck4 *__restrict__ carry)
+// `base` (may be null = zero) is the running checksum in front of aggs[0]; `next_base` (may be
+// null) receives the one behind aggs[world-1] -- the base of the next round when the ranks take
+// the stream's chunks round-robin
+__global__ void k_fold_carry(const Part *__restrict__ aggs, uint32_t rank, Ck4 *__restrict__ carry,
+    const Ck4 *__restrict__ base = nullptr, uint32_t world = 0, Ck4 *__restrict__ next_base = nullptr)
 {
 	Ck4 s = { 0, 0, 0, 0 };
+	if (base != nullptr) s = *base;
 	for (uint32_t r = 0; r < rank; r++) s = apply(s, aggs[r]);
 	*carry = s;
+	if (next_base != nullptr) {
+		for (uint32_t r = rank; r < world; r++) s = apply(s, aggs[r]);
+		*next_base = s;
+	}
 }
 
 } // namespace mtz

@@ -107,7 +107,10 @@ struct mtz_handle {
 	bool nccl_ready = false;
 	// multi-process shard exchange (mtz_comm_init): one rank per process on devs[0]
 	ncclComm_t xcomm = nullptr;
+	bool xcomm_owned = false;
+	mtz::Ck4 *d_xbase = nullptr;       // [0] base of this round (input checksum), [1] base of the next
 	int xrank = 0, xworld = 1;
+	uint32_t xflags = 0;
 	mtz::Part *d_xagg = nullptr, *d_xall = nullptr;
 	uint64_t records_done = 0;
 

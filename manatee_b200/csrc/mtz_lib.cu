@@ -345,10 +345,11 @@ int32_t mtz_close(mtz_handle *h)
 	engine_destroy(h);
 	for (auto &dc : h->devs) { cudaSetDevice(dc.device); cudaDeviceSynchronize(); }
 	fanout_destroy(h);
-	if (h->xcomm) ncclCommDestroy(h->xcomm);
+	if (h->xcomm && h->xcomm_owned) ncclCommDestroy(h->xcomm);
 	cudaSetDevice(h->device);
 	if (h->d_xagg) cudaFree(h->d_xagg);
 	if (h->d_xall) cudaFree(h->d_xall);
+	if (h->d_xbase) cudaFree(h->d_xbase);
 	for (cudaEvent_t e : h->dv_k3ev) cudaEventDestroy(e);
 	if (h->dv_c0) cudaEventDestroy(h->dv_c0);
 	if (h->dv_c1) cudaEventDestroy(h->dv_c1);
@@ -900,24 +901,63 @@ int32_t mtz_comm_init(mtz_handle *h, const uint8_t id[128], int32_t rank, int32_
 	ncclUniqueId u;
 	memcpy(&u, id, 128);
 	MTZ_NCCL(h, ncclCommInitRank(&h->xcomm, world, u, rank));
+	h->xcomm_owned = true;
 	h->xrank = rank; h->xworld = world;
 	MTZ_CU(h, cudaMalloc(&h->d_xagg, sizeof(Part)));
 	MTZ_CU(h, cudaMalloc(&h->d_xall, (size_t)world * sizeof(Part)));
+	MTZ_CU(h, cudaMalloc(&h->d_xbase, 2 * sizeof(Ck4)));
 	return MTZ_OK;
 }
 
-int32_t mtz_dev_finish_exchange(mtz_handle *h, size_t *out_bytes, uint64_t carry[4], uint64_t carry_out[4])
+int32_t mtz_comm_share(mtz_handle *h, mtz_handle *owner)
+{
+	CHECK_H(h);
+	if (owner == nullptr || owner->xcomm == nullptr) return fail(h, MTZ_EINVAL, "the owner has no communicator");
+	if (h->xcomm != nullptr) return fail(h, MTZ_EINVAL, "communicator already initialised");
+	if (h->device != owner->device) return fail(h, MTZ_EINVAL, "a shared communicator needs the same device");
+	MTZ_CU(h, cudaSetDevice(h->device));
+	h->xcomm = owner->xcomm; h->xcomm_owned = false;
+	h->xrank = owner->xrank; h->xworld = owner->xworld;
+	MTZ_CU(h, cudaMalloc(&h->d_xagg, sizeof(Part)));
+	MTZ_CU(h, cudaMalloc(&h->d_xall, (size_t)h->xworld * sizeof(Part)));
+	MTZ_CU(h, cudaMalloc(&h->d_xbase, 2 * sizeof(Ck4)));
+	return MTZ_OK;
+}
+
+int32_t mtz_dev_finish_exchange(mtz_handle *h, const uint64_t round_base_in[4], uint32_t flags,
+    size_t *out_bytes, uint64_t carry[4], uint64_t carry_out[4], uint64_t round_base_out[4])
 {
 	CHECK_H(h);
 	if (h->xcomm == nullptr) return fail(h, MTZ_EINVAL, "mtz_comm_init first");
 	MTZ_CU(h, cudaSetDevice(h->device));
 	cudaStream_t st = h->dv_st ? h->dv_st : h->st;
-	// the 40-byte aggregate of this shard -> all ranks (the path's one collective)
+	h->xflags = flags;
+	if (round_base_in != nullptr) {
+		memcpy(&h->h_carry[2], round_base_in, 32);
+		MTZ_CU(h, cudaMemcpyAsync(&h->d_xbase[0], &h->h_carry[2], 32, cudaMemcpyHostToDevice, st));
+	} else {
+		MTZ_CU(h, cudaMemsetAsync(&h->d_xbase[0], 0, 32, st));
+	}
+	// The output checksum arrives from the rank that holds the chunk before this one.  Communicator
+	// operations execute in issue order, so every rank must issue them in an order compatible with
+	//   AG_0 | S_0 R_1 | S_1 R_2 | ... | S_N-1 R_N | AG_1 | S_N R_N+1 | ...
+	// (chunk j on rank j % N, AG_k the all-gather of round k): rank 0 receives the END of the
+	// previous round BEFORE this round's all-gather, every other rank after it -- any other
+	// placement makes the all-gather and a send wait for each other.
+	const bool hop = is_codec_mode(h->cfg.mode) && (h->cfg.flags & MTZ_FLAG_DEFER_VERIFY) && !(flags & MTZ_XCHG_FIRST);
+	const int from = (h->xrank + h->xworld - 1) % h->xworld;
+	if (hop && h->xrank == 0)
+		MTZ_NCCL(h, ncclRecv(h->d_carry_out, 4, ncclUint64, from, h->xcomm, st));
+	// the 40-byte aggregate of this chunk -> all ranks (the path's one collective)
 	int32_t rc = launch_scan(h, st, h->dv_sums, h->dv_nrec, h->dv_tiles, h->dv_res, 0);
 	if (rc != MTZ_OK) return rc;
 	MTZ_CU(h, cudaMemcpyAsync(h->d_xagg, &h->dv_res->agg, sizeof(Part), cudaMemcpyDeviceToDevice, st));
 	MTZ_NCCL(h, ncclAllGather(h->d_xagg, h->d_xall, sizeof(Part) / 8, ncclUint64, h->xcomm, st));
-	return dev_finish_impl(h, nullptr, h->d_xall, (uint32_t)h->xrank, nullptr, out_bytes, carry, carry_out, true);
+	if (hop && h->xrank != 0)
+		MTZ_NCCL(h, ncclRecv(h->d_carry_out, 4, ncclUint64, from, h->xcomm, st));
+	int32_t rc2 = dev_finish_impl(h, nullptr, h->d_xall, (uint32_t)h->xrank, nullptr, out_bytes, carry, carry_out, true);
+	if (rc2 == MTZ_OK && round_base_out != nullptr) memcpy(round_base_out, &h->h_carry[3], 32);
+	return rc2;
 }
 
 static int32_t dev_finish_impl(mtz_handle *h, const uint64_t carry_in[4], const void *d_all_aggs,
@@ -928,7 +968,13 @@ static int32_t dev_finish_impl(mtz_handle *h, const uint64_t carry_in[4], const 
 	MTZ_CU(h, cudaSetDevice(h->device));
 	cudaStream_t st = h->dv_st ? h->dv_st : h->st;
 	if (d_all_aggs != nullptr) {
-		k_fold_carry<<<1, 1, 0, st>>>((const Part *)d_all_aggs, rank, h->d_carry_in);
+		if (xchg) {
+			k_fold_carry<<<1, 1, 0, st>>>((const Part *)d_all_aggs, rank, h->d_carry_in, &h->d_xbase[0],
+			    (uint32_t)h->xworld, &h->d_xbase[1]);
+			MTZ_CU(h, cudaMemcpyAsync(&h->h_carry[3], &h->d_xbase[1], 32, cudaMemcpyDeviceToHost, st));
+		} else {
+			k_fold_carry<<<1, 1, 0, st>>>((const Part *)d_all_aggs, rank, h->d_carry_in);
+		}
 		MTZ_CU(h, cudaGetLastError());
 		count_launch(h, 1);
 	}
@@ -946,9 +992,8 @@ static int32_t dev_finish_impl(mtz_handle *h, const uint64_t carry_in[4], const 
 	MTZ_CU(h, cudaMemcpyAsync(h->d_carry_in, &h->dv_res->carry, 32, cudaMemcpyDeviceToDevice, st));
 	const bool codec = is_codec_mode(h->cfg.mode) && h->dv_cb.cr != nullptr;
 	const bool hop = xchg && is_codec_mode(h->cfg.mode) && (h->cfg.flags & MTZ_FLAG_DEFER_VERIFY);
-	// the output checksum hops rank to rank: 32 bytes in from the shard before, stamp, 32 out
-	if (hop && h->xrank > 0)
-		MTZ_NCCL(h, ncclRecv(h->d_carry_out, 4, ncclUint64, h->xrank - 1, h->xcomm, st));
+	// (the 32 bytes of output checksum from the chunk before were received by the caller; after the
+	// stamp chain they travel on)
 	if (codec && (h->cfg.flags & MTZ_FLAG_DEFER_VERIFY) && h->dv_nrec > 0) {
 		// shard mode: the stamp chain of the whole shard, from the checksum the previous
 		// shard's output ended with (carry_out_in, uploaded above)
@@ -960,8 +1005,8 @@ static int32_t dev_finish_impl(mtz_handle *h, const uint64_t carry_in[4], const 
 		MTZ_CU(h, cudaGetLastError());
 		count_launch(h, 2);
 	}
-	if (hop && h->xrank + 1 < h->xworld)
-		MTZ_NCCL(h, ncclSend(h->d_carry_out, 4, ncclUint64, h->xrank + 1, h->xcomm, st));
+	if (hop && !(h->xflags & MTZ_XCHG_LAST))
+		MTZ_NCCL(h, ncclSend(h->d_carry_out, 4, ncclUint64, (h->xrank + 1) % h->xworld, h->xcomm, st));
 	if (codec) {
 		MTZ_CU(h, cudaMemcpyAsync(h->dv_cb.h_cres, h->dv_cb.d_cres, sizeof(CodecResult), cudaMemcpyDeviceToHost, st));
 		MTZ_CU(h, cudaMemcpyAsync(h->dv_cb.h_ores, h->dv_cb.d_ores, sizeof(ScanResult), cudaMemcpyDeviceToHost, st));
@@ -1296,13 +1341,29 @@ int32_t mtz_process_host(mtz_handle *h, const void *in, size_t n, void *out, siz
 		MTZ_CU(h, cudaEventSynchronize(s.ev_done));
 		return MTZ_OK;
 	};
-	// output order == submission order: retire the OLDEST batch before cutting the next one once
-	// every slot is taken, so a slot's output copy has a whole ring of batches to finish in
+	// Output order == submission order.  Batches are retired (verdict folded in, output copy ISSUED)
+	// in order as soon as they are done -- looked at every iteration, not only when their slot
+	// comes round again: on a device group several GPUs' output copies then overlap on their own
+	// PCIe links instead of queueing behind one host wait per batch (43 -> ... GiB/s e2e at 4 GPUs,
+	// profiles/r2_scaling.md).  A slot is reused once its batch is retired and its copy has landed.
 	const size_t NS = h->slots.size();
+	uint64_t nr = 0;                                  // batches retired so far
+	auto retire_next = [&](bool block) -> int32_t {   // 1 = the oldest batch is still running
+		Slot &rs = h->slots[nr % NS];
+		if (!block && rs.busy && cudaEventQuery(rs.ev_done) == cudaErrorNotReady) return 1;
+		int32_t r = retire(rs);
+		if (r == MTZ_OK) nr++;
+		return r;
+	};
 	WireState ws;
 	while (off < n && rc == MTZ_OK) {
 		Slot &s = h->slots[b % NS];
-		rc = retire(s);
+		while (rc == MTZ_OK && nr < b) {
+			const int32_t r = retire_next(false);
+			if (r == 1) break;
+			rc = r;
+		}
+		while (rc == MTZ_OK && nr + NS <= b) rc = retire_next(true);
 		if (rc == MTZ_OK) rc = drain_d2h(s);
 		if (rc != MTZ_OK) break;
 		BatchCut bc;
@@ -1349,10 +1410,9 @@ int32_t mtz_process_host(mtz_handle *h, const void *in, size_t n, void *out, siz
 		b++;
 	}
 	// drain in submission order
-	for (size_t k = 0; k < NS; k++) {
-		Slot &s = h->slots[(b + k) % NS];
-		int32_t r2 = retire(s);
-		if (rc == MTZ_OK) rc = r2;
+	while (nr < b) {
+		int32_t r2 = retire_next(true);
+		if (r2 != MTZ_OK) { if (rc == MTZ_OK) rc = r2; nr++; }
 	}
 	for (size_t k = 0; k < NS; k++) {
 		int32_t r2 = drain_d2h(h->slots[k]);

@@ -198,12 +198,25 @@ class GpuSnapshotStage(object):
         buf = (C.c_uint8 * 128).from_buffer_copy(bytes(unique_id))
         self._check(self._L.mtz_comm_init(self._h, buf, rank, world))
 
-    def dev_finish_exchange(self):
+    def comm_share(self, owner):
+        """Ride the communicator of another handle of this process (same device)."""
+        self._check(self._L.mtz_comm_share(self._h, owner._h))
+
+    def dev_finish_exchange(self, round_base=None, flags=None, rank=None, world=None):
+        """Finish the submitted chunk with the library-owned exchange.  Default flags = one
+        contiguous shard per rank (FIRST on rank 0, LAST on the last rank).  Returns
+        (out_bytes, carry, carry_out, round_base_out)."""
+        if flags is None:
+            flags = (N.XCHG_FIRST if rank in (None, 0) else 0) | \
+                (N.XCHG_LAST if (rank is None or world is None or rank == world - 1) else 0)
         ob = C.c_size_t(0)
         c1 = (C.c_uint64 * 4)()
         c2 = (C.c_uint64 * 4)()
-        self._check(self._L.mtz_dev_finish_exchange(self._h, C.byref(ob), C.byref(c1), C.byref(c2)))
-        return ob.value, tuple(int(x) for x in c1), tuple(int(x) for x in c2)
+        nb = (C.c_uint64 * 4)()
+        bi = (C.c_uint64 * 4)(*round_base) if round_base is not None else None
+        self._check(self._L.mtz_dev_finish_exchange(self._h, bi, flags, C.byref(ob), C.byref(c1), C.byref(c2),
+                                                    C.byref(nb)))
+        return ob.value, tuple(int(x) for x in c1), tuple(int(x) for x in c2), tuple(int(x) for x in nb)
 
     def dev_finish(self, carry_in=None, carry_out_in=None):
         ob = C.c_size_t(0)

@@ -101,10 +101,14 @@ template <class P> inline void drain_until(P done)
 		}
 	}
 }
+inline int &cur_dev();
+// everything enqueued on the CURRENT device (what cudaDeviceSynchronize / a blocking cudaMemcpy /
+// cudaFree wait for): another device's stream may be sitting in a collective that waits for us
 inline void drain_all()
 {
-	drain_until([] {
-		for (emu_stream_ *st : S().streams) if (st->busy || !st->q.empty()) return false;
+	const int dev = cur_dev();
+	drain_until([dev] {
+		for (emu_stream_ *st : S().streams) if (st->dev == dev && (st->busy || !st->q.empty())) return false;
 		return true;
 	});
 }
@@ -112,11 +116,26 @@ inline void enqueue(cudaStream_t st_, emu_op &&o)
 {
 	State &s = S();
 	emu_stream_ *st = str(st_);
+	if (!s.async) {
+		// synchronous mode: the operation runs HERE, on the enqueuing thread, as soon as what it
+		// waits for has completed.  (Handing it to whichever thread happens to drain next would let
+		// one rank's thread block inside another rank's blocking collective -- tests/emul/nccl.h.)
+		emu_event_ *wev = o.wait_ev; const unsigned long long wseq = o.wait_seq;
+		drain_until([st, wev, wseq] { return !st->busy && st->q.empty() && (wev == nullptr || wev->completed >= wseq); });
+		{
+			std::lock_guard<std::recursive_mutex> g(s.mu);
+			st->busy = true;
+		}
+		if (o.fn) o.fn();
+		std::lock_guard<std::recursive_mutex> g(s.mu);
+		if (o.rec_ev && o.rec_ev->completed < o.rec_seq) o.rec_ev->completed = o.rec_seq;
+		st->busy = false;
+		return;
+	}
 	{
 		std::lock_guard<std::recursive_mutex> g(s.mu);
 		st->q.push_back(std::move(o));
 	}
-	if (!s.async) drain_until([st] { return !st->busy && st->q.empty(); });
 }
 inline void run(cudaStream_t st, std::function<void()> fn) { emu_op o; o.fn = std::move(fn); enqueue(st, std::move(o)); }
 } // namespace emurt

@@ -70,3 +70,75 @@ def test_multidev_under_adversarial_scheduling(emul_library, seed):
                        env=env, cwd=ROOT, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
     assert " passed" in r.stdout
+
+
+def test_round_robin_chunk_exchange_between_two_ranks(emul_library, oracle):
+    """bench.py's N > 1 resident path on the CPU: two ranks (threads of this process, one emulated
+    GPU each, a two-rank stub communicator) take the 8 chunks of one LZ4 stream round-robin; two
+    handles per rank alternate; per chunk mtz_dev_finish_exchange all-gathers the 40-byte
+    aggregate, carries the round base, and passes the 32-byte output checksum around the ring.
+    The concatenated output must be the oracle's RECOMPRESS of the whole stream, the END checksum
+    the oracle's -- and nothing may deadlock (the issue order of the communicator operations is the
+    one mtz_lib.cu documents)."""
+    import threading
+    import numpy as np
+    from manatee_b200 import GpuSnapshotStage, comm_unique_id, index_host
+    from manatee_b200 import _native as N
+    from test_gpu_codec import _mixed_stream
+    raw = _mixed_stream(oracle, n=64, recsize=16384)
+    rc, c, _ = oracle.stream_compress_plain(raw)
+    c = np.ascontiguousarray(c)
+    rc, want, wst = oracle.stream_recompress(c)
+    recs_all, _ = index_host(c)
+    world, CH = 2, 4
+    C_ALL = world * CH
+    bounds = [(j * len(recs_all)) // C_ALL for j in range(C_ALL + 1)]
+    uid = comm_unique_id()
+    outs, errs, ends = {}, [], {}
+
+    def rank_main(rank):
+        try:
+            hs = [GpuSnapshotStage("recompress", device=rank, flags=N.FLAG_DEFER_VERIFY) for _ in range(2)]
+            hs[0].comm_init(uid, rank, world)
+            hs[1].comm_share(hs[0])
+            chunks = []
+            for k in range(CH):
+                j = k * world + rank
+                r0, r1 = bounds[j], bounds[j + 1]
+                b0 = int(recs_all["off"][r0])
+                b1 = int(recs_all["off"][r1]) if r1 < len(recs_all) else c.size
+                recs = recs_all[r0:r1].copy(); recs["off"] -= b0
+                chunks.append((j, np.ascontiguousarray(c[b0:b1]), recs, np.zeros(raw.size + (1 << 20), dtype=np.uint8)))
+
+            def submit(k):
+                j, d_in, recs, d_out = chunks[k]
+                g = hs[k % 2]
+                g.dev_reset()
+                g.dev_submit(d_in.ctypes.data, d_in.size, recs.ctypes.data, len(recs), d_out.ctypes.data, d_out.size)
+            base = (0, 0, 0, 0)
+            submit(0); submit(1)
+            for k in range(CH):
+                j = chunks[k][0]
+                flags = (N.XCHG_FIRST if j == 0 else 0) | (N.XCHG_LAST if j == C_ALL - 1 else 0)
+                ob, _, _, base = hs[k % 2].dev_finish_exchange(round_base=base, flags=flags)
+                outs[j] = chunks[k][3][:ob].copy()
+                ck = hs[k % 2].end_checksum()
+                if ck is not None:
+                    ends[j] = ck
+                if k + 2 < CH:
+                    submit(k + 2)
+            for g in hs[::-1]:
+                g.close()
+        except Exception as e:  # noqa: BLE001
+            errs.append((rank, repr(e)))
+
+    ts = [threading.Thread(target=rank_main, args=(r,), daemon=True) for r in range(world)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join(240)
+    assert not any(t.is_alive() for t in ts), "the exchange deadlocked"
+    assert not errs, errs
+    got = np.concatenate([outs[j] for j in range(C_ALL)])
+    assert got.size == want.size and np.array_equal(got, want)
+    assert ends == {C_ALL - 1: wst.end_cksum.tuple()}
