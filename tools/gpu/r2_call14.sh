@@ -2,7 +2,7 @@ set -x
 mkdir -p gpurun_out
 N=${1:-4}
 nvidia-smi -L | wc -l; nproc; cat /sys/fs/cgroup/cpu.max; free -g | head -2
-timeout 300 python tools/chain_probe.py 2 > gpurun_out/r2_chain_probe_c.log 2>&1; cat gpurun_out/r2_chain_probe_c.log
+
 timeout 600 python -m pytest tests/test_gpu_multidev.py -x -q > gpurun_out/r2_gputests_multidev_n$N.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r2_gputests_multidev_n$N.log
 tail -4 gpurun_out/r2_gputests_multidev_n$N.log
 timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29519 bench.py --gpus $N --steps 5 --warmup 3 > gpurun_out/r2_bench_n$N.json 2> gpurun_out/r2_bench_n$N.err; echo "bench rc=$?"
