@@ -675,10 +675,20 @@ def run_ours(args):
                 for _ in range(k):
                     n_out = ge.process_host(src, pin_out.array)
                 dt = (time.perf_counter() - t0) / k
+            # the same call with the kernels removed: H2D + D2H of every byte through the same
+            # pinned buffers, slots and device group -- the host/PCIe ceiling of this box for e2e
+            with GpuSnapshotStage("passthrough", device=local, devices=devices, n_slots=4) as gp:
+                gp.process_host(src, pin_out.array)
+                t0 = time.perf_counter()
+                gp.process_host(src, pin_out.array)
+                copy_only = round(total_bytes / GIB / (time.perf_counter() - t0), 3)
             e2e = {"value": round(total_bytes / GIB / dt, 3), "unit": "GiB/s",
                    "logical_gibs": round(logical / GIB / dt, 3), "steps": k,
                    "h2d_bytes_per_step": int(total_bytes + nrec * 32), "d2h_bytes_per_step": int(n_out),
                    "output_equals_input": bool(ok),
+                   "copy_only_gibs": copy_only,
+                   "copy_only": "mtz_process_host in PASSTHROUGH mode on the same buffers and devices: every "
+                                "byte H2D and D2H, no kernels -- what this host's PCIe / memory allows e2e",
                    "call": "mtz_process_host(pinned host stream in, pinned host stream out) on ONE handle over "
                            "%s, host wall clock around the synchronous call" % (
                                "the device group mtz_config.devices[0..%d) of a single process" % world
@@ -696,9 +706,12 @@ def run_ours(args):
                 if not ok:
                     failed.append("ring API leg %s: %s" % (name, det["errors"]))
             ring["call"] = ("write = mtz_write (one producer thread memcpy into the pinned ring); acquire_commit = "
-                            "mtz_ring_acquire/commit with the slice filled by parallel memcpys; pipe = read(2) "
+                            "mtz_ring_acquire/commit with the slice filled by parallel memcpys (producer_alone_gibs = those "
+                            "memcpys with no library behind them: the leg's ceiling on this host); pipe = read(2) "
                             "from a pipe into the slice (zfsSend.stdout shape, bound by the pipe); consumer = "
                             "mtz_out_peek/consume on the pinned output ring")
+            ring["producer_alone_gibs"] = host_memcpy_ceiling(src, pump_threads())
+            ring["producer_threads"] = pump_threads()
             ring["ok"] = all(v.get("ok", True) for v in ring.values() if isinstance(v, dict))
             ring["value"] = ring.get("acquire_commit", {}).get("value")
             ring["unit"] = "GiB/s"

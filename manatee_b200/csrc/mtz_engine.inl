@@ -586,7 +586,7 @@ static int32_t engine_get(mtz_handle *h, Engine **out)
 	if (e->own_out) {
 		for (auto &dc : h->devs) {
 			MTZ_CU(h, cudaSetDevice(dc.device));
-			if (dc.fan_st == nullptr) MTZ_CU(h, cudaStreamCreateWithFlags(&dc.fan_st, cudaStreamNonBlocking));
+			if (dc.fan_st == nullptr) MTZ_CU(h, make_stream(&dc.fan_st, true));
 		}
 		MTZ_CU(h, cudaSetDevice(h->device));
 		// a single peer on a group drains every batch through the GPU that produced it (no

@@ -64,6 +64,7 @@ struct Slot {
 	ScanResult *d_res = nullptr;
 	ScanResult *h_res = nullptr;  // pinned
 	cudaStream_t st = nullptr;
+	cudaStream_t st_k3 = nullptr;      // least-priority side stream of the LZ4 encoder (make_stream)
 	cudaEvent_t ev_start = nullptr, ev_done = nullptr;
 	cudaEvent_t ev_k1a = nullptr, ev_k1b = nullptr;
 	cudaEvent_t ev_c0 = nullptr, ev_c1 = nullptr;     // around K2+K3

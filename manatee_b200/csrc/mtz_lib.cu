@@ -172,6 +172,29 @@ int32_t mtz_index_host(const void *buf, size_t n, mtz_rec *recs, size_t cap,
 }
 
 // ------------------------------------------------------------- lifecycle --
+// Stream priorities (experiment, off by default: MTZ_STREAM_PRIORITIES=1).  The LZ4 encoder owns the
+// machine for tens of milliseconds per launch; with priorities on, its streams get the LEAST
+// priority and every other library stream the GREATEST, so that short kernels (plan, decode of the
+// next sub-batch, assemble, the stamp chain, the NCCL broadcast) are placed the moment an encoder
+// CTA retires.  Measured neutral to -1 % on one GPU and neutral for the fan-out on two
+// (profiles/r2_stream_priorities.md): the encoder is throughput-bound, whatever runs beside it
+// takes its issue slots either way.  What did help a little (+1-2 %) is launching K2/K3 as many
+// short-lived CTAs rather than one persistent wave (lz4_grid), which is the default.
+static bool stream_priorities()
+{
+	static const bool on = [] { const char *e = getenv("MTZ_STREAM_PRIORITIES"); return e != nullptr && atoi(e) != 0; }();
+	return on;
+}
+static cudaError_t make_stream(cudaStream_t *st, bool high)
+{
+	int least = 0, greatest = 0;
+	if (stream_priorities()) {
+		cudaError_t e = cudaDeviceGetStreamPriorityRange(&least, &greatest);
+		if (e != cudaSuccess) return e;
+	}
+	return cudaStreamCreateWithPriority(st, cudaStreamNonBlocking, high ? greatest : least);
+}
+
 static int32_t alloc_slot(mtz_handle *h, Slot &s, int di, size_t cap, size_t rec_cap)
 {
 	s.cap = cap; s.rec_cap = rec_cap; s.di = di;
@@ -183,7 +206,9 @@ static int32_t alloc_slot(mtz_handle *h, Slot &s, int di, size_t cap, size_t rec
 	MTZ_CU(h, cudaMalloc(&s.d_tiles, (rec_cap / SCAN_TILE + 2) * sizeof(Part)));
 	MTZ_CU(h, cudaMalloc(&s.d_res, sizeof(ScanResult)));
 	MTZ_CU(h, cudaHostAlloc(&s.h_res, sizeof(ScanResult), cudaHostAllocPortable));
-	MTZ_CU(h, cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking));
+	MTZ_CU(h, make_stream(&s.st, true));
+	if (stream_priorities() && (h->cfg.mode == MTZ_MODE_COMPRESS || h->cfg.mode == MTZ_MODE_RECOMPRESS))
+		MTZ_CU(h, make_stream(&s.st_k3, false));
 	MTZ_CU(h, cudaEventCreateWithFlags(&s.ev_scan, cudaEventDisableTiming));
 	MTZ_CU(h, cudaEventCreateWithFlags(&s.ev_h2d, cudaEventDisableTiming));
 	MTZ_CU(h, cudaEventCreate(&s.ev_k3a));
@@ -210,6 +235,7 @@ static void free_slot(Slot &s)
 	if (s.d_res) cudaFree(s.d_res);
 	if (s.h_res) cudaFreeHost(s.h_res);
 	if (s.st) cudaStreamDestroy(s.st);
+	if (s.st_k3) cudaStreamDestroy(s.st_k3);
 	if (s.ev_start) cudaEventDestroy(s.ev_start);
 	if (s.ev_done) cudaEventDestroy(s.ev_done);
 	if (s.ev_k1a) cudaEventDestroy(s.ev_k1a);
@@ -576,17 +602,17 @@ static bool all_compact_blocks(const mtz_rec *recs, size_t n)
 static int32_t codec_launch_dec(mtz_handle *h, cudaStream_t st, CodecBufs &cb, const uint8_t *d_in,
     const mtz_rec *d_recs, size_t nrec);
 static int32_t codec_launch_enc(mtz_handle *h, cudaStream_t st, CodecBufs &cb, size_t nrec, bool compact,
-    cudaEvent_t ka = nullptr, cudaEvent_t kb = nullptr);
+    cudaEvent_t ka = nullptr, cudaEvent_t kb = nullptr, cudaStream_t st_k3 = nullptr);
 
 static int32_t codec_launch_pre(mtz_handle *h, cudaStream_t st, CodecBufs &cb, const uint8_t *d_in,
     const mtz_rec *d_recs, size_t nrec, cudaEvent_t ea, cudaEvent_t eb, bool compact,
-    cudaEvent_t ka = nullptr, cudaEvent_t kb = nullptr)
+    cudaEvent_t ka = nullptr, cudaEvent_t kb = nullptr, cudaStream_t st_k3 = nullptr)
 {
 	if (nrec == 0) return MTZ_OK;
 	if (ea) MTZ_CU(h, cudaEventRecord(ea, st));
 	int32_t rc = codec_launch_dec(h, st, cb, d_in, d_recs, nrec);
 	if (rc != MTZ_OK) return rc;
-	rc = codec_launch_enc(h, st, cb, nrec, compact, ka, kb);
+	rc = codec_launch_enc(h, st, cb, nrec, compact, ka, kb, st_k3);
 	if (rc != MTZ_OK) return rc;
 	if (eb) MTZ_CU(h, cudaEventRecord(eb, st));
 	return MTZ_OK;
@@ -613,13 +639,18 @@ static int32_t codec_launch_dec(mtz_handle *h, cudaStream_t st, CodecBufs &cb, c
 }
 
 // K3 (encode) of one (sub-)batch
+// With `st_k3` (and both events) the encoder runs on that low-priority side stream, forked from
+// and joined back into `st`, so that the rest of this slot's work keeps `st`'s high priority.
 static int32_t codec_launch_enc(mtz_handle *h, cudaStream_t st, CodecBufs &cb, size_t nrec, bool compact,
-    cudaEvent_t ka, cudaEvent_t kb)
+    cudaEvent_t ka, cudaEvent_t kb, cudaStream_t st_k3)
 {
 	if (nrec == 0 || h->cfg.mode == MTZ_MODE_DECOMPRESS) return MTZ_OK;
+	if (st_k3 == nullptr || ka == nullptr || kb == nullptr) st_k3 = st;
 	if (ka) MTZ_CU(h, cudaEventRecord(ka, st));
-	int32_t rc = launch_k3(h, st, nullptr, nullptr, cb.enc, (uint32_t)nrec, compact);
-	if (rc == MTZ_OK && kb) MTZ_CU(h, cudaEventRecord(kb, st));
+	if (st_k3 != st) MTZ_CU(h, cudaStreamWaitEvent(st_k3, ka, 0));
+	int32_t rc = launch_k3(h, st_k3, nullptr, nullptr, cb.enc, (uint32_t)nrec, compact);
+	if (rc == MTZ_OK && kb) MTZ_CU(h, cudaEventRecord(kb, st_k3));
+	if (rc == MTZ_OK && st_k3 != st) MTZ_CU(h, cudaStreamWaitEvent(st, kb, 0));
 	return rc;
 }
 
@@ -722,8 +753,8 @@ int32_t mtz_dev_submit(mtz_handle *h, const void *d_in, size_t in_bytes,
 		h->dv_cb2.h_cres = h->dv_cb.h_cres; h->dv_cb2.h_ores = h->dv_cb.h_ores;
 		MTZ_CU(h, cudaEventCreate(&h->dv_c0));
 		MTZ_CU(h, cudaEventCreate(&h->dv_c1));
-		MTZ_CU(h, cudaStreamCreateWithFlags(&h->st_post, cudaStreamNonBlocking));
-		MTZ_CU(h, cudaStreamCreateWithFlags(&h->st_dec, cudaStreamNonBlocking));
+		MTZ_CU(h, make_stream(&h->st_post, true));
+		MTZ_CU(h, make_stream(&h->st_dec, true));
 		for (int i = 0; i < 2; i++) {
 			MTZ_CU(h, cudaEventCreateWithFlags(&h->ev_dec[i], cudaEventDisableTiming));
 			MTZ_CU(h, cudaEventCreateWithFlags(&h->ev_pre[i], cudaEventDisableTiming));
@@ -1255,7 +1286,7 @@ static int32_t submit_batch(mtz_handle *h, Slot &s, const uint8_t *p0, size_t n0
 			// K2/K3 of this batch overlap the previous batch's checksum chains
 			const bool enc = h->cfg.mode != MTZ_MODE_DECOMPRESS && nrec > 0;
 			rc = codec_launch_pre(h, s.st, s.cb, s.d_in, s.d_recs, nrec, s.ev_c0, s.ev_c1,
-			    all_compact_blocks(s.h_recs, nrec), enc ? s.ev_k3a : nullptr, enc ? s.ev_k3b : nullptr);
+			    all_compact_blocks(s.h_recs, nrec), enc ? s.ev_k3a : nullptr, enc ? s.ev_k3b : nullptr, s.st_k3);
 			if (rc != MTZ_OK) return rc;
 			s.k3_timed = enc;
 		}
@@ -1430,9 +1461,19 @@ int32_t mtz_process_host(mtz_handle *h, const void *in, size_t n, void *out, siz
 extern "C" {
 
 // ---------------------------------------------------- LZ4 kernel entries ---
+// One warp per record, one CTA per LZ4_WARPS records: CTAs that live for one record each free
+// their SM slot every few microseconds somewhere on the chip, so kernels of other streams
+// interleave with a long encode and the hardware balances ragged records (+1-2 % over the
+// one-wave grid-stride launch, which MTZ_LZ4_PERSISTENT=1 restores for experiments).
+static bool lz4_persistent()
+{
+	static const bool p = [] { const char *e = getenv("MTZ_LZ4_PERSISTENT"); return e != nullptr && atoi(e) != 0; }();
+	return p;
+}
 static int32_t lz4_grid(mtz_handle *h, uint32_t njobs, int warps_per_sm)
 {
 	const uint32_t blocks_needed = (njobs + LZ4_WARPS - 1) / LZ4_WARPS;
+	if (warps_per_sm <= 0) return (int32_t)std::max(1u, blocks_needed);
 	const uint32_t cap = (uint32_t)h->sm_count * (uint32_t)(warps_per_sm / LZ4_WARPS);
 	return (int32_t)std::max(1u, std::min(blocks_needed, cap));
 }
@@ -1443,7 +1484,7 @@ static int32_t launch_k2(mtz_handle *h, cudaStream_t st, const void *d_src, void
     uint32_t njobs)
 {
 	if (njobs == 0) return MTZ_OK;
-	k2_lz4_decode<<<lz4_grid(h, njobs, 64), LZ4_THREADS, 0, st>>>((const uint8_t *)d_src,
+	k2_lz4_decode<<<lz4_grid(h, njobs, lz4_persistent() ? 64 : 0), LZ4_THREADS, 0, st>>>((const uint8_t *)d_src,
 	    (uint8_t *)d_dst, d_jobs, njobs);
 	MTZ_CU(h, cudaGetLastError());
 	count_launch(h, 1);
@@ -1493,7 +1534,7 @@ static int32_t launch_k3(mtz_handle *h, cudaStream_t st, const void *d_src, void
 		if (e && atoi(e) > 0) blocks_per_sm = std::min(blocks_per_sm, atoi(e));
 	}
 	const uint32_t need = (njobs + K3_WARPS - 1) / K3_WARPS;
-	const int grid = (int)std::max(1u, std::min(need, (uint32_t)h->sm_count * (uint32_t)blocks_per_sm));
+	const int grid = (int)std::max(1u, lz4_persistent() ? std::min(need, (uint32_t)h->sm_count * (uint32_t)blocks_per_sm) : need);
 	if (compact)
 		k3_lz4_encode<true><<<grid, K3_THREADS, smem, st>>>((const uint8_t *)d_src, (uint8_t *)d_dst, d_jobs, njobs);
 	else

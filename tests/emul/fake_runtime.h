@@ -245,6 +245,15 @@ static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned)
 	emurt::S().streams.push_back(*s);
 	return cudaSuccess;
 }
+static inline cudaError_t cudaDeviceGetStreamPriorityRange(int *least, int *greatest)
+{
+	*least = 0; *greatest = -5;
+	return cudaSuccess;
+}
+static inline cudaError_t cudaStreamCreateWithPriority(cudaStream_t *s, unsigned flags, int)
+{
+	return cudaStreamCreateWithFlags(s, flags);
+}
 static inline cudaError_t cudaStreamSynchronize(cudaStream_t st_)
 {
 	emu_stream_ *st = emurt::str(st_);
