@@ -99,6 +99,8 @@ typedef struct mtz_stats {
 	uint64_t k1_launches;
 	double   k3_ms;         /* device time of the LZ4 encode kernel alone (CUDA events) */
 	uint64_t k3_launches;
+	uint64_t lz4_certified; /* RECOMPRESS: records whose input frame was PROVEN to be the encoder's output
+	                           (kernels_lz4.cuh warp_lz4_certify) and passed through; the rest were re-encoded */
 } mtz_stats;
 
 /* One DRR record as seen by the kernels (32 B, little endian). */

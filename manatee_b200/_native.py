@@ -39,7 +39,8 @@ class Stats(C.Structure):
                 ("lz4_encoded", C.c_uint64), ("batches", C.c_uint64), ("bad_record", C.c_uint64),
                 ("kernel_launches", C.c_uint64), ("gpu_ms", C.c_double), ("end_seen", C.c_uint64),
                 ("k1_ms", C.c_double), ("codec_ms", C.c_double), ("k1_launches", C.c_uint64),
-                ("k3_ms", C.c_double), ("k3_launches", C.c_uint64)]
+                ("k3_ms", C.c_double), ("k3_launches", C.c_uint64),
+                ("lz4_certified", C.c_uint64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -44,7 +44,7 @@ struct CodecResult {       // device, mirrored to pinned host
 	uint32_t bad;          // first record whose frame failed to decode (0xffffffff none)
 	uint32_t n_dec;        // records decoded
 	uint32_t n_enc;        // records stored compressed on output
-	uint32_t pad;
+	uint32_t n_cert;       // ... of which certified (input frame == encoder output), not re-encoded
 };
 
 // ---- plan, step 1: flags + scratch need -----------------------------------
@@ -144,7 +144,8 @@ __global__ void k_plan_jobs(const uint8_t *__restrict__ d_in, const mtz_rec *__r
 // ---- layout: output payload length per record -----------------------------
 __global__ void k_layout(const mtz_rec *__restrict__ recs, uint32_t n, CodecRec *__restrict__ cr,
     const mtz_job *__restrict__ dec, const mtz_job *__restrict__ enc,
-    uint64_t *__restrict__ vals, CodecResult *__restrict__ res, uint32_t rec_base)
+    uint64_t *__restrict__ vals, CodecResult *__restrict__ res, uint32_t rec_base,
+    const uint32_t *__restrict__ cert = nullptr)
 {
 	const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
 	if (r >= n) return;
@@ -159,6 +160,7 @@ __global__ void k_layout(const mtz_rec *__restrict__ recs, uint32_t n, CodecRec 
 	if ((c.flags & CF_ENC) && enc[r].out_len < rec.lsize) {
 		len = enc[r].out_len;
 		atomicAdd(&res->n_enc, 1u);
+		if (cert != nullptr && cert[r] != 0u) atomicAdd(&res->n_cert, 1u);
 	}
 	c.out_len = len;
 	cr[r] = c;
@@ -195,7 +197,8 @@ __global__ void __launch_bounds__(ASM_THREADS)
 k_assemble(const uint8_t *__restrict__ d_in, const mtz_rec *__restrict__ recs, uint32_t n,
     uint32_t mode, CodecRec *__restrict__ cr, const uint64_t *__restrict__ out_offs,
     const mtz_job *__restrict__ enc, const uint8_t *d_logical, const uint8_t *d_enc,
-    uint8_t *__restrict__ d_out, mtz_rec *__restrict__ out_recs)
+    uint8_t *__restrict__ d_out, mtz_rec *__restrict__ out_recs,
+    const uint32_t *__restrict__ cert = nullptr)
 {
 	const int lane = threadIdx.x & 31;
 	const uint32_t gw = blockIdx.x * (ASM_THREADS / 32) + (threadIdx.x >> 5);
@@ -212,10 +215,14 @@ k_assemble(const uint8_t *__restrict__ d_in, const mtz_rec *__restrict__ recs, u
 		__syncwarp();
 		uint32_t ocomp = rec.comp;
 		const uint8_t *psrc = hin + DRR_HDR;
+		uint32_t ncopy = c.out_len;
 		if (c.flags & CF_WRITE) {
 			const bool enc_ok = (c.flags & CF_ENC) && enc[r].out_len < rec.lsize;
 			if (enc_ok) {
-				psrc = d_enc + c.scratch; ocomp = ZIO_LZ4;
+				// certified (K3c): the frame is the input's own BE32(clen) + block, zero-padded
+				const uint32_t cl = cert ? cert[r] : 0u;
+				if (cl != 0u) ncopy = cl; else psrc = d_enc + c.scratch;
+				ocomp = ZIO_LZ4;
 				if (lane == 0) {
 					hout[50] = (uint8_t)ZIO_LZ4;
 					*reinterpret_cast<uint64_t *>(hout + 96) = (uint64_t)c.out_len;
@@ -241,7 +248,8 @@ k_assemble(const uint8_t *__restrict__ d_in, const mtz_rec *__restrict__ recs, u
 			}
 			*reinterpret_cast<uint64_t *>(hout + 16) = vi;
 		}
-		warp_copy(hout + DRR_HDR, psrc, c.out_len, lane);
+		warp_copy(hout + DRR_HDR, psrc, ncopy, lane);
+		for (uint32_t i = ncopy + (uint32_t)lane; i < c.out_len; i += 32u) hout[DRR_HDR + i] = 0;
 		if (lane == 0) {
 			mtz_rec o;
 			o.off = oo; o.payload = c.out_len; o.type = rec.type;

@@ -30,9 +30,24 @@ __device__ __forceinline__ uint32_t ld_u8(const uint8_t *p) { return *p; }
 // --------------------------------------------------------------- K2 decode --
 // status: 0 ok, else -MTZ_ECODEC.  All lanes run the same control flow; `ip`,
 // `op` and every parsed field are warp-uniform.
-__device__ __forceinline__ int32_t warp_lz4_decode(const uint8_t *__restrict__ src,
-    uint32_t psize, uint8_t *__restrict__ dst, uint32_t lsize, int lane)
+//
+// Optional by-product (RECOMPRESS, see warp_lz4_certify): the parse of the block as a table of
+// sequences, one u64 per match -- bits 0..23 the decoded position where the match starts (= anchor
+// + literal length), 24..39 the offset, 40..63 the match length -- and their count in *seq_n
+// (LZ4_SEQ_NONE when the table overflowed `seq_cap` or the block is not in the encoder's normal
+// form: the closing literals-only token must have a zero low nibble).
+#define LZ4_SEQ_NONE 0xffffffffu
+__device__ __forceinline__ uint64_t lz4_seq_pack(uint32_t m, uint32_t off, uint32_t ml)
 {
+	return (uint64_t)m | ((uint64_t)off << 24) | ((uint64_t)ml << 40);
+}
+
+__device__ __forceinline__ int32_t warp_lz4_decode(const uint8_t *__restrict__ src,
+    uint32_t psize, uint8_t *__restrict__ dst, uint32_t lsize, int lane,
+    uint64_t *__restrict__ seq = nullptr, uint32_t seq_cap = 0, uint32_t *seq_n = nullptr)
+{
+	uint32_t ns = 0;
+	if (seq_n != nullptr && lane == 0) *seq_n = LZ4_SEQ_NONE;
 	if (psize < 4u) return MTZ_ECODEC;
 	const uint32_t clen = (ld_u8(src) << 24) | (ld_u8(src + 1) << 16) | (ld_u8(src + 2) << 8) | ld_u8(src + 3);
 	if ((uint64_t)clen + 4u > psize || clen == 0u) return MTZ_ECODEC;
@@ -57,7 +72,10 @@ __device__ __forceinline__ int32_t warp_lz4_decode(const uint8_t *__restrict__ s
 		if (len > 32u)
 			for (uint32_t i = 32u + (uint32_t)lane; i < len; i += 32u) dst[op + i] = in[ip + i];
 		ip += len; op += len;
-		if (ip == iend) break;                         // last sequence: literals only
+		if (ip == iend) {                              // last sequence: literals only
+			if ((tok & 15u) != 0u) ns = LZ4_SEQ_NONE;
+			break;
+		}
 
 		if (iend - ip < 2u) return MTZ_ECODEC;
 		const uint32_t off = ld_u8(in + ip) | (ld_u8(in + ip + 1) << 8);
@@ -74,6 +92,10 @@ __device__ __forceinline__ int32_t warp_lz4_decode(const uint8_t *__restrict__ s
 		}
 		ml += LZ4_MINMATCH;
 		if (ml > lsize - op) return MTZ_ECODEC;
+		if (seq != nullptr) {
+			if (ns < seq_cap && lane == 0) seq[ns] = lz4_seq_pack(op, off, ml);
+			ns++;
+		}
 		__syncwarp();                                  // earlier stores -> these loads
 		const uint8_t *ref = dst + (op - off);
 		if (off >= ml) {
@@ -94,7 +116,9 @@ __device__ __forceinline__ int32_t warp_lz4_decode(const uint8_t *__restrict__ s
 		op += ml;
 	}
 	__syncwarp();
-	return (op == lsize) ? MTZ_OK : MTZ_ECODEC;
+	if (op != lsize) return MTZ_ECODEC;
+	if (seq_n != nullptr && lane == 0 && ns <= seq_cap) *seq_n = ns;     // (LZ4_SEQ_NONE > any cap)
+	return MTZ_OK;
 }
 
 #define LZ4_THREADS 128
@@ -102,7 +126,8 @@ __device__ __forceinline__ int32_t warp_lz4_decode(const uint8_t *__restrict__ s
 
 __global__ void __launch_bounds__(LZ4_THREADS)
 k2_lz4_decode(const uint8_t *__restrict__ src_base, uint8_t *__restrict__ dst_base,
-    mtz_job *__restrict__ jobs, uint32_t njobs)
+    mtz_job *__restrict__ jobs, uint32_t njobs,
+    const mtz_job *__restrict__ seq_jobs = nullptr, uint32_t *__restrict__ seq_n = nullptr)
 {
 	const int lane = threadIdx.x & 31;
 	const uint32_t gw = blockIdx.x * LZ4_WARPS + (threadIdx.x >> 5);
@@ -110,8 +135,12 @@ k2_lz4_decode(const uint8_t *__restrict__ src_base, uint8_t *__restrict__ dst_ba
 	for (uint32_t j = gw; j < njobs; j += nw) {
 		const mtz_job job = jobs[j];
 		if (job.lsize == 0u) continue;                 // not a decode job (pipeline: 1 job slot per record)
+		// RECOMPRESS: the parse goes into the record's (still unused) frame slot of the encoder
+		uint64_t *seq = nullptr;
+		if (seq_jobs != nullptr) seq = reinterpret_cast<uint64_t *>((uintptr_t)seq_jobs[j].dst_off);
 		const int32_t st = warp_lz4_decode(src_base + job.src_off, job.src_len,
-		    dst_base + job.dst_off, job.lsize, lane);
+		    dst_base + job.dst_off, job.lsize, lane, seq, seq ? (job.lsize >> 3) : 0u,
+		    seq ? seq_n + j : nullptr);
 		if (lane == 0) {
 			jobs[j].status = st;
 			jobs[j].out_len = (st == MTZ_OK) ? job.lsize : 0u;
@@ -537,6 +566,265 @@ __device__ __forceinline__ uint32_t warp_zfs_lz4_compress(const uint8_t *__restr
 	return psize;
 }
 
+// ------------------------------------------------------ K3c: the certificate --
+// RECOMPRESS re-encodes what it has just decoded.  When the incoming block already IS what
+// lz4_encode (oracle/lz4_zfs.c:85-208) would emit for those bytes -- every block a `zfs send -c` of an
+// lz4 dataset carries, if the declared encoder is ZFS's -- the answer is the input, and PROVING that
+// is far cheaper than recomputing it: the serial matcher is a chain of ~5000 dependent cycles per
+// sequence (profiles/r2_k3_encode.md) because every decision waits for a gather from the source; a
+// replay that is TOLD the parse (K2's sequence table) knows where the hits must be and only has to
+// keep the hash table honest.
+//
+// The proof obligation, exactly: the encoder's run on the decoded bytes D is determined by its hash
+// table trajectory.  Inserted positions are strictly increasing in time (search attempts, then e-2
+// and e after a match ending at e), so "the slot's content" is "the largest inserted position below
+// me with my hash, else 0".  The replay executes the SAME attempts in the SAME order, 32 per round
+// with the in-round forwarding of warp_lz4_encode3, under the hypothesis "the table reads a match at
+// the first attempt >= m_k with offset o_k, and nowhere earlier".  Where the hypothesis says HIT it
+// checks the slot arithmetically (slot == x - o_k; the bytes are equal by construction, D was
+// decoded from this very parse, and o_k <= 65535); where it says MISS it checks the encoder's own
+// test (distance, then 4 bytes) on a load nobody waits for (verified one round later).  A hit the
+// table does not deliver at the first candidate is searched for at the following attempts (the
+// matcher found the match further right and walked back: catch-up), exactly as the encoder would.
+// Per match, without the table: the walk-back stops at m_k (anchor, source start or a differing
+// byte), the extension stops at e_k (matchlimit or a differing byte), and the encoder's output-room
+// tests, evaluated at the same output offsets, never fire.  Any violated check => not certified =>
+// the record takes the serial encoder.  Certified => output frame = BE32(clen) + input block + pad.
+template <class TAB>
+struct TabRound {            // one round of <= 32 time-ordered table operations (lane order = time order)
+	uint32_t oldv, all_same;
+	bool anyclash;
+};
+
+template <class TAB>
+__device__ __forceinline__ uint32_t tab_round_query(const TAB &tab, TabRound<TAB> &r, bool part,
+    uint32_t h, uint32_t x, int lane)
+{
+	const uint32_t lanebit = 1u << lane, lower = lanebit - 1u;
+	r.oldv = part ? tab.get(h) : 0u;
+	__syncwarp();
+	if (part) tab.tag(h, (uint32_t)lane);
+	__syncwarp();
+	const bool clash = part && (tab.tagval(h) != (uint32_t)lane);
+	r.anyclash = __any_sync(0xffffffffu, clash);
+	r.all_same = 0;
+	if (!r.anyclash) return r.oldv;
+	if (part) tab.untag(h, r.oldv);
+	__syncwarp();
+	r.all_same = __match_any_sync(0xffffffffu, h);          // non-participants carry unique fake hashes
+	const uint32_t same = r.all_same & lower;
+	const int from = same ? (31 - __clz((int)same)) : lane;
+	const uint32_t fwd = __shfl_sync(0xffffffffu, x, from);
+	return same ? fwd : r.oldv;
+}
+
+// lanes <= upto keep their insertions, the rest of the round never happened
+template <class TAB>
+__device__ __forceinline__ void tab_round_commit(const TAB &tab, const TabRound<TAB> &r, bool part,
+    uint32_t h, uint32_t x, int upto, int lane)
+{
+	const uint32_t lanebit = 1u << lane, lower = lanebit - 1u;
+	if (!r.anyclash) {
+		if (part) {
+			if (lane <= upto) tab.set_from(h, x, r.oldv); else tab.untag(h, r.oldv);
+		}
+	} else {
+		const uint32_t uptomask = (upto >= 31) ? 0xffffffffu : ((2u << upto) - 1u);
+		const uint32_t later = r.all_same & ~(lanebit | lower) & uptomask;
+		if (part && (lanebit & uptomask) && later == 0u) tab.set_from(h, x, r.oldv);
+	}
+	__syncwarp();
+}
+
+template <class TAB, bool DIST>
+__device__ __forceinline__ bool warp_lz4_certify(const uint8_t *__restrict__ src, uint32_t isize,
+    const uint64_t *__restrict__ seqs, uint32_t ns, uint32_t clen, uint32_t osize,
+    uint32_t *tabmem, int lane)
+{
+	constexpr int LOG = TAB::LOG;
+	const uint32_t mis = (uint32_t)((uintptr_t)src & 3u);
+	const uint32_t *base4 = reinterpret_cast<const uint32_t *>(src - mis);
+#define LDS32(pos) ld32x(base4, (pos) + mis)
+#define SEQ_M(s) ((uint32_t)(s) & 0xffffffu)
+#define SEQ_O(s) ((uint32_t)((s) >> 24) & 0xffffu)
+#define SEQ_L(s) ((uint32_t)((s) >> 40))
+	const uint32_t iend = isize;
+	bool bad = false;
+	if (isize < (uint32_t)LZ4_MINLENGTH) {
+		// the encoder goes straight to its last-literals block
+		bad = (ns != 0u) || (isize + 1u + ((isize + 255u - 15u) / 255u) > osize) ||
+		    (1u + (isize >= 15u ? 1u + (isize - 15u) / 255u : 0u) + isize != clen);
+		return !bad;
+	}
+	const uint32_t mflimit = iend - LZ4_MFLIMIT;
+	const uint32_t matchlimit = iend - LZ4_LASTLITERALS;
+
+	// ---- per match, 32 at a time: catch-up stop, extension stop, output-room tests
+	{
+		uint32_t op = 0, prev_e = 0;
+		for (uint32_t k0 = 0; k0 < ns; k0 += 32u) {
+			const uint32_t k = k0 + (uint32_t)lane;
+			const bool live = k < ns;
+			const uint64_t s = live ? seqs[k] : 0ull;
+			const uint32_t m = SEQ_M(s), o = SEQ_O(s), ml = SEQ_L(s), e = m + ml;
+			uint32_t a = __shfl_up_sync(0xffffffffu, e, 1);
+			if (lane == 0) a = prev_e;
+			const uint32_t litlen = m - a;
+			const uint32_t lb = 1u + (litlen >= 15u ? 1u + (litlen - 15u) / 255u : 0u) + litlen;
+			const uint32_t mlen = ml - LZ4_MINMATCH;
+			const uint32_t mb = 2u + (mlen >= 15u ? 1u + (mlen - 15u) / 255u : 0u);
+			const uint32_t tot = live ? lb + mb : 0u;
+			uint32_t inc = tot;
+#pragma unroll
+			for (int d = 1; d < 32; d <<= 1) {
+				const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+				if (lane >= d) inc += t;
+			}
+			const uint32_t opk = op + inc - tot;
+			if (live) {
+				if (e > matchlimit) bad = true;
+				else if (e < matchlimit && src[e] == src[e - o]) bad = true;            // not extended to the end
+				if (litlen > 0u && m > o && src[m - 1u] == src[m - o - 1u]) bad = true;  // walk-back stops too early
+				if (opk + 1u + litlen + (2u + 1u + LZ4_LASTLITERALS) + (litlen >> 8) > osize) bad = true;
+				if (opk + lb + 2u + (1u + LZ4_LASTLITERALS) + (mlen >> 8) > osize) bad = true;
+			}
+			op += __shfl_sync(0xffffffffu, inc, 31);
+			const uint32_t lastlive = (ns - k0 < 32u) ? (ns - k0 - 1u) : 31u;
+			prev_e = __shfl_sync(0xffffffffu, e, (int)lastlive);
+		}
+		const uint32_t last = iend - prev_e;
+		if (op + last + 1u + ((last + 255u - 15u) / 255u) > osize) bad = true;
+		if (op + 1u + (last >= 15u ? 1u + (last - 15u) / 255u : 0u) + last != clen) bad = true;
+	}
+	if (__any_sync(0xffffffffu, bad)) return false;
+
+	// ---- the table trajectory
+	TAB tab; tab.t = tabmem;
+	tab.clear(lane);
+	__syncwarp();
+	TabRound<TAB> rd;
+	uint32_t p_w = 0, p_v = 1;            // deferred MISS check of the previous round: bad iff equal
+	uint32_t a = 0;                        // anchor: end of the previous match
+	bool follow_hit = false;               // the probe at `a` delivered sequence k (no search)
+	uint64_t s_next = (ns > 0u) ? seqs[0] : 0ull;
+	bool finished = false;
+	for (uint32_t k = 0; k <= ns && !finished; k++) {
+		const bool have = k < ns;
+		const uint64_t s = s_next;
+		s_next = (k + 1u < ns) ? seqs[k + 1u] : 0ull;
+		const uint32_t m = SEQ_M(s), o = SEQ_O(s), e = m + SEQ_L(s);
+		const bool nf = (k + 1u < ns) && (SEQ_M(s_next) == e);     // hypothesis: k+1 follows on at e
+		const uint32_t o_next = SEQ_O(s_next);
+		const bool post_ok = have && e <= mflimit;                   // the encoder inserts e-2 and probes e
+		bool post_done = false, probe_hit = false;
+
+		if (!(have && follow_hit)) {
+			const uint32_t start = a + 1u;
+			const uint32_t target = have ? (m > start ? m : start) : 0xffffffffu;
+			bool found = false;
+			uint32_t a0 = 0;
+			int q1l = 32;
+			// phase 1: the attempts up to and including the first one at or beyond m
+			for (;;) {
+				const uint32_t att = a0 + (uint32_t)lane;
+				const uint32_t x = (a0 == 0u) ? start + (uint32_t)lane : start + skip_dist(att);
+				const uint32_t step = (a0 == 0u) ? 1u : ((67u + att) >> 6);
+				const bool valid = (x + step <= mflimit);
+				const uint32_t cm = __ballot_sync(0xffffffffu, x >= target);
+				const int q1 = cm ? (__ffs((int)cm) - 1) : 32;
+				q1l = q1;
+				const uint32_t inval = __ballot_sync(0xffffffffu, !valid);
+				const int I = inval ? (__ffs((int)inval) - 1) : 32;
+				if (have && I <= q1 && I < 32) return false;            // the encoder runs dry before the hit
+				if (q1 < 32 && __shfl_sync(0xffffffffu, x, q1) + LZ4_MINMATCH > e) return false;
+				// post operations ride in the same round when the hypothesis has room for them
+				const bool ride = (q1 < 30) && post_ok;
+				bool part = valid && lane <= q1 && lane < I;
+				uint32_t xx = x;
+				bool query = part;
+				if (ride && lane == q1 + 1) { part = true; query = false; xx = e - 2u; }
+				if (ride && lane == q1 + 2) { part = true; query = true; xx = e; }
+				const uint32_t v = part ? LDS32(xx) : 0u;
+				const uint32_t h = part ? ((v * 2654435761u) >> (32 - LOG)) : (0xffffffffu - (uint32_t)lane);
+				const uint32_t pred = tab_round_query(tab, rd, part, h, xx, lane);
+				const bool hit1 = (lane == q1) && part && (pred + o == xx);
+				found = __any_sync(0xffffffffu, hit1);
+				const int upto = (q1 < 32) ? ((found && ride) ? q1 + 2 : q1) : 31;
+				tab_round_commit(tab, rd, part, h, xx, upto, lane);
+				bool probe_lane_hit = false;
+				if (found && ride) {
+					probe_lane_hit = (lane == q1 + 2) && nf && (pred + o_next == xx);
+					probe_hit = __any_sync(0xffffffffu, probe_lane_hit);
+					post_done = true;
+				}
+				// deferred MISS checks: every committed query that is not a hypothesised-and-delivered hit
+				bad = bad || (p_w == p_v);
+				const bool chk = part && query && lane <= upto && !hit1 && !probe_lane_hit &&
+				    (!DIST || pred + LZ4_MAXDIST >= xx);
+				p_w = chk ? LDS32(pred) : 0u;
+				p_v = chk ? v : 1u;
+				if (q1 < 32) break;
+				if (I < 32) { finished = true; break; }                    // closing search ran dry (have == false here)
+				a0 += 32u;
+			}
+			if (finished) break;
+			if (!found) {
+				// phase 2: the table did not deliver at the first candidate; keep attempting inside the match
+				uint32_t ac = a0 + (uint32_t)q1l + 1u;                   // the attempt after the first candidate
+				for (;;) {
+					const uint32_t att = ac + (uint32_t)lane;
+					const uint32_t x = start + skip_dist(att);
+					const uint32_t step = (67u + att) >> 6;
+					const bool part = (x + step <= mflimit) && (x + LZ4_MINMATCH <= e);
+					if (!__any_sync(0xffffffffu, part)) return false;      // no attempt left that could be the hit
+					const uint32_t v = part ? LDS32(x) : 0u;
+					const uint32_t h = part ? ((v * 2654435761u) >> (32 - LOG)) : (0xffffffffu - (uint32_t)lane);
+					const uint32_t pred = tab_round_query(tab, rd, part, h, x, lane);
+					const bool hit = part && (pred + o == x);
+					const uint32_t hits = __ballot_sync(0xffffffffu, hit);
+					const int F = hits ? (__ffs((int)hits) - 1) : 32;
+					tab_round_commit(tab, rd, part, h, x, F < 32 ? F : 31, lane);
+					bad = bad || (p_w == p_v);
+					const bool chk = part && lane < F && (!DIST || pred + LZ4_MAXDIST >= x);
+					p_w = chk ? LDS32(pred) : 0u;
+					p_v = chk ? v : 1u;
+					if (F < 32) break;
+					if (!__all_sync(0xffffffffu, part)) return false;
+					ac += 32u;
+				}
+			}
+		}
+		if (!have) break;
+		if (!post_ok) {
+			// the match ends beyond mflimit: the encoder emits its last literals, so this is the last match
+			if (k + 1u != ns) return false;
+			break;
+		}
+		if (!post_done) {
+			const bool part = lane < 2;
+			const uint32_t xx = (lane == 0) ? e - 2u : e;
+			const uint32_t v = part ? LDS32(xx) : 0u;
+			const uint32_t h = part ? ((v * 2654435761u) >> (32 - LOG)) : (0xffffffffu - (uint32_t)lane);
+			const uint32_t pred = tab_round_query(tab, rd, part, h, xx, lane);
+			tab_round_commit(tab, rd, part, h, xx, 1, lane);
+			const bool plh = (lane == 1) && nf && (pred + o_next == xx);
+			probe_hit = __any_sync(0xffffffffu, plh);
+			bad = bad || (p_w == p_v);
+			const bool chk = (lane == 1) && !plh && (!DIST || pred + LZ4_MAXDIST >= xx);
+			p_w = chk ? LDS32(pred) : 0u;
+			p_v = chk ? v : 1u;
+		}
+		follow_hit = probe_hit;
+		a = e;
+	}
+	bad = bad || (p_w == p_v);
+#undef LDS32
+#undef SEQ_M
+#undef SEQ_O
+#undef SEQ_L
+	return !__any_sync(0xffffffffu, bad);
+}
+
 // per-warp shared memory: the hash table.  CTA shape: K3_THREADS/32 encoder warps; the launch
 // picks as many CTAs per SM as tables fit (24 tables of 8.5 KiB at 4 warps x 6 CTAs, 26 at
 // 13 warps x 2 CTAs -- the carve-out has room for 26).
@@ -550,7 +838,7 @@ __device__ __forceinline__ uint32_t warp_zfs_lz4_compress(const uint8_t *__restr
 template <bool COMPACT>
 __global__ void __launch_bounds__(K3_THREADS, K3_MIN_BLOCKS)
 k3_lz4_encode(const uint8_t *__restrict__ src_base, uint8_t *__restrict__ dst_base,
-    mtz_job *__restrict__ jobs, uint32_t njobs)
+    mtz_job *__restrict__ jobs, uint32_t njobs, const uint32_t *__restrict__ skip = nullptr)
 {
 	extern __shared__ uint4 s_dyn[];
 	constexpr uint32_t TABW = COMPACT ? LZ4_TAB_COMPACT_WORDS : LZ4_TAB_BIG_WORDS;
@@ -560,6 +848,7 @@ k3_lz4_encode(const uint8_t *__restrict__ src_base, uint8_t *__restrict__ dst_ba
 	const uint32_t gw = blockIdx.x * K3_WARPS + (uint32_t)warp;
 	const uint32_t nw = gridDim.x * K3_WARPS;
 	for (uint32_t j = gw; j < njobs; j += nw) {
+		if (skip != nullptr && skip[j] != 0u) continue;     // certified: the input frame is the output
 		const mtz_job job = jobs[j];
 		if (job.lsize == 0u) continue;
 		// a compact launch is only made when the host saw nothing but 128 KiB-class
@@ -572,6 +861,55 @@ k3_lz4_encode(const uint8_t *__restrict__ src_base, uint8_t *__restrict__ dst_ba
 			    dst_base + job.dst_off, tab, lane);
 		__syncwarp();
 		if (lane == 0) { jobs[j].out_len = ps; jobs[j].status = MTZ_OK; }
+	}
+}
+
+// K3c: one warp per record.  cert[j] = bytes of the input payload that ARE the output frame
+// (4 + clen; the assembler zero-pads to enc[j].out_len), or 0 = not certified (K3 encodes it).
+template <bool COMPACT>
+__global__ void __launch_bounds__(K3_THREADS, K3_MIN_BLOCKS)
+k3c_lz4_certify(const mtz_job *__restrict__ dec, mtz_job *__restrict__ enc,
+    const uint32_t *__restrict__ seq_n, uint32_t *__restrict__ cert, uint32_t njobs)
+{
+	extern __shared__ uint4 s_dyn[];
+	constexpr uint32_t TABW = COMPACT ? LZ4_TAB_COMPACT_WORDS : LZ4_TAB_BIG_WORDS;
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	uint32_t *tab = reinterpret_cast<uint32_t *>(s_dyn) + warp * TABW;
+	const uint32_t gw = blockIdx.x * K3_WARPS + (uint32_t)warp;
+	const uint32_t nw = gridDim.x * K3_WARPS;
+	for (uint32_t j = gw; j < njobs; j += nw) {
+		const mtz_job jd = dec[j];
+		const mtz_job je = enc[j];
+		const uint32_t ns = seq_n[j];
+		const uint32_t lsize = je.lsize;
+		uint32_t c_len = 0, psize = 0;
+		bool ok = (jd.lsize != 0u && jd.lsize == lsize && jd.status == MTZ_OK && ns != LZ4_SEQ_NONE);
+		// the ranges in which warp_zfs_lz4_compress compresses at all, and this launch's table
+		const uint32_t d_len = lsize - (lsize >> 3);
+		if (lsize < 1024u || lsize >= (1u << 24) || d_len < 4u) ok = false;
+		if (COMPACT && (lsize < (uint32_t)LZ4_64KLIMIT || lsize > 131072u)) ok = false;
+		if (ok) {
+			const uint8_t *f = reinterpret_cast<const uint8_t *>((uintptr_t)jd.src_off);
+			const uint32_t clen = (ld_u8(f) << 24) | (ld_u8(f + 1) << 16) | (ld_u8(f + 2) << 8) | ld_u8(f + 3);
+			c_len = clen + 4u;
+			psize = (c_len + 511u) & ~511u;
+			if (c_len > d_len || psize >= lsize) ok = false;           // zio_compress_data stores it raw
+			if (ok) {
+				const uint8_t *src = reinterpret_cast<const uint8_t *>((uintptr_t)je.src_off);
+				const uint64_t *seqs = reinterpret_cast<const uint64_t *>((uintptr_t)je.dst_off);
+				if (COMPACT)
+					ok = warp_lz4_certify<Tab17, true>(src, lsize, seqs, ns, clen, d_len - 4u, tab, lane);
+				else if (lsize < (uint32_t)LZ4_64KLIMIT)
+					ok = warp_lz4_certify<TabU16, false>(src, lsize, seqs, ns, clen, d_len - 4u, tab, lane);
+				else
+					ok = warp_lz4_certify<TabU32, true>(src, lsize, seqs, ns, clen, d_len - 4u, tab, lane);
+			}
+		}
+		__syncwarp();
+		if (lane == 0) {
+			cert[j] = ok ? c_len : 0u;
+			if (ok) { enc[j].out_len = psize; enc[j].status = MTZ_OK; }
+		}
 	}
 }
 

@@ -27,6 +27,7 @@ struct CodecBufs {
 	RecSums *osums = nullptr;
 	StampStep *steps = nullptr;                         // per-record transitions of the stamp chain
 	uint8_t *d_logical = nullptr, *d_enc = nullptr;
+	uint32_t *seq_n = nullptr, *cert = nullptr;         // RECOMPRESS certificate: K2's parse sizes, K3c's verdicts
 	CodecResult *d_cres = nullptr, *h_cres = nullptr;   // h_: pinned
 	ScanResult *d_ores = nullptr, *h_ores = nullptr;    // output-chain result
 	uint64_t *d_outpos = nullptr;                       // running output offset (device)

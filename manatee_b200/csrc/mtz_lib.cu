@@ -254,7 +254,7 @@ static void free_slot(Slot &s)
 
 static int32_t k3_set_attributes(mtz_handle *h);
 static int32_t launch_k2(mtz_handle *h, cudaStream_t st, const void *d_src, void *d_dst, mtz_job *d_jobs,
-    uint32_t njobs);
+    uint32_t njobs, const mtz_job *seq_jobs = nullptr, uint32_t *seq_n = nullptr);
 
 int32_t mtz_open(const mtz_config *cfg, mtz_handle **out)
 {
@@ -541,6 +541,14 @@ static bool is_codec_mode(uint32_t m)
 	return m == MTZ_MODE_COMPRESS || m == MTZ_MODE_DECOMPRESS || m == MTZ_MODE_RECOMPRESS;
 }
 
+// RECOMPRESS proves, where it can, that a record's input frame already is what the encoder would
+// emit and passes it through (K3c, kernels_lz4.cuh); MTZ_CERTIFY=0 re-encodes every record.
+static bool certify_on(const mtz_handle *h)
+{
+	static const bool on = [] { const char *e = getenv("MTZ_CERTIFY"); return e == nullptr || atoi(e) != 0; }();
+	return on && h->cfg.mode == MTZ_MODE_RECOMPRESS;
+}
+
 static int32_t codec_alloc(mtz_handle *h, CodecBufs &cb, size_t rec_cap, size_t scratch_cap)
 {
 	cb.rec_cap = rec_cap; cb.scratch_cap = scratch_cap;
@@ -555,6 +563,10 @@ static int32_t codec_alloc(mtz_handle *h, CodecBufs &cb, size_t rec_cap, size_t 
 	MTZ_CU(h, cudaMalloc(&cb.steps, rec_cap * sizeof(StampStep)));
 	if (h->cfg.mode != MTZ_MODE_COMPRESS) MTZ_CU(h, cudaMalloc(&cb.d_logical, scratch_cap + 512));
 	if (h->cfg.mode != MTZ_MODE_DECOMPRESS) MTZ_CU(h, cudaMalloc(&cb.d_enc, scratch_cap + 512));
+	if (certify_on(h)) {
+		MTZ_CU(h, cudaMalloc(&cb.seq_n, rec_cap * sizeof(uint32_t)));
+		MTZ_CU(h, cudaMalloc(&cb.cert, rec_cap * sizeof(uint32_t)));
+	}
 	MTZ_CU(h, cudaMalloc(&cb.d_cres, sizeof(CodecResult)));
 	MTZ_CU(h, cudaHostAlloc(&cb.h_cres, sizeof(CodecResult), cudaHostAllocDefault));
 	MTZ_CU(h, cudaMalloc(&cb.d_ores, sizeof(ScanResult)));
@@ -569,7 +581,7 @@ static void codec_free(CodecBufs &cb)
 	cudaFree(cb.cr); cudaFree(cb.vals); cudaFree(cb.offs); cudaFree(cb.out_offs);
 	cudaFree(cb.dec); cudaFree(cb.enc); cudaFree(cb.out_recs); cudaFree(cb.osums); cudaFree(cb.steps);
 	cudaFree(cb.d_logical); cudaFree(cb.d_enc); cudaFree(cb.d_cres); cudaFree(cb.d_ores);
-	cudaFree(cb.d_outpos);
+	cudaFree(cb.d_outpos); cudaFree(cb.seq_n); cudaFree(cb.cert);
 	if (cb.h_cres) cudaFreeHost(cb.h_cres);
 	if (cb.h_ores) cudaFreeHost(cb.h_ores);
 	cb = CodecBufs();
@@ -588,7 +600,8 @@ static int32_t codec_reset(mtz_handle *h, cudaStream_t st, CodecBufs &cb)
 // Part 1 of the re-encoding pipeline of one (sub-)batch: plan + K2 + K3.  It
 // does not touch the running checksums, so it may run ahead of the chain.
 static int32_t launch_k3(mtz_handle *h, cudaStream_t st, const void *d_src, void *d_dst,
-    mtz_job *d_jobs, uint32_t njobs, bool compact);
+    mtz_job *d_jobs, uint32_t njobs, bool compact, const uint32_t *skip = nullptr);
+static int32_t launch_k3c(mtz_handle *h, cudaStream_t st, CodecBufs &cb, uint32_t njobs, bool compact);
 
 // true when every DRR_WRITE of the table has a 128 KiB-class logical size
 static bool all_compact_blocks(const mtz_rec *recs, size_t n)
@@ -632,7 +645,7 @@ static int32_t codec_launch_dec(mtz_handle *h, cudaStream_t st, CodecBufs &cb, c
 	MTZ_CU(h, cudaGetLastError());
 	count_launch(h, 3);
 	if (mode != MTZ_MODE_COMPRESS) {
-		int32_t rc = launch_k2(h, st, nullptr, nullptr, cb.dec, n);
+		int32_t rc = launch_k2(h, st, nullptr, nullptr, cb.dec, n, cb.seq_n ? cb.enc : nullptr, cb.seq_n);
 		if (rc != MTZ_OK) return rc;
 	}
 	return MTZ_OK;
@@ -648,7 +661,9 @@ static int32_t codec_launch_enc(mtz_handle *h, cudaStream_t st, CodecBufs &cb, s
 	if (st_k3 == nullptr || ka == nullptr || kb == nullptr) st_k3 = st;
 	if (ka) MTZ_CU(h, cudaEventRecord(ka, st));
 	if (st_k3 != st) MTZ_CU(h, cudaStreamWaitEvent(st_k3, ka, 0));
-	int32_t rc = launch_k3(h, st_k3, nullptr, nullptr, cb.enc, (uint32_t)nrec, compact);
+	int32_t rc = MTZ_OK;
+	if (cb.cert != nullptr) rc = launch_k3c(h, st_k3, cb, (uint32_t)nrec, compact);
+	if (rc == MTZ_OK) rc = launch_k3(h, st_k3, nullptr, nullptr, cb.enc, (uint32_t)nrec, compact, cb.cert);
 	if (rc == MTZ_OK && kb) MTZ_CU(h, cudaEventRecord(kb, st_k3));
 	if (rc == MTZ_OK && st_k3 != st) MTZ_CU(h, cudaStreamWaitEvent(st, kb, 0));
 	return rc;
@@ -669,11 +684,11 @@ static int32_t codec_launch_post(mtz_handle *h, cudaStream_t st, CodecBufs &cb, 
 	RecSums *osums = all_osums ? all_osums + rec_base : cb.osums;
 	const uint32_t n = (uint32_t)nrec, mode = h->cfg.mode;
 	const unsigned tb = 256, gb = (n + tb - 1) / tb;
-	k_layout<<<gb, tb, 0, st>>>(d_recs, n, cb.cr, cb.dec, cb.enc, cb.vals, cb.d_cres, rec_base);
+	k_layout<<<gb, tb, 0, st>>>(d_recs, n, cb.cr, cb.dec, cb.enc, cb.vals, cb.d_cres, rec_base, cb.cert);
 	k_xscan_u64<<<1, XSCAN_THREADS, 0, st>>>(cb.vals, cb.out_offs, n, cb.d_outpos, cb.d_outpos);
 	const unsigned ga = (unsigned)std::min<size_t>((n + 7) / 8, (size_t)h->sm_count * 8);
 	k_assemble<<<ga, ASM_THREADS, 0, st>>>(d_in, d_recs, n, mode, cb.cr, cb.out_offs, cb.enc,
-	    cb.d_logical, cb.d_enc, d_out, orecs);
+	    cb.d_logical, cb.d_enc, d_out, orecs, cb.cert);
 	MTZ_CU(h, cudaGetLastError());
 	// output records of a codec batch are smaller than the logical size: decide by the input's
 	launch_k1_kernel(h, st, d_out, orecs, n, osums, 312u, cb.avg_out_rec);
@@ -1086,6 +1101,7 @@ static int32_t dev_finish_impl(mtz_handle *h, const uint64_t carry_in[4], const 
 		std::lock_guard<std::mutex> g(h->stats_mu);
 		h->stats.lz4_decoded += c.n_dec;
 		h->stats.lz4_encoded += c.n_enc;
+		h->stats.lz4_certified += c.n_cert;
 	}
 	if (out_bytes) *out_bytes = ob;
 	rc = account_result(h, r, h->dv_first, h->dv_nrec, h->dv_in_bytes, ob);
@@ -1238,6 +1254,7 @@ static int32_t harvest(mtz_handle *h, Slot &s)
 		std::lock_guard<std::mutex> g(h->stats_mu);
 		h->stats.lz4_decoded += c.n_dec;
 		h->stats.lz4_encoded += c.n_enc;
+		h->stats.lz4_certified += c.n_cert;
 	}
 	int32_t rc = account_result(h, *s.h_res, s.first_rec, s.nrec, s.bytes, s.out_bytes);
 	if (rc == MTZ_OK && codec && s.nrec > 0 && s.cb.h_ores->end_seen) {
@@ -1481,11 +1498,11 @@ static int32_t lz4_grid(mtz_handle *h, uint32_t njobs, int warps_per_sm)
 // K2 on `st`, which belongs to the CURRENT device (the caller selected it: a slot of the device
 // group, or devs[0] for the exported entry)
 static int32_t launch_k2(mtz_handle *h, cudaStream_t st, const void *d_src, void *d_dst, mtz_job *d_jobs,
-    uint32_t njobs)
+    uint32_t njobs, const mtz_job *seq_jobs, uint32_t *seq_n)
 {
 	if (njobs == 0) return MTZ_OK;
 	k2_lz4_decode<<<lz4_grid(h, njobs, lz4_persistent() ? 64 : 0), LZ4_THREADS, 0, st>>>((const uint8_t *)d_src,
-	    (uint8_t *)d_dst, d_jobs, njobs);
+	    (uint8_t *)d_dst, d_jobs, njobs, seq_jobs, seq_n);
 	MTZ_CU(h, cudaGetLastError());
 	count_launch(h, 1);
 	return MTZ_OK;
@@ -1498,7 +1515,7 @@ int32_t mtz_k_lz4_decode(mtz_handle *h, const void *d_src, void *d_dst, mtz_job 
 	if (njobs == 0) return MTZ_OK;
 	MTZ_CU(h, cudaSetDevice(h->device));
 	cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : h->st;
-	return launch_k2(h, st, d_src, d_dst, d_jobs, njobs);
+	return launch_k2(h, st, d_src, d_dst, d_jobs, njobs, nullptr, nullptr);
 }
 
 // Function attributes are per DEVICE (and per context): set them for the current device of
@@ -1510,6 +1527,10 @@ static int32_t k3_set_attributes(mtz_handle *h)
 	MTZ_CU(h, cudaFuncSetAttribute(k3_lz4_encode<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
 	    (int)((size_t)K3_WARPS * LZ4_TAB_COMPACT_WORDS * 4)));
 	MTZ_CU(h, cudaFuncSetAttribute(k3_lz4_encode<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+	    (int)((size_t)K3_WARPS * LZ4_TAB_BIG_WORDS * 4)));
+	MTZ_CU(h, cudaFuncSetAttribute(k3c_lz4_certify<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+	    (int)((size_t)K3_WARPS * LZ4_TAB_COMPACT_WORDS * 4)));
+	MTZ_CU(h, cudaFuncSetAttribute(k3c_lz4_certify<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
 	    (int)((size_t)K3_WARPS * LZ4_TAB_BIG_WORDS * 4)));
 	// all of the unified L1/shared array as shared memory: K3 is bound by records in
 	// flight (24 tables of 8.5 KiB per SM), measured 62 vs 46 GiB/s at a 75 % carve-out
@@ -1523,7 +1544,7 @@ static int32_t k3_set_attributes(mtz_handle *h)
 
 // compact = every block is 64 KiB+11 .. 128 KiB: 8.5 KiB tables, more warps per SM
 static int32_t launch_k3(mtz_handle *h, cudaStream_t st, const void *d_src, void *d_dst,
-    mtz_job *d_jobs, uint32_t njobs, bool compact)
+    mtz_job *d_jobs, uint32_t njobs, bool compact, const uint32_t *skip)
 {
 	const size_t tabw = compact ? LZ4_TAB_COMPACT_WORDS : LZ4_TAB_BIG_WORDS;
 	const size_t smem = (size_t)K3_WARPS * tabw * sizeof(uint32_t);
@@ -1536,9 +1557,25 @@ static int32_t launch_k3(mtz_handle *h, cudaStream_t st, const void *d_src, void
 	const uint32_t need = (njobs + K3_WARPS - 1) / K3_WARPS;
 	const int grid = (int)std::max(1u, lz4_persistent() ? std::min(need, (uint32_t)h->sm_count * (uint32_t)blocks_per_sm) : need);
 	if (compact)
-		k3_lz4_encode<true><<<grid, K3_THREADS, smem, st>>>((const uint8_t *)d_src, (uint8_t *)d_dst, d_jobs, njobs);
+		k3_lz4_encode<true><<<grid, K3_THREADS, smem, st>>>((const uint8_t *)d_src, (uint8_t *)d_dst, d_jobs, njobs, skip);
 	else
-		k3_lz4_encode<false><<<grid, K3_THREADS, smem, st>>>((const uint8_t *)d_src, (uint8_t *)d_dst, d_jobs, njobs);
+		k3_lz4_encode<false><<<grid, K3_THREADS, smem, st>>>((const uint8_t *)d_src, (uint8_t *)d_dst, d_jobs, njobs, skip);
+	MTZ_CU(h, cudaGetLastError());
+	count_launch(h, 1);
+	return MTZ_OK;
+}
+
+// K3c over the (sub-)batch: verdicts into cb.cert, which K3 (skip) and the assembler then read
+static int32_t launch_k3c(mtz_handle *h, cudaStream_t st, CodecBufs &cb, uint32_t njobs, bool compact)
+{
+	if (njobs == 0) return MTZ_OK;
+	const size_t tabw = compact ? LZ4_TAB_COMPACT_WORDS : LZ4_TAB_BIG_WORDS;
+	const size_t smem = (size_t)K3_WARPS * tabw * sizeof(uint32_t);
+	const int grid = (int)((njobs + K3_WARPS - 1) / K3_WARPS);
+	if (compact)
+		k3c_lz4_certify<true><<<grid, K3_THREADS, smem, st>>>(cb.dec, cb.enc, cb.seq_n, cb.cert, njobs);
+	else
+		k3c_lz4_certify<false><<<grid, K3_THREADS, smem, st>>>(cb.dec, cb.enc, cb.seq_n, cb.cert, njobs);
 	MTZ_CU(h, cudaGetLastError());
 	count_launch(h, 1);
 	return MTZ_OK;

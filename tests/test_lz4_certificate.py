@@ -1,0 +1,158 @@
+"""RECOMPRESS's certificate (kernels_lz4.cuh warp_lz4_certify, K3c): a record whose incoming LZ4
+block is PROVEN to be what the declared encoder (oracle/lz4_zfs.c) emits for the decoded bytes is
+passed through; every other record is re-encoded by the serial matcher.  Either way the output must
+be the oracle's RECOMPRESS, bit for bit.  The dangerous direction is a false certificate (a block
+that is valid LZ4, decodes to the same bytes, but is not the encoder's parse): tests/lz4_frames.py
+makes such blocks by changing one parse decision at a time -- a split match, a match one byte
+shorter or starting one byte later, another valid offset, a match turned into literals, a closing
+token with a stray low nibble -- and the counts must show that none of them was certified while
+every untouched record was.  CPU: the whole library on the SIMT emulator; `-m gpu`: the product."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import lz4_frames as F
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def emul_library(emul_so):
+    from manatee_b200 import _native as N
+    saved = (N.SO_PATH, N._lib)
+    N.SO_PATH, N._lib = emul_so, None
+    try:
+        yield N.lib()
+    finally:
+        N.SO_PATH, N._lib = saved
+
+
+def _canonical(oracle, n, recsize, kind=None):
+    raw = oracle.synth_stream(n, recsize, oracle.PAYLOAD_PGPAGE if kind is None else kind)
+    rc, c, _ = oracle.stream_compress_plain(raw)
+    assert rc == 0
+    return np.ascontiguousarray(c), raw.size
+
+
+def _recompress(src, cap, **kw):
+    from manatee_b200 import GpuSnapshotStage
+    with GpuSnapshotStage("recompress", **kw) as g:
+        out = np.empty(cap, dtype=np.uint8)
+        n = g.process_host(src, out)
+        return out[:n].copy(), g.stats(), g.end_checksum()
+
+
+def _check(oracle, src, cap, want_certified, **kw):
+    rc, want, st = oracle.stream_recompress(src)
+    assert rc == 0
+    got, gs, end = _recompress(src, cap, **kw)
+    assert np.array_equal(got, want)
+    assert end == st.end_cksum.tuple()
+    if want_certified is not None:
+        assert gs["lz4_certified"] == want_certified, gs
+    return gs
+
+
+def _mutated(oracle, c, kinds, rng, every=2):
+    blocks = F.blocks_of(oracle, c)
+    changes = {}
+    for i, (w, blk) in enumerate(blocks):
+        if i % every:
+            continue
+        kind = kinds[int(rng.integers(len(kinds)))]
+        nb = F.mutate(blk, kind, rng)
+        if nb is not None and nb != blk:
+            assert F.decode(*F.parse(nb)) == F.decode(*F.parse(blk))
+            changes[w] = nb
+    return F.splice(oracle, c, changes), len(blocks) - len(changes), len(changes)
+
+
+def _all_cases(oracle, run):
+    # every record of an encoder-made stream is certified, in all three table flavours
+    for n, recsize in ((5, 131072), (12, 16384), (4, 65536), (3, 262144)):
+        c, cap = _canonical(oracle, n, recsize)
+        gs = run(oracle, c, cap + (1 << 20), n)
+        assert gs["lz4_encoded"] == n
+    # one parse decision changed in every second record
+    rng = np.random.default_rng(20260921)
+    for kind in F.MUTATIONS:
+        for n, recsize in ((6, 131072), (10, 16384)):
+            c, cap = _canonical(oracle, n, recsize)
+            m, untouched, touched = _mutated(oracle, c, (kind,), rng)
+            assert touched > 0, kind
+            run(oracle, m, cap + (1 << 20), untouched)
+
+
+def test_certificate_on_the_emulated_library(emul_library, oracle):
+    _all_cases(oracle, _check)
+
+
+@pytest.mark.parametrize("seed", [1, 2])
+def test_certificate_fuzz_on_the_emulated_library(emul_library, oracle, seed):
+    """random parse changes, several per block, small records so that thousands of decisions are covered"""
+    rng = np.random.default_rng(seed)
+    c, cap = _canonical(oracle, 48, 8192)
+    blocks = F.blocks_of(oracle, c)
+    changes = {}
+    for w, blk in blocks:
+        if rng.integers(4) == 0:
+            continue
+        nb = blk
+        for _ in range(1 + int(rng.integers(3))):
+            t = F.mutate(nb, F.MUTATIONS[int(rng.integers(len(F.MUTATIONS)))], rng)
+            nb = t if t is not None else nb
+        if nb != blk:
+            changes[w] = nb
+    m = F.splice(oracle, c, changes)
+    _check(oracle, m, cap + (1 << 20), len(blocks) - len(changes), batch_bytes=64 << 10)
+
+
+def test_incompressible_and_foreign_records_take_the_encoder(emul_library, oracle):
+    """records stored raw have no block to certify; a literals-only block is valid LZ4 but not what
+    the encoder emits for compressible bytes"""
+    raw = oracle.synth_stream(3, 131072, oracle.PAYLOAD_PCG)
+    rc, c, _ = oracle.stream_compress_plain(raw)
+    _check(oracle, np.ascontiguousarray(c), raw.size + (1 << 20), 0)
+    c, cap = _canonical(oracle, 4, 16384)
+    blocks = F.blocks_of(oracle, c)
+    w, blk = blocks[1]
+    data = F.decode(*F.parse(blk))
+    m = F.splice(oracle, c, {w: F.emit([], data)})
+    # (the literals-only frame is bigger than the record: the header keeps drr_compressiontype lz4)
+    _check(oracle, m, cap + (1 << 20), len(blocks) - 1)
+
+
+def test_certificate_off_gives_the_same_bytes(emul_so, oracle, tmp_path):
+    """MTZ_CERTIFY=0: every record re-encoded, same output, nothing certified"""
+    c, cap = _canonical(oracle, 6, 16384)
+    rc, want, st = oracle.stream_recompress(c)
+    p = tmp_path / "in.bin"
+    c.tofile(p)
+    code = ("import sys, numpy as np; sys.path.insert(0, %r); from manatee_b200 import _native as N; "
+            "N.SO_PATH, N._lib = %r, None; from manatee_b200 import GpuSnapshotStage; "
+            "src = np.fromfile(%r, dtype=np.uint8); out = np.empty(%d, dtype=np.uint8); "
+            "g = GpuSnapshotStage('recompress'); n = g.process_host(src, out); s = g.stats(); g.close(); "
+            "out[:n].tofile(%r); print(s['lz4_certified'], s['lz4_encoded'])"
+            % (ROOT, emul_so, str(p), cap + (1 << 20), str(tmp_path / "out.bin")))
+    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, MTZ_CERTIFY="0"),
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert r.stdout.split() == ["0", "6"]
+    assert np.array_equal(np.fromfile(tmp_path / "out.bin", dtype=np.uint8), want)
+
+
+@pytest.mark.gpu
+def test_certificate_on_the_gpu(oracle):
+    _all_cases(oracle, _check)
+
+
+@pytest.mark.gpu
+def test_certificate_fuzz_on_the_gpu(oracle):
+    rng = np.random.default_rng(7)
+    c, cap = _canonical(oracle, 256, 131072)
+    m, untouched, touched = _mutated(oracle, c, F.MUTATIONS, rng, every=3)
+    assert touched > 50
+    _check(oracle, m, cap + (1 << 20), untouched, batch_bytes=8 << 20)

@@ -27,7 +27,7 @@ for mode in modes:
             ob, _, _ = g.dev_finish()
             torch.cuda.synchronize(); dt = time.time() - t
             stt = g.stats()
-            print("%s resident: %.1f ms  in %.2f GiB/s  logical %.2f GiB/s  out=%d  codec_ms=%.1f k3_ms=%.2f (%d launches) k1_ms=%.2f" % (mode, dt * 1e3, src.size / 2**30 / dt, s.size / 2**30 / dt, ob, stt["codec_ms"], stt["k3_ms"], stt["k3_launches"], stt["k1_ms"]))
+            print("%s resident: %.1f ms  in %.2f GiB/s  logical %.2f GiB/s  out=%d  codec_ms=%.1f k3_ms=%.2f (%d launches) k1_ms=%.2f certified=%d/%d" % (mode, dt * 1e3, src.size / 2**30 / dt, s.size / 2**30 / dt, ob, stt["codec_ms"], stt["k3_ms"], stt["k3_launches"], stt["k1_ms"], stt["lz4_certified"], stt["lz4_encoded"]))
         want = c if mode != "decompress" else None
         if mode in ("recompress", "compress"):
             got = d_out[:ob].cpu().numpy()
