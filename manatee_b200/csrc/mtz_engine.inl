@@ -109,7 +109,49 @@ struct Engine {
 	bool need_bcast = false;       // some peer's egress GPU can differ from the producing GPU
 	std::thread thr;
 	int efd = -1;
+	// debugging aid (MTZ_WATCHDOG_MS): the host call the engine thread is inside of, if any
+	std::atomic<const char *> where { "idle" };
+	std::atomic<uint64_t> loops { 0 };
 };
+
+struct Where {               // RAII marker around calls that can block inside the driver / NCCL
+	Engine *e; const char *prev;
+	Where(Engine *e_, const char *w) : e(e_), prev(e_->where.exchange(w)) {}
+	~Where() { e->where.store(prev); }
+};
+
+// MTZ_WATCHDOG_MS=<n>: a consumer that has waited n ms without a byte prints what the engine holds
+// (racy read of engine-private state: a debugging aid, never on by default)
+static void engine_dump(Engine *e, const char *who, int peer)
+{
+	mtz_handle *h = e->h;
+	fprintf(stderr, "[mtz watchdog] %s(peer %d) starved: engine in '%s', loops %llu, inflight %zu, next_seq %llu, "
+	    "retired %llu, fan_seq {%lld,%lld}, in_head %llu in_tail %llu parse_pos %llu flushed %d eof %d failed %d\n",
+	    who, peer, e->where.load(), (unsigned long long)e->loops.load(), e->inflight.size(),
+	    (unsigned long long)e->next_seq, (unsigned long long)e->retired_seq, (long long)e->fan_seq[0],
+	    (long long)e->fan_seq[1], (unsigned long long)e->in_head, (unsigned long long)e->in_tail,
+	    (unsigned long long)e->parse_pos, (int)e->flushed, (int)e->eof, (int)h->failed.load());
+	for (const InFlight &f : e->inflight) {
+		const Slot &s = h->slots[(size_t)f.slot];
+		cudaSetDevice(h->devs[(size_t)s.di].device);
+		fprintf(stderr, "[mtz watchdog]   batch %llu slot %d dev %d harvested %d bcast %d n_out %zu egress_left %d "
+		    "ev_h2d %d ev_done %d\n", (unsigned long long)f.seq, f.slot, s.di, (int)f.harvested, (int)f.bcast,
+		    f.n_out, s.egress_left, (int)cudaEventQuery(s.ev_h2d), (int)cudaEventQuery(s.ev_done));
+	}
+	for (int p = 0; p < MTZ_MAX_PEERS; p++) {
+		const Peer &pe = e->peers[p];
+		if (!pe.attached) continue;
+		int first = -1;
+		if (!pe.pend.empty()) {
+			cudaSetDevice(h->devs[(size_t)pe.pend.front().di].device);
+			first = (int)cudaEventQuery(pe.pend.front().ev);
+		}
+		fprintf(stderr, "[mtz watchdog]   peer %d egress dev %d cur_seq %llu cur_off %zu issue %llu head %llu pos %llu "
+		    "pending pieces %zu (first: query %d)\n", p, pe.egress_di, (unsigned long long)pe.cur_seq, pe.cur_off,
+		    (unsigned long long)pe.issue, (unsigned long long)pe.head, (unsigned long long)pe.pos, pe.pend.size(), first);
+	}
+	fflush(stderr);
+}
 
 static void signal_efd(Engine *e)
 {
@@ -302,6 +344,7 @@ static int32_t engine_broadcast(Engine *e, InFlight &f)
 	Slot &s = h->slots[(size_t)f.slot];
 	const int k = (int)(f.seq & 1u);
 	const uint8_t *src = is_codec_mode(h->cfg.mode) ? s.d_out : s.d_in;
+	Where w_(e, "ncclBroadcast group");
 	MTZ_NCCL(h, ncclGroupStart());
 	for (size_t d = 0; d < h->devs.size(); d++) {
 		DevCtx &dc = h->devs[d];
@@ -378,6 +421,7 @@ static int32_t engine_egress(Engine *e, const uint64_t *pos, bool *progress)
 			Piece pc;
 			int32_t rc = take_event(h, dc, &pc.ev);
 			if (rc != MTZ_OK) return rc;
+			Where w_(e, "egress D2H");
 			MTZ_CU(h, cudaSetDevice(dc.device));
 			MTZ_CU(h, cudaMemcpyAsync(pe.buf + oo, src + pe.cur_off, c, cudaMemcpyDeviceToHost, dc.fan_st));
 			MTZ_CU(h, cudaEventRecord(pc.ev, dc.fan_st));
@@ -414,6 +458,7 @@ static void engine_main(Engine *e)
 
 		bool progress = false;
 		int32_t rc = MTZ_OK;
+		e->loops.fetch_add(1);
 		uint64_t new_out_head = 0; bool have_out_head = false;
 		uint64_t new_heads[MTZ_MAX_PEERS]; bool head_moved[MTZ_MAX_PEERS];
 		for (int p = 0; p < MTZ_MAX_PEERS; p++) { new_heads[p] = 0; head_moved[p] = false; }
@@ -483,6 +528,7 @@ static void engine_main(Engine *e)
 		if (rc == MTZ_OK && e->inflight.size() < NS) {
 			const uint64_t before = e->parse_pos;
 			bool cut = false;
+			Where w_(e, "parse/submit");
 			rc = engine_parse(e, head, &cut);
 			if (rc == MTZ_OK) {
 				if (e->parse_pos != before) progress = true;
@@ -794,8 +840,13 @@ int32_t mtz_read_peer(mtz_handle *h, int32_t peer_id, void *buf, size_t cap, siz
 		if (rc != MTZ_EAGAIN || !block) return rc;
 		std::unique_lock<std::mutex> lk(e->mu);
 		Peer &pe = e->peers[peer_id];
-		while ((e->own_out ? pe.head : e->out_head) == pe.pos && !e->eof && h->failed.load() == 0 && !e->stop)
+		static const long wd_ms = [] { const char *w = getenv("MTZ_WATCHDOG_MS"); return w ? atol(w) : 0L; }();
+		long waited = 0;
+		while ((e->own_out ? pe.head : e->out_head) == pe.pos && !e->eof && h->failed.load() == 0 && !e->stop) {
 			e->cv_cons.wait_for(lk, std::chrono::milliseconds(200));
+			waited += 200;
+			if (wd_ms > 0 && waited >= wd_ms) { engine_dump(e, "mtz_read_peer", peer_id); waited = 0; }
+		}
 		if (h->failed.load() != 0) return h->failed.load();
 	}
 }
