@@ -57,6 +57,11 @@ extern "C" {
                                   * sums; verdict comes from mtz_dev_aggregate/mtz_dev_finish
                                   * once the preceding shards' checksum is known */
 
+#define MTZ_FLAG_REENCODE_ALL 2u /* RECOMPRESS: run the encoder on every record.  Default: a record whose
+                                  * incoming LZ4 block is PROVEN to be the encoder's own output for the
+                                  * decoded bytes is passed through (mtz_stats.lz4_certified counts them);
+                                  * the output bytes are the same either way */
+
 typedef struct mtz_handle mtz_handle;
 
 #define MTZ_MAX_DEVICES 16

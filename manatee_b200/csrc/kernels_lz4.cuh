@@ -706,22 +706,59 @@ __device__ __forceinline__ bool warp_lz4_certify(const uint8_t *__restrict__ src
 	uint32_t p_w = 0, p_v = 1;            // deferred MISS check of the previous round: bad iff equal
 	uint32_t a = 0;                        // anchor: end of the previous match
 	bool follow_hit = false;               // the probe at `a` delivered sequence k (no search)
-	uint64_t s_next = (ns > 0u) ? seqs[0] : 0ull;
-	bool finished = false;
-	for (uint32_t k = 0; k <= ns && !finished; k++) {
+	uint32_t k = 0;
+	for (;;) {
 		const bool have = k < ns;
-		const uint64_t s = s_next;
-		s_next = (k + 1u < ns) ? seqs[k + 1u] : 0ull;
+		const uint64_t s = have ? seqs[k] : 0ull;
 		const uint32_t m = SEQ_M(s), o = SEQ_O(s), e = m + SEQ_L(s);
-		const bool nf = (k + 1u < ns) && (SEQ_M(s_next) == e);     // hypothesis: k+1 follows on at e
-		const uint32_t o_next = SEQ_O(s_next);
-		const bool post_ok = have && e <= mflimit;                   // the encoder inserts e-2 and probes e
-		bool post_done = false, probe_hit = false;
+		// After a match ending at e the encoder inserts e-2 and probes e; when the probe hits, the
+		// next sequence follows on at once and does the same.  A whole run of such "post" pairs is
+		// replayed in ONE round (pair t on lanes L0+2t, L0+2t+1) under the hypothesis that the
+		// parse tells the truth about which probes hit; the first probe that disagrees ends the run.
+		// CHAIN_SETUP: this lane's operation in the run that starts with sequence k on lane L0.
+		uint32_t c_xx = 0, c_e = 0, c_onext = 0;
+		bool c_part = false, c_query = false, c_nf = false;
+		int c_T = 0;
+#define CHAIN_SETUP(L0)                                                                              \
+		{                                                                                            \
+			const int rl_ = lane - (L0);                                                             \
+			const bool in_ = rl_ >= 0;                                                               \
+			const uint32_t t_ = in_ ? (uint32_t)rl_ >> 1 : 0u;                                       \
+			const uint32_t kk_ = k + t_;                                                             \
+			const bool ex_ = in_ && kk_ < ns;                                                        \
+			const uint64_t s0_ = ex_ ? seqs[kk_] : 0ull;                                             \
+			const uint64_t sp_ = (ex_ && t_ > 0u) ? seqs[kk_ - 1u] : 0ull;                           \
+			const uint64_t sn_ = (ex_ && kk_ + 1u < ns) ? seqs[kk_ + 1u] : 0ull;                     \
+			c_e = SEQ_M(s0_) + SEQ_L(s0_);                                                           \
+			const bool fol_ = (t_ == 0u) || (SEQ_M(s0_) == SEQ_M(sp_) + SEQ_L(sp_));                 \
+			const bool good_ = ex_ && fol_ && c_e <= mflimit;                                        \
+			const uint32_t bm_ = __ballot_sync(0xffffffffu, in_ && (rl_ & 1) && !good_);             \
+			c_T = bm_ ? ((__ffs((int)bm_) - 1 - (L0)) >> 1) : ((32 - (L0)) >> 1);                    \
+			c_part = in_ && (int)t_ < c_T;                                                           \
+			c_query = c_part && (rl_ & 1);                                                           \
+			c_xx = (rl_ & 1) ? c_e : c_e - 2u;                                                       \
+			c_nf = (kk_ + 1u < ns) && (SEQ_M(sn_) == c_e);                                           \
+			c_onext = SEQ_O(sn_);                                                                    \
+		}
+		// CHAIN_FINISH: with `pred` of the round: how many pairs stand, where the encoder is after them
+		int c_upto = 0, c_used = 0;
+		bool c_hitl = false;
+#define CHAIN_FINISH(L0, pred)                                                                       \
+		{                                                                                            \
+			c_hitl = c_query && c_nf && ((pred) + c_onext == c_xx);                                  \
+			const uint32_t mis_ = __ballot_sync(0xffffffffu, c_query && c_nf && !c_hitl);            \
+			const int last_ = (L0) + 2 * c_T - 1;                                                    \
+			c_upto = mis_ ? (__ffs((int)mis_) - 1) : last_;                                          \
+			c_used = ((c_upto - (L0)) >> 1) + 1;                                                     \
+			follow_hit = __shfl_sync(0xffffffffu, (int)c_hitl, c_upto) != 0;                         \
+			a = __shfl_sync(0xffffffffu, c_e, c_upto);                                               \
+		}
 
+		bool post_done = false;
 		if (!(have && follow_hit)) {
 			const uint32_t start = a + 1u;
 			const uint32_t target = have ? (m > start ? m : start) : 0xffffffffu;
-			bool found = false;
+			bool found = false, finished = false;
 			uint32_t a0 = 0;
 			int q1l = 32;
 			// phase 1: the attempts up to and including the first one at or beyond m
@@ -737,29 +774,33 @@ __device__ __forceinline__ bool warp_lz4_certify(const uint8_t *__restrict__ src
 				const int I = inval ? (__ffs((int)inval) - 1) : 32;
 				if (have && I <= q1 && I < 32) return false;            // the encoder runs dry before the hit
 				if (q1 < 32 && __shfl_sync(0xffffffffu, x, q1) + LZ4_MINMATCH > e) return false;
-				// post operations ride in the same round when the hypothesis has room for them
-				const bool ride = (q1 < 30) && post_ok;
-				bool part = valid && lane <= q1 && lane < I;
-				uint32_t xx = x;
+				// the post run rides in the same round when the hypothesis leaves lanes for it
+				bool part = valid && lane <= q1;
 				bool query = part;
-				if (ride && lane == q1 + 1) { part = true; query = false; xx = e - 2u; }
-				if (ride && lane == q1 + 2) { part = true; query = true; xx = e; }
+				uint32_t xx = x;
+				bool ride = false;
+				if (q1 < 30) {
+					CHAIN_SETUP(q1 + 1)
+					ride = c_T > 0;
+					if (ride && c_part) { part = true; query = c_query; xx = c_xx; }
+				}
 				const uint32_t v = part ? LDS32(xx) : 0u;
 				const uint32_t h = part ? ((v * 2654435761u) >> (32 - LOG)) : (0xffffffffu - (uint32_t)lane);
 				const uint32_t pred = tab_round_query(tab, rd, part, h, xx, lane);
 				const bool hit1 = (lane == q1) && part && (pred + o == xx);
 				found = __any_sync(0xffffffffu, hit1);
-				const int upto = (q1 < 32) ? ((found && ride) ? q1 + 2 : q1) : 31;
-				tab_round_commit(tab, rd, part, h, xx, upto, lane);
-				bool probe_lane_hit = false;
+				int upto = (q1 < 32) ? q1 : 31;
+				bool ridehit = false;
 				if (found && ride) {
-					probe_lane_hit = (lane == q1 + 2) && nf && (pred + o_next == xx);
-					probe_hit = __any_sync(0xffffffffu, probe_lane_hit);
+					CHAIN_FINISH(q1 + 1, pred)
+					upto = c_upto; ridehit = c_hitl;
+					k += (uint32_t)c_used;
 					post_done = true;
 				}
+				tab_round_commit(tab, rd, part, h, xx, upto, lane);
 				// deferred MISS checks: every committed query that is not a hypothesised-and-delivered hit
 				bad = bad || (p_w == p_v);
-				const bool chk = part && query && lane <= upto && !hit1 && !probe_lane_hit &&
+				const bool chk = part && query && lane <= upto && !hit1 && !ridehit &&
 				    (!DIST || pred + LZ4_MAXDIST >= xx);
 				p_w = chk ? LDS32(pred) : 0u;
 				p_v = chk ? v : 1u;
@@ -795,28 +836,28 @@ __device__ __forceinline__ bool warp_lz4_certify(const uint8_t *__restrict__ src
 			}
 		}
 		if (!have) break;
-		if (!post_ok) {
+		if (post_done) continue;                                        // (k, a, follow_hit already advanced)
+		if (e > mflimit) {
 			// the match ends beyond mflimit: the encoder emits its last literals, so this is the last match
 			if (k + 1u != ns) return false;
 			break;
 		}
-		if (!post_done) {
-			const bool part = lane < 2;
-			const uint32_t xx = (lane == 0) ? e - 2u : e;
-			const uint32_t v = part ? LDS32(xx) : 0u;
-			const uint32_t h = part ? ((v * 2654435761u) >> (32 - LOG)) : (0xffffffffu - (uint32_t)lane);
-			const uint32_t pred = tab_round_query(tab, rd, part, h, xx, lane);
-			tab_round_commit(tab, rd, part, h, xx, 1, lane);
-			const bool plh = (lane == 1) && nf && (pred + o_next == xx);
-			probe_hit = __any_sync(0xffffffffu, plh);
+		{
+			CHAIN_SETUP(0)
+			const uint32_t v = c_part ? LDS32(c_xx) : 0u;
+			const uint32_t h = c_part ? ((v * 2654435761u) >> (32 - LOG)) : (0xffffffffu - (uint32_t)lane);
+			const uint32_t pred = tab_round_query(tab, rd, c_part, h, c_xx, lane);
+			CHAIN_FINISH(0, pred)
+			tab_round_commit(tab, rd, c_part, h, c_xx, c_upto, lane);
+			k += (uint32_t)c_used;
 			bad = bad || (p_w == p_v);
-			const bool chk = (lane == 1) && !plh && (!DIST || pred + LZ4_MAXDIST >= xx);
+			const bool chk = c_query && lane <= c_upto && !c_hitl && (!DIST || pred + LZ4_MAXDIST >= c_xx);
 			p_w = chk ? LDS32(pred) : 0u;
 			p_v = chk ? v : 1u;
 		}
-		follow_hit = probe_hit;
-		a = e;
 	}
+#undef CHAIN_SETUP
+#undef CHAIN_FINISH
 	bad = bad || (p_w == p_v);
 #undef LDS32
 #undef SEQ_M

@@ -542,11 +542,12 @@ static bool is_codec_mode(uint32_t m)
 }
 
 // RECOMPRESS proves, where it can, that a record's input frame already is what the encoder would
-// emit and passes it through (K3c, kernels_lz4.cuh); MTZ_CERTIFY=0 re-encodes every record.
+// emit and passes it through (K3c, kernels_lz4.cuh); MTZ_FLAG_REENCODE_ALL (or MTZ_CERTIFY=0 in the
+// environment) re-encodes every record.
 static bool certify_on(const mtz_handle *h)
 {
 	static const bool on = [] { const char *e = getenv("MTZ_CERTIFY"); return e == nullptr || atoi(e) != 0; }();
-	return on && h->cfg.mode == MTZ_MODE_RECOMPRESS;
+	return on && h->cfg.mode == MTZ_MODE_RECOMPRESS && !(h->cfg.flags & MTZ_FLAG_REENCODE_ALL);
 }
 
 static int32_t codec_alloc(mtz_handle *h, CodecBufs &cb, size_t rec_cap, size_t scratch_cap)

@@ -71,11 +71,16 @@ def _mutated(oracle, c, kinds, rng, every=2):
 
 
 def _all_cases(oracle, run):
+    from manatee_b200 import _native as N
     # every record of an encoder-made stream is certified, in all three table flavours
     for n, recsize in ((5, 131072), (12, 16384), (4, 65536), (3, 262144)):
         c, cap = _canonical(oracle, n, recsize)
         gs = run(oracle, c, cap + (1 << 20), n)
         assert gs["lz4_encoded"] == n
+    # MTZ_FLAG_REENCODE_ALL: nothing certified, same bytes
+    c, cap = _canonical(oracle, 6, 131072)
+    gs = run(oracle, c, cap + (1 << 20), 0, flags=N.FLAG_REENCODE_ALL)
+    assert gs["lz4_encoded"] == 6
     # one parse decision changed in every second record
     rng = np.random.default_rng(20260921)
     for kind in F.MUTATIONS:
