@@ -306,6 +306,7 @@ static napi_value Stats(napi_env env, napi_callback_info info)
 	PUT("bytesIn", bytes_in); PUT("bytesOut", bytes_out); PUT("records", records);
 	PUT("writeRecords", write_records); PUT("lz4Decoded", lz4_decoded); PUT("lz4Encoded", lz4_encoded);
 	PUT("batches", batches); PUT("gpuMs", gpu_ms); PUT("kernelLaunches", kernel_launches);
+	PUT("lz4Certified", lz4_certified);
 #undef PUT
 	return o;
 }

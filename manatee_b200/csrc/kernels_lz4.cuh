@@ -707,16 +707,33 @@ __device__ __forceinline__ bool warp_lz4_certify(const uint8_t *__restrict__ src
 	uint32_t a = 0;                        // anchor: end of the previous match
 	bool follow_hit = false;               // the probe at `a` delivered sequence k (no search)
 	uint32_t k = 0;
+	// Nothing the chain waits for comes from global memory: lane L keeps sequence kw+L of the parse
+	// (w_s) with the two source words its post pair will hash (w_vm2 at e-2, w_ve at e), refilled 16
+	// sequences ahead of use, and the first round of the next search is requested one step early
+	// from where this step's hypothesis says it will start (pf_start / pf_v).
+	uint32_t kw = 0;
+	uint64_t w_s = 0; uint32_t w_vm2 = 0, w_ve = 0;
+	uint32_t pf_start = 0xffffffffu, pf_v = 0;
+	bool w_init = false;
 	for (;;) {
 		const bool have = k < ns;
-		const uint64_t s = have ? seqs[k] : 0ull;
+		if (have && (!w_init || k - kw > 15u)) {
+			kw = k; w_init = true;
+			const uint32_t j = kw + (uint32_t)lane;
+			w_s = (j < ns) ? seqs[j] : 0ull;
+			const uint32_t we = SEQ_M(w_s) + SEQ_L(w_s);
+			const bool wok = (j < ns) && we <= mflimit && we >= 2u;
+			w_vm2 = wok ? LDS32(we - 2u) : 0u;
+			w_ve = wok ? LDS32(we) : 0u;
+		}
+		const uint64_t s = have ? __shfl_sync(0xffffffffu, w_s, (int)(k - kw)) : 0ull;
 		const uint32_t m = SEQ_M(s), o = SEQ_O(s), e = m + SEQ_L(s);
 		// After a match ending at e the encoder inserts e-2 and probes e; when the probe hits, the
 		// next sequence follows on at once and does the same.  A whole run of such "post" pairs is
 		// replayed in ONE round (pair t on lanes L0+2t, L0+2t+1) under the hypothesis that the
 		// parse tells the truth about which probes hit; the first probe that disagrees ends the run.
 		// CHAIN_SETUP: this lane's operation in the run that starts with sequence k on lane L0.
-		uint32_t c_xx = 0, c_e = 0, c_onext = 0;
+		uint32_t c_xx = 0, c_e = 0, c_onext = 0, c_v = 0;
 		bool c_part = false, c_query = false, c_nf = false;
 		int c_T = 0;
 #define CHAIN_SETUP(L0)                                                                              \
@@ -725,10 +742,14 @@ __device__ __forceinline__ bool warp_lz4_certify(const uint8_t *__restrict__ src
 			const bool in_ = rl_ >= 0;                                                               \
 			const uint32_t t_ = in_ ? (uint32_t)rl_ >> 1 : 0u;                                       \
 			const uint32_t kk_ = k + t_;                                                             \
-			const bool ex_ = in_ && kk_ < ns;                                                        \
-			const uint64_t s0_ = ex_ ? seqs[kk_] : 0ull;                                             \
-			const uint64_t sp_ = (ex_ && t_ > 0u) ? seqs[kk_ - 1u] : 0ull;                           \
-			const uint64_t sn_ = (ex_ && kk_ + 1u < ns) ? seqs[kk_ + 1u] : 0ull;                     \
+			const uint32_t ix_ = kk_ - kw;                  /* window lane of the pair's sequence */ \
+			const bool ex_ = in_ && kk_ < ns && ix_ <= 30u;                                          \
+			const int sl_ = ex_ ? (int)ix_ : 0;                                                      \
+			const uint64_t s0_ = __shfl_sync(0xffffffffu, w_s, sl_);                                 \
+			const uint64_t sp_ = __shfl_sync(0xffffffffu, w_s, sl_ > 0 ? sl_ - 1 : 0);               \
+			const uint64_t sn_ = __shfl_sync(0xffffffffu, w_s, sl_ + 1);                             \
+			const uint32_t vm_ = __shfl_sync(0xffffffffu, w_vm2, sl_);                               \
+			const uint32_t ve_ = __shfl_sync(0xffffffffu, w_ve, sl_);                                \
 			c_e = SEQ_M(s0_) + SEQ_L(s0_);                                                           \
 			const bool fol_ = (t_ == 0u) || (SEQ_M(s0_) == SEQ_M(sp_) + SEQ_L(sp_));                 \
 			const bool good_ = ex_ && fol_ && c_e <= mflimit;                                        \
@@ -737,8 +758,15 @@ __device__ __forceinline__ bool warp_lz4_certify(const uint8_t *__restrict__ src
 			c_part = in_ && (int)t_ < c_T;                                                           \
 			c_query = c_part && (rl_ & 1);                                                           \
 			c_xx = (rl_ & 1) ? c_e : c_e - 2u;                                                       \
+			c_v = (rl_ & 1) ? ve_ : vm_;                                                             \
 			c_nf = (kk_ + 1u < ns) && (SEQ_M(sn_) == c_e);                                           \
 			c_onext = SEQ_O(sn_);                                                                    \
+			/* the search that follows this run, if the hypothesis holds, starts here */            \
+			if (c_T > 0) {                                                                           \
+				pf_start = __shfl_sync(0xffffffffu, c_e, (L0) + 2 * c_T - 1) + 1u;                   \
+				const uint32_t px_ = pf_start + (uint32_t)lane;                                      \
+				pf_v = (px_ + 4u <= iend) ? LDS32(px_) : 0u;                                         \
+			}                                                                                        \
 		}
 		// CHAIN_FINISH: with `pred` of the round: how many pairs stand, where the encoder is after them
 		int c_upto = 0, c_used = 0;
@@ -757,6 +785,7 @@ __device__ __forceinline__ bool warp_lz4_certify(const uint8_t *__restrict__ src
 		bool post_done = false;
 		if (!(have && follow_hit)) {
 			const uint32_t start = a + 1u;
+			const uint32_t pf_start_in = pf_start, pf_v_in = pf_v;      // (CHAIN_SETUP below overwrites them)
 			const uint32_t target = have ? (m > start ? m : start) : 0xffffffffu;
 			bool found = false, finished = false;
 			uint32_t a0 = 0;
@@ -784,7 +813,12 @@ __device__ __forceinline__ bool warp_lz4_certify(const uint8_t *__restrict__ src
 					ride = c_T > 0;
 					if (ride && c_part) { part = true; query = c_query; xx = c_xx; }
 				}
-				const uint32_t v = part ? LDS32(xx) : 0u;
+				uint32_t v = 0;
+				if (part) {
+					if (lane > q1) v = c_v;                                   // post pair: from the window
+					else if (a0 == 0u && start == pf_start_in) v = pf_v_in;   // search: requested a step ago
+					else v = LDS32(xx);
+				}
 				const uint32_t h = part ? ((v * 2654435761u) >> (32 - LOG)) : (0xffffffffu - (uint32_t)lane);
 				const uint32_t pred = tab_round_query(tab, rd, part, h, xx, lane);
 				const bool hit1 = (lane == q1) && part && (pred + o == xx);
@@ -844,7 +878,7 @@ __device__ __forceinline__ bool warp_lz4_certify(const uint8_t *__restrict__ src
 		}
 		{
 			CHAIN_SETUP(0)
-			const uint32_t v = c_part ? LDS32(c_xx) : 0u;
+			const uint32_t v = c_part ? c_v : 0u;
 			const uint32_t h = c_part ? ((v * 2654435761u) >> (32 - LOG)) : (0xffffffffu - (uint32_t)lane);
 			const uint32_t pred = tab_round_query(tab, rd, c_part, h, c_xx, lane);
 			CHAIN_FINISH(0, pred)

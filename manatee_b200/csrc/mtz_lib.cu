@@ -1533,6 +1533,14 @@ static int32_t k3_set_attributes(mtz_handle *h)
 	    (int)((size_t)K3_WARPS * LZ4_TAB_COMPACT_WORDS * 4)));
 	MTZ_CU(h, cudaFuncSetAttribute(k3c_lz4_certify<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
 	    (int)((size_t)K3_WARPS * LZ4_TAB_BIG_WORDS * 4)));
+	{
+		// experiments: a smaller carve-out trades certificate warps per SM for L1 (profiles/r2_k3c_certify.md)
+		const char *c = getenv("MTZ_K3C_CARVEOUT");
+		if (c != nullptr && atoi(c) > 0) {
+			MTZ_CU(h, cudaFuncSetAttribute(k3c_lz4_certify<true>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(c)));
+			MTZ_CU(h, cudaFuncSetAttribute(k3c_lz4_certify<false>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(c)));
+		}
+	}
 	// all of the unified L1/shared array as shared memory: K3 is bound by records in
 	// flight (24 tables of 8.5 KiB per SM), measured 62 vs 46 GiB/s at a 75 % carve-out
 	// (profiles/r1_k3_encode.md).  MTZ_K3_CARVEOUT overrides for experiments.
