@@ -703,7 +703,19 @@ __device__ __forceinline__ bool warp_lz4_certify(const uint8_t *__restrict__ src
 	tab.clear(lane);
 	__syncwarp();
 	TabRound<TAB> rd;
-	uint32_t p_w = 0, p_v = 1;            // deferred MISS check of the previous round: bad iff equal
+	// deferred MISS check of the previous round: the candidate's two source words are REQUESTED when the
+	// round ends and only looked at when the next one does (a load's first consumer stalls the warp:
+	// nothing here may touch the words early, not even the funnel shift that aligns them)
+	uint32_t p_lo = 0, p_hi = 0, p_sh = 0, p_v = 1;
+#define CHK_EVAL() { bad = bad || (__funnelshift_r(p_lo, p_hi, p_sh) == p_v); }
+#define CHK_ISSUE(chk_, pred_, v_)                                                                   \
+	{                                                                                                \
+		const uint32_t cx_ = (pred_) + mis;                                                          \
+		p_lo = (chk_) ? __ldg(base4 + (cx_ >> 2)) : 0u;                                              \
+		p_hi = (chk_) ? __ldg(base4 + (cx_ >> 2) + 1u) : 0u;                                         \
+		p_sh = (cx_ & 3u) * 8u;                                                                      \
+		p_v = (chk_) ? (v_) : 1u;                                                                    \
+	}
 	uint32_t a = 0;                        // anchor: end of the previous match
 	bool follow_hit = false;               // the probe at `a` delivered sequence k (no search)
 	uint32_t k = 0;
@@ -712,8 +724,8 @@ __device__ __forceinline__ bool warp_lz4_certify(const uint8_t *__restrict__ src
 	// sequences ahead of use, and the first round of the next search is requested one step early
 	// from where this step's hypothesis says it will start (pf_start / pf_v).
 	uint32_t kw = 0;
-	uint64_t w_s = 0; uint32_t w_vm2 = 0, w_ve = 0;
-	uint32_t pf_start = 0xffffffffu, pf_v = 0;
+	uint64_t w_s = 0; uint32_t w_0 = 0, w_1 = 0, w_2 = 0;   // the three aligned words that hold [e-2, e+4)
+	uint32_t pf_start = 0xffffffffu, pf_lo = 0, pf_hi = 0;
 	bool w_init = false;
 	for (;;) {
 		const bool have = k < ns;
@@ -723,8 +735,10 @@ __device__ __forceinline__ bool warp_lz4_certify(const uint8_t *__restrict__ src
 			w_s = (j < ns) ? seqs[j] : 0ull;
 			const uint32_t we = SEQ_M(w_s) + SEQ_L(w_s);
 			const bool wok = (j < ns) && we <= mflimit && we >= 2u;
-			w_vm2 = wok ? LDS32(we - 2u) : 0u;
-			w_ve = wok ? LDS32(we) : 0u;
+			const uint32_t wi = (we - 2u + mis) >> 2;
+			w_0 = wok ? __ldg(base4 + wi) : 0u;
+			w_1 = wok ? __ldg(base4 + wi + 1u) : 0u;
+			w_2 = wok ? __ldg(base4 + wi + 2u) : 0u;
 		}
 		const uint64_t s = have ? __shfl_sync(0xffffffffu, w_s, (int)(k - kw)) : 0ull;
 		const uint32_t m = SEQ_M(s), o = SEQ_O(s), e = m + SEQ_L(s);
@@ -748,8 +762,9 @@ __device__ __forceinline__ bool warp_lz4_certify(const uint8_t *__restrict__ src
 			const uint64_t s0_ = __shfl_sync(0xffffffffu, w_s, sl_);                                 \
 			const uint64_t sp_ = __shfl_sync(0xffffffffu, w_s, sl_ > 0 ? sl_ - 1 : 0);               \
 			const uint64_t sn_ = __shfl_sync(0xffffffffu, w_s, sl_ + 1);                             \
-			const uint32_t vm_ = __shfl_sync(0xffffffffu, w_vm2, sl_);                               \
-			const uint32_t ve_ = __shfl_sync(0xffffffffu, w_ve, sl_);                                \
+			const uint32_t g0_ = __shfl_sync(0xffffffffu, w_0, sl_);                                 \
+			const uint32_t g1_ = __shfl_sync(0xffffffffu, w_1, sl_);                                 \
+			const uint32_t g2_ = __shfl_sync(0xffffffffu, w_2, sl_);                                 \
 			c_e = SEQ_M(s0_) + SEQ_L(s0_);                                                           \
 			const bool fol_ = (t_ == 0u) || (SEQ_M(s0_) == SEQ_M(sp_) + SEQ_L(sp_));                 \
 			const bool good_ = ex_ && fol_ && c_e <= mflimit;                                        \
@@ -758,14 +773,19 @@ __device__ __forceinline__ bool warp_lz4_certify(const uint8_t *__restrict__ src
 			c_part = in_ && (int)t_ < c_T;                                                           \
 			c_query = c_part && (rl_ & 1);                                                           \
 			c_xx = (rl_ & 1) ? c_e : c_e - 2u;                                                       \
-			c_v = (rl_ & 1) ? ve_ : vm_;                                                             \
+			{                                                                                        \
+				const uint32_t sh_ = ((c_e - 2u + mis) & 3u) * 8u + ((rl_ & 1) ? 16u : 0u);          \
+				c_v = (sh_ < 32u) ? __funnelshift_r(g0_, g1_, sh_) : __funnelshift_r(g1_, g2_, sh_ - 32u); \
+			}                                                                                        \
 			c_nf = (kk_ + 1u < ns) && (SEQ_M(sn_) == c_e);                                           \
 			c_onext = SEQ_O(sn_);                                                                    \
 			/* the search that follows this run, if the hypothesis holds, starts here */            \
 			if (c_T > 0) {                                                                           \
 				pf_start = __shfl_sync(0xffffffffu, c_e, (L0) + 2 * c_T - 1) + 1u;                   \
 				const uint32_t px_ = pf_start + (uint32_t)lane;                                      \
-				pf_v = (px_ + 4u <= iend) ? LDS32(px_) : 0u;                                         \
+				const bool pk_ = (px_ + 4u <= iend);                                                 \
+				pf_lo = pk_ ? __ldg(base4 + ((px_ + mis) >> 2)) : 0u;                                \
+				pf_hi = pk_ ? __ldg(base4 + ((px_ + mis) >> 2) + 1u) : 0u;                           \
 			}                                                                                        \
 		}
 		// CHAIN_FINISH: with `pred` of the round: how many pairs stand, where the encoder is after them
@@ -785,7 +805,7 @@ __device__ __forceinline__ bool warp_lz4_certify(const uint8_t *__restrict__ src
 		bool post_done = false;
 		if (!(have && follow_hit)) {
 			const uint32_t start = a + 1u;
-			const uint32_t pf_start_in = pf_start, pf_v_in = pf_v;      // (CHAIN_SETUP below overwrites them)
+			const uint32_t pf_start_in = pf_start, pf_lo_in = pf_lo, pf_hi_in = pf_hi;   // (CHAIN_SETUP below overwrites them)
 			const uint32_t target = have ? (m > start ? m : start) : 0xffffffffu;
 			bool found = false, finished = false;
 			uint32_t a0 = 0;
@@ -796,13 +816,22 @@ __device__ __forceinline__ bool warp_lz4_certify(const uint8_t *__restrict__ src
 				const uint32_t x = (a0 == 0u) ? start + (uint32_t)lane : start + skip_dist(att);
 				const uint32_t step = (a0 == 0u) ? 1u : ((67u + att) >> 6);
 				const bool valid = (x + step <= mflimit);
-				const uint32_t cm = __ballot_sync(0xffffffffu, x >= target);
-				const int q1 = cm ? (__ffs((int)cm) - 1) : 32;
+				int q1, I;                                     // first candidate lane, first lane past mflimit
+				uint32_t xq1;
+				if (a0 == 0u) {                                // x = start + lane: no votes needed
+					q1 = (target - start < 32u) ? (int)(target - start) : 32;
+					I = (start + 1u > mflimit) ? 0 : ((mflimit - start < 32u) ? (int)(mflimit - start) : 32);
+					xq1 = start + (uint32_t)q1;
+				} else {
+					const uint32_t cm = __ballot_sync(0xffffffffu, x >= target);
+					q1 = cm ? (__ffs((int)cm) - 1) : 32;
+					const uint32_t inval = __ballot_sync(0xffffffffu, !valid);
+					I = inval ? (__ffs((int)inval) - 1) : 32;
+					xq1 = __shfl_sync(0xffffffffu, x, q1 & 31);
+				}
 				q1l = q1;
-				const uint32_t inval = __ballot_sync(0xffffffffu, !valid);
-				const int I = inval ? (__ffs((int)inval) - 1) : 32;
 				if (have && I <= q1 && I < 32) return false;            // the encoder runs dry before the hit
-				if (q1 < 32 && __shfl_sync(0xffffffffu, x, q1) + LZ4_MINMATCH > e) return false;
+				if (q1 < 32 && xq1 + LZ4_MINMATCH > e) return false;
 				// the post run rides in the same round when the hypothesis leaves lanes for it
 				bool part = valid && lane <= q1;
 				bool query = part;
@@ -816,7 +845,8 @@ __device__ __forceinline__ bool warp_lz4_certify(const uint8_t *__restrict__ src
 				uint32_t v = 0;
 				if (part) {
 					if (lane > q1) v = c_v;                                   // post pair: from the window
-					else if (a0 == 0u && start == pf_start_in) v = pf_v_in;   // search: requested a step ago
+					else if (a0 == 0u && start == pf_start_in)                // search: requested a step ago
+						v = __funnelshift_r(pf_lo_in, pf_hi_in, ((xx + mis) & 3u) * 8u);
 					else v = LDS32(xx);
 				}
 				const uint32_t h = part ? ((v * 2654435761u) >> (32 - LOG)) : (0xffffffffu - (uint32_t)lane);
@@ -833,11 +863,10 @@ __device__ __forceinline__ bool warp_lz4_certify(const uint8_t *__restrict__ src
 				}
 				tab_round_commit(tab, rd, part, h, xx, upto, lane);
 				// deferred MISS checks: every committed query that is not a hypothesised-and-delivered hit
-				bad = bad || (p_w == p_v);
+				CHK_EVAL()
 				const bool chk = part && query && lane <= upto && !hit1 && !ridehit &&
 				    (!DIST || pred + LZ4_MAXDIST >= xx);
-				p_w = chk ? LDS32(pred) : 0u;
-				p_v = chk ? v : 1u;
+				CHK_ISSUE(chk, pred, v)
 				if (q1 < 32) break;
 				if (I < 32) { finished = true; break; }                    // closing search ran dry (have == false here)
 				a0 += 32u;
@@ -859,10 +888,9 @@ __device__ __forceinline__ bool warp_lz4_certify(const uint8_t *__restrict__ src
 					const uint32_t hits = __ballot_sync(0xffffffffu, hit);
 					const int F = hits ? (__ffs((int)hits) - 1) : 32;
 					tab_round_commit(tab, rd, part, h, x, F < 32 ? F : 31, lane);
-					bad = bad || (p_w == p_v);
+					CHK_EVAL()
 					const bool chk = part && lane < F && (!DIST || pred + LZ4_MAXDIST >= x);
-					p_w = chk ? LDS32(pred) : 0u;
-					p_v = chk ? v : 1u;
+					CHK_ISSUE(chk, pred, v)
 					if (F < 32) break;
 					if (!__all_sync(0xffffffffu, part)) return false;
 					ac += 32u;
@@ -884,15 +912,16 @@ __device__ __forceinline__ bool warp_lz4_certify(const uint8_t *__restrict__ src
 			CHAIN_FINISH(0, pred)
 			tab_round_commit(tab, rd, c_part, h, c_xx, c_upto, lane);
 			k += (uint32_t)c_used;
-			bad = bad || (p_w == p_v);
+			CHK_EVAL()
 			const bool chk = c_query && lane <= c_upto && !c_hitl && (!DIST || pred + LZ4_MAXDIST >= c_xx);
-			p_w = chk ? LDS32(pred) : 0u;
-			p_v = chk ? v : 1u;
+			CHK_ISSUE(chk, pred, v)
 		}
 	}
 #undef CHAIN_SETUP
 #undef CHAIN_FINISH
-	bad = bad || (p_w == p_v);
+	CHK_EVAL()
+#undef CHK_EVAL
+#undef CHK_ISSUE
 #undef LDS32
 #undef SEQ_M
 #undef SEQ_O
