@@ -810,10 +810,13 @@ __device__ __forceinline__ bool warp_lz4_certify(const uint8_t *__restrict__ src
 			bool found = false, finished = false;
 			uint32_t a0 = 0;
 			int q1l = 32;
-			// phase 1: the attempts up to and including the first one at or beyond m
+			// phase 1: the attempts up to and including the first one at or beyond m.  A literal run
+			// longer than one round asks for the next round's source words before working on this one.
+			uint32_t xn = 0, n_lo = 0, n_hi = 0;
 			for (;;) {
 				const uint32_t att = a0 + (uint32_t)lane;
-				const uint32_t x = (a0 == 0u) ? start + (uint32_t)lane : start + skip_dist(att);
+				const uint32_t x = (a0 == 0u) ? start + (uint32_t)lane : xn;
+				const uint32_t c_lo = n_lo, c_hi = n_hi;              // (this round's words, if a0 > 0)
 				const uint32_t step = (a0 == 0u) ? 1u : ((67u + att) >> 6);
 				const bool valid = (x + step <= mflimit);
 				int q1, I;                                     // first candidate lane, first lane past mflimit
@@ -830,6 +833,12 @@ __device__ __forceinline__ bool warp_lz4_certify(const uint8_t *__restrict__ src
 					xq1 = __shfl_sync(0xffffffffu, x, q1 & 31);
 				}
 				q1l = q1;
+				if (q1 == 32 && I == 32) {                     // another round will follow: ask for its words now
+					xn = start + skip_dist(att + 32u);
+					const bool nk = (xn + 4u <= iend);
+					n_lo = nk ? __ldg(base4 + ((xn + mis) >> 2)) : 0u;
+					n_hi = nk ? __ldg(base4 + ((xn + mis) >> 2) + 1u) : 0u;
+				}
 				if (have && I <= q1 && I < 32) return false;            // the encoder runs dry before the hit
 				if (q1 < 32 && xq1 + LZ4_MINMATCH > e) return false;
 				// the post run rides in the same round when the hypothesis leaves lanes for it
@@ -847,6 +856,7 @@ __device__ __forceinline__ bool warp_lz4_certify(const uint8_t *__restrict__ src
 					if (lane > q1) v = c_v;                                   // post pair: from the window
 					else if (a0 == 0u && start == pf_start_in)                // search: requested a step ago
 						v = __funnelshift_r(pf_lo_in, pf_hi_in, ((xx + mis) & 3u) * 8u);
+					else if (a0 != 0u) v = __funnelshift_r(c_lo, c_hi, ((xx + mis) & 3u) * 8u);
 					else v = LDS32(xx);
 				}
 				const uint32_t h = part ? ((v * 2654435761u) >> (32 - LOG)) : (0xffffffffu - (uint32_t)lane);
