@@ -728,6 +728,7 @@ __device__ __forceinline__ bool warp_lz4_certify(const uint8_t *__restrict__ src
 	uint32_t pf_start = 0xffffffffu, pf_lo = 0, pf_hi = 0;
 	bool w_init = false;
 	for (;;) {
+		if (__any_sync(0xffffffffu, bad)) return false;      // (a foreign encoder's block usually fails early)
 		const bool have = k < ns;
 		if (have && (!w_init || k - kw > 15u)) {
 			kw = k; w_init = true;
