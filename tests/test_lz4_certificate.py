@@ -91,8 +91,48 @@ def _all_cases(oracle, run):
             run(oracle, m, cap + (1 << 20), untouched)
 
 
+def _shaped(oracle, n, recsize, seed):
+    """pg-page records with stretches that stress the replay: tens of kilobytes of noise (literal runs
+    of thousands of attempts, step > 1, 64-attempt rounds and their clashes), long zero runs (match
+    lengths with many 255 extension bytes, overlapping offset 1), short periodic patterns."""
+    rng = np.random.default_rng(seed)
+    raw = oracle.synth_stream(n, recsize, oracle.PAYLOAD_PGPAGE).copy()
+    cnt, offs = oracle.stream_index(raw)
+    for k in range(cnt):
+        o = int(offs[k])
+        if int(raw[o]) != 3:
+            continue
+        pay = raw[o + 312:o + 312 + recsize]
+        a = int(rng.integers(0, recsize // 4)); ln = int(rng.integers(recsize // 16, recsize // 3))
+        pay[a:a + ln] = rng.integers(0, 256, min(ln, recsize - a), dtype=np.uint8)
+        b = int(rng.integers(recsize // 2, recsize - recsize // 8)); lz = int(rng.integers(300, recsize // 8))
+        pay[b:b + lz] = 0
+        c = int(rng.integers(0, recsize - 700))
+        pay[c:c + 600] = np.resize(np.frombuffer(b"abcdefg", dtype=np.uint8), 600)
+    assert oracle.stream_restamp(raw)[0] == 0
+    rc, cs, _ = oracle.stream_compress_plain(raw)
+    assert rc == 0
+    return np.ascontiguousarray(cs), raw.size
+
+
+def _shaped_cases(oracle, run, sizes):
+    rng = np.random.default_rng(5)
+    for n, recsize in sizes:
+        c, cap = _shaped(oracle, n, recsize, seed=recsize + n)
+        nblk = len(F.blocks_of(oracle, c))
+        assert nblk >= n - 1                                   # (a record may end up stored raw)
+        run(oracle, c, cap + (1 << 20), nblk)
+        m, untouched, touched = _mutated(oracle, c, F.MUTATIONS, rng)
+        assert touched > 0
+        run(oracle, m, cap + (1 << 20), untouched)
+
+
 def test_certificate_on_the_emulated_library(emul_library, oracle):
     _all_cases(oracle, _check)
+
+
+def test_long_literal_runs_and_long_matches_on_the_emulated_library(emul_library, oracle):
+    _shaped_cases(oracle, _check, ((4, 131072), (6, 32768)))
 
 
 @pytest.mark.parametrize("seed", [1, 2])
@@ -152,6 +192,11 @@ def test_certificate_off_gives_the_same_bytes(emul_so, oracle, tmp_path):
 @pytest.mark.gpu
 def test_certificate_on_the_gpu(oracle):
     _all_cases(oracle, _check)
+
+
+@pytest.mark.gpu
+def test_long_literal_runs_and_long_matches_on_the_gpu(oracle):
+    _shaped_cases(oracle, _check, ((96, 131072), (64, 32768), (8, 1 << 20)))
 
 
 @pytest.mark.gpu
