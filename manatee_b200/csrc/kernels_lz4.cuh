@@ -707,13 +707,7 @@ __device__ __forceinline__ bool warp_lz4_certify(const uint8_t *__restrict__ src
 	// round ends and only looked at when the next one does (a load's first consumer stalls the warp:
 	// nothing here may touch the words early, not even the funnel shift that aligns them)
 	uint32_t p_lo = 0, p_hi = 0, p_sh = 0, p_v = 1;
-	uint32_t q_lo = 0, q_hi = 0, q_v = 1;            // second check of a 64-attempt round (shift in p_sh >> 8)
-#define CHK_EVAL()                                                                                   \
-	{                                                                                                \
-		bad = bad || (__funnelshift_r(p_lo, p_hi, p_sh & 31u) == p_v) ||                             \
-		    (__funnelshift_r(q_lo, q_hi, p_sh >> 8) == q_v);                                         \
-		q_lo = 0; q_hi = 0; q_v = 1;                                                                 \
-	}
+#define CHK_EVAL() { bad = bad || (__funnelshift_r(p_lo, p_hi, p_sh) == p_v); }
 #define CHK_ISSUE(chk_, pred_, v_)                                                                   \
 	{                                                                                                \
 		const uint32_t cx_ = (pred_) + mis;                                                          \
@@ -721,14 +715,6 @@ __device__ __forceinline__ bool warp_lz4_certify(const uint8_t *__restrict__ src
 		p_hi = (chk_) ? __ldg(base4 + (cx_ >> 2) + 1u) : 0u;                                         \
 		p_sh = (cx_ & 3u) * 8u;                                                                      \
 		p_v = (chk_) ? (v_) : 1u;                                                                    \
-	}
-#define CHK2_ISSUE(chk_, pred_, v_)       /* after CHK_ISSUE of the same round */                    \
-	{                                                                                                \
-		const uint32_t cx_ = (pred_) + mis;                                                          \
-		q_lo = (chk_) ? __ldg(base4 + (cx_ >> 2)) : 0u;                                              \
-		q_hi = (chk_) ? __ldg(base4 + (cx_ >> 2) + 1u) : 0u;                                         \
-		p_sh |= ((cx_ & 3u) * 8u) << 8;                                                              \
-		q_v = (chk_) ? (v_) : 1u;                                                                    \
 	}
 	uint32_t a = 0;                        // anchor: end of the previous match
 	bool follow_hit = false;               // the probe at `a` delivered sequence k (no search)
@@ -825,58 +811,13 @@ __device__ __forceinline__ bool warp_lz4_certify(const uint8_t *__restrict__ src
 			bool found = false, finished = false;
 			uint32_t a0 = 0;
 			int q1l = 32;
-			// phase 1: the attempts up to and including the first one at or beyond m.
-			// Inside a literal run (no candidate and no limit among the next 64 attempts) a round takes
-			// TWO attempts per lane: when the 64 slots are distinct -- the tag test again, ids 0..63 --
-			// nobody needs forwarding and everybody inserts; a clash hands the round to the 32-wide form.
-			uint32_t g_lo0 = 0, g_hi0 = 0, g_lo1 = 0, g_hi1 = 0, g_a0 = 0xffffffffu;   // words requested a round early
-			uint32_t v_keep = 0; bool v_kept = false;                                  // (a clashed round's first half)
+			// phase 1: the attempts up to and including the first one at or beyond m.  A literal run
+			// longer than one round asks for the next round's source words before working on this one.
+			uint32_t xn = 0, n_lo = 0, n_hi = 0;
 			for (;;) {
-				for (;;) {
-					const uint32_t xl = start + skip_dist(a0 + 63u);
-					if (!(xl < target && xl + ((67u + a0 + 63u) >> 6) <= mflimit)) break;
-					const uint32_t xA = start + skip_dist(a0 + (uint32_t)lane);
-					const uint32_t xB = start + skip_dist(a0 + 32u + (uint32_t)lane);
-					if (g_a0 != a0) {
-						if (a0 == 0u && start == pf_start_in) { g_lo0 = pf_lo_in; g_hi0 = pf_hi_in; }
-						else { g_lo0 = __ldg(base4 + ((xA + mis) >> 2)); g_hi0 = __ldg(base4 + ((xA + mis) >> 2) + 1u); }
-						g_lo1 = __ldg(base4 + ((xB + mis) >> 2)); g_hi1 = __ldg(base4 + ((xB + mis) >> 2) + 1u);
-					}
-					const uint32_t vA = __funnelshift_r(g_lo0, g_hi0, ((xA + mis) & 3u) * 8u);
-					const uint32_t vB = __funnelshift_r(g_lo1, g_hi1, ((xB + mis) & 3u) * 8u);
-					{
-						const uint32_t yA = start + skip_dist(a0 + 64u + (uint32_t)lane);
-						const uint32_t yB = start + skip_dist(a0 + 96u + (uint32_t)lane);
-						const bool kA = yA + 4u <= iend, kB = yB + 4u <= iend;
-						g_lo0 = kA ? __ldg(base4 + ((yA + mis) >> 2)) : 0u;
-						g_hi0 = kA ? __ldg(base4 + ((yA + mis) >> 2) + 1u) : 0u;
-						g_lo1 = kB ? __ldg(base4 + ((yB + mis) >> 2)) : 0u;
-						g_hi1 = kB ? __ldg(base4 + ((yB + mis) >> 2) + 1u) : 0u;
-						g_a0 = a0 + 64u;
-					}
-					const uint32_t hA = (vA * 2654435761u) >> (32 - LOG), hB = (vB * 2654435761u) >> (32 - LOG);
-					const uint32_t oA = tab.get(hA), oB = tab.get(hB);
-					__syncwarp();
-					tab.tag(hA, (uint32_t)lane);
-					tab.tag(hB, 32u + (uint32_t)lane);
-					__syncwarp();
-					const bool cl = (tab.tagval(hA) != (uint32_t)lane) || (tab.tagval(hB) != 32u + (uint32_t)lane);
-					if (__any_sync(0xffffffffu, cl)) {
-						tab.untag(hA, oA); tab.untag(hB, oB);
-						__syncwarp();
-						v_keep = vA; v_kept = true;
-						break;
-					}
-					tab.set_from(hA, xA, oA);
-					tab.set_from(hB, xB, oB);
-					__syncwarp();
-					CHK_EVAL()
-					CHK_ISSUE(!DIST || oA + LZ4_MAXDIST >= xA, oA, vA)
-					CHK2_ISSUE(!DIST || oB + LZ4_MAXDIST >= xB, oB, vB)
-					a0 += 64u;
-				}
 				const uint32_t att = a0 + (uint32_t)lane;
-				const uint32_t x = (a0 == 0u) ? start + (uint32_t)lane : start + skip_dist(att);
+				const uint32_t x = (a0 == 0u) ? start + (uint32_t)lane : xn;
+				const uint32_t c_lo = n_lo, c_hi = n_hi;              // (this round's words, if a0 > 0)
 				const uint32_t step = (a0 == 0u) ? 1u : ((67u + att) >> 6);
 				const bool valid = (x + step <= mflimit);
 				int q1, I;                                     // first candidate lane, first lane past mflimit
@@ -893,6 +834,12 @@ __device__ __forceinline__ bool warp_lz4_certify(const uint8_t *__restrict__ src
 					xq1 = __shfl_sync(0xffffffffu, x, q1 & 31);
 				}
 				q1l = q1;
+				if (q1 == 32 && I == 32) {                     // another round will follow: ask for its words now
+					xn = start + skip_dist(att + 32u);
+					const bool nk = (xn + 4u <= iend);
+					n_lo = nk ? __ldg(base4 + ((xn + mis) >> 2)) : 0u;
+					n_hi = nk ? __ldg(base4 + ((xn + mis) >> 2) + 1u) : 0u;
+				}
 				if (have && I <= q1 && I < 32) return false;            // the encoder runs dry before the hit
 				if (q1 < 32 && xq1 + LZ4_MINMATCH > e) return false;
 				// the post run rides in the same round when the hypothesis leaves lanes for it
@@ -910,10 +857,9 @@ __device__ __forceinline__ bool warp_lz4_certify(const uint8_t *__restrict__ src
 					if (lane > q1) v = c_v;                                   // post pair: from the window
 					else if (a0 == 0u && start == pf_start_in)                // search: requested a step ago
 						v = __funnelshift_r(pf_lo_in, pf_hi_in, ((xx + mis) & 3u) * 8u);
-					else if (v_kept) v = v_keep;                               // a clashed 64-attempt round's first half
+					else if (a0 != 0u) v = __funnelshift_r(c_lo, c_hi, ((xx + mis) & 3u) * 8u);
 					else v = LDS32(xx);
 				}
-				v_kept = false;
 				const uint32_t h = part ? ((v * 2654435761u) >> (32 - LOG)) : (0xffffffffu - (uint32_t)lane);
 				const uint32_t pred = tab_round_query(tab, rd, part, h, xx, lane);
 				const bool hit1 = (lane == q1) && part && (pred + o == xx);
@@ -987,7 +933,6 @@ __device__ __forceinline__ bool warp_lz4_certify(const uint8_t *__restrict__ src
 	CHK_EVAL()
 #undef CHK_EVAL
 #undef CHK_ISSUE
-#undef CHK2_ISSUE
 #undef LDS32
 #undef SEQ_M
 #undef SEQ_O
