@@ -329,12 +329,14 @@ def host_memcpy_ceiling(src, nthreads, chunk=64 << 20):
     return round(n / GIB / dt, 3)
 
 
-def ring_run(g, src, peers=(0,), producer="write", nthreads=4, chunk=64 << 20):
+def ring_run(g, src, peers=(0,), producer="write", nthreads=4, chunk=64 << 20, limit_s=240.0):
     """Drive the streaming API: one producer feeding `src` (numpy u8), one zero-copy consumer thread
     per peer (mtz_out_peek_peer / mtz_out_consume_peer).  producer = "write" (mtz_write: one thread,
     one memcpy into the pinned ring), "acquire" (mtz_ring_acquire / commit, the slice filled by
     `nthreads` parallel memcpys, native: tools/ringpump.c) or "pipe" (a pipe(2) read(2) straight into
-    the acquired slice -- the shape of zfsSend.stdout).  Returns (seconds, ok, detail)."""
+    the acquired slice -- the shape of zfsSend.stdout).  Returns (seconds, ok, detail).  A leg that has not
+    finished after `limit_s` is cancelled (mtz_cancel) and reported as failed: a stuck leg must not cost
+    the JSON line."""
     import ctypes as C
     from manatee_b200 import _native as N
     L = N.lib()
@@ -392,9 +394,14 @@ def ring_run(g, src, peers=(0,), producer="write", nthreads=4, chunk=64 << 20):
     tp.start()
     for t in ts:
         t.start()
-    tp.join()
-    for t in ts:
-        t.join()
+    deadline = time.time() + limit_s
+    for t in [tp] + ts:
+        t.join(max(0.0, deadline - time.time()))
+    if any(t.is_alive() for t in [tp] + ts):
+        errs.append("leg not finished after %.0f s: cancelled" % limit_s)
+        g.cancel()
+        for t in [tp] + ts:
+            t.join(30.0)
     dt = time.perf_counter() - t0
     return dt, (not errs), {"errors": errs[:3], "delivered": got}
 
