@@ -70,21 +70,23 @@ def _mutated(oracle, c, kinds, rng, every=2):
     return F.splice(oracle, c, changes), len(blocks) - len(changes), len(changes)
 
 
-def _all_cases(oracle, run):
+def _all_cases(oracle, run, small=False):
     from manatee_b200 import _native as N
     # every record of an encoder-made stream is certified, in all three table flavours
-    for n, recsize in ((5, 131072), (12, 16384), (4, 65536), (3, 262144)):
+    for n, recsize in (((3, 131072), (8, 16384), (2, 65536), (2, 262144)) if small else
+                       ((5, 131072), (12, 16384), (4, 65536), (3, 262144))):
         c, cap = _canonical(oracle, n, recsize)
         gs = run(oracle, c, cap + (1 << 20), n)
         assert gs["lz4_encoded"] == n
     # MTZ_FLAG_REENCODE_ALL: nothing certified, same bytes
-    c, cap = _canonical(oracle, 6, 131072)
+    nf = 2 if small else 6
+    c, cap = _canonical(oracle, nf, 131072)
     gs = run(oracle, c, cap + (1 << 20), 0, flags=N.FLAG_REENCODE_ALL)
-    assert gs["lz4_encoded"] == 6
+    assert gs["lz4_encoded"] == nf
     # one parse decision changed in every second record
     rng = np.random.default_rng(20260921)
     for kind in F.MUTATIONS:
-        for n, recsize in ((6, 131072), (10, 16384)):
+        for n, recsize in (((2, 131072), (6, 16384)) if small else ((6, 131072), (10, 16384))):
             c, cap = _canonical(oracle, n, recsize)
             m, untouched, touched = _mutated(oracle, c, (kind,), rng)
             assert touched > 0, kind
@@ -128,7 +130,7 @@ def _shaped_cases(oracle, run, sizes):
 
 
 def test_certificate_on_the_emulated_library(emul_library, oracle):
-    _all_cases(oracle, _check)
+    _all_cases(oracle, _check, small=True)
 
 
 def test_long_literal_runs_and_long_matches_on_the_emulated_library(emul_library, oracle):
