@@ -725,10 +725,6 @@ __device__ __forceinline__ bool warp_lz4_certify(const uint8_t *__restrict__ src
 	// from where this step's hypothesis says it will start (pf_start / pf_v).
 	uint32_t kw = 0;
 	uint64_t w_s = 0; uint32_t w_0 = 0, w_1 = 0, w_2 = 0;   // the three aligned words that hold [e-2, e+4)
-	// what a post pair needs of its sequence j and of j+1, packed once per refill:
-	//   w_a = e_j | follows(j) << 24 | (e_j <= mflimit) << 25        follows(j): m_j == e_(j-1)
-	//   w_b = o_(j+1) | follows(j+1) << 16                             (0 when j+1 is not in the window / the parse)
-	uint32_t w_a = 0, w_b = 0;
 	uint32_t pf_start = 0xffffffffu, pf_lo = 0, pf_hi = 0;
 	bool w_init = false;
 	for (;;) {
@@ -744,12 +740,6 @@ __device__ __forceinline__ bool warp_lz4_certify(const uint8_t *__restrict__ src
 			w_0 = wok ? __ldg(base4 + wi) : 0u;
 			w_1 = wok ? __ldg(base4 + wi + 1u) : 0u;
 			w_2 = wok ? __ldg(base4 + wi + 2u) : 0u;
-			const uint32_t pe = __shfl_up_sync(0xffffffffu, we, 1);            // (lane 0: only ever pair 0 of a run)
-			const uint32_t fl = ((j < ns) && lane > 0 && SEQ_M(w_s) == pe) ? 1u : 0u;
-			w_a = we | (fl << 24) | (wok ? 1u << 25 : 0u);
-			const uint32_t nx = SEQ_O(w_s) | (fl << 16);
-			w_b = __shfl_down_sync(0xffffffffu, nx, 1);
-			if (lane == 31) w_b = 0u;
 		}
 		const uint64_t s = have ? __shfl_sync(0xffffffffu, w_s, (int)(k - kw)) : 0ull;
 		const uint32_t m = SEQ_M(s), o = SEQ_O(s), e = m + SEQ_L(s);
@@ -770,14 +760,15 @@ __device__ __forceinline__ bool warp_lz4_certify(const uint8_t *__restrict__ src
 			const uint32_t ix_ = kk_ - kw;                  /* window lane of the pair's sequence */ \
 			const bool ex_ = in_ && kk_ < ns && ix_ <= 30u;                                          \
 			const int sl_ = ex_ ? (int)ix_ : 0;                                                      \
-			const uint32_t pa_ = __shfl_sync(0xffffffffu, w_a, sl_);                                 \
-			const uint32_t pb_ = __shfl_sync(0xffffffffu, w_b, sl_);                                 \
+			const uint64_t s0_ = __shfl_sync(0xffffffffu, w_s, sl_);                                 \
+			const uint64_t sp_ = __shfl_sync(0xffffffffu, w_s, sl_ > 0 ? sl_ - 1 : 0);               \
+			const uint64_t sn_ = __shfl_sync(0xffffffffu, w_s, sl_ + 1);                             \
 			const uint32_t g0_ = __shfl_sync(0xffffffffu, w_0, sl_);                                 \
 			const uint32_t g1_ = __shfl_sync(0xffffffffu, w_1, sl_);                                 \
 			const uint32_t g2_ = __shfl_sync(0xffffffffu, w_2, sl_);                                 \
-			c_e = pa_ & 0xffffffu;                                                                   \
-			const bool fol_ = (t_ == 0u) || ((pa_ >> 24) & 1u);                                      \
-			const bool good_ = ex_ && fol_ && ((pa_ >> 25) & 1u);                                    \
+			c_e = SEQ_M(s0_) + SEQ_L(s0_);                                                           \
+			const bool fol_ = (t_ == 0u) || (SEQ_M(s0_) == SEQ_M(sp_) + SEQ_L(sp_));                 \
+			const bool good_ = ex_ && fol_ && c_e <= mflimit;                                        \
 			const uint32_t bm_ = __ballot_sync(0xffffffffu, in_ && (rl_ & 1) && !good_);             \
 			c_T = bm_ ? ((__ffs((int)bm_) - 1 - (L0)) >> 1) : ((32 - (L0)) >> 1);                    \
 			c_part = in_ && (int)t_ < c_T;                                                           \
@@ -787,8 +778,8 @@ __device__ __forceinline__ bool warp_lz4_certify(const uint8_t *__restrict__ src
 				const uint32_t sh_ = ((c_e - 2u + mis) & 3u) * 8u + ((rl_ & 1) ? 16u : 0u);          \
 				c_v = (sh_ < 32u) ? __funnelshift_r(g0_, g1_, sh_) : __funnelshift_r(g1_, g2_, sh_ - 32u); \
 			}                                                                                        \
-			c_nf = ((pb_ >> 16) & 1u) != 0u;                                                         \
-			c_onext = pb_ & 0xffffu;                                                                 \
+			c_nf = (kk_ + 1u < ns) && (SEQ_M(sn_) == c_e);                                           \
+			c_onext = SEQ_O(sn_);                                                                    \
 			/* the search that follows this run, if the hypothesis holds, starts here */            \
 			if (c_T > 0) {                                                                           \
 				pf_start = __shfl_sync(0xffffffffu, c_e, (L0) + 2 * c_T - 1) + 1u;                   \
@@ -835,12 +826,6 @@ __device__ __forceinline__ bool warp_lz4_certify(const uint8_t *__restrict__ src
 					q1 = (target - start < 32u) ? (int)(target - start) : 32;
 					I = (start + 1u > mflimit) ? 0 : ((mflimit - start < 32u) ? (int)(mflimit - start) : 32);
 					xq1 = start + (uint32_t)q1;
-				} else if (a0 == 32u && target - start <= 60u && start + 67u <= mflimit) {
-					// the usual second round: the candidate is among attempts 32..60 (step 1 up to 60) and
-					// the limit is far: again no votes
-					q1 = (int)(target - start) - 32;
-					I = 32;
-					xq1 = target;
 				} else {
 					const uint32_t cm = __ballot_sync(0xffffffffu, x >= target);
 					q1 = cm ? (__ffs((int)cm) - 1) : 32;
@@ -850,8 +835,7 @@ __device__ __forceinline__ bool warp_lz4_certify(const uint8_t *__restrict__ src
 				}
 				q1l = q1;
 				if (q1 == 32 && I == 32) {                     // another round will follow: ask for its words now
-					// (attempts 32..63 of a search: step 1 up to attempt 60, then 2)
-					xn = (a0 == 0u) ? start + att + 32u + (att > 29u ? att - 29u : 0u) : start + skip_dist(att + 32u);
+					xn = start + skip_dist(att + 32u);
 					const bool nk = (xn + 4u <= iend);
 					n_lo = nk ? __ldg(base4 + ((xn + mis) >> 2)) : 0u;
 					n_hi = nk ? __ldg(base4 + ((xn + mis) >> 2) + 1u) : 0u;
