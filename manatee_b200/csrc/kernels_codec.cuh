@@ -405,7 +405,6 @@ k_stamp_chain(uint8_t *__restrict__ d_out, const mtz_rec *__restrict__ out_recs,
 {
 	__shared__ StampStep s_steps[2][STAMP_GROUP + 1];     // +1: the weight prefetch of step i+1 needs no bounds check
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	const int j = lane & 3;
 	if (n == 0u) return;
 	const uint32_t T = n - 1u;                                    // transitions
 	const uint32_t ngroups = (T + STAMP_GROUP - 1u) / STAMP_GROUP;
@@ -431,55 +430,62 @@ k_stamp_chain(uint8_t *__restrict__ d_out, const mtz_rec *__restrict__ out_recs,
 	if (warp >= 1 && ngroups > 0u) stage(0);
 	__syncthreads();
 
+	// Every lane of warp 0 carries the WHOLE running value and computes all four components of the
+	// next one: 32 multiply-adds of 64x32 bits per step instead of 8, but nothing crosses lanes -- the
+	// four-lane form (one component per lane, eight shuffles per step) spent its time in the
+	// exchange: a step was ~275 cycles of which the arithmetic is ~60 (profiles/r2_stamp_chain.md).
+	// Sixteen independent accumulate chains keep the multiplier busy; the weights of step i+1 are
+	// read from shared memory (same address in every lane: a broadcast) while step i computes.
 	Ck4 x = { 0, 0, 0, 0 };
-	uint64_t own = 0;
-	if (warp == 0) {
-		x = stamp_enter(*carry_out, d_out, out_recs, osums, 0u, res, lane);
-		own = (j == 0) ? x.a : (j == 1) ? x.b : (j == 2) ? x.c : x.d;
-	}
+	if (warp == 0) x = stamp_enter(*carry_out, d_out, out_recs, osums, 0u, res, lane);
 	for (uint32_t g = 0; g < ngroups; g++) {
 		if (warp >= 1) {
 			if (g + 1u < ngroups) stage(g + 1u);
 		} else {
 			const uint32_t r0 = g * STAMP_GROUP, cnt = min((uint32_t)STAMP_GROUP, T - r0);
-			// The weights of transition i+1 are loaded from shared memory (29 cycles) while transition
-			// i is computed; two register sets alternate so that no value is ever copied.
 			const StampStep *sg = &s_steps[g & 1u][0];
-			uint64_t ca[9], cb[9];
+			uint64_t ca[4][9], cb[4][9];
 			uint64_t woa = sg[0].woff, wob = 0;
 			uint32_t fa = sg[0].fast, fb = 0;
 #pragma unroll
-			for (int q = 0; q < 9; q++) { ca[q] = sg[0].c[j][q]; cb[q] = 0; }
+			for (int jj = 0; jj < 4; jj++) {
+#pragma unroll
+				for (int q = 0; q < 9; q++) { ca[jj][q] = sg[0].c[jj][q]; cb[jj][q] = 0; }
+			}
+#define STAMP_ROW(C, JJ, OUT)                                                                    \
+				{                                                                                \
+					uint64_t p0 = C[JJ][8] + C[JJ][0] * (uint64_t)w0 + C[JJ][1] * (uint64_t)w1;  \
+					uint64_t p1 = C[JJ][2] * (uint64_t)w2 + C[JJ][3] * (uint64_t)w3;             \
+					uint64_t p2 = C[JJ][4] * (uint64_t)w4 + C[JJ][5] * (uint64_t)w5;             \
+					uint64_t p3 = C[JJ][6] * (uint64_t)w6 + C[JJ][7] * (uint64_t)w7;             \
+					MTZ_PIN64(p0); MTZ_PIN64(p1); MTZ_PIN64(p2); MTZ_PIN64(p3);                  \
+					OUT = (p0 + p1) + (p2 + p3);                                                 \
+				}
 #define STAMP_STEP(C, WOFF, FAST, NC, NWOFF, NFAST, IDX)                                         \
 			{                                                                                    \
 				const uint32_t i_ = (IDX);                                                       \
 				{                                                                                \
 					const StampStep &nx = sg[i_ + 1u];       /* (slot 32 is padding) */          \
-					_Pragma("unroll") for (int q = 0; q < 9; q++) NC[q] = nx.c[j][q];            \
+					_Pragma("unroll") for (int jj = 0; jj < 4; jj++) {                           \
+						_Pragma("unroll") for (int q = 0; q < 9; q++) NC[jj][q] = nx.c[jj][q];   \
+					}                                                                            \
 					NWOFF = nx.woff; NFAST = nx.fast;                                            \
 				}                                                                                \
-				const uint32_t lo = (uint32_t)own, hi = (uint32_t)(own >> 32);                   \
-				const uint32_t w0 = __shfl_sync(0xffffffffu, lo, 0), w1 = __shfl_sync(0xffffffffu, hi, 0); \
-				const uint32_t w2 = __shfl_sync(0xffffffffu, lo, 1), w3 = __shfl_sync(0xffffffffu, hi, 1); \
-				const uint32_t w4 = __shfl_sync(0xffffffffu, lo, 2), w5 = __shfl_sync(0xffffffffu, hi, 2); \
-				const uint32_t w6 = __shfl_sync(0xffffffffu, lo, 3), w7 = __shfl_sync(0xffffffffu, hi, 3); \
 				if (FAST != 0u) {                                                                \
-					/* four independent multiply-add chains (pinned: left alone the compiler     \
-					 * folds them into ONE dependent chain of ~10 cycles per term) */            \
-					uint64_t p0 = C[8] + C[0] * (uint64_t)w0 + C[1] * (uint64_t)w1;              \
-					uint64_t p1 = C[2] * (uint64_t)w2 + C[3] * (uint64_t)w3;                     \
-					uint64_t p2 = C[4] * (uint64_t)w4 + C[5] * (uint64_t)w5;                     \
-					uint64_t p3 = C[6] * (uint64_t)w6 + C[7] * (uint64_t)w7;                     \
-					MTZ_PIN64(p0); MTZ_PIN64(p1); MTZ_PIN64(p2); MTZ_PIN64(p3);                  \
-					own = (p0 + p1) + (p2 + p3);                                                 \
-					/* every lane stores (lanes 4..31 repeat lanes 0..3): no divergent branch */   \
-					*reinterpret_cast<uint64_t *>(d_out + WOFF + 8u * (uint32_t)j) = own;        \
+					const uint32_t w0 = (uint32_t)x.a, w1 = (uint32_t)(x.a >> 32);               \
+					const uint32_t w2 = (uint32_t)x.b, w3 = (uint32_t)(x.b >> 32);               \
+					const uint32_t w4 = (uint32_t)x.c, w5 = (uint32_t)(x.c >> 32);               \
+					const uint32_t w6 = (uint32_t)x.d, w7 = (uint32_t)(x.d >> 32);               \
+					Ck4 y;                                                                       \
+					STAMP_ROW(C, 0, y.a) STAMP_ROW(C, 1, y.b) STAMP_ROW(C, 2, y.c) STAMP_ROW(C, 3, y.d) \
+					x = y;                                                                       \
+					if (lane == 0) {                                                             \
+						uint64_t *ck_ = reinterpret_cast<uint64_t *>(d_out + WOFF);              \
+						ck_[0] = x.a; ck_[1] = x.b; ck_[2] = x.c; ck_[3] = x.d;                  \
+					}                                                                            \
 				} else {                                                                         \
-					x.a = ((uint64_t)w1 << 32) | w0; x.b = ((uint64_t)w3 << 32) | w2;            \
-					x.c = ((uint64_t)w5 << 32) | w4; x.d = ((uint64_t)w7 << 32) | w6;            \
 					const Ck4 s_ = stamp_leave(x, osums, r0 + i_);                               \
 					x = stamp_enter(s_, d_out, out_recs, osums, r0 + i_ + 1u, res, lane);        \
-					own = (j == 0) ? x.a : (j == 1) ? x.b : (j == 2) ? x.c : x.d;                \
 				}                                                                                \
 			}
 			uint32_t i = 0;
@@ -489,15 +495,11 @@ k_stamp_chain(uint8_t *__restrict__ d_out, const mtz_rec *__restrict__ out_recs,
 			}
 			if (i < cnt) STAMP_STEP(ca, woa, fa, cb, wob, fb, i)
 #undef STAMP_STEP
+#undef STAMP_ROW
 		}
 		__syncthreads();
 	}
 	if (warp == 0) {
-		const uint32_t lo = (uint32_t)own, hi = (uint32_t)(own >> 32);
-		x.a = ((uint64_t)__shfl_sync(0xffffffffu, hi, 0) << 32) | __shfl_sync(0xffffffffu, lo, 0);
-		x.b = ((uint64_t)__shfl_sync(0xffffffffu, hi, 1) << 32) | __shfl_sync(0xffffffffu, lo, 1);
-		x.c = ((uint64_t)__shfl_sync(0xffffffffu, hi, 2) << 32) | __shfl_sync(0xffffffffu, lo, 2);
-		x.d = ((uint64_t)__shfl_sync(0xffffffffu, hi, 3) << 32) | __shfl_sync(0xffffffffu, lo, 3);
 		const Ck4 s = stamp_leave(x, osums, n - 1u);
 		if (lane == 0) { *carry_out = s; res->carry = s; }
 	}
