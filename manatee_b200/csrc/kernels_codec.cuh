@@ -430,76 +430,73 @@ k_stamp_chain(uint8_t *__restrict__ d_out, const mtz_rec *__restrict__ out_recs,
 	if (warp >= 1 && ngroups > 0u) stage(0);
 	__syncthreads();
 
-	// Every lane of warp 0 carries the WHOLE running value and computes all four components of the
-	// next one: 32 multiply-adds of 64x32 bits per step instead of 8, but nothing crosses lanes -- the
-	// four-lane form (one component per lane, eight shuffles per step) spent its time in the
-	// exchange: a step was ~275 cycles of which the arithmetic is ~60 (profiles/r2_stamp_chain.md).
-	// Sixteen independent accumulate chains keep the multiplier busy; the weights of step i+1 are
-	// read from shared memory (same address in every lane: a broadcast) while step i computes.
+	// One product per lane.  Lane (j, k) = 8 j + k holds half k of the running value (w_k, replicated
+	// in the four groups) and the weight C_jk of the current transition; a step is
+	//     p = C_jk * w_k (+ the constant in lane k = 0);  three xor-shuffle adds inside the 8-lane
+	//     group -> every lane of group j holds component j of the next value;  one more shuffle
+	//     hands lane (j, k) its new half (lane 8 (k >> 1) + (k & 1) offers lo when even, hi when odd).
+	// ~25 warp-instructions per step.  Measured alternatives (profiles/r2_stamp_chain.md): one
+	// component per lane with an 8-shuffle exchange, 55 instructions, 140 ns per record; the whole
+	// value in every lane, no exchange but 110 instructions, 305 ns -- a single warp issues about one
+	// instruction every 5 cycles, so it is the instruction COUNT of the step that has to go down.
+	const int j = lane >> 3, k = lane & 7;
 	Ck4 x = { 0, 0, 0, 0 };
-	if (warp == 0) x = stamp_enter(*carry_out, d_out, out_recs, osums, 0u, res, lane);
+	uint32_t w = 0;
+	auto half_of = [&](const Ck4 &v) -> uint32_t {
+		const uint64_t q = (k < 2) ? v.a : (k < 4) ? v.b : (k < 6) ? v.c : v.d;
+		return (k & 1) ? (uint32_t)(q >> 32) : (uint32_t)q;
+	};
+	if (warp == 0) {
+		x = stamp_enter(*carry_out, d_out, out_recs, osums, 0u, res, lane);
+		w = half_of(x);
+	}
 	for (uint32_t g = 0; g < ngroups; g++) {
 		if (warp >= 1) {
 			if (g + 1u < ngroups) stage(g + 1u);
 		} else {
 			const uint32_t r0 = g * STAMP_GROUP, cnt = min((uint32_t)STAMP_GROUP, T - r0);
 			const StampStep *sg = &s_steps[g & 1u][0];
-			uint64_t ca[4][9], cb[4][9];
-			uint64_t woa = sg[0].woff, wob = 0;
-			uint32_t fa = sg[0].fast, fb = 0;
-#pragma unroll
-			for (int jj = 0; jj < 4; jj++) {
-#pragma unroll
-				for (int q = 0; q < 9; q++) { ca[jj][q] = sg[0].c[jj][q]; cb[jj][q] = 0; }
-			}
-#define STAMP_ROW(C, JJ, OUT)                                                                    \
-				{                                                                                \
-					uint64_t p0 = C[JJ][8] + C[JJ][0] * (uint64_t)w0 + C[JJ][1] * (uint64_t)w1;  \
-					uint64_t p1 = C[JJ][2] * (uint64_t)w2 + C[JJ][3] * (uint64_t)w3;             \
-					uint64_t p2 = C[JJ][4] * (uint64_t)w4 + C[JJ][5] * (uint64_t)w5;             \
-					uint64_t p3 = C[JJ][6] * (uint64_t)w6 + C[JJ][7] * (uint64_t)w7;             \
-					MTZ_PIN64(p0); MTZ_PIN64(p1); MTZ_PIN64(p2); MTZ_PIN64(p3);                  \
-					OUT = (p0 + p1) + (p2 + p3);                                                 \
+			uint64_t c_cur = sg[0].c[j][k], g_cur = (k == 0) ? sg[0].c[j][8] : 0ull;
+			uint64_t wo_cur = sg[0].woff;
+			uint32_t f_cur = sg[0].fast;
+			for (uint32_t i = 0; i < cnt; i++) {
+				// the next transition's weight, constant, offset and kind (slot 32 is padding)
+				const StampStep &nx = sg[i + 1u];
+				const uint64_t c_nx = nx.c[j][k], g_nx = (k == 0) ? nx.c[j][8] : 0ull;
+				const uint64_t wo_nx = nx.woff;
+				const uint32_t f_nx = nx.fast;
+				if (f_cur != 0u) {
+					uint64_t p = c_cur * (uint64_t)w + g_cur;
+					p += __shfl_xor_sync(0xffffffffu, p, 1);
+					p += __shfl_xor_sync(0xffffffffu, p, 2);
+					p += __shfl_xor_sync(0xffffffffu, p, 4);            // component j of the stamped value
+					if (k == 0) *reinterpret_cast<uint64_t *>(d_out + wo_cur + 8u * (uint32_t)j) = p;
+					const uint32_t offer = (lane & 1) ? (uint32_t)(p >> 32) : (uint32_t)p;
+					w = __shfl_sync(0xffffffffu, offer, 8 * (k >> 1) + (k & 1));
+				} else {
+					// generic transition: rebuild the whole value in every lane, leave / enter, split again
+					const uint32_t h0 = __shfl_sync(0xffffffffu, w, 0), h1 = __shfl_sync(0xffffffffu, w, 1);
+					const uint32_t h2 = __shfl_sync(0xffffffffu, w, 2), h3 = __shfl_sync(0xffffffffu, w, 3);
+					const uint32_t h4 = __shfl_sync(0xffffffffu, w, 4), h5 = __shfl_sync(0xffffffffu, w, 5);
+					const uint32_t h6 = __shfl_sync(0xffffffffu, w, 6), h7 = __shfl_sync(0xffffffffu, w, 7);
+					x.a = ((uint64_t)h1 << 32) | h0; x.b = ((uint64_t)h3 << 32) | h2;
+					x.c = ((uint64_t)h5 << 32) | h4; x.d = ((uint64_t)h7 << 32) | h6;
+					const Ck4 s_ = stamp_leave(x, osums, r0 + i);
+					x = stamp_enter(s_, d_out, out_recs, osums, r0 + i + 1u, res, lane);
+					w = half_of(x);
 				}
-#define STAMP_STEP(C, WOFF, FAST, NC, NWOFF, NFAST, IDX)                                         \
-			{                                                                                    \
-				const uint32_t i_ = (IDX);                                                       \
-				{                                                                                \
-					const StampStep &nx = sg[i_ + 1u];       /* (slot 32 is padding) */          \
-					_Pragma("unroll") for (int jj = 0; jj < 4; jj++) {                           \
-						_Pragma("unroll") for (int q = 0; q < 9; q++) NC[jj][q] = nx.c[jj][q];   \
-					}                                                                            \
-					NWOFF = nx.woff; NFAST = nx.fast;                                            \
-				}                                                                                \
-				if (FAST != 0u) {                                                                \
-					const uint32_t w0 = (uint32_t)x.a, w1 = (uint32_t)(x.a >> 32);               \
-					const uint32_t w2 = (uint32_t)x.b, w3 = (uint32_t)(x.b >> 32);               \
-					const uint32_t w4 = (uint32_t)x.c, w5 = (uint32_t)(x.c >> 32);               \
-					const uint32_t w6 = (uint32_t)x.d, w7 = (uint32_t)(x.d >> 32);               \
-					Ck4 y;                                                                       \
-					STAMP_ROW(C, 0, y.a) STAMP_ROW(C, 1, y.b) STAMP_ROW(C, 2, y.c) STAMP_ROW(C, 3, y.d) \
-					x = y;                                                                       \
-					if (lane == 0) {                                                             \
-						uint64_t *ck_ = reinterpret_cast<uint64_t *>(d_out + WOFF);              \
-						ck_[0] = x.a; ck_[1] = x.b; ck_[2] = x.c; ck_[3] = x.d;                  \
-					}                                                                            \
-				} else {                                                                         \
-					const Ck4 s_ = stamp_leave(x, osums, r0 + i_);                               \
-					x = stamp_enter(s_, d_out, out_recs, osums, r0 + i_ + 1u, res, lane);        \
-				}                                                                                \
+				c_cur = c_nx; g_cur = g_nx; wo_cur = wo_nx; f_cur = f_nx;
 			}
-			uint32_t i = 0;
-			for (; i + 1u < cnt; i += 2u) {
-				STAMP_STEP(ca, woa, fa, cb, wob, fb, i)
-				STAMP_STEP(cb, wob, fb, ca, woa, fa, i + 1u)
-			}
-			if (i < cnt) STAMP_STEP(ca, woa, fa, cb, wob, fb, i)
-#undef STAMP_STEP
-#undef STAMP_ROW
 		}
 		__syncthreads();
 	}
 	if (warp == 0) {
+		const uint32_t h0 = __shfl_sync(0xffffffffu, w, 0), h1 = __shfl_sync(0xffffffffu, w, 1);
+		const uint32_t h2 = __shfl_sync(0xffffffffu, w, 2), h3 = __shfl_sync(0xffffffffu, w, 3);
+		const uint32_t h4 = __shfl_sync(0xffffffffu, w, 4), h5 = __shfl_sync(0xffffffffu, w, 5);
+		const uint32_t h6 = __shfl_sync(0xffffffffu, w, 6), h7 = __shfl_sync(0xffffffffu, w, 7);
+		x.a = ((uint64_t)h1 << 32) | h0; x.b = ((uint64_t)h3 << 32) | h2;
+		x.c = ((uint64_t)h5 << 32) | h4; x.d = ((uint64_t)h7 << 32) | h6;
 		const Ck4 s = stamp_leave(x, osums, n - 1u);
 		if (lane == 0) { *carry_out = s; res->carry = s; }
 	}
