@@ -398,6 +398,8 @@ __device__ __forceinline__ Ck4 stamp_leave(const Ck4 &x, const RecSums *__restri
 // memory.  One loader warp with one load in flight per lane took ~12 000 cycles per group, four
 // times what the chain needs for it (profiles/r2_stamp_chain.md): three warps, four loads in
 // flight per lane
+struct alignas(16) StampProducts { uint64_t p[2][4][8]; };   // the 32 products of a step, two steps' worth
+
 __global__ void __launch_bounds__(STAMP_THREADS)
 k_stamp_chain(uint8_t *__restrict__ d_out, const mtz_rec *__restrict__ out_recs,
     const RecSums *__restrict__ osums, const StampStep *__restrict__ steps, uint32_t n,
@@ -430,15 +432,18 @@ k_stamp_chain(uint8_t *__restrict__ d_out, const mtz_rec *__restrict__ out_recs,
 	if (warp >= 1 && ngroups > 0u) stage(0);
 	__syncthreads();
 
-	// One product per lane.  Lane (j, k) = 8 j + k holds half k of the running value (w_k, replicated
-	// in the four groups) and the weight C_jk of the current transition; a step is
-	//     p = C_jk * w_k (+ the constant in lane k = 0);  three xor-shuffle adds inside the 8-lane
-	//     group -> every lane of group j holds component j of the next value;  one more shuffle
-	//     hands lane (j, k) its new half (lane 8 (k >> 1) + (k & 1) offers lo when even, hi when odd).
-	// ~25 warp-instructions per step.  Measured alternatives (profiles/r2_stamp_chain.md): one
-	// component per lane with an 8-shuffle exchange, 55 instructions, 140 ns per record; the whole
-	// value in every lane, no exchange but 110 instructions, 305 ns -- a single warp issues about one
-	// instruction every 5 cycles, so it is the instruction COUNT of the step that has to go down.
+	// One product per lane, exchanged through shared memory.  Lane (j, k) = 8 j + k holds half k of the
+	// running value (w_k, replicated in the four groups) and the weight C_jk of the current transition:
+	//     p = C_jk * w_k (+ the constant in lane k = 0)  ->  s_p[j][k];
+	//     lane (j, k) then reads ROW k >> 1 (eight products, four 16-byte loads, the same addresses
+	//     in every group: broadcasts), adds them -- that is component k >> 1 of the next value -- and
+	//     keeps its half k & 1: its next w.  No shuffle, no redistribution; two buffers alternate.
+	// Measured forms (profiles/r2_stamp_chain.md): one component per lane + 8-shuffle exchange, 55
+	// instructions, 140 ns per record; whole value per lane, 110 instructions, 305 ns; one product per
+	// lane + three xor-shuffle adds + a redistribution shuffle, 45 instructions but four DEPENDENT
+	// shuffles, 150 ns.
+	__shared__ StampProducts s_pb;
+	uint64_t (*s_p)[4][8] = s_pb.p;
 	const int j = lane >> 3, k = lane & 7;
 	Ck4 x = { 0, 0, 0, 0 };
 	uint32_t w = 0;
@@ -446,10 +451,19 @@ k_stamp_chain(uint8_t *__restrict__ d_out, const mtz_rec *__restrict__ out_recs,
 		const uint64_t q = (k < 2) ? v.a : (k < 4) ? v.b : (k < 6) ? v.c : v.d;
 		return (k & 1) ? (uint32_t)(q >> 32) : (uint32_t)q;
 	};
+	auto whole = [&]() {                                  // all lanes: the running value from lanes 0..7
+		const uint32_t h0 = __shfl_sync(0xffffffffu, w, 0), h1 = __shfl_sync(0xffffffffu, w, 1);
+		const uint32_t h2 = __shfl_sync(0xffffffffu, w, 2), h3 = __shfl_sync(0xffffffffu, w, 3);
+		const uint32_t h4 = __shfl_sync(0xffffffffu, w, 4), h5 = __shfl_sync(0xffffffffu, w, 5);
+		const uint32_t h6 = __shfl_sync(0xffffffffu, w, 6), h7 = __shfl_sync(0xffffffffu, w, 7);
+		x.a = ((uint64_t)h1 << 32) | h0; x.b = ((uint64_t)h3 << 32) | h2;
+		x.c = ((uint64_t)h5 << 32) | h4; x.d = ((uint64_t)h7 << 32) | h6;
+	};
 	if (warp == 0) {
 		x = stamp_enter(*carry_out, d_out, out_recs, osums, 0u, res, lane);
 		w = half_of(x);
 	}
+	uint32_t flip = 0;
 	for (uint32_t g = 0; g < ngroups; g++) {
 		if (warp >= 1) {
 			if (g + 1u < ngroups) stage(g + 1u);
@@ -466,21 +480,22 @@ k_stamp_chain(uint8_t *__restrict__ d_out, const mtz_rec *__restrict__ out_recs,
 				const uint64_t wo_nx = nx.woff;
 				const uint32_t f_nx = nx.fast;
 				if (f_cur != 0u) {
-					uint64_t p = c_cur * (uint64_t)w + g_cur;
-					p += __shfl_xor_sync(0xffffffffu, p, 1);
-					p += __shfl_xor_sync(0xffffffffu, p, 2);
-					p += __shfl_xor_sync(0xffffffffu, p, 4);            // component j of the stamped value
-					if (k == 0) *reinterpret_cast<uint64_t *>(d_out + wo_cur + 8u * (uint32_t)j) = p;
-					const uint32_t offer = (lane & 1) ? (uint32_t)(p >> 32) : (uint32_t)p;
-					w = __shfl_sync(0xffffffffu, offer, 8 * (k >> 1) + (k & 1));
+					s_p[flip][j][k] = c_cur * (uint64_t)w + g_cur;
+					__syncwarp();
+					const uint4 *row = reinterpret_cast<const uint4 *>(&s_p[flip][k >> 1][0]);
+					const uint4 q0 = row[0], q1 = row[1], q2 = row[2], q3 = row[3];
+					const uint64_t a0 = ((uint64_t)q0.y << 32 | q0.x) + ((uint64_t)q0.w << 32 | q0.z);
+					const uint64_t a1 = ((uint64_t)q1.y << 32 | q1.x) + ((uint64_t)q1.w << 32 | q1.z);
+					const uint64_t a2 = ((uint64_t)q2.y << 32 | q2.x) + ((uint64_t)q2.w << 32 | q2.z);
+					const uint64_t a3 = ((uint64_t)q3.y << 32 | q3.x) + ((uint64_t)q3.w << 32 | q3.z);
+					const uint64_t v = (a0 + a1) + (a2 + a3);          // component k >> 1 of the stamped value
+					if (j == 0 && (k & 1) == 0)
+						*reinterpret_cast<uint64_t *>(d_out + wo_cur + 8u * (uint32_t)(k >> 1)) = v;
+					w = (k & 1) ? (uint32_t)(v >> 32) : (uint32_t)v;
+					flip ^= 1u;
 				} else {
-					// generic transition: rebuild the whole value in every lane, leave / enter, split again
-					const uint32_t h0 = __shfl_sync(0xffffffffu, w, 0), h1 = __shfl_sync(0xffffffffu, w, 1);
-					const uint32_t h2 = __shfl_sync(0xffffffffu, w, 2), h3 = __shfl_sync(0xffffffffu, w, 3);
-					const uint32_t h4 = __shfl_sync(0xffffffffu, w, 4), h5 = __shfl_sync(0xffffffffu, w, 5);
-					const uint32_t h6 = __shfl_sync(0xffffffffu, w, 6), h7 = __shfl_sync(0xffffffffu, w, 7);
-					x.a = ((uint64_t)h1 << 32) | h0; x.b = ((uint64_t)h3 << 32) | h2;
-					x.c = ((uint64_t)h5 << 32) | h4; x.d = ((uint64_t)h7 << 32) | h6;
+					// generic transition: the whole value in every lane, leave / enter, split again
+					whole();
 					const Ck4 s_ = stamp_leave(x, osums, r0 + i);
 					x = stamp_enter(s_, d_out, out_recs, osums, r0 + i + 1u, res, lane);
 					w = half_of(x);
@@ -491,12 +506,7 @@ k_stamp_chain(uint8_t *__restrict__ d_out, const mtz_rec *__restrict__ out_recs,
 		__syncthreads();
 	}
 	if (warp == 0) {
-		const uint32_t h0 = __shfl_sync(0xffffffffu, w, 0), h1 = __shfl_sync(0xffffffffu, w, 1);
-		const uint32_t h2 = __shfl_sync(0xffffffffu, w, 2), h3 = __shfl_sync(0xffffffffu, w, 3);
-		const uint32_t h4 = __shfl_sync(0xffffffffu, w, 4), h5 = __shfl_sync(0xffffffffu, w, 5);
-		const uint32_t h6 = __shfl_sync(0xffffffffu, w, 6), h7 = __shfl_sync(0xffffffffu, w, 7);
-		x.a = ((uint64_t)h1 << 32) | h0; x.b = ((uint64_t)h3 << 32) | h2;
-		x.c = ((uint64_t)h5 << 32) | h4; x.d = ((uint64_t)h7 << 32) | h6;
+		whole();
 		const Ck4 s = stamp_leave(x, osums, n - 1u);
 		if (lane == 0) { *carry_out = s; res->carry = s; }
 	}
