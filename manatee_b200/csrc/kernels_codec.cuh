@@ -398,8 +398,6 @@ __device__ __forceinline__ Ck4 stamp_leave(const Ck4 &x, const RecSums *__restri
 // memory.  One loader warp with one load in flight per lane took ~12 000 cycles per group, four
 // times what the chain needs for it (profiles/r2_stamp_chain.md): three warps, four loads in
 // flight per lane
-struct alignas(16) StampProducts { uint64_t p[2][4][8]; };   // the 32 products of a step, two steps' worth
-
 __global__ void __launch_bounds__(STAMP_THREADS)
 k_stamp_chain(uint8_t *__restrict__ d_out, const mtz_rec *__restrict__ out_recs,
     const RecSums *__restrict__ osums, const StampStep *__restrict__ steps, uint32_t n,
@@ -407,6 +405,7 @@ k_stamp_chain(uint8_t *__restrict__ d_out, const mtz_rec *__restrict__ out_recs,
 {
 	__shared__ StampStep s_steps[2][STAMP_GROUP + 1];     // +1: the weight prefetch of step i+1 needs no bounds check
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const int j = lane & 3;
 	if (n == 0u) return;
 	const uint32_t T = n - 1u;                                    // transitions
 	const uint32_t ngroups = (T + STAMP_GROUP - 1u) / STAMP_GROUP;
@@ -432,81 +431,73 @@ k_stamp_chain(uint8_t *__restrict__ d_out, const mtz_rec *__restrict__ out_recs,
 	if (warp >= 1 && ngroups > 0u) stage(0);
 	__syncthreads();
 
-	// One product per lane, exchanged through shared memory.  Lane (j, k) = 8 j + k holds half k of the
-	// running value (w_k, replicated in the four groups) and the weight C_jk of the current transition:
-	//     p = C_jk * w_k (+ the constant in lane k = 0)  ->  s_p[j][k];
-	//     lane (j, k) then reads ROW k >> 1 (eight products, four 16-byte loads, the same addresses
-	//     in every group: broadcasts), adds them -- that is component k >> 1 of the next value -- and
-	//     keeps its half k & 1: its next w.  No shuffle, no redistribution; two buffers alternate.
-	// Measured forms (profiles/r2_stamp_chain.md): one component per lane + 8-shuffle exchange, 55
-	// instructions, 140 ns per record; whole value per lane, 110 instructions, 305 ns; one product per
-	// lane + three xor-shuffle adds + a redistribution shuffle, 45 instructions but four DEPENDENT
-	// shuffles, 150 ns.
-	__shared__ StampProducts s_pb;
-	uint64_t (*s_p)[4][8] = s_pb.p;
-	const int j = lane >> 3, k = lane & 7;
 	Ck4 x = { 0, 0, 0, 0 };
-	uint32_t w = 0;
-	auto half_of = [&](const Ck4 &v) -> uint32_t {
-		const uint64_t q = (k < 2) ? v.a : (k < 4) ? v.b : (k < 6) ? v.c : v.d;
-		return (k & 1) ? (uint32_t)(q >> 32) : (uint32_t)q;
-	};
-	auto whole = [&]() {                                  // all lanes: the running value from lanes 0..7
-		const uint32_t h0 = __shfl_sync(0xffffffffu, w, 0), h1 = __shfl_sync(0xffffffffu, w, 1);
-		const uint32_t h2 = __shfl_sync(0xffffffffu, w, 2), h3 = __shfl_sync(0xffffffffu, w, 3);
-		const uint32_t h4 = __shfl_sync(0xffffffffu, w, 4), h5 = __shfl_sync(0xffffffffu, w, 5);
-		const uint32_t h6 = __shfl_sync(0xffffffffu, w, 6), h7 = __shfl_sync(0xffffffffu, w, 7);
-		x.a = ((uint64_t)h1 << 32) | h0; x.b = ((uint64_t)h3 << 32) | h2;
-		x.c = ((uint64_t)h5 << 32) | h4; x.d = ((uint64_t)h7 << 32) | h6;
-	};
+	uint64_t own = 0;
 	if (warp == 0) {
 		x = stamp_enter(*carry_out, d_out, out_recs, osums, 0u, res, lane);
-		w = half_of(x);
+		own = (j == 0) ? x.a : (j == 1) ? x.b : (j == 2) ? x.c : x.d;
 	}
-	uint32_t flip = 0;
 	for (uint32_t g = 0; g < ngroups; g++) {
 		if (warp >= 1) {
 			if (g + 1u < ngroups) stage(g + 1u);
 		} else {
 			const uint32_t r0 = g * STAMP_GROUP, cnt = min((uint32_t)STAMP_GROUP, T - r0);
+			// The weights of transition i+1 are loaded from shared memory (29 cycles) while transition
+			// i is computed; two register sets alternate so that no value is ever copied.
 			const StampStep *sg = &s_steps[g & 1u][0];
-			uint64_t c_cur = sg[0].c[j][k], g_cur = (k == 0) ? sg[0].c[j][8] : 0ull;
-			uint64_t wo_cur = sg[0].woff;
-			uint32_t f_cur = sg[0].fast;
-			for (uint32_t i = 0; i < cnt; i++) {
-				// the next transition's weight, constant, offset and kind (slot 32 is padding)
-				const StampStep &nx = sg[i + 1u];
-				const uint64_t c_nx = nx.c[j][k], g_nx = (k == 0) ? nx.c[j][8] : 0ull;
-				const uint64_t wo_nx = nx.woff;
-				const uint32_t f_nx = nx.fast;
-				if (f_cur != 0u) {
-					s_p[flip][j][k] = c_cur * (uint64_t)w + g_cur;
-					__syncwarp();
-					const uint4 *row = reinterpret_cast<const uint4 *>(&s_p[flip][k >> 1][0]);
-					const uint4 q0 = row[0], q1 = row[1], q2 = row[2], q3 = row[3];
-					const uint64_t a0 = ((uint64_t)q0.y << 32 | q0.x) + ((uint64_t)q0.w << 32 | q0.z);
-					const uint64_t a1 = ((uint64_t)q1.y << 32 | q1.x) + ((uint64_t)q1.w << 32 | q1.z);
-					const uint64_t a2 = ((uint64_t)q2.y << 32 | q2.x) + ((uint64_t)q2.w << 32 | q2.z);
-					const uint64_t a3 = ((uint64_t)q3.y << 32 | q3.x) + ((uint64_t)q3.w << 32 | q3.z);
-					const uint64_t v = (a0 + a1) + (a2 + a3);          // component k >> 1 of the stamped value
-					if (j == 0 && (k & 1) == 0)
-						*reinterpret_cast<uint64_t *>(d_out + wo_cur + 8u * (uint32_t)(k >> 1)) = v;
-					w = (k & 1) ? (uint32_t)(v >> 32) : (uint32_t)v;
-					flip ^= 1u;
-				} else {
-					// generic transition: the whole value in every lane, leave / enter, split again
-					whole();
-					const Ck4 s_ = stamp_leave(x, osums, r0 + i);
-					x = stamp_enter(s_, d_out, out_recs, osums, r0 + i + 1u, res, lane);
-					w = half_of(x);
-				}
-				c_cur = c_nx; g_cur = g_nx; wo_cur = wo_nx; f_cur = f_nx;
+			uint64_t ca[9], cb[9];
+			uint64_t woa = sg[0].woff, wob = 0;
+			uint32_t fa = sg[0].fast, fb = 0;
+#pragma unroll
+			for (int q = 0; q < 9; q++) { ca[q] = sg[0].c[j][q]; cb[q] = 0; }
+#define STAMP_STEP(C, WOFF, FAST, NC, NWOFF, NFAST, IDX)                                         \
+			{                                                                                    \
+				const uint32_t i_ = (IDX);                                                       \
+				{                                                                                \
+					const StampStep &nx = sg[i_ + 1u];       /* (slot 32 is padding) */          \
+					_Pragma("unroll") for (int q = 0; q < 9; q++) NC[q] = nx.c[j][q];            \
+					NWOFF = nx.woff; NFAST = nx.fast;                                            \
+				}                                                                                \
+				const uint32_t lo = (uint32_t)own, hi = (uint32_t)(own >> 32);                   \
+				const uint32_t w0 = __shfl_sync(0xffffffffu, lo, 0), w1 = __shfl_sync(0xffffffffu, hi, 0); \
+				const uint32_t w2 = __shfl_sync(0xffffffffu, lo, 1), w3 = __shfl_sync(0xffffffffu, hi, 1); \
+				const uint32_t w4 = __shfl_sync(0xffffffffu, lo, 2), w5 = __shfl_sync(0xffffffffu, hi, 2); \
+				const uint32_t w6 = __shfl_sync(0xffffffffu, lo, 3), w7 = __shfl_sync(0xffffffffu, hi, 3); \
+				if (FAST != 0u) {                                                                \
+					/* four independent multiply-add chains (pinned: left alone the compiler     \
+					 * folds them into ONE dependent chain of ~10 cycles per term) */            \
+					uint64_t p0 = C[8] + C[0] * (uint64_t)w0 + C[1] * (uint64_t)w1;              \
+					uint64_t p1 = C[2] * (uint64_t)w2 + C[3] * (uint64_t)w3;                     \
+					uint64_t p2 = C[4] * (uint64_t)w4 + C[5] * (uint64_t)w5;                     \
+					uint64_t p3 = C[6] * (uint64_t)w6 + C[7] * (uint64_t)w7;                     \
+					MTZ_PIN64(p0); MTZ_PIN64(p1); MTZ_PIN64(p2); MTZ_PIN64(p3);                  \
+					own = (p0 + p1) + (p2 + p3);                                                 \
+					/* every lane stores (lanes 4..31 repeat lanes 0..3): no divergent branch */   \
+					*reinterpret_cast<uint64_t *>(d_out + WOFF + 8u * (uint32_t)j) = own;        \
+				} else {                                                                         \
+					x.a = ((uint64_t)w1 << 32) | w0; x.b = ((uint64_t)w3 << 32) | w2;            \
+					x.c = ((uint64_t)w5 << 32) | w4; x.d = ((uint64_t)w7 << 32) | w6;            \
+					const Ck4 s_ = stamp_leave(x, osums, r0 + i_);                               \
+					x = stamp_enter(s_, d_out, out_recs, osums, r0 + i_ + 1u, res, lane);        \
+					own = (j == 0) ? x.a : (j == 1) ? x.b : (j == 2) ? x.c : x.d;                \
+				}                                                                                \
 			}
+			uint32_t i = 0;
+			for (; i + 1u < cnt; i += 2u) {
+				STAMP_STEP(ca, woa, fa, cb, wob, fb, i)
+				STAMP_STEP(cb, wob, fb, ca, woa, fa, i + 1u)
+			}
+			if (i < cnt) STAMP_STEP(ca, woa, fa, cb, wob, fb, i)
+#undef STAMP_STEP
 		}
 		__syncthreads();
 	}
 	if (warp == 0) {
-		whole();
+		const uint32_t lo = (uint32_t)own, hi = (uint32_t)(own >> 32);
+		x.a = ((uint64_t)__shfl_sync(0xffffffffu, hi, 0) << 32) | __shfl_sync(0xffffffffu, lo, 0);
+		x.b = ((uint64_t)__shfl_sync(0xffffffffu, hi, 1) << 32) | __shfl_sync(0xffffffffu, lo, 1);
+		x.c = ((uint64_t)__shfl_sync(0xffffffffu, hi, 2) << 32) | __shfl_sync(0xffffffffu, lo, 2);
+		x.d = ((uint64_t)__shfl_sync(0xffffffffu, hi, 3) << 32) | __shfl_sync(0xffffffffu, lo, 3);
 		const Ck4 s = stamp_leave(x, osums, n - 1u);
 		if (lane == 0) { *carry_out = s; res->carry = s; }
 	}
