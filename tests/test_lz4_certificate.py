@@ -172,6 +172,35 @@ def test_incompressible_and_foreign_records_take_the_encoder(emul_library, oracl
     _check(oracle, m, cap + (1 << 20), len(blocks) - 1)
 
 
+def _many_tiny_sequences(oracle, recsize):
+    """a record whose incoming block has more matches than K2's parse table holds (lsize / 8): one
+    literal + a 4-byte match, over and over -- valid LZ4, decodes fine, must simply not be certified"""
+    seqs = [(b"abcdefgh", 8, 4)]
+    pos = 12
+    while pos + 5 + 16 <= recsize:
+        seqs.append((bytes([65 + (pos * 7) % 23]), 5, 4))
+        pos += 5
+    tail = bytes(range(48, 48 + recsize - pos))
+    data = F.decode(seqs, tail)
+    assert len(data) == recsize and len(seqs) > recsize // 8
+    raw = oracle.synth_stream(3, recsize, oracle.PAYLOAD_PGPAGE).copy()
+    cnt, offs = oracle.stream_index(raw)
+    writes = [int(offs[k]) for k in range(cnt) if int(raw[int(offs[k])]) == 3]
+    raw[writes[1] + 312:writes[1] + 312 + recsize] = np.frombuffer(data, dtype=np.uint8)
+    assert oracle.stream_restamp(raw)[0] == 0
+    rc, c, _ = oracle.stream_compress_plain(raw)
+    c = np.ascontiguousarray(c)
+    blocks = F.blocks_of(oracle, c)
+    assert [w for w, _ in blocks] == [0, 1, 2]
+    return F.splice(oracle, c, {1: F.emit(seqs, tail)}), raw.size, len(blocks)
+
+
+def test_parse_table_overflow_is_not_certified(emul_library, oracle):
+    for recsize in (16384, 131072):
+        m, cap, nblk = _many_tiny_sequences(oracle, recsize)
+        _check(oracle, m, cap + (1 << 20), nblk - 1)
+
+
 def test_certificate_off_gives_the_same_bytes(emul_so, oracle, tmp_path):
     """MTZ_CERTIFY=0: every record re-encoded, same output, nothing certified"""
     c, cap = _canonical(oracle, 6, 16384)
